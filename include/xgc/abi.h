@@ -1,0 +1,346 @@
+/* xgc C ABI — the drop-in boundary of the B200-native weekly epidemic step.
+ *
+ * What this replaces.  In the reference every weekly module is an R closure `FUN(dat, at) -> dat` handed to
+ * control_msm() (/root/reference/burnin/cal/sim1_02_lhs.r:195-218; inst/analysis02_screening/02.00_epi.r:289-313)
+ * and run once per week by EpiModel::netsim (sim1_02_lhs.r:232).  The modules themselves live in the un-vendored
+ * EpiModelHIV fork (renv.lock:26-31).  An R-side maintainer binds this header with `.Call` shims
+ * (see INTEGRATION.md); tests and benchmarks bind it with Python ctypes.  No torch / R types cross this boundary:
+ * plain pointers, sizes and status codes only.
+ *
+ * Conventions: node ids are 1-based R positions (rank among living agents, in attribute-vector order);
+ * edge lists are column-major int32 [E,2] as tergmLite stores them; races 1..4 = B,H,O,W; sites ordered rect,ureth,phar;
+ * `at` starts at 2 (at = 1 is initialisation).  Every function returns 0 on success, non-zero on error, and never
+ * throws or exits; xgc_last_error() gives the message.  The caller owns every buffer it passes; the library copies.
+ */
+#ifndef XGC_ABI_H
+#define XGC_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XGC_ABI_VERSION 1
+#ifdef __CUDACC__
+#define XGC_HD __host__ __device__
+#else
+#define XGC_HD
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Parameters: one double vector per replicate (every replicate of a calibration sweep carries its own LHS draw,
+ * sim1_02_lhs.r:34-43).  Index enum generated from params.def.
+ * ---------------------------------------------------------------------------------------------------------------- */
+enum xgc_param_index {
+#define XGC_PARAM(name, count, dflt) XGC_P_##name, XGC_P_##name##_END = XGC_P_##name + (count) - 1,
+#include "params.def"
+#undef XGC_PARAM
+  XGC_NPARAM
+};
+
+/* Tables shared by all replicates of a handle (contents of netstats / epistats in the reference: sim1_02_lhs.r:60-61).
+ * Flat double array; offsets below. */
+#define XGC_ASMR_AGES 101           /* integer ages 0..100                                                          */
+#define XGC_GLM_NCOEF 26            /* b0,dur,dur2,pt2,dur_pt2,ca,ca2,hcp,prep, pad, rc[4][4]                        */
+enum xgc_glm_coef { XGC_G_B0 = 0, XGC_G_DUR, XGC_G_DUR2, XGC_G_PT2, XGC_G_DUR_PT2, XGC_G_CA, XGC_G_CA2, XGC_G_HCP,
+                    XGC_G_PREP, XGC_G_PAD, XGC_G_RC = 10 };
+enum xgc_table_offset {
+  XGC_T_ASMR      = 0,                                   /* [4][XGC_ASMR_AGES] weekly death prob by race, floor(age) */
+  XGC_T_GLM_AI    = XGC_T_ASMR + 4 * XGC_ASMR_AGES,      /* anal acts/yr, main+casual: log link                     */
+  XGC_T_GLM_OI    = XGC_T_GLM_AI + XGC_GLM_NCOEF,        /* oral acts/yr, main+casual: log link                     */
+  XGC_T_GLM_CONDMC= XGC_T_GLM_OI + XGC_GLM_NCOEF,        /* condom prob, main+casual: logit link                    */
+  XGC_T_GLM_CONDOO= XGC_T_GLM_CONDMC + XGC_GLM_NCOEF,    /* condom prob, one-off: logit link                        */
+  XGC_T_RACE_PROP = XGC_T_GLM_CONDOO + XGC_GLM_NCOEF,    /* [4] race distribution of arrivals                       */
+  XGC_T_ROLE_PROB = XGC_T_RACE_PROP + 4,                 /* [4][3] role class I,R,V by race                         */
+  XGC_T_NET_DEG   = XGC_T_ROLE_PROB + 12,                /* [3] surrogate network: target mean degree by layer      */
+  XGC_T_NET_DUR   = XGC_T_NET_DEG + 3,                   /* [3] surrogate network: mean duration (weeks), [2] unused*/
+  XGC_NTABLE      = XGC_T_NET_DUR + 3
+};
+
+/* Control flags, one int vector per replicate (scenario arms differ per replicate: 02.00_epi.r:315-326). */
+enum xgc_control_index {
+  XGC_C_transRoute_Kissing = 0,     /* sim1_02_lhs.r:220 */
+  XGC_C_transRoute_Rimming,         /* :221 */
+  XGC_C_gcUntreatedRecovDist,       /* :222   0 = "geom", 1 = "pois" (analysis01_epi/03_sens_poisdurat.r:225) */
+  XGC_C_stiScreeningProtocol,       /* :223   0 base, 1 symptomatic, 2 cdc, 3 universal (02.00_epi.r:318) */
+  XGC_C_cdcExposureSite_Kissing,    /* :225 */
+  XGC_C_network_mode,               /* 0 = host supplies edge lists each week (simnet_msm stays in R); 1 = on-device surrogate */
+  XGC_NCONTROL = 8
+};
+enum { XGC_RECOV_GEOM = 0, XGC_RECOV_POIS = 1 };
+enum { XGC_SCREEN_BASE = 0, XGC_SCREEN_SYMPTOMATIC = 1, XGC_SCREEN_CDC = 2, XGC_SCREEN_UNIVERSAL = 3 };
+
+/* Module mask bits, in the order the reference names the modules (sim1_02_lhs.r:201-218).  xgc_step() runs the
+ * selected modules in exactly this order. */
+enum xgc_module_bit {
+  XGC_M_AGING       = 1u << 0,
+  XGC_M_DEPARTURE   = 1u << 1,
+  XGC_M_ARRIVAL     = 1u << 2,
+  XGC_M_HIVTEST     = 1u << 3,
+  XGC_M_HIVTX       = 1u << 4,
+  XGC_M_HIVPROGRESS = 1u << 5,
+  XGC_M_HIVVL       = 1u << 6,
+  XGC_M_RESIM_NETS  = 1u << 7,      /* surrogate only; with network_mode 0 the host calls xgc_set_edgelist instead   */
+  XGC_M_ACTS        = 1u << 8,
+  XGC_M_CONDOMS     = 1u << 9,      /* act-level condom use: evaluated lazily per act, see DESIGN.md                 */
+  XGC_M_POSITION    = 1u << 10,     /* act-level position/site pairing: evaluated lazily per act                     */
+  XGC_M_PREP        = 1u << 11,     /* includes risk-history update                                                  */
+  XGC_M_HIVTRANS    = 1u << 12,
+  XGC_M_STIRECOV    = 1u << 13,
+  XGC_M_STITX       = 1u << 14,
+  XGC_M_STITRANS    = 1u << 15,
+  XGC_M_PREV        = 1u << 16,
+  XGC_M_ALL         = (1u << 17) - 1
+};
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Random draws.  Every stochastic decision consumes an *indexed* uniform u(replicate, at, stream, entity, k):
+ *   native   : Philox4x32-10, key = (seed, global replicate id), counter = (at, stream<<16 | k>>2, e0, e1), lane k&3,
+ *              u = (x + 0.5) * 2^-32;
+ *   injected : the caller supplies the table (xgc_inject), index = off(stream) + entity_index * K(stream) + k.
+ * Entity kinds: agent (e0 = uid, e1 = 0; index = uid), edge (e0,e1 = uids of the endpoints as stored; index =
+ * position in the layer's edge list), replicate (0,0; index 0), formed edge (e0 = j, e1 = 0; index = j).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define XGC_MAX_ACTS 32             /* per edge, per act type, per week (Poisson draws are truncated here)          */
+#define XGC_FORM_TRIES 4
+enum xgc_stream {
+  /* agent streams */
+  XGC_S_DEPART = 0,    /* k0 natural mortality, k1 AIDS mortality                                                   */
+  XGC_S_HIVTEST,       /* k0 interval test                                                                          */
+  XGC_S_HIVTX,         /* k0 initiation, k1 halting, k2 re-initiation                                               */
+  XGC_S_PREP,          /* k0 start, k1 adherence class, k2 discontinuation                                          */
+  XGC_S_STIRECOV,      /* k0..2 untreated recovery r,u,p; k3..5 treated recovery r,u,p                              */
+  XGC_S_STITX,         /* k0..2 symptomatic care seeking r,u,p; k3 asymptomatic visit; k4..6 site tested r,u,p      */
+  XGC_S_INFECT,        /* k0..2 symptomatic r,u,p; k3..5 Poisson duration r,u,p                                     */
+  XGC_S_ARRIVE_ATTR,   /* k0 race, k1 role, k2 ins.quot, k3 circ, k4 late.tester, k5 tt.traj, k6 act.stopper, k7 risk.grp */
+  /* replicate streams */
+  XGC_S_ARRIVE_N,      /* k = Poisson chunk index (mean split into chunks of <= 32)                                 */
+  XGC_S_PATHORDER,     /* k0..5 Fisher-Yates draws for the weekly pathway permutation (stitrans_msm_rand)           */
+  XGC_S_NET_N,         /* k = layer: number of edges to form                                                        */
+  /* formed-edge streams (surrogate network), stream id + layer */
+  XGC_S_FORM,          /* XGC_S_FORM + layer; k = 2*try, 2*try+1                                                    */
+  /* edge streams: stream id + XGC_EDGE_STREAMS * layer */
+  XGC_S_EDGE0 = XGC_S_FORM + 3,
+  XGC_S_DISSOLVE = XGC_S_EDGE0, /* k0 (surrogate network)                                                           */
+  XGC_S_ACTS,          /* k0 anal, k1 oral, k2 kissing, k3 rimming counts                                           */
+  XGC_S_COND,          /* k = anal act index: condom                                                                */
+  XGC_S_POS,           /* k = anal act index: position (versatile pairs)                                            */
+  XGC_S_OIDIR,         /* k = oral act index: direction                                                             */
+  XGC_S_RIMDIR,        /* k = rimming act index: direction                                                          */
+  XGC_S_HIVTRANS,      /* k = anal act index                                                                        */
+  XGC_S_GC_AI_A,       /* k = act index; A = insertive->receptive (u2r), B = receptive->insertive (r2u)             */
+  XGC_S_GC_AI_B,
+  XGC_S_GC_OI_A,       /* u2p / p2u                                                                                 */
+  XGC_S_GC_OI_B,
+  XGC_S_GC_RIM_A,      /* p2r / r2p                                                                                 */
+  XGC_S_GC_RIM_B,
+  XGC_S_GC_KISS_A,     /* p1->p2 / p2->p1                                                                           */
+  XGC_S_GC_KISS_B,
+  XGC_S_EDGE_END
+};
+#define XGC_EDGE_STREAMS (XGC_S_EDGE_END - XGC_S_EDGE0)
+#define XGC_NSTREAM (XGC_S_EDGE0 + 3 * XGC_EDGE_STREAMS)
+
+/* Draws per entity for each stream (table width in injected mode). */
+static inline XGC_HD int xgc_stream_width(int s) {
+  if (s < XGC_S_EDGE0) {
+    switch (s) {
+      case XGC_S_DEPART: return 2;  case XGC_S_HIVTEST: return 1;  case XGC_S_HIVTX: return 3;
+      case XGC_S_PREP: return 3;    case XGC_S_STIRECOV: return 6; case XGC_S_STITX: return 7;
+      case XGC_S_INFECT: return 6;  case XGC_S_ARRIVE_ATTR: return 8;
+      case XGC_S_ARRIVE_N: return 64; case XGC_S_PATHORDER: return 6; case XGC_S_NET_N: return 3;
+      default: return 2 * XGC_FORM_TRIES;      /* XGC_S_FORM + layer */
+    }
+  }
+  s = (s - XGC_S_EDGE0) % XGC_EDGE_STREAMS + XGC_S_EDGE0;
+  if (s == XGC_S_DISSOLVE) return 1;
+  if (s == XGC_S_ACTS) return 4;
+  return XGC_MAX_ACTS;
+}
+
+/* Injected-draw table for ONE replicate and ONE week.  Layout: for each stream s in increasing order, a block of
+ * n_entities(s) * xgc_stream_width(s) doubles, where n_entities is uid_cap for agent streams, 1 for replicate streams,
+ * form_cap for formed-edge streams and e_cap[layer] for edge streams. */
+typedef struct xgc_inject {
+  const double* u;        /* [n_replicates][stride] or NULL for native Philox                                       */
+  size_t        stride;   /* doubles per replicate = xgc_inject_size(...)                                           */
+  int32_t       uid_cap;
+  int32_t       e_cap[3];
+  int32_t       form_cap;
+} xgc_inject;
+
+static inline int xgc_stream_entities(const xgc_inject* d, int s) {
+  if (s <= XGC_S_ARRIVE_ATTR) return d->uid_cap;
+  if (s < XGC_S_FORM) return 1;
+  if (s < XGC_S_EDGE0) return d->form_cap;
+  return d->e_cap[(s - XGC_S_EDGE0) / XGC_EDGE_STREAMS];
+}
+static inline size_t xgc_inject_offset(const xgc_inject* d, int s) {
+  size_t off = 0;
+  for (int t = 0; t < s; ++t) off += (size_t)xgc_stream_entities(d, t) * (size_t)xgc_stream_width(t);
+  return off;
+}
+static inline size_t xgc_inject_size(const xgc_inject* d) { return xgc_inject_offset(d, XGC_NSTREAM); }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Epi counters: raw integer tallies per (replicate, week); every epi series of SURVEY Appendix C is a ratio or sum of
+ * these (xgc_get_epi).  Stratified groups hold 20 cells: cell = (race-1)*5 + (age.grp-1).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define XGC_NCELL 20
+enum xgc_counter_group {           /* each group = XGC_NCELL consecutive counters */
+  XGC_K_NUM = 0, XGC_K_INUM, XGC_K_INUM_DX, XGC_K_VSUPP, XGC_K_INCID_HIV, XGC_K_PREPELIG, XGC_K_PREPCURR,
+  XGC_K_INUM_GC, XGC_K_INUM_RGC, XGC_K_INUM_UGC, XGC_K_INUM_PGC, XGC_K_INCID_RGC, XGC_K_INCID_UGC, XGC_K_INCID_PGC,
+  XGC_K_NGROUP
+};
+enum xgc_counter_scalar {
+  XGC_K_PATH = XGC_K_NGROUP * XGC_NCELL, /* [7] incidence by pathway: u2r, p2r, r2u, p2u, u2p, r2p, p2p               */
+  XGC_K_VISITS = XGC_K_PATH + 7,   /* clinic visits (symptomatic + screening)                                       */
+  XGC_K_VISITS_SYMPT,
+  XGC_K_TESTED,                    /* [3] site tests r,u,p  (num.rgc.test ...)                                       */
+  XGC_K_POS = XGC_K_TESTED + 3,    /* [3] positive site tests                                                        */
+  XGC_K_TXSTART = XGC_K_POS + 3,   /* [3] treatments started                                                         */
+  XGC_K_DEP_GEN = XGC_K_TXSTART + 3,
+  XGC_K_DEP_AIDS,
+  XGC_K_NNEW,
+  XGC_K_HIVTESTS,
+  XGC_K_NEDGES,                    /* [3] edges per layer after resim                                               */
+  XGC_K_NACTS = XGC_K_NEDGES + 3,  /* [4] total anal, oral, kissing, rimming acts                                   */
+  XGC_NCOUNTER_RAW = XGC_K_NACTS + 4
+};
+#define XGC_NCOUNTER ((XGC_NCOUNTER_RAW + 3) & ~3)
+/* pathway bit order inside XGC_K_PATH and inside the per-agent new-infection mask */
+enum { XGC_PATH_U2R = 0, XGC_PATH_P2R, XGC_PATH_R2U, XGC_PATH_P2U, XGC_PATH_U2P, XGC_PATH_R2P, XGC_PATH_P2P, XGC_NPATH };
+
+/* Targets vector produced by xgc_targets(): tail-window means, NA/NaN -> 0
+ * (R/calculate_targets.r:14-190; inst/cal/sim0.0_setup.r:205-308). */
+enum xgc_target_index {
+  XGC_TG_NUM = 0,
+  XGC_TG_I_PREV,                  /* ct_hiv_prev                       */
+  XGC_TG_IR100_POP,               /* ct_hiv_incid_per100pop            */
+  XGC_TG_HIVDX_RACE,              /* [4] i.prev.dx.inf.<race> = prob.hivdx.<race> */
+  XGC_TG_HIVDX_AGE = XGC_TG_HIVDX_RACE + 4,   /* [5] */
+  XGC_TG_VLS_RACE  = XGC_TG_HIVDX_AGE + 5,    /* [4] cc.vsupp.<race> */
+  XGC_TG_VLS_AGE   = XGC_TG_VLS_RACE + 4,     /* [5] */
+  XGC_TG_PREPCOV_RACE = XGC_TG_VLS_AGE + 5,   /* [4] */
+  XGC_TG_PROP_TESTED = XGC_TG_PREPCOV_RACE + 4, /* [3] prop.{rect,ureth,phar}.tested */
+  XGC_TG_PROB_POS  = XGC_TG_PROP_TESTED + 3,  /* [3] prob.{rGC,uGC,pGC}.tested      */
+  XGC_TG_PREV_GC   = XGC_TG_PROB_POS + 3,     /* [4] prev.gc, prev.rgc, prev.ugc, prev.pgc */
+  XGC_TG_IR100_GC  = XGC_TG_PREV_GC + 4,      /* [4] ir100.gc, .rgc, .ugc, .pgc     */
+  XGC_NTARGET      = XGC_TG_IR100_GC + 4
+};
+
+/* Attribute dtypes for upload/download. */
+enum xgc_dtype { XGC_F64 = 0, XGC_I32 = 1 };
+
+/* Status bits in xgc_status(). */
+enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_ST_GC_EXTINCT = 4, XGC_ST_BAD_EDGE = 8 };
+
+/* Named constants of this header, so that bindings (ctypes, .Call) need not re-declare the enums. */
+#define XGC_CONSTANT_LIST(X) \
+  X(XGC_ABI_VERSION) X(XGC_NPARAM) X(XGC_NTABLE) X(XGC_NCONTROL) X(XGC_NCOUNTER) X(XGC_NTARGET) X(XGC_NSTREAM) X(XGC_NCELL) \
+  X(XGC_NPATH) X(XGC_MAX_ACTS) X(XGC_FORM_TRIES) X(XGC_ASMR_AGES) X(XGC_GLM_NCOEF) X(XGC_EDGE_STREAMS) \
+  X(XGC_G_B0) X(XGC_G_DUR) X(XGC_G_DUR2) X(XGC_G_PT2) X(XGC_G_DUR_PT2) X(XGC_G_CA) X(XGC_G_CA2) X(XGC_G_HCP) X(XGC_G_PREP) X(XGC_G_RC) \
+  X(XGC_T_ASMR) X(XGC_T_GLM_AI) X(XGC_T_GLM_OI) X(XGC_T_GLM_CONDMC) X(XGC_T_GLM_CONDOO) X(XGC_T_RACE_PROP) X(XGC_T_ROLE_PROB) \
+  X(XGC_T_NET_DEG) X(XGC_T_NET_DUR) \
+  X(XGC_C_transRoute_Kissing) X(XGC_C_transRoute_Rimming) X(XGC_C_gcUntreatedRecovDist) X(XGC_C_stiScreeningProtocol) \
+  X(XGC_C_cdcExposureSite_Kissing) X(XGC_C_network_mode) \
+  X(XGC_M_AGING) X(XGC_M_DEPARTURE) X(XGC_M_ARRIVAL) X(XGC_M_HIVTEST) X(XGC_M_HIVTX) X(XGC_M_HIVPROGRESS) X(XGC_M_HIVVL) \
+  X(XGC_M_RESIM_NETS) X(XGC_M_ACTS) X(XGC_M_CONDOMS) X(XGC_M_POSITION) X(XGC_M_PREP) X(XGC_M_HIVTRANS) X(XGC_M_STIRECOV) \
+  X(XGC_M_STITX) X(XGC_M_STITRANS) X(XGC_M_PREV) X(XGC_M_ALL) \
+  X(XGC_S_DEPART) X(XGC_S_HIVTEST) X(XGC_S_HIVTX) X(XGC_S_PREP) X(XGC_S_STIRECOV) X(XGC_S_STITX) X(XGC_S_INFECT) \
+  X(XGC_S_ARRIVE_ATTR) X(XGC_S_ARRIVE_N) X(XGC_S_PATHORDER) X(XGC_S_NET_N) X(XGC_S_FORM) X(XGC_S_EDGE0) X(XGC_S_DISSOLVE) \
+  X(XGC_S_ACTS) X(XGC_S_COND) X(XGC_S_POS) X(XGC_S_OIDIR) X(XGC_S_RIMDIR) X(XGC_S_HIVTRANS) X(XGC_S_GC_AI_A) X(XGC_S_GC_AI_B) \
+  X(XGC_S_GC_OI_A) X(XGC_S_GC_OI_B) X(XGC_S_GC_RIM_A) X(XGC_S_GC_RIM_B) X(XGC_S_GC_KISS_A) X(XGC_S_GC_KISS_B) \
+  X(XGC_K_NUM) X(XGC_K_INUM) X(XGC_K_INUM_DX) X(XGC_K_VSUPP) X(XGC_K_INCID_HIV) X(XGC_K_PREPELIG) X(XGC_K_PREPCURR) \
+  X(XGC_K_INUM_GC) X(XGC_K_INUM_RGC) X(XGC_K_INUM_UGC) X(XGC_K_INUM_PGC) X(XGC_K_INCID_RGC) X(XGC_K_INCID_UGC) X(XGC_K_INCID_PGC) \
+  X(XGC_K_NGROUP) X(XGC_K_PATH) X(XGC_K_VISITS) X(XGC_K_VISITS_SYMPT) X(XGC_K_TESTED) X(XGC_K_POS) X(XGC_K_TXSTART) \
+  X(XGC_K_DEP_GEN) X(XGC_K_DEP_AIDS) X(XGC_K_NNEW) X(XGC_K_HIVTESTS) X(XGC_K_NEDGES) X(XGC_K_NACTS) \
+  X(XGC_TG_NUM) X(XGC_TG_I_PREV) X(XGC_TG_IR100_POP) X(XGC_TG_HIVDX_RACE) X(XGC_TG_HIVDX_AGE) X(XGC_TG_VLS_RACE) X(XGC_TG_VLS_AGE) \
+  X(XGC_TG_PREPCOV_RACE) X(XGC_TG_PROP_TESTED) X(XGC_TG_PROB_POS) X(XGC_TG_PREV_GC) X(XGC_TG_IR100_GC) \
+  X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_F64) X(XGC_I32)
+int  xgc_constant(const char* name, int64_t* value);          /* 0 if found */
+int  xgc_param_index(const char* name, int* offset, int* count);   /* params.def lookup */
+
+typedef struct xgc_config {
+  int32_t  abi_version;        /* XGC_ABI_VERSION                                                                   */
+  int32_t  device;             /* CUDA device ordinal                                                               */
+  int32_t  n_replicates;       /* replicates resident on this handle (this GPU's shard)                             */
+  int32_t  replicate_offset;   /* global id of local replicate 0 (Philox key), so results do not depend on sharding */
+  int32_t  n_cap;              /* agent slots per replicate (>= initial N + head-room; multiple of 128)             */
+  int32_t  e_cap[3];           /* edge capacity per layer: main, casual, one-off                                    */
+  int32_t  t_cap;              /* weeks of epi counters kept (at < t_cap)                                           */
+  int32_t  compact_every;      /* weeks between slot compactions inside xgc_run (0 = default 64)                    */
+  uint64_t seed;
+} xgc_config;
+
+typedef struct xgc_handle xgc_handle;
+
+/* life cycle -------------------------------------------------------------------------------------------------------- */
+int  xgc_create(const xgc_config* cfg, xgc_handle** out);
+int  xgc_destroy(xgc_handle* h);
+const char* xgc_last_error(const xgc_handle* h);      /* h may be NULL: error of a failed xgc_create */
+int  xgc_abi_version(void);
+
+/* configuration: replaces param_msm()/control_msm() objects (sim1_02_lhs.r:58-230).  r = -1 applies to all replicates. */
+int  xgc_set_params (xgc_handle* h, int r, const double* params /*[XGC_NPARAM]*/);
+int  xgc_get_params (xgc_handle* h, int r, double* params);
+int  xgc_set_params_all(xgc_handle* h, const double* params /*[n_replicates][XGC_NPARAM]*/);
+int  xgc_set_control(xgc_handle* h, int r, const int32_t* control /*[XGC_NCONTROL]*/);
+int  xgc_set_tables (xgc_handle* h, const double* tables /*[XGC_NTABLE]*/);
+
+/* state exchange: replaces dat$attr / dat$el.  Attribute vectors are in R position order.
+ * xgc_set_population sets N for replicate r, marks slots 0..n-1 alive, assigns uid = 0..n-1 and resets all attributes
+ * to their "new susceptible agent" values; at is the week the attributes refer to (1 after initialisation). */
+int  xgc_set_population(xgc_handle* h, int r, int n, int at);
+int  xgc_num_agents   (xgc_handle* h, int r, int* n);
+int  xgc_upload_attr  (xgc_handle* h, int r, const char* name, const void* data, size_t n, int dtype);
+int  xgc_download_attr(xgc_handle* h, int r, const char* name, void* data, size_t cap, int dtype, size_t* n_out);
+int  xgc_attr_names   (const char** names, int cap);           /* returns the number of known attribute names */
+int  xgc_set_edgelist (xgc_handle* h, int r, int layer, const int32_t* el /*[E,2] col-major, 1-based*/, int n_edges,
+                       const int32_t* start_time /*[E] or NULL -> current week*/);
+int  xgc_get_edgelist (xgc_handle* h, int r, int layer, int32_t* el, int cap, int* n_edges, int32_t* start_time);
+int  xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts /*[E,4] col-major: ai,oi,kiss,rim*/, int cap,
+                       int* n_edges);
+/* materialise the act list of week `at` (dat$temp$al): rows (layer, edge index, act type 0 ai/1 oi/2 kiss/3 rim,
+ * act index, uai (1 = condomless; anal only), p1_active (1 = p1 insertive / rimmer)).  Column-major int32 [A,6]. */
+int  xgc_get_actlist  (xgc_handle* h, int r, int at, int32_t* al, int cap, int* n_acts, const xgc_inject* inj);
+
+/* the step: runs the modules selected by module_mask for week `at` on every replicate, in reference order.
+ * inj = NULL -> native Philox; otherwise draws come from the injected table. */
+int  xgc_step(xgc_handle* h, int at, uint32_t module_mask, const xgc_inject* inj);
+/* batched loop at0..at1 inclusive, all modules, native draws, no host synchronisation inside (CUDA-graph replay). */
+int  xgc_run (xgc_handle* h, int at0, int at1);
+int  xgc_sync(xgc_handle* h);
+int  xgc_compact(xgc_handle* h);                          /* squeeze out slots of departed agents (positions kept) */
+int  xgc_status (xgc_handle* h, int r, uint32_t* status); /* XGC_ST_* bits */
+
+/* outputs: replaces dat$epi and the calculate_targets family (R/calculate_targets.r:14-190). */
+int  xgc_get_counters(xgc_handle* h, int r, int at0, int at1, uint32_t* out /*[at1-at0+1][XGC_NCOUNTER]*/);
+int  xgc_get_epi     (xgc_handle* h, int r, const char* var, double* out, int at0, int at1);
+int  xgc_epi_names   (const char** names, int cap);
+int  xgc_targets     (xgc_handle* h, int at_last, int tailn, double* out /*[n_replicates][XGC_NTARGET]*/);
+
+/* checkpoint / scenario fork (02.00_epi.r:40-76,292,296: burn-in output reused as the start of 5 screening arms). */
+int  xgc_snapshot_size(xgc_handle* h, size_t* bytes);
+int  xgc_snapshot(xgc_handle* h, void* buf, size_t bytes);
+int  xgc_restore (xgc_handle* h, const void* buf, size_t bytes);
+int  xgc_fork    (xgc_handle* src, int src_r, xgc_handle* dst, int dst_r);   /* device-to-device copy of one replicate */
+
+/* e2e helpers with caller-owned pinned host buffers: one call moves every replicate's edge lists in, or the week's
+ * counters out (the two transfers the weekly R<->device contract needs; DESIGN.md "boundary cost"). */
+int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][e_cap] 1-based positions*/,
+                           const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][e_cap] or NULL*/);
+int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);
+
+/* instrumentation */
+int  xgc_kernel_launches(xgc_handle* h, uint64_t* n);     /* kernels launched by this handle so far */
+int  xgc_stream_ptr(xgc_handle* h, void** cuda_stream);   /* the stream all work is issued on (for event timing) */
+int  xgc_debug_exp(const double* x, double* y, int n, int device);   /* device xgc_exp, for the math parity test */
+int  xgc_debug_philox(uint32_t seed, uint32_t rep, const uint32_t* ctr4, uint32_t* out4, int n, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XGC_ABI_H */

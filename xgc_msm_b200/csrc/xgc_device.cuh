@@ -1,0 +1,177 @@
+// Device-side layout and arithmetic of the B200 epidemic step (sm_100a).
+//
+// Packed structure-of-arrays agent state: every plane is indexed [replicate * n_cap + slot].  Slots are stable
+// (departed agents leave a tombstone; xgc_compact squeezes them out on a schedule), so edges store slot indices and
+// never need re-numbering when agents depart.  The R position of an agent (the index the reference uses in dat$attr
+// and dat$el) is its rank among living slots.
+//
+// All probabilities are evaluated in IEEE double with the exact operation order of DESIGN.md §"arithmetic contract";
+// the library is compiled with --fmad=false so that results are bit-identical to the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "xgc/abi.h"
+
+#define XGC_WEEK (7.0 / 365.0)
+#define XGC_LOG10_200 2.301029995663981
+#define XGC_LN_2_45 0.8960880245566357
+#define XGC_NA16 ((short)-1)
+
+// ---- core plane: uint4 {x uid, y demo, z gc, w hiv}: one 128-bit load per agent, one 128-bit gather per edge endpoint
+// demo word
+#define DM_RACE(d)      ((d) & 3u)                 // race-1
+#define DM_AGEGRP(d)    (((d) >> 2) & 7u)          // age.grp-1
+#define DM_ROLE(d)      (((d) >> 5) & 3u)          // 0 I, 1 R, 2 V
+#define DM_RISK(d)      (((d) >> 7) & 7u)          // risk.grp-1
+#define DM_CIRC         (1u << 10)
+#define DM_LATE         (1u << 11)
+#define DM_TTTRAJ(d)    (((d) >> 12) & 3u)         // 1..3
+#define DM_STOPPER      (1u << 14)
+#define DM_ACTIVE       (1u << 15)
+#define DM_CELL(d)      (DM_RACE(d) * 5u + DM_AGEGRP(d))
+// gc word: bit s status, 3+s sympt, 6+s tx (s = 0 rect, 1 ureth, 2 phar); 9..17 snapshot taken at the start of the
+// prep/stirecov/stitx pass (what acts/condoms/hivtrans saw); 18..22 exposure history; 24..30 new-infection pathways
+#define GC_ST(s)        (1u << (s))
+#define GC_SY(s)        (1u << (3 + (s)))
+#define GC_TX(s)        (1u << (6 + (s)))
+#define GC_CUR_MASK     0x1FFu
+#define GC_PRE_SHIFT    9
+#define GC_EXPO_SHIFT   18
+#define GC_EXPO_MASK    (0x1Fu << GC_EXPO_SHIFT)
+#define GC_NEW_SHIFT    24
+#define GC_NEW_MASK     (0x7Fu << GC_NEW_SHIFT)
+// hiv word
+#define HV_STATUS       (1u << 0)
+#define HV_STAGE(h)     (((h) >> 1) & 7u)
+#define HV_STAGE_MASK   (7u << 1)
+#define HV_DIAG         (1u << 4)
+#define HV_TX           (1u << 5)
+#define HV_PREP         (1u << 6)
+#define HV_PREPCLASS(h) (((h) >> 7) & 3u)
+#define HV_PREPCLASS_MASK (3u << 7)
+#define HV_PREPELIG     (1u << 9)
+#define HV_PREP_PRE     (1u << 10)               // prepStat as acts/condoms saw it (before this week's prep module)
+#define HV_NEW          (1u << 31)
+
+struct __align__(16) Aux { double age_ref; float vl; float ins_quot; };
+// clock planes (short4, NA = -1):
+//   gck_a {infT r,u,p, last_screen}   gck_b {txT r,u,p, spare}   gck_d {dur r,u,p, spare} ("pois" mode only)
+//   hck_a {inf_time, diag_time, stage_time, tx_init_time}         hck_b {cuml_on, cuml_off, spare, spare}
+//   tck   {last_neg_test, prep_ind_last, prep_last_risk, prep_start_time}
+// edge record: int4 {p1 slot, p2 slot, start week, acts = ai | oi<<8 | kiss<<16 | rim<<24}
+
+struct Rep {                 // per-replicate scalars
+  int n_slots;               // high-water mark of used slots
+  int n_slots_pre;           // n_slots before this week's arrivals (arrivals are not aged / exposed to mortality)
+  int next_uid;
+  int n_alive;
+  int t_ref, t_age;          // age(at) = age_ref + (t_age - t_ref) * 7/365
+  int ne[3];
+  unsigned status;
+  int path_rank[XGC_NPATH];  // this week's pathway order (stitrans_msm_rand)
+  int pad;
+};
+
+struct Inj {                 // injected-draw table (device copy), u == nullptr -> native Philox
+  const double* u; size_t stride; size_t off[XGC_NSTREAM]; int form_cap;
+};
+
+struct Dev {                 // everything a kernel needs; passed by value
+  int R, n_cap, t_cap, rep0; int e_cap[3]; size_t e_off[3]; size_t e_stride;
+  unsigned seed;
+  uint4* core; Aux* aux; short4 *gck_a, *gck_b, *gck_d, *hck_a, *hck_b, *tck; int* arr_t;
+  unsigned* alive;           // [R][n_cap/32] bitmap of living slots
+  int* pos2slot;             // [R][n_cap] rank -> slot (built by k_rank)
+  int4* edge;                // [R][e_stride]: layer l at e_off[l]
+  Rep* rep; const double* params; const int* control; const double* tables;
+  unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
+  const int* at_ptr;
+};
+
+// ---- Philox4x32-10 (Salmon et al. SC'11), counter-based: draw = pure function of (replicate, week, stream, entity, k)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct Draw {                // one stream of one entity; caches the Philox block of 4
+  const Inj* inj; size_t base; unsigned seed, rep, at, stream, e0, e1; int blk; uint4 v;
+  __device__ __forceinline__ Draw(const Inj& j, const Dev& g, int r, int at_, int stream_, unsigned e0_, unsigned e1_, size_t idx)
+      : inj(&j), seed(g.seed), rep((unsigned)(g.rep0 + r)), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
+    base = j.u ? (size_t)r * j.stride + j.off[stream_] + idx * (size_t)xgc_stream_width(stream_) : 0;
+  }
+  __device__ __forceinline__ double operator()(int k) {
+    if (inj->u) return inj->u[base + k];
+    int b = k >> 2;
+    if (b != blk) { v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b; }
+    unsigned x = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+    return ((double)x + 0.5) * (1.0 / 4294967296.0);
+  }
+};
+
+// ---- arithmetic contract (mirrors the oracle operation for operation; no FMA)
+__device__ __forceinline__ double xgc_exp(double x) {
+  if (x < -700.0) x = -700.0;
+  if (x > 700.0) x = 700.0;
+  double kf = floor(x * 1.4426950408889634 + 0.5);
+  double r = x - kf * 6.93147180369123816490e-01;
+  r = r - kf * 1.90821492927058770002e-10;
+  double q = 1.0 / 6227020800.0;
+  q = q * r + 1.0 / 479001600.0;
+  q = q * r + 1.0 / 39916800.0;
+  q = q * r + 1.0 / 3628800.0;
+  q = q * r + 1.0 / 362880.0;
+  q = q * r + 1.0 / 40320.0;
+  q = q * r + 1.0 / 5040.0;
+  q = q * r + 1.0 / 720.0;
+  q = q * r + 1.0 / 120.0;
+  q = q * r + 1.0 / 24.0;
+  q = q * r + 1.0 / 6.0;
+  q = q * r + 0.5;
+  q = q * r + 1.0;
+  q = q * r + 1.0;
+  long long k = (long long)kf;
+  return q * __longlong_as_double((k + 1023) << 52);
+}
+__device__ __forceinline__ int xgc_bern(double u, double p) { return p <= 0.5 ? (u >= 1.0 - p) : (u < p); }
+__device__ __forceinline__ int xgc_pois(double u, double mu, int kmax) {
+  if (!(mu > 0.0)) return 0;
+  double pr = xgc_exp(-mu), cdf = pr;
+  int k = 0;
+  while (u > cdf && k < kmax) { k++; pr = pr * mu / (double)k; cdf = cdf + pr; }
+  return k;
+}
+__device__ __forceinline__ int xgc_categorical(double u, const double* prob, int n) {
+  int r = 0; double c = prob[0];
+  while (u >= c && r < n - 1) { r++; c = c + prob[r]; }
+  return r;
+}
+__device__ __forceinline__ unsigned xgc_age_group(double age) {   // age.grp - 1
+  return (unsigned)((age >= 25.0) + (age >= 35.0) + (age >= 45.0) + (age >= 55.0));
+}
+__device__ __forceinline__ double xgc_glm_eta(const double* b, double dur, int casual, double ca, int hcp, int prep, int r1, int r2) {
+  double eta = b[XGC_G_B0];
+  eta = eta + b[XGC_G_DUR] * dur;
+  eta = eta + b[XGC_G_DUR2] * (dur * dur);
+  eta = eta + b[XGC_G_RC + r1 * 4 + r2];
+  eta = eta + b[XGC_G_PT2] * (double)casual;
+  eta = eta + b[XGC_G_DUR_PT2] * (dur * (double)casual);
+  eta = eta + b[XGC_G_CA] * ca;
+  eta = eta + b[XGC_G_CA2] * (ca * ca);
+  eta = eta + b[XGC_G_HCP] * (double)hcp;
+  eta = eta + b[XGC_G_PREP] * (double)prep;
+  return eta;
+}
+__device__ __forceinline__ bool roles_compatible(unsigned da, unsigned db) {
+  unsigned ra = DM_ROLE(da), rb = DM_ROLE(db);
+  return !((ra == 0 && rb == 0) || (ra == 1 && rb == 1));
+}
+__device__ __forceinline__ bool act_stopped(unsigned demo, unsigned gc) {
+  return (demo & DM_STOPPER) && (gc & 0x1F8u);      // any site symptomatic or on treatment
+}

@@ -1,0 +1,935 @@
+// Hand-written sm_100a kernels of the weekly epidemic step.  No tensor cores: the path is scan / gather / compaction
+// work bound by HBM bandwidth.  One week =
+//   k_begin   (1 warp / replicate)    week bookkeeping, arrivals (arrival_msm), pathway order
+//   k_agent1  (1 thread / slot)       aging, departure, hivtest, hivtx, hivprogress, hivvl        [reads core+aux]
+//   k_edges_prune / k_rank / k_form   edge deletion for departed agents; surrogate for simnet_msm
+//   k_edge1   (1 thread / edge)       acts (+ exposure history, PrEP risk history)                [gathers core+aux]
+//   k_agent2  (1 thread / slot)       prep, stirecov, stitx                                       [reads core+clocks]
+//   k_edge2   (1 thread / edge)       condoms + position (lazily per act), hivtrans, stitrans     [gathers core]
+//   k_agent3  (1 thread / slot)       apply new infections, prevalence tallies                    [reads core]
+// Module semantics follow DESIGN.md §3; reference call sites are cited there and in include/xgc/abi.h.
+#pragma once
+#include "xgc_device.cuh"
+
+#define TPB 256
+
+__device__ __forceinline__ void warp_tally(unsigned* row, int idx, bool pred) {
+  unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(row + idx, (unsigned)__popc(m));
+}
+__device__ __forceinline__ void warp_tally_n(unsigned* row, int idx, unsigned v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (v && (threadIdx.x & 31) == 0) atomicAdd(row + idx, v);
+}
+__device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
+  return g.counters + ((size_t)r * g.t_cap + (size_t)at) * XGC_NCOUNTER;
+}
+__device__ __forceinline__ short4 na4() { return make_short4(-1, -1, -1, -1); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_begin: one warp per replicate.  Sets the week, zeroes its tally row, draws the pathway order, appends arrivals.
+// arrival_msm: /root/reference/burnin/cal/sim1_02_lhs.r:204, 63-66
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
+  int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= g.R) return;
+  Rep* rp = g.rep + r;
+  int at = at_host >= 0 ? at_host : g.at_ptr[r] + 1;
+  unsigned* row = counter_row(g, r, at);
+  if (zero_row) for (int k = lane; k < XGC_NCOUNTER; k += 32) row[k] = 0u;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  int n_slots = rp->n_slots, t_ref = rp->t_ref;
+  int t_age = (mask & XGC_M_AGING) ? at : rp->t_age;
+  __syncwarp();
+  if (lane == 0) {
+    ((int*)g.at_ptr)[r] = at;
+    rp->n_slots_pre = n_slots;
+    rp->t_age = t_age;
+    if (mask & XGC_M_STITRANS) {          // weekly random pathway order (stitrans_msm_rand, ambiguity A2)
+      Draw d(inj, g, r, at, XGC_S_PATHORDER, 0u, 0u, 0);
+      int perm[XGC_NPATH];
+      for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
+      for (int i = XGC_NPATH - 1; i >= 1; --i) {
+        int j = (int)(d(XGC_NPATH - 1 - i) * (double)(i + 1)); if (j > i) j = i;
+        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+      }
+      for (int k = 0; k < XGC_NPATH; ++k) rp->path_rank[perm[k]] = k;
+    }
+  }
+  if (!(mask & XGC_M_ARRIVAL)) return;
+  // nNew ~ Poisson(a.rate * num[1]), mean split into chunks of <= 32 so the CDF walk never underflows
+  double mu = P[XGC_P_a_rate] * P[XGC_P_n_init];
+  int m = (int)ceil(mu / 32.0); if (m < 1) m = 1; if (m > 64) m = 64;
+  double muc = mu / (double)m;
+  int nnew = 0;
+  {
+    Draw d(inj, g, r, at, XGC_S_ARRIVE_N, 0u, 0u, 0);
+    for (int ch = lane; ch < m; ch += 32) nnew += xgc_pois(d(ch), muc, 255);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
+  }
+  if (n_slots + nnew > g.n_cap) { nnew = g.n_cap - n_slots; if (lane == 0) atomicOr(&rp->status, XGC_ST_AGENT_OVERFLOW); }
+  int uid0 = rp->next_uid;
+  for (int j = lane; j < nnew; j += 32) {
+    int i = n_slots + j; size_t idx = (size_t)r * g.n_cap + i;
+    unsigned uid = (unsigned)(uid0 + j);
+    Draw d(inj, g, r, at, XGC_S_ARRIVE_ATTR, uid, 0u, uid);
+    int race = xgc_categorical(d(0), g.tables + XGC_T_RACE_PROP, 4);
+    int role = xgc_categorical(d(1), g.tables + XGC_T_ROLE_PROB + race * 3, 3);
+    float insq = role == 0 ? 1.0f : role == 1 ? 0.0f : (float)d(2);
+    unsigned circ = xgc_bern(d(3), P[XGC_P_circ_prob + race]);
+    unsigned late = xgc_bern(d(4), P[XGC_P_hiv_test_late_prob + race]);
+    double tt[3] = { P[XGC_P_tt_part_supp + race], P[XGC_P_tt_full_supp + race], P[XGC_P_tt_dur_supp + race] };
+    unsigned traj = 1 + xgc_categorical(d(5), tt, 3);
+    unsigned stopper = xgc_bern(d(6), P[XGC_P_act_stopper_prob]);
+    int rg = (int)(d(7) * 5.0); if (rg > 4) rg = 4;
+    Aux ax; ax.age_ref = P[XGC_P_arrival_age] - (double)(t_age - t_ref) * XGC_WEEK; ax.vl = 0.f; ax.ins_quot = insq;
+    double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
+    unsigned demo = (unsigned)race | (xgc_age_group(age) << 2) | ((unsigned)role << 5) | ((unsigned)rg << 7) |
+                    (circ ? DM_CIRC : 0u) | (late ? DM_LATE : 0u) | (traj << 12) | (stopper ? DM_STOPPER : 0u) | DM_ACTIVE;
+    g.core[idx] = make_uint4(uid, demo, 0u, 0u);
+    g.aux[idx] = ax;
+    g.gck_a[idx] = na4(); g.gck_b[idx] = na4(); g.gck_d[idx] = na4();
+    g.hck_a[idx] = na4(); g.hck_b[idx] = make_short4(0, 0, -1, -1); g.tck[idx] = na4();
+    g.arr_t[idx] = at;
+    atomicOr(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), 1u << (i & 31));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    rp->n_slots = n_slots + nnew; rp->next_uid = uid0 + nnew; atomicAdd(&rp->n_alive, nnew);
+    atomicAdd(row + XGC_K_NNEW, (unsigned)nnew);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_agent1: aging_msm, departure_msm, hivtest_msm, hivtx_msm, hivprogress_msm, hivvl_msm (sim1_02_lhs.r:202-208)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  const Rep* rp = g.rep + r;
+  int n_slots = rp->n_slots;
+  if ((int)(blockIdx.x * TPB) >= n_slots) return;
+  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  int n_pre = rp->n_slots_pre, t_ref = rp->t_ref, t_age = rp->t_age;
+  size_t idx = (size_t)r * g.n_cap + i;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  unsigned* row = counter_row(g, r, at);
+  bool live = i < n_slots;
+  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
+  live = live && (c.y & DM_ACTIVE);
+  unsigned uid = c.x, demo = c.y, hiv = c.w;
+  bool isnew = i >= n_pre;
+  Aux ax; ax.age_ref = 0; ax.vl = 0; ax.ins_quot = 0;
+  bool hivpos = live && (hiv & HV_STATUS);
+  if (live && ((!isnew && (mask & (XGC_M_AGING | XGC_M_DEPARTURE))) || (hivpos && (mask & XGC_M_HIVVL)))) ax = g.aux[idx];
+  double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
+  int race = (int)DM_RACE(demo);
+  if ((mask & XGC_M_AGING) && live && !isnew) demo = (demo & ~(7u << 2)) | (xgc_age_group(age) << 2);
+  bool dep_g = false, dep_a = false;
+  if ((mask & XGC_M_DEPARTURE) && live && !isnew) {
+    int ai = (int)floor(age); if (ai < 0) ai = 0; if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
+    Draw d(inj, g, r, at, XGC_S_DEPART, uid, 0u, uid);
+    dep_g = xgc_bern(d(0), g.tables[XGC_T_ASMR + race * XGC_ASMR_AGES + ai]);
+    if (HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
+  }
+  if (mask & XGC_M_DEPARTURE) {
+    warp_tally(row, XGC_K_DEP_GEN, dep_g); warp_tally(row, XGC_K_DEP_AIDS, dep_a);
+    unsigned dm = __ballot_sync(0xffffffffu, dep_g || dep_a);
+    if (dm && (threadIdx.x & 31) == 0) {
+      g.alive[(size_t)r * (g.n_cap / 32) + (i >> 5)] &= ~dm;
+      atomicSub((int*)&rp->n_alive, __popc(dm));
+    }
+  }
+  if (dep_g || dep_a) { demo &= ~DM_ACTIVE; live = false; hivpos = false; }
+  // ---- HIV care cascade
+  bool tested = false;
+  short4 ha = na4(), hb = make_short4(0, 0, -1, -1);
+  bool ha_dirty = false, hb_dirty = false;
+  if (hivpos && (mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL))) { ha = g.hck_a[idx]; hb = g.hck_b[idx]; }
+  if ((mask & XGC_M_HIVTEST) && live && !(hiv & HV_DIAG)) {
+    short lnt = g.tck[idx].x;
+    int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
+    double tsl = (double)(at - last);
+    if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) {
+      Draw d(inj, g, r, at, XGC_S_HIVTEST, uid, 0u, uid);
+      tested = xgc_bern(d(0), P[XGC_P_hiv_test_rate + race]);
+    }
+    if (HV_STAGE(hiv) == 4 && tsl >= P[XGC_P_aids_test_int]) tested = true;
+    if ((hiv & HV_PREP) && tsl >= P[XGC_P_prep_tst_int]) tested = true;
+    if (tested) {
+      if ((hiv & HV_STATUS) && (double)(at - (int)ha.x) >= P[XGC_P_test_window_int]) { hiv |= HV_DIAG; ha.y = (short)at; ha_dirty = true; }
+      else g.tck[idx].x = (short)at;
+    }
+  }
+  if (mask & XGC_M_HIVTEST) warp_tally(row, XGC_K_HIVTESTS, tested);
+  if (hivpos) {
+    unsigned traj = DM_TTTRAJ(demo);
+    if (mask & XGC_M_HIVTX) {
+      if (hiv & HV_DIAG) {
+        Draw d(inj, g, r, at, XGC_S_HIVTX, uid, 0u, uid);
+        if (!(hiv & HV_TX) && hb.x == 0) {
+          if (xgc_bern(d(0), P[XGC_P_tx_init_prob + race])) { hiv |= HV_TX; ha.w = (short)at; ha_dirty = true; }
+        } else if (hiv & HV_TX) {
+          double rr = traj == 2 ? P[XGC_P_tx_halt_full_rr + race] : traj == 3 ? P[XGC_P_tx_halt_dur_rr + race] : 1.0;
+          if (xgc_bern(d(1), P[XGC_P_tx_halt_part_prob + race] * rr)) hiv &= ~HV_TX;
+        } else {
+          double rr = traj == 2 ? P[XGC_P_tx_reinit_full_rr + race] : traj == 3 ? P[XGC_P_tx_reinit_dur_rr + race] : 1.0;
+          if (xgc_bern(d(2), P[XGC_P_tx_reinit_part_prob + race] * rr)) hiv |= HV_TX;
+        }
+      }
+      if (hiv & HV_TX) hb.x++; else hb.y++;
+      hb_dirty = true;
+    }
+    double tsi = (double)(at - (int)ha.x);
+    if (mask & XGC_M_HIVPROGRESS) {
+      unsigned stage = HV_STAGE(hiv);
+      if (stage == 1 && tsi >= P[XGC_P_vl_acute_rise_int]) { stage = 2; ha.z = (short)at; ha_dirty = true; }
+      if (stage == 2 && tsi >= P[XGC_P_vl_acute_rise_int] + P[XGC_P_vl_acute_fall_int]) { stage = 3; ha.z = (short)at; ha_dirty = true; }
+      if (stage == 3) {
+        bool aids = false; double on = (double)hb.x, off = (double)hb.y;
+        if (on == 0.0 && tsi >= P[XGC_P_vl_aids_onset_int]) aids = true;
+        if (traj == 1 && on > 0.0 && off / P[XGC_P_max_time_off_tx_part_int] + on / P[XGC_P_max_time_on_tx_part_int] >= 1.0) aids = true;
+        if (traj >= 2 && !(hiv & HV_TX) && on > 0.0 && off >= P[XGC_P_max_time_off_tx_full_int]) aids = true;
+        if (aids) { stage = 4; ha.z = (short)at; ha_dirty = true; }
+      }
+      hiv = (hiv & ~HV_STAGE_MASK) | (stage << 1);
+    }
+    if (mask & XGC_M_HIVVL) {
+      unsigned stage = HV_STAGE(hiv);
+      double v, vl = (double)ax.vl, peak = P[XGC_P_vl_acute_peak], sp = P[XGC_P_vl_set_point];
+      if (!(hiv & HV_TX)) {
+        if (stage == 1) { v = peak * (tsi / P[XGC_P_vl_acute_rise_int]); if (v > peak) v = peak; }
+        else if (stage == 2) { v = peak - (peak - sp) * ((tsi - P[XGC_P_vl_acute_rise_int]) / P[XGC_P_vl_acute_fall_int]); if (v < sp) v = sp; }
+        else if (stage == 3) { if (hb.x == 0) v = sp; else { v = vl + P[XGC_P_vl_tx_up_slope]; if (v > sp) v = sp; } }
+        else { double tsa = (double)(at - (int)ha.z);
+               v = sp + (tsa / P[XGC_P_vl_aids_int]) * (P[XGC_P_vl_aids_peak] - sp); if (v > P[XGC_P_vl_aids_peak]) v = P[XGC_P_vl_aids_peak]; }
+      } else {
+        double target = traj == 1 ? P[XGC_P_vl_part_supp] : P[XGC_P_vl_full_supp];
+        double slope = stage == 4 ? P[XGC_P_vl_tx_aids_down_slope] : P[XGC_P_vl_tx_down_slope];
+        v = vl - slope; if (v < target) v = target;
+      }
+      float vf = (float)v;
+      if (vf != ax.vl) g.aux[idx].vl = vf;
+    }
+    if (ha_dirty) g.hck_a[idx] = ha;
+    if (hb_dirty) g.hck_b[idx] = hb;
+  }
+  if (demo != c.y || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; if (demo != c.y) q[0].y = demo; if (hiv != c.w) q[1].y = hiv; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Edge maintenance.  k_edges_resim: per (replicate, layer) one CTA; stable ballot compaction in place:
+//   drops edges with a departed endpoint (tergmLite::delete_vertices semantics, departure_msm) and, in surrogate mode,
+//   dissolves edges with prob 1/duration (main, casual) or clears the layer (one-off).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
+  int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Rep* rp = g.rep + r;
+  int ne = rp->ne[l], at = g.at_ptr[r];
+  int surrogate = dissolve && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1;
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  __shared__ int wsum[TPB / 32];
+  __shared__ int base;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  if (surrogate && l == 2) ne = 0;
+  double pd = surrogate && l < 2 ? 1.0 / g.tables[XGC_T_NET_DUR + l] : 0.0;
+  int es = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_DISSOLVE - XGC_S_EDGE0);
+  for (int e0 = 0; e0 < ne; e0 += TPB) {
+    int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
+    if (e < ne) {
+      ed = E[e];
+      uint4 ca = core[ed.x], cb = core[ed.y];
+      keep = (ca.y & DM_ACTIVE) && (cb.y & DM_ACTIVE);
+      if (keep && surrogate) { Draw d(inj, g, r, at, es, ca.x, cb.x, (size_t)e); keep = !xgc_bern(d(0), pd); }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    if (keep) E[off + __popc(m & ((1u << lane) - 1u))] = ed;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) rp->ne[l] = base;
+}
+
+// k_rank: pos2slot[r][rank] = slot, from the alive bitmap (one CTA per replicate)
+__global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
+  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int nw = (g.rep[r].n_slots + 31) >> 5;
+  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  __shared__ int wsum[TPB / 32];
+  __shared__ int base;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int w0 = 0; w0 < nw; w0 += TPB) {
+    unsigned bits = w0 + tid < nw ? A[w0 + tid] : 0u;
+    int cnt = __popc(bits), inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int off = base + inc - cnt;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    while (bits) { int b = __ffs(bits) - 1; bits &= bits - 1; P2S[off++] = ((w0 + tid) << 5) + b; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    __syncthreads();
+  }
+}
+
+// k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order
+__global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+  int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
+  Rep* rp = g.rep + r;
+  int at = g.at_ptr[r], n = rp->n_alive, ne = rp->ne[l];
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  __shared__ int wsum[TPB / 32];
+  __shared__ int base;
+  if (tid == 0) base = ne;
+  __syncthreads();
+  double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
+  double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
+  double fl = floor(mu);
+  Draw dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
+  int nform = (int)fl + (dn(l) < mu - fl);
+  if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
+  if (n < 2) nform = 0;
+  bool overflow = false;
+  for (int j0 = 0; j0 < nform; j0 += TPB) {
+    int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
+    if (j < nform) {
+      Draw d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+      for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
+        int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
+        int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+        if (b >= a) b++;
+        int sa = P2S[a < b ? a : b], sb = P2S[a < b ? b : a];
+        if (roles_compatible(core[sa].y, core[sb].y)) { ok = true; ed.x = sa; ed.y = sb; }
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (ok) { if (off < g.e_cap[l]) E[off] = ed; else overflow = true; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    __syncthreads();
+  }
+  if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);
+  if (tid == 0) {
+    int nn = base < g.e_cap[l] ? base : g.e_cap[l];
+    rp->ne[l] = nn;
+    counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)nn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-edge helpers shared by k_edge1 / k_edge2 / k_actlist (condoms_msm, position_msm evaluated lazily per act)
+// ---------------------------------------------------------------------------------------------------------------------
+struct EdgeCtx {
+  int r, l, e, at; int4 ed; uint4 ca, cb; double age_a, age_b; float insq_a, insq_b; int base;
+};
+__device__ __forceinline__ double edge_cond_prob(const Dev& g, const double* P, const EdgeCtx& x, bool use_pre) {
+  int hcp = (x.ca.w & HV_DIAG) && (x.cb.w & HV_DIAG);
+  unsigned pb = use_pre ? HV_PREP_PRE : HV_PREP;
+  int prep = (x.ca.w & pb) || (x.cb.w & pb);
+  double ca = x.age_a + x.age_b;
+  int r1 = (int)DM_RACE(x.ca.y), r2 = (int)DM_RACE(x.cb.y);
+  double eta = x.l < 2 ? xgc_glm_eta(g.tables + XGC_T_GLM_CONDMC, (double)(x.at - x.ed.z), x.l == 1, ca, hcp, prep, r1, r2)
+                       : xgc_glm_eta(g.tables + XGC_T_GLM_CONDOO, 0.0, 0, ca, hcp, prep, r1, r2);
+  double pc = 1.0 / (1.0 + xgc_exp(-eta));
+  pc = pc * P[XGC_P_cond_scale];
+  if (pc > 1.0) pc = 1.0;
+  return pc;
+}
+// position of anal act k: 1 = p1 insertive
+__device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x, Draw& dpos, int k) {
+  unsigned r1 = DM_ROLE(x.ca.y), r2 = DM_ROLE(x.cb.y);
+  if (r1 == 0 || r2 == 1) return 1;
+  if (r1 == 1 || r2 == 0) return 0;
+  double q1 = (double)x.insq_a, q2 = (double)x.insq_b;
+  double pi = q1 + q2 > 0.0 ? q1 / (q1 + q2) : 0.5;
+  return xgc_bern(dpos(k), pi);
+}
+
+// k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
+__global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.z, l = blockIdx.y;
+  const Rep* rp = g.rep + r;
+  int ne = rp->ne[l];
+  if ((int)(blockIdx.x * TPB) >= ne) return;
+  int e = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  unsigned* row = counter_row(g, r, at);
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  uint4* core = g.core + (size_t)r * g.n_cap;
+  const Aux* aux = g.aux + (size_t)r * g.n_cap;
+  bool live = e < ne;
+  unsigned nai = 0, noi = 0, nki = 0, nri = 0;
+  if (live) {
+    EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
+    x.ca = core[x.ed.x]; x.cb = core[x.ed.y];
+    x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+    double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
+    Aux aa = aux[x.ed.x], ab = aux[x.ed.y];
+    x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
+    if (mask & XGC_M_ACTS) {
+      int ai = 0, oi = 0, ki = 0, ri = 0;
+      if (!(act_stopped(x.ca.y, x.ca.z) || act_stopped(x.cb.y, x.cb.z))) {
+        bool compat = roles_compatible(x.ca.y, x.cb.y);
+        Draw d(inj, g, r, at, x.base + (XGC_S_ACTS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        if (l < 2) {
+          double dur = (double)(at - x.ed.z), ca = x.age_a + x.age_b;
+          int hcp = (x.ca.w & HV_DIAG) && (x.cb.w & HV_DIAG);
+          int r1 = (int)DM_RACE(x.ca.y), r2 = (int)DM_RACE(x.cb.y);
+          double rai = xgc_exp(xgc_glm_eta(g.tables + XGC_T_GLM_AI, dur, l == 1, ca, hcp, 0, r1, r2)) / 52.0 * P[XGC_P_ai_acts_scale_mc];
+          double roi = xgc_exp(xgc_glm_eta(g.tables + XGC_T_GLM_OI, dur, l == 1, ca, hcp, 0, r1, r2)) / 52.0 * P[XGC_P_oi_acts_scale_mc];
+          ai = compat ? xgc_pois(d(0), rai, XGC_MAX_ACTS) : 0;
+          oi = xgc_pois(d(1), roi, XGC_MAX_ACTS);
+          ki = xgc_pois(d(2), l == 0 ? P[XGC_P_kiss_rate_main] : P[XGC_P_kiss_rate_casl], XGC_MAX_ACTS);
+          ri = xgc_pois(d(3), l == 0 ? P[XGC_P_rim_rate_main] : P[XGC_P_rim_rate_casl], XGC_MAX_ACTS);
+        } else {
+          ai = compat ? 1 : 0;
+          oi = xgc_bern(d(1), P[XGC_P_oi_prob_oo]);
+          ki = xgc_bern(d(2), P[XGC_P_kiss_prob_oo]);
+          ri = xgc_bern(d(3), P[XGC_P_rim_prob_oo]);
+        }
+      }
+      x.ed.w = ai | (oi << 8) | (ki << 16) | (ri << 24);
+      E[e].w = x.ed.w;
+      nai = ai; noi = oi; nki = ki; nri = ri;
+      // exposure history for the CDC screening protocol (ambiguity A4)
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        unsigned role = DM_ROLE(side ? x.cb.y : x.ca.y), ex = 0;
+        if (ai > 0 && role != 0) ex |= 1;
+        if ((ai > 0 && role != 1) || oi > 0) ex |= 2;
+        if (oi > 0 || ri > 0) ex |= 4;
+        if (ki > 0) ex |= 8;
+        if (l != 0 && (ai | oi | ki | ri)) ex |= 16;
+        unsigned cur = side ? x.cb.z : x.ca.z;
+        if ((ex << GC_EXPO_SHIFT) & ~cur) atomicOr(&core[side ? x.ed.y : x.ed.x].z, ex << GC_EXPO_SHIFT);
+      }
+    }
+    if (mask & XGC_M_PREP) {              // risk history: needs condom use of this week's anal acts
+      int ai = x.ed.w & 0xFF;
+      bool ua = !(x.ca.w & HV_DIAG), ub = !(x.cb.w & HV_DIAG);
+      if (ai > 0 && (ua || ub)) {
+        bool uai = false;
+        double pc = edge_cond_prob(g, P, x, false);
+        Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        for (int k = 0; k < ai && !uai; ++k) uai = xgc_bern(dc(k), 1.0 - pc);
+        short4* tck = g.tck + (size_t)r * g.n_cap;
+        if (ua && (uai || (x.cb.w & HV_DIAG))) tck[x.ed.x].y = (short)at;
+        if (ub && (uai || (x.ca.w & HV_DIAG))) tck[x.ed.y].y = (short)at;
+      }
+    }
+  }
+  if (mask & XGC_M_ACTS) {
+    warp_tally_n(row, XGC_K_NACTS, nai); warp_tally_n(row, XGC_K_NACTS + 1, noi);
+    warp_tally_n(row, XGC_K_NACTS + 2, nki); warp_tally_n(row, XGC_K_NACTS + 3, nri);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_agent2: prep_msm, stirecov_msm, stitx_msm (sim1_02_lhs.r:213, 215-216).  Takes the snapshot of the GC / PrEP bits
+// that hivtrans_msm and the lazily evaluated condom model must see (they run before these modules in the reference).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  const Rep* rp = g.rep + r;
+  int n_slots = rp->n_slots;
+  if ((int)(blockIdx.x * TPB) >= n_slots) return;
+  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  size_t idx = (size_t)r * g.n_cap + i;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  unsigned* row = counter_row(g, r, at);
+  bool live = i < n_slots;
+  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
+  live = live && (c.y & DM_ACTIVE);
+  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
+  int race = (int)DM_RACE(demo);
+  unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
+  if (live) {
+    gc = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
+    hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
+    short4 tk = na4();
+    bool ind_sti = false;
+    // ---- stirecov
+    short4 ga = na4(), gb = na4(), gd = na4(); bool g_loaded = false, ga_dirty = false, gb_dirty = false, gd_dirty = false;
+    if ((gc & 7u) && (mask & (XGC_M_STIRECOV | XGC_M_STITX))) { ga = g.gck_a[idx]; gb = g.gck_b[idx]; g_loaded = true;
+      if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS) gd = g.gck_d[idx]; }
+    // prep first (reference order: prep, hivtrans, stirecov, stitx)
+    if (mask & XGC_M_PREP) {
+      tk = g.tck[idx];
+      bool diag = hiv & HV_DIAG;
+      bool ind = tk.y != XGC_NA16 && (double)tk.y >= (double)at - P[XGC_P_prep_risk_int];
+      hiv = (hiv & ~HV_PREPELIG) | ((!diag && ind) ? HV_PREPELIG : 0u);
+      if (hiv & HV_PREP) {
+        bool stop = false;
+        Draw d(inj, g, r, at, XGC_S_PREP, uid, 0u, uid);
+        if (diag) stop = true;
+        else if (xgc_bern(d(2), P[XGC_P_prep_discont_rate + race])) stop = true;
+        else if ((int)tk.x == at && (double)(at - (int)tk.z) >= P[XGC_P_prep_reassess_int]) {
+          if (!ind) stop = true; else g.tck[idx].z = (short)at;
+        }
+        if (stop) hiv &= ~(HV_PREP | HV_PREPCLASS_MASK);
+      } else if (!diag && (double)at >= P[XGC_P_prep_start] && (int)tk.x == at && ind) {
+        Draw d(inj, g, r, at, XGC_S_PREP, uid, 0u, uid);
+        if (xgc_bern(d(0), P[XGC_P_prep_start_prob + race])) {
+          unsigned cl = 1 + xgc_categorical(d(1), P + XGC_P_prep_adhr_dist, 3);
+          hiv = (hiv & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
+          short4* q = g.tck + idx; q->z = (short)at; q->w = (short)at;
+        }
+      }
+    }
+    if ((mask & XGC_M_STIRECOV) && (gc & 7u)) {
+      Draw d(inj, g, r, at, XGC_S_STIRECOV, uid, 0u, uid);
+      const int txpr[3] = { XGC_P_rgc_tx_recov_pr, XGC_P_ugc_tx_recov_pr, XGC_P_pgc_tx_recov_pr };
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (!(gc & GC_ST(s))) continue;
+        short infT = s == 0 ? ga.x : s == 1 ? ga.y : ga.z, txT = s == 0 ? gb.x : s == 1 ? gb.y : gb.z;
+        short dur = s == 0 ? gd.x : s == 1 ? gd.y : gd.z;
+        bool recov = false;
+        if (gc & GC_TX(s)) {
+          int k = at - (int)txT;
+          if (k >= 1) recov = xgc_bern(d(3 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
+        } else if ((int)infT < at) {
+          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(s), 1.0 / P[XGC_P_gc_ntx_int + s]);
+          else recov = (at - (int)infT) >= (int)dur;
+        }
+        if (recov) {
+          gc &= ~(GC_ST(s) | GC_SY(s) | GC_TX(s));
+          if (s == 0) { ga.x = -1; gb.x = -1; gd.x = -1; } else if (s == 1) { ga.y = -1; gb.y = -1; gd.y = -1; } else { ga.z = -1; gb.z = -1; gd.z = -1; }
+          ga_dirty = gb_dirty = true; gd_dirty = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
+        }
+      }
+    }
+    if (mask & XGC_M_STITX) {
+      int proto = C[XGC_C_stiScreeningProtocol], kissx = C[XGC_C_cdcExposureSite_Kissing];
+      Draw d(inj, g, r, at, XGC_S_STITX, uid, 0u, uid);
+      bool sv = false, av = false;
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        if ((gc & GC_ST(s)) && (gc & GC_SY(s)) && !(gc & GC_TX(s))) {
+          double rr = s == 0 ? P[XGC_P_rgc_sympt_seek_test_rr] : s == 2 ? P[XGC_P_pgc_sympt_seek_test_rr] : 1.0;
+          if (xgc_bern(d(s), P[XGC_P_ugc_sympt_seek_test_prob] * rr)) sv = true;
+        }
+      unsigned ex = (gc >> GC_EXPO_SHIFT) & 0x1Fu;
+      if (!sv) {
+        if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = xgc_bern(d(3), P[XGC_P_gc_asympt_visit_prob]);
+        else if (proto == XGC_SCREEN_CDC) {
+          bool active = (ex & 7u) || (kissx && (ex & 8u));
+          bool hr = (hiv & HV_PREP) || (ex & 16u);
+          double interval = (hr ? P[XGC_P_cdc_sti_hr_int] : P[XGC_P_cdc_sti_int]) * (52.0 / 12.0);
+          short ls = g_loaded ? ga.w : g.gck_a[idx].w;
+          bool due = ls == XGC_NA16 || (double)(at - (int)ls) >= interval;
+          av = active && due;
+        }
+      }
+      if (sv || av) {
+        visit = 1; svisit = sv;
+        if (!g_loaded) { ga = g.gck_a[idx]; gb = g.gck_b[idx]; g_loaded = true; }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          bool inf = gc & GC_ST(s), symp = inf && (gc & GC_SY(s)), tested;
+          bool exposed = (ex >> s) & 1u; if (s == 2 && kissx && (ex & 8u)) exposed = true;
+          if (proto == XGC_SCREEN_CDC && !symp && !exposed) tested = false;
+          else if (proto == XGC_SCREEN_UNIVERSAL) tested = true;
+          else tested = xgc_bern(d(4 + s), symp ? P[XGC_P_gc_sympt_prob_test + s] : P[XGC_P_gc_asympt_prob_test + s]);
+          if (!tested) continue;
+          tst[s] = 1;
+          if (inf) {
+            pos[s] = 1; ind_sti = true;
+            if (!(gc & GC_TX(s))) { gc |= GC_TX(s); txs[s] = 1; gb_dirty = true;
+              if (s == 0) gb.x = (short)at; else if (s == 1) gb.y = (short)at; else gb.z = (short)at; }
+          }
+        }
+        ga.w = (short)at; ga_dirty = true;
+        gc &= ~GC_EXPO_MASK;
+      }
+    }
+    if (ind_sti) g.tck[idx].y = (short)at;
+    if (ga_dirty) g.gck_a[idx] = ga;
+    if (gb_dirty) g.gck_b[idx] = gb;
+    if (gd_dirty) g.gck_d[idx] = gd;
+    if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
+  }
+  if (mask & XGC_M_STITX) {
+    unsigned any = __ballot_sync(0xffffffffu, visit != 0);
+    if (any) {
+      warp_tally(row, XGC_K_VISITS, visit); warp_tally(row, XGC_K_VISITS_SYMPT, svisit);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) { warp_tally(row, XGC_K_TESTED + s, tst[s]); warp_tally(row, XGC_K_POS + s, pos[s]); warp_tally(row, XGC_K_TXSTART + s, txs[s]); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_edge2: hivtrans_msm + stitrans_msm_rand over the site-/sero-discordant edges (sim1_02_lhs.r:214, 217).
+// Condom use and position of each act are evaluated lazily from their indexed draws (condoms_msm, position_msm).
+// New infections are OR-ed into the agents' core words; k_agent3 applies them (unique() semantics).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_edge2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.z, l = blockIdx.y;
+  const Rep* rp = g.rep + r;
+  int ne = rp->ne[l];
+  if ((int)(blockIdx.x * TPB) >= ne) return;
+  int e = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  if (e >= ne) return;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  uint4* core = g.core + (size_t)r * g.n_cap;
+  EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
+  if (x.ed.w == 0) return;
+  x.ca = core[x.ed.x]; x.cb = core[x.ed.y];
+  x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+  int ai = x.ed.w & 0xFF, oi = (x.ed.w >> 8) & 0xFF, ki = (x.ed.w >> 16) & 0xFF, ri = (x.ed.w >> 24) & 0xFF;
+  unsigned ga = x.ca.z & 7u, gb = x.cb.z & 7u;              // current site status: bit0 r, bit1 u, bit2 p
+  bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((x.ca.w ^ x.cb.w) & HV_STATUS);
+  bool gct = mask & XGC_M_STITRANS;
+  // discordance per act type (either direction)
+  bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
+                                (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
+  bool d_oi = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
+                                (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
+  bool d_ri = gct && ri > 0 && C[XGC_C_transRoute_Rimming] &&
+              (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
+  bool d_ki = gct && ki > 0 && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
+  if (!(hivdisc || d_ai || d_oi || d_ri || d_ki)) return;
+  unsigned new_a = 0, new_b = 0; bool hiv_a = false, hiv_b = false;
+  if (hivdisc || d_ai) {
+    const Aux* aux = g.aux + (size_t)r * g.n_cap;
+    Aux aa = aux[x.ed.x], ab = aux[x.ed.y];
+    double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
+    x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
+    double pc = edge_cond_prob(g, P, x, true);
+    Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dh(inj, g, r, at, x.base + (XGC_S_HIVTRANS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_AI_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_AI_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    // HIV per-act probability pieces that do not depend on the act
+    bool a_pos = x.ca.w & HV_STATUS;
+    uint4 cp = a_pos ? x.ca : x.cb, cn = a_pos ? x.cb : x.ca;
+    double vlf = 0.0; int nrace = (int)DM_RACE(cn.y);
+    if (hivdisc) vlf = xgc_exp(((double)(a_pos ? aa.vl : ab.vl) - 4.5) * XGC_LN_2_45);
+    unsigned gpre_n = (cn.z >> GC_PRE_SHIFT) & 7u;          // negative partner's GC status as hivtrans saw it
+    for (int k = 0; k < ai; ++k) {
+      int uai = xgc_bern(dc(k), 1.0 - pc);
+      int p1ins = edge_ai_p1ins(x, dp, k);
+      if (hivdisc) {
+        bool pos_ins = (p1ins != 0) == a_pos;
+        double t;
+        if (pos_ins) { t = P[XGC_P_urai_prob] * vlf; if (gpre_n & 1u) t = t * P[XGC_P_hiv_rgc_rr]; }
+        else { t = P[XGC_P_uiai_prob] * vlf; if (cn.y & DM_CIRC) t = t * P[XGC_P_circ_rr]; if (gpre_n & 2u) t = t * P[XGC_P_hiv_ugc_rr]; }
+        if (!uai) t = t * (1.0 - P[XGC_P_cond_eff] * (1.0 - P[XGC_P_cond_fail + nrace]));
+        unsigned st = HV_STAGE(cp.w);
+        if (st == 1 || st == 2) t = t * P[XGC_P_acute_rr];
+        if (cn.w & HV_PREP) { unsigned cl = HV_PREPCLASS(cn.w); if (cl >= 1) t = t * P[XGC_P_prep_adhr_hr + cl - 1]; }
+        t = t * P[XGC_P_trans_scale + nrace];
+        if (t > 1.0) t = 1.0;
+        if (xgc_bern(dh(k), t)) { if (a_pos) hiv_b = true; else hiv_a = true; }
+      }
+      if (d_ai) {
+        // x = insertive (urethra), y = receptive (rectum)
+        unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
+        bool ux = (gx >> 1) & 1u, ry = gy & 1u;
+        if (ux && !ry) {
+          double t = P[XGC_P_u2rgc_tprob];
+          if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? x.cb.y : x.ca.y)]));
+          if (xgc_bern(dA(k), t)) { if (p1ins) new_b |= 1u << XGC_PATH_U2R; else new_a |= 1u << XGC_PATH_U2R; }
+        }
+        if (ry && !ux) {
+          double t = P[XGC_P_r2ugc_tprob];
+          if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? x.ca.y : x.cb.y)]));
+          if (xgc_bern(dB(k), t)) { if (p1ins) new_a |= 1u << XGC_PATH_R2U; else new_b |= 1u << XGC_PATH_R2U; }
+        }
+      }
+    }
+  }
+  if (d_oi) {
+    Draw dd(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_OI_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_OI_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    for (int k = 0; k < oi; ++k) {
+      int p1ins = xgc_bern(dd(k), 0.5);
+      unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
+      bool ux = (gx >> 1) & 1u, py = (gy >> 2) & 1u;
+      if (ux && !py && xgc_bern(dA(k), P[XGC_P_u2pgc_tprob])) { if (p1ins) new_b |= 1u << XGC_PATH_U2P; else new_a |= 1u << XGC_PATH_U2P; }
+      if (py && !ux && xgc_bern(dB(k), P[XGC_P_p2ugc_tprob])) { if (p1ins) new_a |= 1u << XGC_PATH_P2U; else new_b |= 1u << XGC_PATH_P2U; }
+    }
+  }
+  if (d_ri) {
+    Draw dd(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_RIM_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_RIM_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    for (int k = 0; k < ri; ++k) {
+      int p1rim = xgc_bern(dd(k), 0.5);
+      unsigned gx = p1rim ? ga : gb, gy = p1rim ? gb : ga;      // x = rimmer (pharynx), y = rimmee (rectum)
+      bool px = (gx >> 2) & 1u, ry = gy & 1u;
+      if (px && !ry && xgc_bern(dA(k), P[XGC_P_p2rgc_tprob])) { if (p1rim) new_b |= 1u << XGC_PATH_P2R; else new_a |= 1u << XGC_PATH_P2R; }
+      if (ry && !px && xgc_bern(dB(k), P[XGC_P_r2pgc_tprob])) { if (p1rim) new_a |= 1u << XGC_PATH_R2P; else new_b |= 1u << XGC_PATH_R2P; }
+    }
+  }
+  if (d_ki) {
+    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_KISS_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_KISS_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+    bool pa = (ga >> 2) & 1u;
+    for (int k = 0; k < ki; ++k) {
+      if (pa) { if (xgc_bern(dA(k), P[XGC_P_p2pgc_tprob])) new_b |= 1u << XGC_PATH_P2P; }
+      else    { if (xgc_bern(dB(k), P[XGC_P_p2pgc_tprob])) new_a |= 1u << XGC_PATH_P2P; }
+    }
+  }
+  if (new_a) atomicOr(&core[x.ed.x].z, new_a << GC_NEW_SHIFT);
+  if (new_b) atomicOr(&core[x.ed.y].z, new_b << GC_NEW_SHIFT);
+  if (hiv_a) atomicOr(&core[x.ed.x].w, HV_NEW);
+  if (hiv_b) atomicOr(&core[x.ed.y].w, HV_NEW);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_agent3: apply this week's new infections (unique ids; pathway attribution by the weekly random order) and tally
+// prevalence_msm (sim1_02_lhs.r:218).  Per-CTA shared-memory histogram, one flush per CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+#define A3_NHIST (XGC_K_NGROUP * XGC_NCELL + XGC_NPATH)
+__global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  const Rep* rp = g.rep + r;
+  int n_slots = rp->n_slots;
+  if ((int)(blockIdx.x * TPB) >= n_slots) return;
+  __shared__ unsigned hist[A3_NHIST];
+  for (int k = threadIdx.x; k < A3_NHIST; k += TPB) hist[k] = 0u;
+  __syncthreads();
+  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  size_t idx = (size_t)r * g.n_cap + i;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  bool live = i < n_slots;
+  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
+  live = live && (c.y & DM_ACTIVE);
+  if (live) {
+    unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w, cell = DM_CELL(demo);
+    unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
+    if (nm && (mask & XGC_M_STITRANS)) {
+      short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
+      bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
+      if (pois) gd = g.gck_d[idx];
+      Draw d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
+      const unsigned site_mask[3] = { (1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R), (1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U),
+                                      (1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P) };
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        unsigned cand = nm & site_mask[s];
+        if (!cand || (gc & GC_ST(s))) continue;
+        int win = -1, wr = 99;
+        for (int k = 0; k < XGC_NPATH; ++k) if ((cand >> k) & 1u) { int rk = rp->path_rank[k]; if (rk < wr) { wr = rk; win = k; } }
+        gc = (gc | GC_ST(s)) & ~(GC_SY(s) | GC_TX(s));
+        if (xgc_bern(d(s), P[XGC_P_gc_sympt_prob + s])) gc |= GC_SY(s);
+        short du = -1;
+        if (pois) { int q = xgc_pois(d(3 + s), P[XGC_P_gc_ntx_int + s], 255); du = (short)(q < 1 ? 1 : q); }
+        if (s == 0) { ga.x = (short)at; gb.x = -1; gd.x = du; } else if (s == 1) { ga.y = (short)at; gb.y = -1; gd.y = du; } else { ga.z = (short)at; gb.z = -1; gd.z = du; }
+        atomicAdd(&hist[(XGC_K_INCID_RGC + s) * XGC_NCELL + cell], 1u);
+        atomicAdd(&hist[XGC_K_NGROUP * XGC_NCELL + win], 1u);
+      }
+      g.gck_a[idx] = ga; g.gck_b[idx] = gb; if (pois) g.gck_d[idx] = gd;
+    }
+    if (mask & XGC_M_STITRANS) gc &= ~GC_NEW_MASK;
+    if ((hiv & HV_NEW) && (mask & XGC_M_HIVTRANS)) {
+      if (!(hiv & HV_STATUS)) {
+        hiv = (hiv & ~(HV_STAGE_MASK | HV_DIAG | HV_TX)) | HV_STATUS | (1u << 1);
+        short4 ha = g.hck_a[idx]; ha.x = (short)at; ha.z = (short)at; g.hck_a[idx] = ha;
+        short4 hb = g.hck_b[idx]; hb.x = 0; hb.y = 0; g.hck_b[idx] = hb;
+        g.aux[idx].vl = 0.f;
+        atomicAdd(&hist[XGC_K_INCID_HIV * XGC_NCELL + cell], 1u);
+      }
+    }
+    if (mask & XGC_M_HIVTRANS) hiv &= ~HV_NEW;
+    if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
+    if (mask & XGC_M_PREV) {
+      atomicAdd(&hist[XGC_K_NUM * XGC_NCELL + cell], 1u);
+      if (hiv & HV_STATUS) atomicAdd(&hist[XGC_K_INUM * XGC_NCELL + cell], 1u);
+      if (hiv & HV_DIAG) {
+        atomicAdd(&hist[XGC_K_INUM_DX * XGC_NCELL + cell], 1u);
+        if ((double)g.aux[idx].vl <= XGC_LOG10_200) atomicAdd(&hist[XGC_K_VSUPP * XGC_NCELL + cell], 1u);
+      }
+      if (hiv & HV_PREPELIG) atomicAdd(&hist[XGC_K_PREPELIG * XGC_NCELL + cell], 1u);
+      if (hiv & HV_PREP) atomicAdd(&hist[XGC_K_PREPCURR * XGC_NCELL + cell], 1u);
+      if (gc & 7u) {
+        atomicAdd(&hist[XGC_K_INUM_GC * XGC_NCELL + cell], 1u);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) if (gc & GC_ST(s)) atomicAdd(&hist[(XGC_K_INUM_RGC + s) * XGC_NCELL + cell], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned* row = counter_row(g, r, at);
+  for (int k = threadIdx.x; k < A3_NHIST; k += TPB) {
+    unsigned v = hist[k];
+    if (v) atomicAdd(row + (k < XGC_K_NGROUP * XGC_NCELL ? k : XGC_K_PATH + (k - XGC_K_NGROUP * XGC_NCELL)), v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_targets: tail-window means of the target ratios, NA/NaN -> 0 per week (inst/cal/sim0.0_setup.r:205-224,272,299-308;
+// R/calculate_targets.r:14-190).  One thread per (replicate, target); sequential in `at` so the sum order is fixed.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gsum(const unsigned* c, int group, unsigned cells) {
+  double s = 0.0;
+  for (int k = 0; k < XGC_NCELL; ++k) if ((cells >> k) & 1u) s += (double)c[group * XGC_NCELL + k];
+  return s;
+}
+__device__ __forceinline__ double nz(double x) { return (x != x || x > 1.7e308 || x < -1.7e308) ? 0.0 : x; }
+__device__ double target_week(const unsigned* c, int k) {
+  const unsigned ALL = 0xFFFFFu;
+  double num = gsum(c, XGC_K_NUM, ALL);
+  if (k == XGC_TG_NUM) return num;
+  if (k == XGC_TG_I_PREV) return gsum(c, XGC_K_INUM, ALL) / num;
+  if (k == XGC_TG_IR100_POP) return gsum(c, XGC_K_INCID_HIV, ALL) / num * 5200.0;
+  if (k < XGC_TG_PROP_TESTED) {
+    unsigned m; int what;
+    if (k < XGC_TG_HIVDX_AGE) { m = 0x1Fu << ((k - XGC_TG_HIVDX_RACE) * 5); what = 0; }
+    else if (k < XGC_TG_VLS_RACE) { m = 0x08421u << (k - XGC_TG_HIVDX_AGE); what = 0; }
+    else if (k < XGC_TG_VLS_AGE) { m = 0x1Fu << ((k - XGC_TG_VLS_RACE) * 5); what = 1; }
+    else if (k < XGC_TG_PREPCOV_RACE) { m = 0x08421u << (k - XGC_TG_VLS_AGE); what = 1; }
+    else { m = 0x1Fu << ((k - XGC_TG_PREPCOV_RACE) * 5); what = 2; }
+    if (what == 0) { double n = gsum(c, XGC_K_NUM, m); return (gsum(c, XGC_K_INUM_DX, m) / n) / (gsum(c, XGC_K_INUM, m) / n); }
+    if (what == 1) return gsum(c, XGC_K_VSUPP, m) / gsum(c, XGC_K_INUM_DX, m);
+    return gsum(c, XGC_K_PREPCURR, m) / gsum(c, XGC_K_PREPELIG, m);
+  }
+  if (k < XGC_TG_PROB_POS) return (double)c[XGC_K_TESTED + k - XGC_TG_PROP_TESTED] / (double)c[XGC_K_VISITS];
+  if (k < XGC_TG_PREV_GC) return (double)c[XGC_K_POS + k - XGC_TG_PROB_POS] / (double)c[XGC_K_TESTED + k - XGC_TG_PROB_POS];
+  if (k == XGC_TG_PREV_GC) return gsum(c, XGC_K_INUM_GC, ALL) / num;
+  if (k < XGC_TG_IR100_GC) return gsum(c, XGC_K_INUM_RGC + (k - XGC_TG_PREV_GC - 1), ALL) / num;
+  if (k == XGC_TG_IR100_GC) {
+    double inc = 0.0;
+    for (int s = 0; s < 3; ++s) inc += gsum(c, XGC_K_INCID_RGC + s, ALL);
+    return inc / (num - gsum(c, XGC_K_INUM_GC, ALL)) * 5200.0;
+  }
+  int s = k - XGC_TG_IR100_GC - 1;
+  return gsum(c, XGC_K_INCID_RGC + s, ALL) / (num - gsum(c, XGC_K_INUM_RGC + s, ALL)) * 5200.0;
+}
+__global__ void k_targets(const __grid_constant__ Dev g, int at_last, int tailn, double* out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.R * XGC_NTARGET) return;
+  int r = t / XGC_NTARGET, k = t % XGC_NTARGET;
+  double s = 0.0;
+  for (int at = at_last - tailn + 1; at <= at_last; ++at) s += nz(target_week(counter_row(g, r, at), k));
+  out[t] = s / (double)tailn;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_compact: squeeze tombstones out of one replicate (stable, in place, one CTA per replicate) and re-number edges.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ Dev g, int* remap /*[R][n_cap] old slot -> new slot*/) {
+  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Rep* rp = g.rep + r;
+  int n_slots = rp->n_slots;
+  size_t o = (size_t)r * g.n_cap;
+  int* RM = remap + o;
+  __shared__ int wsum[TPB / 32];
+  __shared__ int base;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n_slots; i0 += TPB) {
+    int i = i0 + tid; bool keep = false;
+    uint4 c; Aux ax; short4 a, b, d, ha, hb, tk; int arr = 0;
+    if (i < n_slots) {
+      c = g.core[o + i]; keep = c.y & DM_ACTIVE;
+      if (keep) { ax = g.aux[o + i]; a = g.gck_a[o + i]; b = g.gck_b[o + i]; d = g.gck_d[o + i]; ha = g.hck_a[o + i]; hb = g.hck_b[o + i]; tk = g.tck[o + i]; arr = g.arr_t[o + i]; }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (i < n_slots) RM[i] = keep ? off : -1;
+    if (keep) { g.core[o + off] = c; g.aux[o + off] = ax; g.gck_a[o + off] = a; g.gck_b[o + off] = b; g.gck_d[o + off] = d;
+                g.hck_a[o + off] = ha; g.hck_b[o + off] = hb; g.tck[o + off] = tk; g.arr_t[o + off] = arr; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    __syncthreads();
+  }
+  int n = base;
+  // clear the freed tail (active bit off) and rebuild the alive bitmap
+  for (int i = n + tid; i < n_slots; i += TPB) g.core[o + i] = make_uint4(0, 0, 0, 0);
+  unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  for (int wd = tid; wd < g.n_cap / 32; wd += TPB) {
+    int lo = wd * 32;
+    A[wd] = n >= lo + 32 ? 0xFFFFFFFFu : n <= lo ? 0u : ((1u << (n - lo)) - 1u);
+  }
+  if (tid == 0) { rp->n_slots = n; rp->n_slots_pre = n; rp->n_alive = n; }
+}
+__global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ Dev g, const int* remap) {
+  int r = blockIdx.z, l = blockIdx.y;
+  int ne = g.rep[r].ne[l];
+  int e = blockIdx.x * TPB + threadIdx.x;
+  if (e >= ne) return;
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const int* RM = remap + (size_t)r * g.n_cap;
+  int4 ed = E[e];
+  ed.x = RM[ed.x]; ed.y = RM[ed.y];
+  E[e] = ed;
+}
+
+// k_actlist: materialise dat$temp$al for one replicate (debug / parity of condoms_msm + position_msm)
+__global__ void k_actlist(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* al, int cap, int* n_out) {
+  // single thread: tiny test-only kernel, rows must come out in (layer, edge, type, k) order
+  if (blockIdx.x || threadIdx.x) return;
+  const Rep* rp = g.rep + r;
+  int at = g.at_ptr[r], n = 0;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  const Aux* aux = g.aux + (size_t)r * g.n_cap;
+  double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
+  for (int l = 0; l < 3; ++l) {
+    const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+    for (int e = 0; e < rp->ne[l]; ++e) {
+      EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
+      x.ca = core[x.ed.x]; x.cb = core[x.ed.y]; x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+      Aux aa = aux[x.ed.x], ab = aux[x.ed.y];
+      x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
+      int cnt[4] = { x.ed.w & 0xFF, (x.ed.w >> 8) & 0xFF, (x.ed.w >> 16) & 0xFF, (x.ed.w >> 24) & 0xFF };
+      double pc = cnt[0] > 0 ? edge_cond_prob(g, P, x, false) : 0.0;
+      Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      Draw dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      Draw doi(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      Draw dri(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      for (int type = 0; type < 4; ++type)
+        for (int k = 0; k < cnt[type]; ++k) {
+          int uai = 0, p1 = 0;
+          if (type == 0) { uai = xgc_bern(dc(k), 1.0 - pc); p1 = edge_ai_p1ins(x, dp, k); }
+          else if (type == 1) p1 = xgc_bern(doi(k), 0.5);
+          else if (type == 3) p1 = xgc_bern(dri(k), 0.5);
+          if (n < cap) { al[n] = l; al[cap + n] = e; al[2 * cap + n] = type; al[3 * cap + n] = k; al[4 * cap + n] = uai; al[5 * cap + n] = p1; }
+          n++;
+        }
+    }
+  }
+  *n_out = n;
+}
+
+__global__ void k_debug_exp(const double* x, double* y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = xgc_exp(x[i]);
+}
+__global__ void k_debug_philox(unsigned seed, unsigned rep, const uint4* ctr, uint4* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox4x32_10(ctr[i], make_uint2(seed, rep));
+}

@@ -1,0 +1,778 @@
+// libxgc.so — host side of the C ABI declared in include/xgc/abi.h.  Owns the device state of one GPU's shard of
+// replicates, sequences the weekly kernels in the reference's module order (sim1_02_lhs.r:200-218), and converts
+// between the reference's dat$attr / dat$el view (R positions, one vector per attribute) and the packed device planes.
+// There is NO CPU fallback: every entry point that computes launches the CUDA kernels in xgc_kernels.cuh.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+#include "xgc/abi.h"
+#include "xgc_kernels.cuh"
+
+static thread_local std::string g_create_error;
+
+struct HostRep {                      // host mirror of one replicate (cache for attribute / edge exchange)
+  int r = -1; bool dirty = false;
+  Rep rep;
+  std::vector<uint4> core; std::vector<Aux> aux;
+  std::vector<short4> gck_a, gck_b, gck_d, hck_a, hck_b, tck; std::vector<int> arr_t;
+  std::vector<int4> edge[3];
+  std::vector<int> pos2slot, slot2pos;
+};
+
+struct xgc_handle {
+  xgc_config cfg;
+  Dev g;                               // device pointers + geometry
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int last_at = -1;
+  HostRep cache;
+  double* d_inj = nullptr; size_t d_inj_cap = 0;
+  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr;
+  int* d_el_stage = nullptr; size_t el_stage_cap = 0;
+  cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
+  std::vector<void*> allocs;
+  size_t n_agent() const { return (size_t)cfg.n_replicates * cfg.n_cap; }
+};
+
+#define FAIL(h, code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); (h)->err = _b; return (code); } while (0)
+#define CU(h, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) FAIL(h, 100 + (int)_e, "%s failed: %s", #call, cudaGetErrorString(_e)); } while (0)
+#define CHECK_R(h, r) do { if ((r) < 0 || (r) >= (h)->cfg.n_replicates) FAIL(h, 2, "replicate %d out of range [0,%d)", (r), (h)->cfg.n_replicates); } while (0)
+
+template <typename T> static int dalloc(xgc_handle* h, T** p, size_t n) {
+  CU(h, cudaMalloc((void**)p, n * sizeof(T)));
+  CU(h, cudaMemset(*p, 0, n * sizeof(T)));
+  h->allocs.push_back(*p);
+  return 0;
+}
+
+static Inj make_inj(const xgc_handle* h, const xgc_inject* inj, const double* d_u) {
+  Inj j; memset(&j, 0, sizeof j);
+  if (inj && inj->u) {
+    j.u = d_u; j.stride = inj->stride; j.form_cap = inj->form_cap;
+    for (int s = 0; s < XGC_NSTREAM; ++s) j.off[s] = xgc_inject_offset(inj, s);
+  }
+  (void)h;
+  return j;
+}
+
+extern "C" int xgc_constant(const char* name, int64_t* value) {
+#define X(c) if (!strcmp(name, #c)) { *value = (int64_t)(c); return 0; }
+  XGC_CONSTANT_LIST(X)
+#undef X
+  return 1;
+}
+extern "C" int xgc_param_index(const char* name, int* offset, int* count) {
+#define XGC_PARAM(n, c, v) if (!strcmp(name, #n)) { *offset = XGC_P_##n; *count = (c); return 0; }
+#include "xgc/params.def"
+#undef XGC_PARAM
+  return 1;
+}
+extern "C" int xgc_abi_version(void) { return XGC_ABI_VERSION; }
+extern "C" const char* xgc_last_error(const xgc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+  if (cfg->abi_version != XGC_ABI_VERSION) { g_create_error = "ABI version mismatch"; return 1; }
+  if (cfg->n_replicates < 1 || cfg->n_replicates > 65535 || cfg->n_cap < 128 || cfg->n_cap % 128 || cfg->t_cap < 2) {
+    g_create_error = "bad config: need 1 <= n_replicates <= 65535, n_cap a positive multiple of 128, t_cap >= 2"; return 1;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libxgc has no CPU fallback)"; return 3; }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return 1; }
+  xgc_handle* h = new xgc_handle();
+  h->cfg = *cfg;
+  if (h->cfg.compact_every <= 0) h->cfg.compact_every = 64;
+  auto fail = [&](int code) { g_create_error = h->err; xgc_destroy(h); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(3); }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return fail(3); }
+  Dev& g = h->g; memset(&g, 0, sizeof g);
+  g.R = cfg->n_replicates; g.n_cap = cfg->n_cap; g.t_cap = cfg->t_cap; g.rep0 = cfg->replicate_offset; g.seed = (unsigned)cfg->seed;
+  size_t eo = 0;
+  for (int l = 0; l < 3; ++l) { g.e_cap[l] = std::max(cfg->e_cap[l], 1); g.e_off[l] = eo; eo += ((size_t)g.e_cap[l] + 31) & ~(size_t)31; }
+  g.e_stride = eo;
+  size_t NA = h->n_agent(); int rc = 0;
+  rc |= dalloc(h, &g.core, NA); rc |= dalloc(h, &g.aux, NA);
+  rc |= dalloc(h, &g.gck_a, NA); rc |= dalloc(h, &g.gck_b, NA); rc |= dalloc(h, &g.gck_d, NA);
+  rc |= dalloc(h, &g.hck_a, NA); rc |= dalloc(h, &g.hck_b, NA); rc |= dalloc(h, &g.tck, NA); rc |= dalloc(h, &g.arr_t, NA);
+  rc |= dalloc(h, &g.alive, NA / 32); rc |= dalloc(h, &g.pos2slot, NA);
+  rc |= dalloc(h, &g.edge, (size_t)g.R * g.e_stride);
+  rc |= dalloc(h, &g.rep, (size_t)g.R);
+  double* dp; int* dc; double* dt; int* dat;
+  rc |= dalloc(h, &dp, (size_t)g.R * XGC_NPARAM); rc |= dalloc(h, &dc, (size_t)g.R * XGC_NCONTROL);
+  rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
+  rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
+  rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
+  if (rc) return fail(rc);
+  g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat;
+  // defaults: parameter defaults from params.def, kissing/rimming routes on
+  std::vector<double> P(XGC_NPARAM);
+#define XGC_PARAM(name, count, v) for (int k = 0; k < (count); ++k) P[XGC_P_##name + k] = (v);
+#include "xgc/params.def"
+#undef XGC_PARAM
+  std::vector<int32_t> C(XGC_NCONTROL, 0); C[XGC_C_transRoute_Kissing] = 1; C[XGC_C_transRoute_Rimming] = 1;
+  if (xgc_set_params(h, -1, P.data()) || xgc_set_control(h, -1, C.data())) return fail(4);
+  *out = h;
+  return 0;
+}
+
+extern "C" int xgc_destroy(xgc_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->week_graph) cudaGraphExecDestroy(h->week_graph);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->d_inj) cudaFree(h->d_inj);
+  if (h->d_el_stage) cudaFree(h->d_el_stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int xgc_sync(xgc_handle* h) { CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream)); return 0; }
+extern "C" int xgc_kernel_launches(xgc_handle* h, uint64_t* n) { *n = h->launches; return 0; }
+extern "C" int xgc_stream_ptr(xgc_handle* h, void** s) { *s = (void*)h->stream; return 0; }
+
+// --------------------------------------------------------------------------------------------------------------------
+// configuration
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int xgc_set_params(xgc_handle* h, int r, const double* p) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  if (r >= h->cfg.n_replicates) FAIL(h, 2, "replicate out of range");
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int k = r < 0 ? 0 : r; k < (r < 0 ? h->cfg.n_replicates : r + 1); ++k)
+    CU(h, cudaMemcpy((double*)h->g.params + (size_t)k * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int xgc_set_params_all(xgc_handle* h, const double* p /*[R][XGC_NPARAM]*/) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy((double*)h->g.params, p, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int xgc_get_params(xgc_handle* h, int r, double* p) {
+  CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(p, h->g.params + (size_t)r * XGC_NPARAM, sizeof(double) * XGC_NPARAM, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int xgc_set_control(xgc_handle* h, int r, const int32_t* c) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  if (r >= h->cfg.n_replicates) FAIL(h, 2, "replicate out of range");
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int k = r < 0 ? 0 : r; k < (r < 0 ? h->cfg.n_replicates : r + 1); ++k)
+    CU(h, cudaMemcpy((int*)h->g.control + (size_t)k * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// host cache of one replicate
+// --------------------------------------------------------------------------------------------------------------------
+template <typename T> static int pull(xgc_handle* h, std::vector<T>& v, const T* d, size_t n) {
+  v.resize(n); if (n) CU(h, cudaMemcpy(v.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return 0;
+}
+template <typename T> static int push(xgc_handle* h, const std::vector<T>& v, T* d) {
+  if (!v.empty()) CU(h, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return 0;
+}
+static void rebuild_maps(HostRep& c) {
+  c.pos2slot.clear(); c.slot2pos.assign(c.core.size(), -1);
+  for (size_t i = 0; i < c.core.size(); ++i) if (c.core[i].y & DM_ACTIVE) { c.slot2pos[i] = (int)c.pos2slot.size(); c.pos2slot.push_back((int)i); }
+}
+static int cache_flush(xgc_handle* h) {
+  HostRep& c = h->cache;
+  if (c.r < 0 || !c.dirty) { return 0; }
+  const Dev& g = h->g; size_t o = (size_t)c.r * g.n_cap;
+  CU(h, cudaSetDevice(h->cfg.device));
+  int rc = 0;
+  rc |= push(h, c.core, g.core + o); rc |= push(h, c.aux, g.aux + o);
+  rc |= push(h, c.gck_a, g.gck_a + o); rc |= push(h, c.gck_b, g.gck_b + o); rc |= push(h, c.gck_d, g.gck_d + o);
+  rc |= push(h, c.hck_a, g.hck_a + o); rc |= push(h, c.hck_b, g.hck_b + o); rc |= push(h, c.tck, g.tck + o); rc |= push(h, c.arr_t, g.arr_t + o);
+  if (rc) return rc;
+  std::vector<unsigned> alive(g.n_cap / 32, 0u);
+  for (size_t i = 0; i < c.core.size(); ++i) if (c.core[i].y & DM_ACTIVE) alive[i >> 5] |= 1u << (i & 31);
+  CU(h, cudaMemcpy(g.alive + (size_t)c.r * (g.n_cap / 32), alive.data(), alive.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  for (int l = 0; l < 3; ++l) {
+    c.rep.ne[l] = (int)c.edge[l].size();
+    if (!c.edge[l].empty()) CU(h, cudaMemcpy(g.edge + (size_t)c.r * g.e_stride + g.e_off[l], c.edge[l].data(), c.edge[l].size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
+  CU(h, cudaMemcpy(g.rep + c.r, &c.rep, sizeof(Rep), cudaMemcpyHostToDevice));
+  c.dirty = false;
+  return 0;
+}
+static int cache_load(xgc_handle* h, int r) {
+  HostRep& c = h->cache;
+  if (c.r == r) return 0;
+  int rc = cache_flush(h); if (rc) return rc;
+  const Dev& g = h->g; size_t o = (size_t)r * g.n_cap;
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(&c.rep, g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));
+  size_t n = (size_t)c.rep.n_slots;
+  rc |= pull(h, c.core, g.core + o, n); rc |= pull(h, c.aux, g.aux + o, n);
+  rc |= pull(h, c.gck_a, g.gck_a + o, n); rc |= pull(h, c.gck_b, g.gck_b + o, n); rc |= pull(h, c.gck_d, g.gck_d + o, n);
+  rc |= pull(h, c.hck_a, g.hck_a + o, n); rc |= pull(h, c.hck_b, g.hck_b + o, n); rc |= pull(h, c.tck, g.tck + o, n); rc |= pull(h, c.arr_t, g.arr_t + o, n);
+  for (int l = 0; l < 3; ++l) rc |= pull(h, c.edge[l], g.edge + (size_t)r * g.e_stride + g.e_off[l], (size_t)c.rep.ne[l]);
+  if (rc) return rc;
+  rebuild_maps(c);
+  c.r = r; c.dirty = false;
+  return 0;
+}
+static int cache_drop(xgc_handle* h) { int rc = cache_flush(h); h->cache.r = -1; return rc; }
+
+// --------------------------------------------------------------------------------------------------------------------
+// attributes (dat$attr)
+// --------------------------------------------------------------------------------------------------------------------
+struct AttrDef { const char* name; std::function<double(const HostRep&, int)> get; std::function<void(HostRep&, int, double)> set; };
+static inline short S16(double v) { return (short)(int)v; }
+static void setbits(unsigned& w, unsigned mask, int shift, double v) { w = (w & ~(mask << shift)) | (((unsigned)(int)v & mask) << shift); }
+static std::vector<AttrDef> build_attrs() {
+  std::vector<AttrDef> A;
+  A.push_back({"uid", [](const HostRep& c, int i) { return (double)c.core[i].x; }, [](HostRep& c, int i, double v) { c.core[i].x = (unsigned)v; }});
+  A.push_back({"age", [](const HostRep& c, int i) { return c.aux[i].age_ref + (double)(c.rep.t_age - c.rep.t_ref) * XGC_WEEK; },
+               [](HostRep& c, int i, double v) { c.aux[i].age_ref = v; setbits(c.core[i].y, 7u, 2, (double)((v >= 25.0) + (v >= 35.0) + (v >= 45.0) + (v >= 55.0))); }});
+  A.push_back({"race", [](const HostRep& c, int i) { return (double)(DM_RACE(c.core[i].y) + 1); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 3u, 0, v - 1); }});
+  A.push_back({"age.grp", [](const HostRep& c, int i) { return (double)(DM_AGEGRP(c.core[i].y) + 1); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 7u, 2, v - 1); }});
+  A.push_back({"role.class", [](const HostRep& c, int i) { return (double)DM_ROLE(c.core[i].y); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 3u, 5, v); }});
+  A.push_back({"ins.quot", [](const HostRep& c, int i) { return (double)c.aux[i].ins_quot; }, [](HostRep& c, int i, double v) { c.aux[i].ins_quot = (float)v; }});
+  A.push_back({"risk.grp", [](const HostRep& c, int i) { return (double)(DM_RISK(c.core[i].y) + 1); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 7u, 7, v - 1); }});
+  A.push_back({"circ", [](const HostRep& c, int i) { return (double)((c.core[i].y >> 10) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 1u, 10, v); }});
+  A.push_back({"late.tester", [](const HostRep& c, int i) { return (double)((c.core[i].y >> 11) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 1u, 11, v); }});
+  A.push_back({"tt.traj", [](const HostRep& c, int i) { return (double)DM_TTTRAJ(c.core[i].y); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 3u, 12, v); }});
+  A.push_back({"act.stopper", [](const HostRep& c, int i) { return (double)((c.core[i].y >> 14) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].y, 1u, 14, v); }});
+  A.push_back({"arrival.time", [](const HostRep& c, int i) { return (double)c.arr_t[i]; }, [](HostRep& c, int i, double v) { c.arr_t[i] = (int)v; }});
+  static const char* const site[3] = { "rGC", "uGC", "pGC" };
+  for (int s = 0; s < 3; ++s) {
+    static std::string names[3][6];
+    const char* suf[6] = { "", ".infTime", ".sympt", ".tx", ".txTime", ".dur" };
+    for (int k = 0; k < 6; ++k) names[s][k] = std::string(site[s]) + suf[k];
+    A.push_back({names[s][0].c_str(), [s](const HostRep& c, int i) { return (double)((c.core[i].z >> s) & 1u); }, [s](HostRep& c, int i, double v) { setbits(c.core[i].z, 1u, s, v); }});
+    A.push_back({names[s][1].c_str(), [s](const HostRep& c, int i) { return (double)(&c.gck_a[i].x)[s]; }, [s](HostRep& c, int i, double v) { (&c.gck_a[i].x)[s] = S16(v); }});
+    A.push_back({names[s][2].c_str(), [s](const HostRep& c, int i) { return (double)((c.core[i].z >> (3 + s)) & 1u); }, [s](HostRep& c, int i, double v) { setbits(c.core[i].z, 1u, 3 + s, v); }});
+    A.push_back({names[s][3].c_str(), [s](const HostRep& c, int i) { return (double)((c.core[i].z >> (6 + s)) & 1u); }, [s](HostRep& c, int i, double v) { setbits(c.core[i].z, 1u, 6 + s, v); }});
+    A.push_back({names[s][4].c_str(), [s](const HostRep& c, int i) { return (double)(&c.gck_b[i].x)[s]; }, [s](HostRep& c, int i, double v) { (&c.gck_b[i].x)[s] = S16(v); }});
+    A.push_back({names[s][5].c_str(), [s](const HostRep& c, int i) { return (double)(&c.gck_d[i].x)[s]; }, [s](HostRep& c, int i, double v) { (&c.gck_d[i].x)[s] = S16(v); }});
+  }
+  A.push_back({"last.screen", [](const HostRep& c, int i) { return (double)c.gck_a[i].w; }, [](HostRep& c, int i, double v) { c.gck_a[i].w = S16(v); }});
+  A.push_back({"sti.expo", [](const HostRep& c, int i) { return (double)((c.core[i].z >> GC_EXPO_SHIFT) & 0x1Fu); }, [](HostRep& c, int i, double v) { setbits(c.core[i].z, 0x1Fu, GC_EXPO_SHIFT, v); }});
+  A.push_back({"status", [](const HostRep& c, int i) { return (double)(c.core[i].w & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 0, v); }});
+  A.push_back({"inf.time", [](const HostRep& c, int i) { return (double)c.hck_a[i].x; }, [](HostRep& c, int i, double v) { c.hck_a[i].x = S16(v); }});
+  A.push_back({"stage", [](const HostRep& c, int i) { return (double)HV_STAGE(c.core[i].w); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 7u, 1, v); }});
+  A.push_back({"stage.time", [](const HostRep& c, int i) { return (double)c.hck_a[i].z; }, [](HostRep& c, int i, double v) { c.hck_a[i].z = S16(v); }});
+  A.push_back({"diag.status", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 4) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 4, v); }});
+  A.push_back({"diag.time", [](const HostRep& c, int i) { return (double)c.hck_a[i].y; }, [](HostRep& c, int i, double v) { c.hck_a[i].y = S16(v); }});
+  A.push_back({"last.neg.test", [](const HostRep& c, int i) { return (double)c.tck[i].x; }, [](HostRep& c, int i, double v) { c.tck[i].x = S16(v); }});
+  A.push_back({"tx.status", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 5) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 5, v); }});
+  A.push_back({"cuml.time.on.tx", [](const HostRep& c, int i) { return (double)c.hck_b[i].x; }, [](HostRep& c, int i, double v) { c.hck_b[i].x = S16(v); }});
+  A.push_back({"cuml.time.off.tx", [](const HostRep& c, int i) { return (double)c.hck_b[i].y; }, [](HostRep& c, int i, double v) { c.hck_b[i].y = S16(v); }});
+  A.push_back({"tx.init.time", [](const HostRep& c, int i) { return (double)c.hck_a[i].w; }, [](HostRep& c, int i, double v) { c.hck_a[i].w = S16(v); }});
+  A.push_back({"vl", [](const HostRep& c, int i) { return (double)c.aux[i].vl; }, [](HostRep& c, int i, double v) { c.aux[i].vl = (float)v; }});
+  A.push_back({"prepStat", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 6) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 6, v); }});
+  A.push_back({"prepClass", [](const HostRep& c, int i) { return (double)HV_PREPCLASS(c.core[i].w); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 3u, 7, v); }});
+  A.push_back({"prepElig", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 9) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 9, v); }});
+  A.push_back({"prepStartTime", [](const HostRep& c, int i) { return (double)c.tck[i].w; }, [](HostRep& c, int i, double v) { c.tck[i].w = S16(v); }});
+  A.push_back({"prepLastRisk", [](const HostRep& c, int i) { return (double)c.tck[i].z; }, [](HostRep& c, int i, double v) { c.tck[i].z = S16(v); }});
+  A.push_back({"prep.ind.last", [](const HostRep& c, int i) { return (double)c.tck[i].y; }, [](HostRep& c, int i, double v) { c.tck[i].y = S16(v); }});
+  return A;
+}
+static const std::vector<AttrDef>& attrs() { static std::vector<AttrDef> A = build_attrs(); return A; }
+
+extern "C" int xgc_attr_names(const char** names, int cap) {
+  const auto& A = attrs();
+  for (int k = 0; k < (int)A.size() && k < cap; ++k) names[k] = A[k].name;
+  return (int)A.size();
+}
+
+extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
+  CHECK_R(h, r);
+  if (n < 0 || n > h->cfg.n_cap) FAIL(h, 2, "n = %d exceeds n_cap = %d", n, h->cfg.n_cap);
+  if (at < 0 || at >= h->cfg.t_cap) FAIL(h, 2, "at = %d outside [0, t_cap = %d)", at, h->cfg.t_cap);
+  int rc = cache_drop(h); if (rc) return rc;
+  HostRep& c = h->cache;
+  memset(&c.rep, 0, sizeof(Rep));
+  c.rep.n_slots = c.rep.n_slots_pre = c.rep.n_alive = c.rep.next_uid = n; c.rep.t_ref = c.rep.t_age = at;
+  for (int k = 0; k < XGC_NPATH; ++k) c.rep.path_rank[k] = k;
+  Aux ax; ax.age_ref = 18.0; ax.vl = 0.f; ax.ins_quot = 0.f;
+  c.core.assign(n, make_uint4(0, 0, 0, 0)); c.aux.assign(n, ax);
+  short4 na = make_short4(-1, -1, -1, -1);
+  c.gck_a.assign(n, na); c.gck_b.assign(n, na); c.gck_d.assign(n, na); c.hck_a.assign(n, na);
+  c.hck_b.assign(n, make_short4(0, 0, -1, -1)); c.tck.assign(n, na); c.arr_t.assign(n, at);
+  for (int i = 0; i < n; ++i) c.core[i] = make_uint4((unsigned)i, DM_ACTIVE | (2u << 12), 0u, 0u);
+  for (int l = 0; l < 3; ++l) c.edge[l].clear();
+  rebuild_maps(c);
+  c.r = r; c.dirty = true;
+  // wipe the tail beyond n on the device (stale slots of a previous population)
+  const Dev& g = h->g;
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemset(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap));
+  CU(h, cudaMemcpy((int*)g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice));
+  h->last_at = -1;
+  return cache_flush(h);
+}
+extern "C" int xgc_num_agents(xgc_handle* h, int r, int* n) {
+  CHECK_R(h, r); int rc = cache_load(h, r); if (rc) return rc;
+  *n = (int)h->cache.pos2slot.size(); return 0;
+}
+static const AttrDef* find_attr(const char* name) { for (const auto& a : attrs()) if (!strcmp(a.name, name)) return &a; return nullptr; }
+
+extern "C" int xgc_upload_attr(xgc_handle* h, int r, const char* name, const void* data, size_t n, int dtype) {
+  CHECK_R(h, r);
+  const AttrDef* a = find_attr(name);
+  if (!a) FAIL(h, 5, "unknown attribute '%s'", name);
+  int rc = cache_load(h, r); if (rc) return rc;
+  HostRep& c = h->cache;
+  if (n != c.pos2slot.size()) FAIL(h, 6, "attribute '%s': length %zu != number of agents %zu", name, n, c.pos2slot.size());
+  for (size_t p = 0; p < n; ++p) {
+    double v = dtype == XGC_F64 ? ((const double*)data)[p] : (double)((const int32_t*)data)[p];
+    a->set(c, c.pos2slot[p], v);
+  }
+  if (!strcmp(name, "age")) c.rep.t_ref = c.rep.t_age;      // re-base the closed-form age clock
+  if (!strcmp(name, "uid")) { unsigned mx = 0; for (size_t p = 0; p < n; ++p) mx = std::max(mx, c.core[c.pos2slot[p]].x + 1u); c.rep.next_uid = (int)mx; }
+  c.dirty = true;
+  return 0;
+}
+extern "C" int xgc_download_attr(xgc_handle* h, int r, const char* name, void* data, size_t cap, int dtype, size_t* n_out) {
+  CHECK_R(h, r);
+  const AttrDef* a = find_attr(name);
+  if (!a) FAIL(h, 5, "unknown attribute '%s'", name);
+  int rc = cache_load(h, r); if (rc) return rc;
+  const HostRep& c = h->cache;
+  size_t n = c.pos2slot.size();
+  if (n_out) *n_out = n;
+  if (cap < n) FAIL(h, 6, "attribute '%s': buffer of %zu too small for %zu agents", name, cap, n);
+  for (size_t p = 0; p < n; ++p) {
+    double v = a->get(c, c.pos2slot[p]);
+    if (dtype == XGC_F64) ((double*)data)[p] = v; else ((int32_t*)data)[p] = (int32_t)v;
+  }
+  return 0;
+}
+
+extern "C" int xgc_set_edgelist(xgc_handle* h, int r, int layer, const int32_t* el, int n_edges, const int32_t* start) {
+  CHECK_R(h, r);
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
+  if (n_edges < 0 || n_edges > h->g.e_cap[layer]) FAIL(h, 6, "layer %d: %d edges exceed e_cap %d", layer, n_edges, h->g.e_cap[layer]);
+  int rc = cache_load(h, r); if (rc) return rc;
+  HostRep& c = h->cache; int n = (int)c.pos2slot.size();
+  std::vector<int4> E(n_edges);
+  for (int e = 0; e < n_edges; ++e) {
+    int a = el[e], b = el[n_edges + e];
+    if (a < 1 || a > n || b < 1 || b > n || a == b) FAIL(h, 7, "layer %d edge %d: node ids (%d,%d) outside 1..%d", layer, e, a, b, n);
+    E[e] = make_int4(c.pos2slot[a - 1], c.pos2slot[b - 1], start ? start[e] : c.rep.t_age, 0);
+  }
+  c.edge[layer] = E; c.dirty = true;
+  return 0;
+}
+extern "C" int xgc_get_edgelist(xgc_handle* h, int r, int layer, int32_t* el, int cap, int* n_edges, int32_t* start) {
+  CHECK_R(h, r);
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
+  int rc = cache_load(h, r); if (rc) return rc;
+  const HostRep& c = h->cache; int ne = (int)c.edge[layer].size();
+  if (n_edges) *n_edges = ne;
+  if (cap < ne) FAIL(h, 6, "edge buffer of %d too small for %d edges", cap, ne);
+  for (int e = 0; e < ne; ++e) {
+    int4 ed = c.edge[layer][e];
+    el[e] = c.slot2pos[ed.x] + 1; el[ne + e] = c.slot2pos[ed.y] + 1;
+    if (start) start[e] = ed.z;
+  }
+  return 0;
+}
+extern "C" int xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts, int cap, int* n_edges) {
+  CHECK_R(h, r);
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
+  int rc = cache_load(h, r); if (rc) return rc;
+  const HostRep& c = h->cache; int ne = (int)c.edge[layer].size();
+  if (n_edges) *n_edges = ne;
+  if (cap < ne) FAIL(h, 6, "buffer too small");
+  for (int e = 0; e < ne; ++e) {
+    int w = c.edge[layer][e].w;
+    counts[e] = w & 0xFF; counts[ne + e] = (w >> 8) & 0xFF; counts[2 * ne + e] = (w >> 16) & 0xFF; counts[3 * ne + e] = (w >> 24) & 0xFF;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// the step
+// --------------------------------------------------------------------------------------------------------------------
+static int upload_inject(xgc_handle* h, const xgc_inject* inj, Inj* out) {
+  if (!inj || !inj->u) { *out = make_inj(h, nullptr, nullptr); return 0; }
+  size_t need = inj->stride * (size_t)h->cfg.n_replicates;
+  if (inj->stride != xgc_inject_size(inj)) FAIL(h, 8, "xgc_inject.stride %zu != xgc_inject_size %zu", inj->stride, xgc_inject_size(inj));
+  if (need > h->d_inj_cap) {
+    if (h->d_inj) cudaFree(h->d_inj);
+    h->d_inj = nullptr; h->d_inj_cap = 0;
+    CU(h, cudaMalloc((void**)&h->d_inj, need * sizeof(double)));
+    h->d_inj_cap = need;
+  }
+  CU(h, cudaMemcpyAsync(h->d_inj, inj->u, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  *out = make_inj(h, inj, h->d_inj);
+  return 0;
+}
+
+#define LAUNCH(h, kern, grid, block, ...) do { kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); (h)->launches++; } while (0)
+
+// enqueue one week.  at_host < 0: week = previous + 1 (graph replay).
+static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& inj, int zero_row) {
+  const Dev& g = h->g;
+  dim3 ga((g.n_cap + TPB - 1) / TPB, g.R);
+  int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
+  dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
+  LAUNCH(h, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
+  if (mask & (XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL))
+    LAUNCH(h, k_agent1, ga, TPB, g, inj, mask);
+  bool native = inj.u == nullptr;
+  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
+  if (mask & XGC_M_RESIM_NETS) {
+    LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, inj, 1);
+    LAUNCH(h, k_rank, g.R, TPB, g);
+    LAUNCH(h, k_form, dim3(3, g.R), TPB, g, inj);
+  }
+  if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCH(h, k_edge1, ge, TPB, g, inj, mask);
+  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCH(h, k_agent2, ga, TPB, g, inj, mask);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCH(h, k_edge2, ge, TPB, g, inj, mask);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3, ga, TPB, g, inj, mask);
+  return 0;
+}
+
+extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* inj) {
+  if (at < 1 || at >= h->cfg.t_cap) FAIL(h, 2, "at = %d outside [1, t_cap = %d)", at, h->cfg.t_cap);
+  if (at > 32766) FAIL(h, 2, "at = %d exceeds the 16-bit week clocks", at);
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
+  int zero_row = at != h->last_at; h->last_at = at;
+  rc = enqueue_week(h, at, mask, j, zero_row); if (rc) return rc;
+  CU(h, cudaGetLastError());
+  if (inj && inj->u) CU(h, cudaStreamSynchronize(h->stream));     // caller may free the table after return
+  return 0;
+}
+
+extern "C" int xgc_compact(xgc_handle* h) {
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const Dev& g = h->g;
+  int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
+  LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, make_inj(h, nullptr, nullptr), 0);   // no dangling endpoints before re-numbering
+  LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
+  LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
+  if (at0 < 1 || at1 >= h->cfg.t_cap || at1 < at0 - 1) FAIL(h, 2, "bad week range [%d,%d], t_cap = %d", at0, at1, h->cfg.t_cap);
+  if (at1 > 32766) FAIL(h, 2, "at exceeds the 16-bit week clocks");
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  Inj j = make_inj(h, nullptr, nullptr);
+  if (!h->week_graph) {                   // capture one week (week = previous + 1) once, replay it for every later week
+    cudaGraph_t graph;
+    uint64_t l0 = h->launches;
+    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_week(h, -1, XGC_M_ALL, j, 1);
+    CU(h, cudaStreamEndCapture(h->stream, &graph));
+    CU(h, cudaGraphInstantiate(&h->week_graph, graph, 0));
+    CU(h, cudaGraphDestroy(graph));
+    h->graph_launches = h->launches - l0;
+    h->launches = l0;
+  }
+  // the graph advances the device-side week itself; make sure it continues from at0 - 1
+  std::vector<int> atv(h->cfg.n_replicates, at0 - 1);
+  CU(h, cudaMemcpyAsync((int*)h->g.at_ptr, atv.data(), sizeof(int) * atv.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int at = at0; at <= at1; ++at) {
+    CU(h, cudaGraphLaunch(h->week_graph, h->stream));
+    h->launches += h->graph_launches;
+    if (at % h->cfg.compact_every == 0) { rc = xgc_compact(h); if (rc) return rc; }
+  }
+  h->last_at = at1;
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
+  CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  Rep rp; CU(h, cudaMemcpy(&rp, h->g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));
+  *status = rp.status; return 0;
+}
+
+extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int cap, int* n_acts, const xgc_inject* inj) {
+  CHECK_R(h, r);
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
+  int* d_al; CU(h, cudaMalloc((void**)&d_al, sizeof(int) * 6 * (size_t)std::max(cap, 1)));
+  CU(h, cudaMemcpyAsync((int*)h->g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
+  int n = 0;
+  cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  if (e1 == cudaSuccess && e2 == cudaSuccess && n <= cap) e1 = cudaMemcpy(al, d_al, sizeof(int) * 6 * (size_t)cap, cudaMemcpyDeviceToHost);
+  cudaFree(d_al);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) FAIL(h, 100, "xgc_get_actlist: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  if (n_acts) *n_acts = n;
+  if (n > cap) FAIL(h, 6, "act list has %d rows, buffer holds %d", n, cap);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// outputs: dat$epi
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int xgc_get_counters(xgc_handle* h, int r, int at0, int at1, uint32_t* out) {
+  CHECK_R(h, r);
+  if (at0 < 0 || at1 >= h->cfg.t_cap || at1 < at0) FAIL(h, 2, "bad week range");
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(out, h->g.counters + ((size_t)r * h->g.t_cap + at0) * XGC_NCOUNTER, sizeof(uint32_t) * XGC_NCOUNTER * (size_t)(at1 - at0 + 1), cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int xgc_get_counters_all(xgc_handle* h, int at, uint32_t* out) {
+  if (at < 0 || at >= h->cfg.t_cap) FAIL(h, 2, "bad week");
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemcpy2DAsync(out, sizeof(uint32_t) * XGC_NCOUNTER, h->g.counters + (size_t)at * XGC_NCOUNTER, sizeof(uint32_t) * XGC_NCOUNTER * (size_t)h->g.t_cap,
+                          sizeof(uint32_t) * XGC_NCOUNTER, (size_t)h->g.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static double hsum(const uint32_t* c, int group, uint32_t cells) {
+  double s = 0.0;
+  for (int k = 0; k < XGC_NCELL; ++k) if ((cells >> k) & 1u) s += (double)c[group * XGC_NCELL + k];
+  return s;
+}
+// stratum suffix -> cell mask: "" | B/H/O/W | age1 / age.1 / 1 | B.age1
+static uint32_t stratum(const std::string& s) {
+  if (s.empty()) return 0xFFFFFu;
+  int race = -1, age = -1; size_t p = 0;
+  static const std::string R = "BHOW";
+  if (R.find(s[0]) != std::string::npos && (s.size() == 1 || s[1] == '.')) { race = (int)R.find(s[0]); p = s.size() == 1 ? 1 : 2; }
+  if (p < s.size()) {
+    std::string t = s.substr(p);
+    if (t.rfind("age.", 0) == 0) t = t.substr(4); else if (t.rfind("age", 0) == 0) t = t.substr(3);
+    if (t.size() == 1 && t[0] >= '1' && t[0] <= '5') age = t[0] - '1'; else return 0;
+  }
+  uint32_t m = 0;
+  for (int r = 0; r < 4; ++r) for (int a = 0; a < 5; ++a) if ((race < 0 || race == r) && (age < 0 || age == a)) m |= 1u << (r * 5 + a);
+  return m;
+}
+static bool split(const std::string& v, const char* base, std::string* rest) {
+  std::string b(base);
+  if (v == b) { rest->clear(); return true; }
+  if (v.rfind(b + ".", 0) == 0) { *rest = v.substr(b.size() + 1); return true; }
+  return false;
+}
+static bool epi_eval(const uint32_t* c, const std::string& v, double* out) {
+  static const char* const pathn[XGC_NPATH] = { "incid.u2rgc", "incid.p2rgc", "incid.r2ugc", "incid.p2ugc", "incid.u2pgc", "incid.r2pgc", "incid.p2pgc" };
+  static const char* const tst[3] = { "num.rgc.test", "num.ugc.test", "num.pgc.test" };
+  static const char* const propt[3] = { "prop.rect.tested", "prop.ureth.tested", "prop.phar.tested" };
+  static const char* const probt[3] = { "prob.rGC.tested", "prob.uGC.tested", "prob.pGC.tested" };
+  static const char* const sites[4] = { "gc", "rgc", "ugc", "pgc" };
+  for (int k = 0; k < XGC_NPATH; ++k) if (v == pathn[k]) { *out = (double)c[XGC_K_PATH + k]; return true; }
+  for (int s = 0; s < 3; ++s) {
+    if (v == tst[s]) { *out = (double)c[XGC_K_TESTED + s]; return true; }
+    if (v == propt[s]) { *out = (double)c[XGC_K_TESTED + s] / (double)c[XGC_K_VISITS]; return true; }
+    if (v == probt[s]) { *out = (double)c[XGC_K_POS + s] / (double)c[XGC_K_TESTED + s]; return true; }
+  }
+  if (v == "num.visits") { *out = (double)c[XGC_K_VISITS]; return true; }
+  if (v == "dep.gen") { *out = (double)c[XGC_K_DEP_GEN]; return true; }
+  if (v == "dep.AIDS") { *out = (double)c[XGC_K_DEP_AIDS]; return true; }
+  if (v == "nNew") { *out = (double)c[XGC_K_NNEW]; return true; }
+  std::string rest; uint32_t cells;
+  for (int s = 0; s < 4; ++s) {                  // GC series: <kind>[.<stratum>].<site>
+    std::string suf = std::string(".") + sites[s];
+    if (v.size() <= suf.size() || v.compare(v.size() - suf.size(), suf.size(), suf) != 0) continue;
+    std::string head = v.substr(0, v.size() - suf.size());
+    int kind = split(head, "i.num", &rest) ? 0 : split(head, "prev", &rest) ? 1 : split(head, "ir100", &rest) ? 3 : split(head, "incid", &rest) ? 2 : -1;
+    if (kind < 0 || !(cells = stratum(rest))) continue;
+    double num = hsum(c, XGC_K_NUM, cells), inum, incid;
+    if (s == 0) { inum = hsum(c, XGC_K_INUM_GC, cells); incid = hsum(c, XGC_K_INCID_RGC, cells) + hsum(c, XGC_K_INCID_UGC, cells) + hsum(c, XGC_K_INCID_PGC, cells); }
+    else { inum = hsum(c, XGC_K_INUM_RGC + s - 1, cells); incid = hsum(c, XGC_K_INCID_RGC + s - 1, cells); }
+    *out = kind == 0 ? inum : kind == 1 ? inum / num : kind == 2 ? incid : incid / (num - inum) * 5200.0;
+    return true;
+  }
+  if (split(v, "num", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_NUM, cells); return true; }
+  if (split(v, "i.num.dx", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INUM_DX, cells); return true; }
+  if (split(v, "i.num", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INUM, cells); return true; }
+  if (split(v, "i.prev.dx", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INUM_DX, cells) / hsum(c, XGC_K_NUM, cells); return true; }
+  if (split(v, "i.prev", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INUM, cells) / hsum(c, XGC_K_NUM, cells); return true; }
+  if (split(v, "incid", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INCID_HIV, cells); return true; }
+  if (split(v, "cc.vsupp", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_VSUPP, cells) / hsum(c, XGC_K_INUM_DX, cells); return true; }
+  if (split(v, "ir100", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_INCID_HIV, cells) / (hsum(c, XGC_K_NUM, cells) - hsum(c, XGC_K_INUM, cells)) * 5200.0; return true; }
+  if (split(v, "prepElig", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_PREPELIG, cells); return true; }
+  if (split(v, "prepCurr", &rest) && (cells = stratum(rest))) { *out = hsum(c, XGC_K_PREPCURR, cells); return true; }
+  return false;
+}
+extern "C" int xgc_get_epi(xgc_handle* h, int r, const char* var, double* out, int at0, int at1) {
+  CHECK_R(h, r);
+  if (at0 < 0 || at1 >= h->cfg.t_cap || at1 < at0) FAIL(h, 2, "bad week range");
+  std::vector<uint32_t> c((size_t)(at1 - at0 + 1) * XGC_NCOUNTER);
+  int rc = xgc_get_counters(h, r, at0, at1, c.data()); if (rc) return rc;
+  for (int at = at0; at <= at1; ++at)
+    if (!epi_eval(c.data() + (size_t)(at - at0) * XGC_NCOUNTER, var, out + (at - at0))) FAIL(h, 5, "unknown epi variable '%s'", var);
+  return 0;
+}
+static std::vector<std::string> build_epi_names() {
+  std::vector<std::string> N;
+  const char* R[4] = { "B", "H", "O", "W" };
+  auto strat = [&](const std::string& b, bool dot_age) {
+    N.push_back(b);
+    for (int r = 0; r < 4; ++r) N.push_back(b + "." + R[r]);
+    for (int a = 1; a <= 5; ++a) N.push_back(b + (dot_age ? ".age." : ".age") + std::to_string(a));
+  };
+  strat("num", true); strat("i.num", false); strat("i.prev", true); strat("i.num.dx", false); strat("i.prev.dx", true);
+  strat("incid", false); strat("cc.vsupp", false); strat("ir100", false);
+  for (const char* b : { "prepElig", "prepCurr" }) { N.push_back(b); for (int r = 0; r < 4; ++r) N.push_back(std::string(b) + "." + R[r]); }
+  for (int r = 0; r < 4; ++r) for (int a = 1; a <= 5; ++a) { N.push_back(std::string("i.num.") + R[r] + ".age" + std::to_string(a)); N.push_back(std::string("i.num.dx.") + R[r] + ".age" + std::to_string(a)); }
+  for (const char* s : { "gc", "rgc", "ugc", "pgc" }) for (const char* k : { "i.num", "prev", "incid", "ir100" }) N.push_back(std::string(k) + "." + s);
+  for (const char* s : { "rgc", "ugc", "pgc" }) {
+    for (int r = 0; r < 4; ++r) N.push_back(std::string("incid.") + R[r] + "." + s);
+    for (int a = 1; a <= 5; ++a) N.push_back(std::string("incid.age.") + std::to_string(a) + "." + s);
+  }
+  for (const char* p : { "incid.u2rgc", "incid.p2rgc", "incid.r2ugc", "incid.p2ugc", "incid.u2pgc", "incid.r2pgc", "incid.p2pgc",
+                         "num.rgc.test", "num.ugc.test", "num.pgc.test", "prop.rect.tested", "prop.ureth.tested", "prop.phar.tested",
+                         "prob.rGC.tested", "prob.uGC.tested", "prob.pGC.tested", "num.visits", "dep.gen", "dep.AIDS", "nNew" }) N.push_back(p);
+  return N;
+}
+extern "C" int xgc_epi_names(const char** names, int cap) {
+  static std::vector<std::string> N = build_epi_names();
+  for (int k = 0; k < (int)N.size() && k < cap; ++k) names[k] = N[k].c_str();
+  return (int)N.size();
+}
+extern "C" int xgc_targets(xgc_handle* h, int at_last, int tailn, double* out) {
+  if (tailn < 1 || at_last - tailn + 1 < 0 || at_last >= h->cfg.t_cap) FAIL(h, 2, "bad tail window");
+  CU(h, cudaSetDevice(h->cfg.device));
+  int n = h->g.R * XGC_NTARGET;
+  LAUNCH(h, k_targets, (n + 127) / 128, 128, h->g, at_last, tailn, h->d_targets);
+  CU(h, cudaMemcpyAsync(out, h->d_targets, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// checkpoint / fork
+// --------------------------------------------------------------------------------------------------------------------
+struct Seg { void* p; size_t bytes; };
+static std::vector<Seg> segments(xgc_handle* h) {
+  const Dev& g = h->g; size_t NA = h->n_agent();
+  return { { g.core, NA * sizeof(uint4) }, { g.aux, NA * sizeof(Aux) }, { g.gck_a, NA * 8 }, { g.gck_b, NA * 8 }, { g.gck_d, NA * 8 },
+           { g.hck_a, NA * 8 }, { g.hck_b, NA * 8 }, { g.tck, NA * 8 }, { g.arr_t, NA * 4 }, { g.alive, NA / 8 },
+           { g.edge, (size_t)g.R * g.e_stride * sizeof(int4) }, { g.rep, (size_t)g.R * sizeof(Rep) }, { (void*)g.at_ptr, (size_t)g.R * 4 },
+           { (void*)g.params, (size_t)g.R * XGC_NPARAM * 8 }, { (void*)g.control, (size_t)g.R * XGC_NCONTROL * 4 }, { (void*)g.tables, (size_t)XGC_NTABLE * 8 },
+           { g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER * 4 } };
+}
+extern "C" int xgc_snapshot_size(xgc_handle* h, size_t* bytes) {
+  size_t s = sizeof(xgc_config);
+  for (auto& sg : segments(h)) s += sg.bytes;
+  *bytes = s; return 0;
+}
+extern "C" int xgc_snapshot(xgc_handle* h, void* buf, size_t bytes) {
+  size_t need; xgc_snapshot_size(h, &need);
+  if (bytes < need) FAIL(h, 6, "snapshot buffer too small: %zu < %zu", bytes, need);
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  char* p = (char*)buf; memcpy(p, &h->cfg, sizeof(xgc_config)); p += sizeof(xgc_config);
+  for (auto& sg : segments(h)) { CU(h, cudaMemcpy(p, sg.p, sg.bytes, cudaMemcpyDeviceToHost)); p += sg.bytes; }
+  return 0;
+}
+extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
+  size_t need; xgc_snapshot_size(h, &need);
+  if (bytes < need) FAIL(h, 6, "snapshot buffer too small");
+  const xgc_config* c = (const xgc_config*)buf;
+  if (c->n_replicates != h->cfg.n_replicates || c->n_cap != h->cfg.n_cap || c->t_cap != h->cfg.t_cap ||
+      c->e_cap[0] != h->cfg.e_cap[0] || c->e_cap[1] != h->cfg.e_cap[1] || c->e_cap[2] != h->cfg.e_cap[2]) FAIL(h, 9, "snapshot geometry differs from handle");
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  const char* p = (const char*)buf + sizeof(xgc_config);
+  for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
+  h->last_at = -1;
+  return 0;
+}
+extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
+  CHECK_R(src, sr); CHECK_R(dst, dr);
+  if (src->cfg.n_cap != dst->cfg.n_cap || src->g.e_stride != dst->g.e_stride || src->cfg.t_cap != dst->cfg.t_cap) FAIL(dst, 9, "fork: geometry differs");
+  int rc = cache_drop(src); if (rc) return rc;
+  rc = cache_drop(dst); if (rc) return rc;
+  CU(src, cudaSetDevice(src->cfg.device)); CU(src, cudaStreamSynchronize(src->stream));
+  CU(dst, cudaSetDevice(dst->cfg.device)); CU(dst, cudaStreamSynchronize(dst->stream));
+  const Dev &a = src->g, &b = dst->g; size_t n = a.n_cap, so = (size_t)sr * n, doff = (size_t)dr * n;
+  auto cp = [&](void* d, const void* s, size_t bytes) { return cudaMemcpy(d, s, bytes, cudaMemcpyDefault); };
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  acc(cp(b.core + doff, a.core + so, n * sizeof(uint4))); acc(cp(b.aux + doff, a.aux + so, n * sizeof(Aux)));
+  acc(cp(b.gck_a + doff, a.gck_a + so, n * 8)); acc(cp(b.gck_b + doff, a.gck_b + so, n * 8)); acc(cp(b.gck_d + doff, a.gck_d + so, n * 8));
+  acc(cp(b.hck_a + doff, a.hck_a + so, n * 8)); acc(cp(b.hck_b + doff, a.hck_b + so, n * 8)); acc(cp(b.tck + doff, a.tck + so, n * 8));
+  acc(cp(b.arr_t + doff, a.arr_t + so, n * 4)); acc(cp(b.alive + doff / 32, a.alive + so / 32, n / 8));
+  acc(cp(b.edge + (size_t)dr * b.e_stride, a.edge + (size_t)sr * a.e_stride, a.e_stride * sizeof(int4)));
+  acc(cp(b.rep + dr, a.rep + sr, sizeof(Rep))); acc(cp((int*)b.at_ptr + dr, a.at_ptr + sr, 4));
+  acc(cp(b.counters + (size_t)dr * b.t_cap * XGC_NCOUNTER, a.counters + (size_t)sr * a.t_cap * XGC_NCOUNTER, (size_t)a.t_cap * XGC_NCOUNTER * 4));
+  if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
+  dst->last_at = -1;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// bulk edge-list upload for the weekly host<->device contract (host network resimulation)
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el /*[R][2][e_cap]*/, const int* ne /*[R]*/, const int* start /*[R][e_cap] or null*/) {
+  int r = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = ne[r], cap = g.e_cap[l];
+  if (e == 0) { g.rep[r].ne[l] = n < cap ? n : cap; if (n > cap) atomicOr(&g.rep[r].status, XGC_ST_EDGE_OVERFLOW); }
+  if (e >= n || e >= cap) return;
+  const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  int na = g.rep[r].n_alive;
+  int a = el[((size_t)r * 2 + 0) * cap + e], b = el[((size_t)r * 2 + 1) * cap + e];
+  if (a < 1 || a > na || b < 1 || b > na) { atomicOr(&g.rep[r].status, XGC_ST_BAD_EDGE); a = b = 1; }
+  g.edge[(size_t)r * g.e_stride + g.e_off[l] + e] = make_int4(P2S[a - 1], P2S[b - 1], start ? start[(size_t)r * cap + e] : g.at_ptr[r], 0);
+}
+extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el, const int32_t* n_edges, const int32_t* start) {
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer out of range");
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const Dev& g = h->g; size_t cap = g.e_cap[layer], R = g.R;
+  size_t need = R * cap * 3 + R;
+  if (need > h->el_stage_cap) {
+    if (h->d_el_stage) cudaFree(h->d_el_stage);
+    h->d_el_stage = nullptr; h->el_stage_cap = 0;
+    CU(h, cudaMalloc((void**)&h->d_el_stage, need * sizeof(int)));
+    h->el_stage_cap = need;
+  }
+  int* d_el = h->d_el_stage; int* d_start = d_el + R * cap * 2; int* d_ne = d_start + R * cap;
+  CU(h, cudaMemcpyAsync(d_el, el, R * cap * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (start) CU(h, cudaMemcpyAsync(d_start, start, R * cap * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_rank, g.R, TPB, g);
+  LAUNCH(h, k_edges_upload, dim3((unsigned)((cap + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr);
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// debug entry points for the arithmetic-contract parity tests
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int xgc_debug_exp(const double* x, double* y, int n, int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return 3;
+  double *dx, *dy;
+  if (cudaMalloc((void**)&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc((void**)&dy, sizeof(double) * n) != cudaSuccess) return 100;
+  cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+  k_debug_exp<<<(n + 255) / 256, 256>>>(dx, dy, n);
+  cudaError_t e = cudaMemcpy(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy);
+  return e == cudaSuccess ? 0 : 100 + (int)e;
+}
+extern "C" int xgc_debug_philox(uint32_t seed, uint32_t rep, const uint32_t* ctr4, uint32_t* out4, int n, int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return 3;
+  uint4 *dc, *dout;
+  if (cudaMalloc((void**)&dc, sizeof(uint4) * n) != cudaSuccess || cudaMalloc((void**)&dout, sizeof(uint4) * n) != cudaSuccess) return 100;
+  cudaMemcpy(dc, ctr4, sizeof(uint4) * n, cudaMemcpyHostToDevice);
+  k_debug_philox<<<(n + 255) / 256, 256>>>(seed, rep, dc, dout, n);
+  cudaError_t e = cudaMemcpy(out4, dout, sizeof(uint4) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dc); cudaFree(dout);
+  return e == cudaSuccess ? 0 : 100 + (int)e;
+}
