@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
         if (recov) {
           gc &= ~(GC_ST(s) | GC_SY(s) | GC_TX(s));
           if (s == 0) { ga.x = -1; gb.x = -1; gd.x = -1; } else if (s == 1) { ga.y = -1; gb.y = -1; gd.y = -1; } else { ga.z = -1; gb.z = -1; gd.z = -1; }
-          ga_dirty = gb_dirty = true; gd_dirty = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
+          ga_dirty = gb_dirty = true;
+          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS) gd_dirty = true; else (&g.gck_d[idx].x)[s] = -1;
         }
       }
     }
