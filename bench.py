@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — agent-weeks/s of the weekly epidemic step (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (libxgc.so through the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU restatement on the host cores
+
+Workload (N = 1): BASELINE.json configs[1], "calibration sweep: 1000 replicates x 10k agents batched on 1 B200"; a
+*step* is one simulated week of all replicates (all 17 modules).  For N > 1 every rank holds its own 1000 replicates
+(weak scaling; replicates are independent, the only exchange is the final gather of the targets matrix).
+The reference's R modules cannot run here (R absent, module source not in /root/reference: SURVEY §8c), so the
+reference arm and `cpu_baseline` time the in-repo C restatement (oracle/, kind "port"), one single-threaded process per
+replicate per core like the reference's SLURM arrays.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "agent-weeks/sec", "agent-weeks/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=52)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="xgc", choices=["xgc", "reference"])
+    ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU")
+    ap.add_argument("--agents", type=int, default=10000)
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--profile-steps", type=int, default=6)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1971)
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(args, parallelism):
+    return {"workload": f"calibration sweep (BASELINE configs[1]): {args.replicates} replicates x {args.agents} agents per GPU, "
+                        "per-replicate LHS parameters over the reference prior box, all 17 weekly modules, one step = one week",
+            "replicates_per_gpu": args.replicates, "agents_per_replicate": args.agents, "network": "on-device surrogate for simnet_msm",
+            "parallelism": parallelism,
+            "l2": "no flush needed: per-step working set (~1 GB of agent planes for 1000x10k) is >> 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement on all host cores (rank 0 only)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    from xgc_msm_b200.params import MODULE_BIT
+    mask = sum(MODULE_BIT.values())
+    cores = os.cpu_count() or 1
+    reps = cores * 2                                  # bounded sample: 2 replicates per core per step
+    pool = cpu_bench.PersistentPool(args.agents, reps, args.seed, mask, cores)
+    at = 2
+    for _ in range(args.warmup):
+        pool.step(at); at += 1
+    aw = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        aw += pool.step(at); at += 1
+    dt = time.perf_counter() - t0
+    pool.close()
+    v = aw / dt
+    sample = f"{reps} of the workload's {args.replicates} replicates x {args.agents} agents, one week per step, {cores} single-threaded processes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int",
+        "data": "synthetic", "config": workload_config(args, "cpu: one process per replicate per core"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "R and the EpiModelHIV modules are not available; this arm times oracle/ (plain-C restatement, -O2, scalar)"}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# helpers for the CUDA arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def week_stats(h, K, at):
+    """Population fractions of week `at` over all replicates of this rank (inputs of roofline.kernel_bytes)."""
+    c = h.counters_all(at).astype(np.float64).sum(0)
+    G = K.NCELL
+    grp = lambda g: c[g * G:(g + 1) * G].sum()
+    n = grp(K.K_NUM)
+    return {"n": n, "f_hiv": grp(K.K_INUM) / n, "f_dx": grp(K.K_INUM_DX) / n, "f_gc": grp(K.K_INUM_GC) / n,
+            "edges": float(c[K.K_NEDGES:K.K_NEDGES + 3].sum())}
+
+
+def host_network_pool(R, e_cap, n_lo, rng, torch):
+    """Pinned host edge lists standing for what host-side simnet_msm returns each week: [R][2][e_cap] 1-based positions."""
+    bufs = []
+    for l in range(3):
+        ne = int(e_cap[l] / 1.35) - 100
+        a = rng.integers(1, n_lo, size=(R, e_cap[l]), dtype=np.int32)
+        b = rng.integers(1, n_lo - 1, size=(R, e_cap[l]), dtype=np.int32)
+        b = np.where(b >= a, b + 1, b)
+        el = np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1).astype(np.int32)          # [R,2,e_cap]
+        t_el = torch.from_numpy(el).pin_memory()
+        t_ne = torch.full((R,), ne, dtype=torch.int32).pin_memory()
+        t_st = torch.from_numpy((1 - rng.geometric(1 / 100.0, size=(R, e_cap[l]))).astype(np.int32)).pin_memory()
+        bufs.append((t_el, t_ne, t_st, ne))
+    return bufs
+
+
+def run_xgc(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from xgc_msm_b200 import roofline, workload
+    from xgc_msm_b200.abi import Handle, K
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the xgc arm has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    R = args.replicates
+    spec = workload.SweepSpec(n_agents=args.agents, seed=args.seed)
+    W, Kt, Pn, En = max(args.warmup, 3), args.steps, args.profile_steps, args.e2e_steps
+    t_cap = 2 + W + Kt + Pn + En + 8
+    h = Handle(R, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rank * R,
+               compact_every=spec.weeks_between_compactions)
+    workload.load_sweep(h, spec, rid0=rank * R)
+    stream = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local_rank))
+
+    # ---- kernel-resident throughput: W warm-up weeks, then exactly K timed weeks (CUDA-graph replay, no host sync)
+    at = 2
+    h.run(at, at + W - 1); at += W
+    barrier()
+    clocks = ClockSampler(local_rank)
+    l0 = h.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    h.run(at, at + Kt - 1)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = h.kernel_launches() - l0
+    clk = clocks.stop()
+    t_first, t_last = at, at + Kt - 1
+    at += Kt
+    G = K.NCELL
+    aw = 0.0
+    for t in range(t_first, t_last + 1):
+        aw += float(h.counters_all(t)[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        ta = torch.tensor([aw], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw = float(ta.item())
+    value = aw / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events around every launch on the launching stream) -> roofline of the top kernel
+    h.profile(True)
+    for _ in range(Pn):
+        h.step(at); at += 1
+    prof = h.profile_read()
+    h.profile(False)
+    stats = week_stats(h, K, at - 1)
+    kb = roofline.kernel_bytes(stats)
+    per = {k: v[0] / max(v[1], 1) * (v[1] / Pn) for k, v in prof.items()}          # ms per week per kernel
+    step_ms_prof = sum(per.values())
+    top = max((k for k in per if k in kb), key=lambda k: per[k])
+    peak, peak_src = measured_peak()
+    top_ms = prof[top][0] / prof[top][1]
+    achieved = kb[top] / (top_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": kb[top], "launch_ms": top_ms, "share_of_step": per[top] / step_ms_prof,
+            "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
+            "step": {"algorithmic_bytes": roofline.step_bytes(stats), "achieved": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9,
+                     "frac": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9 / peak}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")          # ncu dram bytes per launch, committed with the profile
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(top)
+        except Exception:
+            pass
+
+    # ---- end to end through the C ABI with HOST buffers: the weekly R <-> device contract with simnet_msm on the host
+    #      (pre-network modules -> living counts to host -> three edge lists from pinned host memory -> remaining
+    #       modules -> the week's tallies back to host)
+    from xgc_msm_b200.params import control_msm
+    h.set_control(control_msm(network_mode="host").flags)
+    rng = np.random.default_rng(args.seed + rank)
+    nmin = int(h.num_agents_all().min())
+    pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch)
+    pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
+    post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
+    n_host = torch.empty(R, dtype=torch.int32).pin_memory()
+    c_host = torch.empty((R, K.NCOUNTER), dtype=torch.int32).pin_memory()
+    h2d = sum(t_el.numel() * 4 + t_ne.numel() * 4 + t_st.numel() * 4 for t_el, t_ne, t_st, _ in pool)
+    d2h = n_host.numel() * 4 + c_host.numel() * 4
+
+    def e2e_week(t):
+        h.step(t, pre)
+        h.num_agents_all(n_host.numpy())
+        for l, (t_el, t_ne, t_st, _) in enumerate(pool):
+            h.set_edgelists_all(l, t_el.data_ptr(), t_ne.data_ptr(), t_st.data_ptr())
+        h.step(t, post)
+        h.counters_all(t, c_host.numpy().view(np.uint32))
+        return float(c_host[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
+
+    for _ in range(3):
+        e2e_week(at); at += 1
+    barrier()
+    t0 = time.perf_counter()
+    aw_e = 0.0
+    for _ in range(En):
+        aw_e += e2e_week(at); at += 1
+    barrier()
+    dt_e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt_e], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt_e = float(tt.item())
+        ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
+    e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
+           "ms_per_step": dt_e / En * 1e3, "path": "xgc_step(pre) -> xgc_num_agents_all -> 3x xgc_set_edgelists_all (pinned) -> xgc_step(post) -> xgc_get_counters_all"}
+
+    # ---- final exchange of the path: gather the [R x K] targets matrix (NCCL all_gather), outside the timed regions
+    tg = torch.from_numpy(h.targets(t_last, min(Kt, 52))).cuda()
+    if world > 1:
+        parts = [torch.empty_like(tg) for _ in range(world)]
+        dist.all_gather(parts, tg)
+        tg = torch.cat(parts)
+    status = [h.status(r) for r in range(0, R, max(R // 16, 1))]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        cores = os.cpu_count() or 1
+        reps = cores * 2
+        weeks = max(int(args.cpu_seconds * 0.9e6 / (2 * args.agents)), 4)        # ~0.9M agent-weeks/s/core for the C port
+        aw_c, dt_c, cores, _ = cpu_bench.run_batch(args.agents, reps, weeks, args.seed, K.M_ALL, cores)
+        cpu = {"value": aw_c / dt_c, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} replicates x {args.agents} agents x {weeks} weeks of the same sweep, one single-threaded process per core "
+                         f"(oracle/xgc_oracle.c, gcc -O2)",
+               "reference_floor": "the reference's SLURM limits imply >= 5.8k-8.7k agent-weeks/s/core for the whole R loop incl. network resimulation (BASELINE.md)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kt, "warmup": W, "ms_per_step": ms / Kt,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int", "data": "synthetic",
+            "config": workload_config(args, f"replicates sharded over {world} GPU(s), no data-path collective; final all_gather of targets"),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "targets_shape": list(tg.shape), "status_sample_or": int(np.bitwise_or.reduce(status)),
+            "agent_weeks_timed": aw}), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun (one process per GPU); see the module docstring")
+    run_xgc(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

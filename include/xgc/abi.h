@@ -333,9 +333,12 @@ int  xgc_fork    (xgc_handle* src, int src_r, xgc_handle* dst, int dst_r);   /* 
 int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][e_cap] 1-based positions*/,
                            const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][e_cap] or NULL*/);
 int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);
+int  xgc_num_agents_all   (xgc_handle* h, int32_t* out /*[R]*/);   /* living agents per replicate (what simnet_msm needs) */
 
 /* instrumentation */
 int  xgc_kernel_launches(xgc_handle* h, uint64_t* n);     /* kernels launched by this handle so far */
+int  xgc_profile(xgc_handle* h, int enable);              /* bracket every kernel launch of xgc_step with CUDA events */
+int  xgc_profile_read(xgc_handle* h, const char** names, double* ms_total, uint64_t* launches, int cap); /* returns #kernels */
 int  xgc_stream_ptr(xgc_handle* h, void** cuda_stream);   /* the stream all work is issued on (for event timing) */
 int  xgc_debug_exp(const double* x, double* y, int n, int device);   /* device xgc_exp, for the math parity test */
 int  xgc_debug_philox(uint32_t seed, uint32_t rep, const uint32_t* ctr4, uint32_t* out4, int n, int device);

@@ -1,0 +1,117 @@
+"""TEST/BENCH INFRASTRUCTURE — times the CPU oracle on the host cores.
+
+Used only by bench.py (`cpu_baseline` leg and `--impl reference`).  Parallelism mirrors the reference's own mechanism:
+one single-threaded process per replicate per core (SLURM job array `--array=1-1000`, `-n 1`, NSIMS=1:
+/root/reference/burnin/cal/sim1/sim1_batch1.sh:2-9).  Kept free of torch/CUDA imports so workers start fast.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _build_replicates(n_agents: int, ids, seed: int):
+    """Same synthetic workload as bench.py's GPU arm: population `rid % n_distinct`, LHS parameter row `rid`."""
+    from oracle.oracle import Oracle
+    from xgc_msm_b200 import workload as W
+    spec = W.SweepSpec(n_agents=n_agents, seed=seed)
+    out = []
+    for rid in ids:
+        case = W.replicate_case(spec, rid)
+        o = Oracle(spec.n_cap_oracle, spec.e_cap, spec.t_cap_oracle, seed=seed, replicate_id=rid)
+        o.set_params(case["params"]); o.set_control(case["control"]); o.set_tables(case["tables"])
+        o.set_population(n_agents, 1)
+        for k, v in case["attrs"].items():
+            o.set_attr(k, v)
+        for l in range(3):
+            o.set_edgelist(l, case["els"][l], case["starts"][l])
+        out.append(o)
+    return out
+
+
+def _batch_worker(args):
+    n_agents, ids, seed, weeks, mask = args
+    reps = _build_replicates(n_agents, ids, seed)
+    t0 = time.perf_counter()
+    aw = 0
+    for o in reps:
+        for at in range(2, 2 + weeks):
+            o.step(at, mask)
+            aw += o.num_agents()
+    return aw, time.perf_counter() - t0
+
+
+def run_batch(n_agents: int, n_replicates: int, weeks: int, seed: int, mask: int, cores: int | None = None):
+    """One-shot sample: n_replicates replicates x weeks, spread over `cores` single-threaded processes.
+    Returns (agent_weeks, wall_seconds, cores)."""
+    cores = cores or os.cpu_count() or 1
+    cores = min(cores, n_replicates)
+    chunks = [list(range(c, n_replicates, cores)) for c in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_noop, range(cores))               # start the workers before the clock
+        t0 = time.perf_counter()
+        res = pool.map(_batch_worker, [(n_agents, ids, seed, weeks, mask) for ids in chunks])
+        wall = time.perf_counter() - t0
+    # building the replicates is inside `wall`; subtract nothing: report the steady stepping rate from worker clocks
+    aw = sum(r[0] for r in res)
+    step_wall = max(r[1] for r in res)
+    return aw, step_wall, cores, wall
+
+
+def _noop(_):
+    return 0
+
+
+def _persistent_worker(conn, n_agents, ids, seed, mask):
+    reps = _build_replicates(n_agents, ids, seed)
+    conn.send(("ready", len(reps)))
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        at = msg
+        n = 0
+        for o in reps:
+            o.step(at, mask)
+            n += o.num_agents()
+        conn.send(n)
+    conn.close()
+
+
+class PersistentPool:
+    """`cores` workers, each owning a fixed set of replicates; step(at) advances every replicate by one week."""
+
+    def __init__(self, n_agents: int, n_replicates: int, seed: int, mask: int, cores: int | None = None):
+        self.cores = min(cores or os.cpu_count() or 1, n_replicates)
+        ctx = mp.get_context("spawn")
+        self.conns, self.procs = [], []
+        for c in range(self.cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_persistent_worker, args=(b, n_agents, list(range(c, n_replicates, self.cores)), seed, mask), daemon=True)
+            p.start()
+            self.conns.append(a); self.procs.append(p)
+        for a in self.conns:
+            assert a.recv()[0] == "ready"
+
+    def step(self, at: int) -> int:
+        for a in self.conns:
+            a.send(at)
+        return sum(a.recv() for a in self.conns)
+
+    def close(self):
+        for a in self.conns:
+            try:
+                a.send(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)

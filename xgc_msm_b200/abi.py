@@ -56,7 +56,8 @@ def _load() -> C.CDLL:
         "xgc_snapshot_size": [vp, C.POINTER(C.c_size_t)], "xgc_snapshot": [vp, vp, C.c_size_t],
         "xgc_restore": [vp, vp, C.c_size_t], "xgc_fork": [vp, ci, vp, ci],
         "xgc_set_edgelists_all": [vp, ci, vp, vp, vp], "xgc_get_counters_all": [vp, ci, vp],
-        "xgc_kernel_launches": [vp, C.POINTER(C.c_uint64)], "xgc_stream_ptr": [vp, C.POINTER(vp)],
+        "xgc_kernel_launches": [vp, C.POINTER(C.c_uint64)], "xgc_profile": [vp, ci],
+        "xgc_profile_read": [vp, C.POINTER(C.c_char_p), pd, C.POINTER(C.c_uint64), ci], "xgc_num_agents_all": [vp, vp], "xgc_stream_ptr": [vp, C.POINTER(vp)],
         "xgc_debug_exp": [pd, pd, ci, ci], "xgc_debug_philox": [cu, cu, pu, pu, ci, ci],
         "xgc_constant": [C.c_char_p, C.POINTER(C.c_int64)], "xgc_param_index": [C.c_char_p, pi, pi],
     }
@@ -293,6 +294,22 @@ class Handle:
     def set_edgelists_all(self, layer: int, el_ptr: int, ne_ptr: int, start_ptr: int = 0):
         """Raw-pointer variant for pinned host buffers: el [R][2][e_cap] int32 1-based positions, n_edges [R]."""
         self._ck(lib.xgc_set_edgelists_all(self._h, layer, el_ptr, ne_ptr, start_ptr or None))
+
+    def num_agents_all(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_replicates, dtype=np.int32)
+        self._ck(lib.xgc_num_agents_all(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def profile(self, enable: bool):
+        self._ck(lib.xgc_profile(self._h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kernel: (total ms, launches)} from CUDA events recorded on the launching stream."""
+        cap = 32
+        nm, ms, cnt = (C.c_char_p * cap)(), (C.c_double * cap)(), (C.c_uint64 * cap)()
+        n = lib.xgc_profile_read(self._h, nm, ms, cnt, cap)
+        return {nm[k].decode(): (ms[k], cnt[k]) for k in range(n)}
 
     def kernel_launches(self) -> int:
         n = C.c_uint64()

@@ -36,6 +36,9 @@ struct xgc_handle {
   int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
+  bool profiling = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
   std::vector<void*> allocs;
   size_t n_agent() const { return (size_t)cfg.n_replicates * cfg.n_cap; }
 };
@@ -417,7 +420,15 @@ static int upload_inject(xgc_handle* h, const xgc_inject* inj, Inj* out) {
   return 0;
 }
 
-#define LAUNCH(h, kern, grid, block, ...) do { kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); (h)->launches++; } while (0)
+static void prof_begin(xgc_handle* h, const char* name) {
+  if (!h->profiling) return;
+  xgc_handle::ProfRec r; r.name = name;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, h->stream);
+  h->prof.push_back(r);
+}
+static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream); }
+#define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
 
 // enqueue one week.  at_host < 0: week = previous + 1 (graph replay).
 static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& inj, int zero_row) {
@@ -498,6 +509,31 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   return 0;
 }
 
+// per-kernel device timing with CUDA events on the launching stream (bench.py roofline leg)
+extern "C" int xgc_profile(xgc_handle* h, int enable) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  h->profiling = enable != 0;
+  return 0;
+}
+extern "C" int xgc_profile_read(xgc_handle* h, const char** names, double* ms, uint64_t* count, int cap) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (auto& r : h->prof) {
+    float t = 0.f; if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    int k = 0; for (; k < n; ++k) if (!strcmp(names[k], r.name)) break;
+    if (k == n) { if (n == cap) continue; names[n] = r.name; ms[n] = 0.0; count[n] = 0; n++; }
+    ms[k] += (double)t; count[k]++;
+  }
+  return n;     // number of distinct kernels (not an error code)
+}
+extern "C" int xgc_num_agents_all(xgc_handle* h, int32_t* out /*[R]*/) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  CU(h, cudaMemcpy2DAsync(out, sizeof(int), &h->g.rep[0].n_alive, sizeof(Rep), sizeof(int), (size_t)h->g.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
 extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   Rep rp; CU(h, cudaMemcpy(&rp, h->g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));

@@ -1,0 +1,37 @@
+"""Algorithmic HBM bytes of each weekly kernel (DESIGN.md §5 states the same numbers).
+
+"Algorithmic" = bytes the kernel's work item must move given the packed layout of xgc_device.cuh, counted once per
+reference: a whole plane element when any field of it is needed, gathers counted per endpoint.  These are the
+numerators of roofline.achieved in bench.py; ncu's dram__bytes_read+write per launch is the cross-check (traffic).
+
+Plane element sizes: core 16 B, aux 16 B, each clock plane 8 B, edge record 16 B.
+Population fractions come from the week's own tallies (HIV prevalence, diagnosed fraction, GC prevalence).
+"""
+from __future__ import annotations
+
+
+def kernel_bytes(stats: dict) -> dict:
+    """stats: n (living agents, all replicates), f_hiv, f_dx, f_gc (fractions of n), edges (all layers, all replicates),
+    f_disc (fraction of edges with any discordance; only used for k_edge2's optional aux gathers).
+    Returns {kernel: algorithmic bytes per launch}."""
+    n, e = stats["n"], stats["edges"]
+    f_hiv, f_dx, f_gc = stats["f_hiv"], stats["f_dx"], stats["f_gc"]
+    f_disc = stats.get("f_disc", 0.15)
+    return {
+        # core R + aux R (age for aging/mortality) + tck R (last.neg.test, undiagnosed) + HIV+: hck_a R, hck_b R+W
+        "k_agent1": n * (16 + 16 + 8 * (1 - f_dx) + f_hiv * (8 + 8 + 8)),
+        # core R + tck R (prep indications) + infected: gck_a R, gck_b R
+        "k_agent2": n * (16 + 8 + f_gc * 16),
+        # core R + diagnosed: aux R (viral load for cc.vsupp)
+        "k_agent3": n * (16 + f_dx * 16),
+        # edge record R + acts W(4) + 2 endpoints x (core + aux)
+        "k_edge1": e * (16 + 4 + 2 * 32),
+        # edge record R + 2 endpoints x core; discordant edges also gather aux
+        "k_edge2": e * (16 + 2 * 16 + f_disc * 2 * 16),
+        # in-place stable compaction: record R, survivors W, endpoint core gathers
+        "k_edges_resim": e * (16 + 16 + 2 * 16),
+    }
+
+
+def step_bytes(stats: dict) -> float:
+    return float(sum(kernel_bytes(stats).values()))
