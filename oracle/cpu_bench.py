@@ -18,15 +18,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def _build_replicates(n_agents: int, ids, seed: int):
+def _build_replicates(n_agents: int, ids, seed: int, spec_kw=None, philox_seed=None):
     """Same synthetic workload as bench.py's GPU arm: population `rid % n_distinct`, LHS parameter row `rid`."""
     from oracle.oracle import Oracle
     from xgc_msm_b200 import workload as W
-    spec = W.SweepSpec(n_agents=n_agents, seed=seed)
+    spec = W.SweepSpec(n_agents=n_agents, seed=seed, **(spec_kw or {}))
     out = []
     for rid in ids:
         case = W.replicate_case(spec, rid)
-        o = Oracle(spec.n_cap_oracle, spec.e_cap, spec.t_cap_oracle, seed=seed, replicate_id=rid)
+        o = Oracle(spec.n_cap_oracle, spec.e_cap, spec.t_cap_oracle, seed=seed if philox_seed is None else philox_seed, replicate_id=rid)
         o.set_params(case["params"]); o.set_control(case["control"]); o.set_tables(case["tables"])
         o.set_population(n_agents, 1)
         for k, v in case["attrs"].items():
@@ -115,3 +115,30 @@ class PersistentPool:
                 pass
         for p in self.procs:
             p.join(timeout=5)
+
+
+def _targets_worker(args):
+    n_agents, ids, seed, weeks, tailn, mask, spec_kw, philox_seed = args
+    reps = _build_replicates(n_agents, ids, seed, spec_kw, philox_seed)
+    out = []
+    for o in reps:
+        for at in range(2, 2 + weeks):
+            o.step(at, mask)
+        out.append(o.targets(1 + weeks, tailn))
+        o.close()
+    return ids, np.stack(out)
+
+
+def run_targets(n_agents: int, n_replicates: int, weeks: int, tailn: int, seed: int, mask: int, spec_kw=None,
+                philox_seed=None, cores: int | None = None) -> np.ndarray:
+    """[n_replicates, NTARGET] tail-window targets of the oracle (statistical tests)."""
+    cores = min(cores or os.cpu_count() or 1, n_replicates)
+    chunks = [list(range(c, n_replicates, cores)) for c in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_targets_worker, [(n_agents, ids, seed, weeks, tailn, mask, spec_kw, philox_seed) for ids in chunks])
+    out = None
+    for ids, t in res:
+        if out is None:
+            out = np.empty((n_replicates, t.shape[1]))
+        out[ids] = t
+    return out

@@ -30,14 +30,19 @@ def random_midcourse_state(a: dict, seed: int, at: int) -> dict:
     rng = np.random.default_rng(seed + 31337)
     n = a["race"].size
     a = {k: v.copy() for k, v in a.items()}
+
+    def clock(valid, t):            # a week clock that is never the NA code -1
+        t = np.asarray(t, dtype=float)
+        return np.where(valid, np.where(t == -1, -2, t), -1.0)
+
     for site in ("rGC", "uGC", "pGC"):
         inf = a[site] == 1
-        a[site + ".infTime"] = np.where(inf, at - 1 - rng.integers(0, 12, n), -1).astype(float)
+        a[site + ".infTime"] = clock(inf, at - 1 - rng.integers(0, 12, n))
         tx = inf & (rng.random(n) < 0.35)
         a[site + ".tx"] = tx.astype(float)
-        a[site + ".txTime"] = np.where(tx, np.maximum(a[site + ".infTime"], at - 1 - rng.integers(0, 4, n)), -1).astype(float)
+        a[site + ".txTime"] = clock(tx, np.maximum(a[site + ".infTime"], at - 1 - rng.integers(0, 4, n)))
         a[site + ".dur"] = np.where(inf, rng.integers(1, 20, n), -1).astype(float)
-    a["last.screen"] = np.where(rng.random(n) < 0.5, at - 1 - rng.integers(0, 80, n), -1).astype(float)
+    a["last.screen"] = clock(rng.random(n) < 0.5, at - 1 - rng.integers(0, 80, n))
     a["sti.expo"] = rng.integers(0, 32, n).astype(float)
     pos = a["status"] == 1
     stage = np.where(pos, rng.integers(1, 5, n), 0)
@@ -47,16 +52,16 @@ def random_midcourse_state(a: dict, seed: int, at: int) -> dict:
     a["inf.time"] = np.where(pos & (a["inf.time"] == -1), -2, a["inf.time"])
     a["stage.time"] = np.where(pos, np.where(a["inf.time"] + 5 == -1, -2, a["inf.time"] + 5), -1).astype(float)
     diag = a["diag.status"] == 1
-    a["last.neg.test"] = np.where(~diag & (rng.random(n) < 0.6), at - 1 - rng.integers(0, 60, n), -1).astype(float)
+    a["last.neg.test"] = clock(~diag & (rng.random(n) < 0.6), at - 1 - rng.integers(0, 60, n))
     a["last.neg.test"] = np.where(rng.random(n) < 0.05, at, a["last.neg.test"]) * (~diag) + (-1.0) * diag
     a["vl"] = np.where(pos, rng.random(n) * 6.5, 0.0).astype(np.float32).astype(float)
     a["tt.traj"] = rng.integers(1, 4, n).astype(float)
     prep = ~diag & (rng.random(n) < 0.15)
     a["prepStat"] = prep.astype(float)
     a["prepClass"] = np.where(prep, rng.integers(1, 4, n), 0).astype(float)
-    a["prepStartTime"] = np.where(prep, at - 1 - rng.integers(0, 100, n), -1).astype(float)
-    a["prepLastRisk"] = np.where(prep, at - 1 - rng.integers(0, 70, n), -1).astype(float)
-    a["prep.ind.last"] = np.where(rng.random(n) < 0.4, at - 1 - rng.integers(0, 60, n), -1).astype(float)
+    a["prepStartTime"] = clock(prep, at - 1 - rng.integers(0, 100, n))
+    a["prepLastRisk"] = clock(prep, at - 1 - rng.integers(0, 70, n))
+    a["prep.ind.last"] = clock(rng.random(n) < 0.4, at - 1 - rng.integers(0, 60, n))
     return a
 
 

@@ -1,0 +1,85 @@
+"""GPU tests of the reference-facing host interface (param_msm / control_msm / init_msm / netsim, module(dat, at) -> dat)
+and north_star's second correctness test: with native RNG, prevalence / incidence / screening targets across >= 1000
+replicates are statistically indistinguishable between the CUDA path and the CPU oracle run with DIFFERENT seeds."""
+import numpy as np
+import pytest
+
+from common import K, P
+
+pytestmark = pytest.mark.gpu
+
+
+def test_netsim_mirror_and_module_contract():
+    from xgc_msm_b200 import modules as M
+    from xgc_msm_b200 import control_msm, init_msm, param_msm
+    param = param_msm(u2rgc_tprob=0.2, u2pgc_tprob=0.2, r2ugc_tprob=0.25, p2ugc_tprob=0.1, rgc_ntx_int=12, gc_asympt_visit_prob=0.02,
+                      a_rate=0.00049 + 1.285 / 20000)
+    init = init_msm(prev_ugc=0.05, prev_rgc=0.05, prev_pgc=0.05)
+    x = {"n": 3000, "seed": 5}
+    ctl = control_msm(nsims=3, nsteps=30, ncores=1, network_mode="surrogate", stiScreeningProtocol="base", gcUntreatedRecovDist="geom",
+                      skip_check=True, tergmLite=True, verbose=False)
+    sim = M.netsim(x, param, init, ctl)                                   # fused weeks (xgc_run)
+    epi = sim.epi
+    assert epi["num"].shape == (30, 3) and np.all(epi["num"][0] == 3000)   # at = 1 row holds the initial prevalence_msm
+    assert np.all(epi["prev.gc"][-1] > 0) and not np.array_equal(epi["incid.gc"][:, 0], epi["incid.gc"][:, 1])
+    calls = []
+
+    def my_stitx(dat, at):                                                # a user-supplied module forces the module loop
+        calls.append(at)
+        return M.stitx_msm(dat, at)
+
+    ctl2 = control_msm(nsims=3, nsteps=30, network_mode="surrogate", stitx_FUN=my_stitx, aging_FUN=M.aging_msm)
+    sim2 = M.netsim(x, param, init, ctl2)
+    assert calls == list(range(2, 31))
+    for v in ("num", "incid.gc", "prev.rgc", "i.prev", "prop.ureth.tested", "incid.p2pgc"):
+        assert np.array_equal(np.nan_to_num(sim2.epi[v]), np.nan_to_num(epi[v])), v
+    # host-side network step (simnet_msm stays on the host): the hook re-wires layer 2 every week through dat.set_el
+    seen = []
+
+    def hook(dat, at):
+        for s in range(dat.nsims):
+            n = dat.h.num_agents(s)
+            el = np.stack([np.arange(1, 41), np.arange(n - 39, n + 1)], axis=1)
+            dat.set_el(2, el, sim=s)
+        seen.append(at)
+
+    ctl3 = control_msm(nsims=2, nsteps=8, network_mode="host")
+    sim3 = M.netsim({"n": 1000, "seed": 2}, param, init, ctl3, network_hook=hook)
+    assert seen == list(range(2, 9)) and sim3.dat.el(2)[0].shape == (40, 2)
+    # restart from the finished object with another screening arm (02.00_epi.r:292-296)
+    base = M.netsim({"n": 1500, "seed": 3, "t_cap": 64}, param, init, control_msm(nsims=2, nsteps=20, network_mode="surrogate"), checkpoint=True)
+    arm = M.netsim(base, param, init, control_msm(nsims=2, nsteps=40, start=21, network_mode="surrogate", stiScreeningProtocol="universal"))
+    assert arm.dat.at == 40 and arm.epi["num.rgc.test"][25:].sum() > base.epi["num.rgc.test"][:20].sum()
+
+
+def test_statistical_equivalence_1000_replicates():
+    """1000 GPU replicates (Philox seed 1971) vs 1000 oracle replicates (Philox seed 424242): two-sample KS at
+    alpha = 0.001 per target and |difference of means| <= 5 standard errors.  Same parameters and starting population."""
+    from scipy.stats import ks_2samp
+    from oracle import cpu_bench
+    from xgc_msm_b200 import targets as T, workload
+    from xgc_msm_b200.abi import Handle
+    R, N, WEEKS, TAIL = 1000, 1200, 60, 26
+    kw = dict(lhs=False, n_distinct=1)
+    spec = workload.SweepSpec(n_agents=N, seed=1971, **kw)
+    h = Handle(R, spec.n_cap, spec.e_cap, WEEKS + 3, seed=1971)
+    workload.load_sweep(h, spec)
+    h.run(2, WEEKS + 1)
+    g = h.targets(WEEKS + 1, TAIL)
+    c = cpu_bench.run_targets(N, R, WEEKS, TAIL, 1971, K.M_ALL, kw, philox_seed=424242)
+    assert np.isfinite(g).all() and np.isfinite(c).all() and not np.array_equal(g, c)
+    names = T.device_target_names()
+    report = {}
+    for k in ("num", "i.prev", "ir100.pop", "i.prev.dx.inf.W", "cc.vsupp.W", "prop.rect.tested", "prop.ureth.tested", "prop.phar.tested",
+              "prob.rGC.tested", "prob.uGC.tested", "prob.pGC.tested", "prev.gc", "prev.rgc", "prev.ugc", "prev.pgc",
+              "ir100.gc", "ir100.rgc", "ir100.ugc", "ir100.pgc"):
+        j = names.index(k)
+        p = ks_2samp(g[:, j], c[:, j]).pvalue
+        se = np.sqrt(g[:, j].var(ddof=1) / R + c[:, j].var(ddof=1) / R)
+        z = abs(g[:, j].mean() - c[:, j].mean()) / max(se, 1e-300)
+        report[k] = (round(float(p), 4), round(float(z), 2))
+        assert p > 1e-3 and z < 5.0, (k, report[k], g[:, j].mean(), c[:, j].mean())
+    print("KS p-value, |z| per target:", report)
+    # and the same seed gives the same numbers exactly (counter-based RNG): one replicate, CPU vs GPU
+    c0 = cpu_bench.run_targets(N, 2, WEEKS, TAIL, 1971, K.M_ALL, kw, philox_seed=1971, cores=2)
+    assert np.array_equal(c0.view(np.uint64), g[:2].view(np.uint64))

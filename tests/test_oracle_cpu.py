@@ -1,0 +1,216 @@
+"""CPU tests (`-m "not gpu"`): pin the oracle to everything the reference DOES hold for this path, and check the
+host logic and the C-ABI surface.  The reference has no tests or golden vectors of its own, so the pins
+are: the calibration targets recomputed from inst/cal/calval_targets.r literals, the prior box and
+its size (burnin/cal/sim1_01_lhs_params.r:22-119), published Philox4x32-10 known answers, and libm's exp."""
+import ctypes as C
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import K, P, ROOT, load_oracle, make_case
+from oracle import oracle as O
+from xgc_msm_b200 import synth, targets as T
+
+
+# ---- arithmetic contract ------------------------------------------------------------------------------------------
+def _philox(ctr, key):
+    out = (C.c_uint32 * 4)()
+    O.lib.orc_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return list(out)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert _philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_exp_within_one_ulp_of_libm():
+    for x in np.concatenate([np.linspace(-40, 40, 40001), np.linspace(-1e-3, 1e-3, 2001)]):
+        a, b = O.lib.orc_exp(float(x)), math.exp(float(x))
+        assert abs(a - b) <= 2.3e-16 * b
+
+
+def test_bernoulli_follows_r_inversion():
+    # rbinom(1,1,p): p <= .5 -> (u >= 1-p); p > .5 -> (u < p)   
+    assert O.lib.orc_bern(0.95, 0.1) == 1 and O.lib.orc_bern(0.85, 0.1) == 0
+    assert O.lib.orc_bern(0.65, 0.7) == 1 and O.lib.orc_bern(0.75, 0.7) == 0
+    assert O.lib.orc_bern(0.5, 0.0) == 0 and O.lib.orc_bern(0.999999, 1.0) == 1
+    u = np.random.default_rng(1).random(20000)
+    for p in (0.03, 0.5, 0.83):
+        assert abs(np.mean([O.lib.orc_bern(float(v), p) for v in u]) - p) < 0.01
+
+
+def test_poisson_cdf_walk_matches_scipy():
+    from scipy.stats import poisson
+    for mu in (0.2, 1.7, 9.5):
+        for u in np.linspace(0.001, 0.999, 97):
+            assert O.lib.orc_pois(float(u), mu, 255) == int(poisson.ppf(u, mu))
+    assert O.lib.orc_pois(0.999999999, 10.0, 32) == 32 and O.lib.orc_pois(0.5, 0.0, 32) == 0
+
+
+# ---- golden values recomputed from the reference's literals ----------------------------------------------------------
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "caltargets.json")))
+
+
+def test_caltargets_match_reference_literals():
+    got = {(t, s): (v, lo, hi) for t, v, s, lo, hi in T.caltargets()}
+    assert len(got) == len(GOLD["rows"]) == 30
+    for row in GOLD["rows"]:
+        v, lo, hi = got[(row["target"], row["subgroup"])]
+        assert v == pytest.approx(row["value"], abs=5e-5), row
+        if row["ll95"] is not None:
+            assert lo == pytest.approx(row["ll95"], abs=1.5e-3) and hi == pytest.approx(row["ul95"], abs=1.5e-3), row
+
+
+def test_prior_box_matches_reference():
+    assert len(P.PRIORS) == 62                                            # length(priors)
+    assert sum(1 for _, lo, hi in P.PRIORS if lo == hi) == 7              # 7 fixed -> 55 free inputs
+    d = {k: (lo, hi) for k, lo, hi in P.PRIORS}
+    assert d["U2RGC_PROB"] == (0, 0.35) and d["PHAR_GC_DURAT_NOTX"] == (3, 20) and d["HIV_TRANS_RR_RGC"] == (1.2, 6.4)
+    assert d["HIV_RX_HALT_PROB_BLACK"][0] == pytest.approx(1 - (1 - 0.464) ** (1 / 52))
+    # the reference's own source text, when present in this container, must agree line by line
+    src = "/root/reference/burnin/cal/sim1_01_lhs_params.r"
+    if os.path.exists(src):
+        txt = open(src).read()
+        found = re.findall(r'pvec\(([^,]+),\s*([^,]+),\s*"(\w+)"\)', txt)
+        assert len(found) == 62
+        for lo, hi, name in found:
+            lo_v, hi_v = (eval(s.strip().replace("^", "**")) for s in (lo, hi))
+            assert d[name] == pytest.approx((lo_v, hi_v)), name
+    env = P.prior_midpoint_env()
+    p = P.params_from_env(env)
+    assert P.get(p, "rgc_tx_recov_pr").tolist() == pytest.approx([1 - 0.06, 0.5, 1.0])     # c(1 - INFPR_WK1, 0.5, 1)
+    assert P.get(p, "a_rate")[0] == pytest.approx(0.00049 + 1.285 / 20000)
+    lhs = P.lhs_envs(50, 1971)
+    u = np.array([[(e[k] - lo) / (hi - lo) if hi > lo else 0.5 for k, lo, hi in P.PRIORS] for e in lhs])
+    free = [j for j, (_, lo, hi) in enumerate(P.PRIORS) if hi > lo]
+    for j in free:                                                       # Latin property: one point per stratum
+        assert sorted(np.floor(u[:, j] * 50).astype(int).tolist()) == list(range(50))
+
+
+def test_params_def_consistent_across_python_c_and_cuda():
+    assert P.NPARAM == O.NPARAM == K.NPARAM
+    off, cnt = C.c_int(), C.c_int()
+    from xgc_msm_b200 import abi
+    for name, (o, c, _) in P.PARAM_INDEX.items():
+        assert abi.lib.xgc_param_index(name.encode(), C.byref(off), C.byref(cnt)) == 0
+        assert (off.value, cnt.value) == (o, c), name
+    for nm in ("NTABLE", "NCONTROL", "NCOUNTER", "NTARGET", "NSTREAM", "M_ALL", "S_EDGE0", "K_PATH", "T_NET_DUR"):
+        assert getattr(K, nm) == O.const(nm)
+    assert synth.NTABLE == K.NTABLE and synth.T_GLM_CONDOO == K.T_GLM_CONDOO and synth.T_NET_DEG == K.T_NET_DEG
+    assert [P.MODULE_BIT[m] for m in P.MODULE_ORDER] == [getattr(K, "M_" + m.upper()) for m in P.MODULE_ORDER]
+    assert len(T.device_target_names()) == K.NTARGET
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from xgc_msm_b200 import abi
+    hdr = open(os.path.join(ROOT, "include", "xgc", "abi.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(xgc_\w+)\s*\(", hdr, flags=re.M))
+    declared -= {"xgc_stream_width", "xgc_stream_entities"}              # static inline helpers
+    assert len(declared) >= 40
+    for sym in sorted(declared):
+        assert hasattr(abi.lib, sym), f"libxgc.so does not export {sym}"
+    assert abi.lib.xgc_abi_version() == K.ABI_VERSION
+    # no GPU here: creation must fail loudly, never fall back to a CPU path
+    if not __import__("torch").cuda.is_available():
+        with pytest.raises(abi.XgcError, match="no CUDA device|CPU fallback"):
+            abi.Handle(1, 128, [8, 8, 8], 8)
+
+
+def test_inject_layout_agrees_between_python_and_c():
+    from xgc_msm_b200 import abi
+    j = abi.make_inject(None, 300, [40, 50, 10], 16)
+    assert j.stride == sum(abi.stream_entities(s, 300, [40, 50, 10], 16) * abi.stream_width(s) for s in range(K.NSTREAM))
+    # the oracle reads draw (stream, entity, k) at off(stream) + entity*width + k: plant one value and watch it being used
+    case = make_case(200, 3, network_mode="surrogate")
+    o = load_oracle(case, 1, 0)
+    stride = abi.inject_size(case["cap"], case["e_cap"], 64)
+    u = np.full(stride, 0.5)
+    off = sum(abi.stream_entities(s, case["cap"], case["e_cap"], 64) * abi.stream_width(s) for s in range(K.S_DEPART))
+    u[off + 17 * abi.stream_width(K.S_DEPART) + 0] = 1.0 - 1e-9              # uid 17, natural-mortality draw -> dies
+    o.step(2, K.M_AGING | K.M_DEPARTURE, O.make_inject(u, stride, case["cap"], case["e_cap"], 64))
+    gone = sorted(set(range(200)) - set(o.get_attr("uid").astype(int)))
+    assert 17 in gone and all(g == 17 or case["attrs"]["age"][g] + 7 / 365 >= 65 for g in gone)   # others only by ageing out
+
+
+# ---- oracle behaviour ------------------------------------------------------------------------------------------------
+def test_oracle_module_invariants():
+    case = make_case(1500, 5, midcourse=True, network_mode="surrogate")
+    o = load_oracle(case, 1971, 0)
+    n0 = o.num_agents()
+    for at in range(2, 14):
+        before = o.num_agents()
+        o.step(at, K.M_AGING | K.M_DEPARTURE)
+        c = o.counters(at)
+        dead = before - o.num_agents()
+        assert 0 <= dead <= c[K.K_DEP_GEN] + c[K.K_DEP_AIDS]
+        for l in range(3):                                               # delete_vertices: ids stay inside 1..n, tail < head
+            el, _ = o.get_edgelist(l)
+            assert el.size == 0 or (el.min() >= 1 and el.max() <= o.num_agents() and np.all(el[:, 0] < el[:, 1]))
+        o.step(at, K.M_ALL & ~(K.M_AGING | K.M_DEPARTURE))
+        c = o.counters(at)
+        assert c[K.K_NUM * K.NCELL:(K.K_NUM + 1) * K.NCELL].sum() == o.num_agents()
+        for s, site in enumerate(("rGC", "uGC", "pGC")):
+            st, sy, tx, it = (o.get_attr(site + x) for x in ("", ".sympt", ".tx", ".infTime"))
+            assert np.all(sy <= st) and np.all(tx <= st) and np.all((it != -1) == (st == 1))
+            assert c[(K.K_INUM_RGC + s) * K.NCELL:(K.K_INUM_RGC + s + 1) * K.NCELL].sum() == st.sum()
+        assert np.all(o.get_attr("tx.status") <= o.get_attr("diag.status")) and np.all(o.get_attr("diag.status") <= o.get_attr("status"))
+        assert c[K.K_PATH:K.K_PATH + K.NPATH].sum() == sum(c[(K.K_INCID_RGC + s) * K.NCELL:(K.K_INCID_RGC + s + 1) * K.NCELL].sum() for s in range(3))
+    age = o.get_attr("age")
+    assert age.min() >= 18 and age.max() < 65.2 and abs(o.num_agents() - n0) < 0.1 * n0
+    assert np.all(np.diff(o.get_attr("uid")) > 0)                       # arrivals are appended, order is kept
+
+
+def test_oracle_control_flags_change_behaviour():
+    tot = {}
+    for proto in ("base", "symptomatic", "cdc", "universal"):
+        case = make_case(1500, 9, midcourse=True, network_mode="surrogate", stiScreeningProtocol=proto)
+        o = load_oracle(case, 1971, 0)
+        t = np.zeros(K.NCOUNTER, dtype=np.int64)
+        for at in range(2, 28):
+            o.step(at, K.M_ALL); t += o.counters(at)
+        tot[proto] = t
+    v = {k: t[K.K_VISITS] - t[K.K_VISITS_SYMPT] for k, t in tot.items()}
+    assert v["symptomatic"] == 0 and v["base"] > 0 and v["cdc"] > 0
+    tested = {k: t[K.K_TESTED:K.K_TESTED + 3].sum() / max(t[K.K_VISITS], 1) for k, t in tot.items()}
+    assert tested["universal"] == pytest.approx(3.0) and tested["base"] < 3.0
+    # kissing / rimming routes off -> no p2p / p2r / r2p infections (sim1_02_lhs.r:220-221)
+    case = make_case(1500, 9, midcourse=True, network_mode="surrogate", transRoute_Kissing=False, transRoute_Rimming=False)
+    o = load_oracle(case, 1971, 0); t = np.zeros(K.NCOUNTER, dtype=np.int64)
+    for at in range(2, 20):
+        o.step(at, K.M_ALL); t += o.counters(at)
+    assert t[K.K_PATH + K.NPATH - 1] == 0 and t[K.K_PATH + 1] == 0 and t[K.K_PATH + 5] == 0 and t[K.K_PATH + 0] > 0
+
+
+def test_epi_series_and_target_pipeline():
+    case = make_case(2000, 13, network_mode="surrogate")
+    o = load_oracle(case, 1971, 0, t_cap=80)
+    for at in range(2, 70):
+        o.step(at, K.M_ALL)
+    from xgc_msm_b200 import abi
+    epi = {v: o.epi(v, 2, 69) for v in abi.names("epi")}                  # every name the library advertises parses
+    assert np.allclose(epi["num"], epi["num.B"] + epi["num.H"] + epi["num.O"] + epi["num.W"])
+    assert np.allclose(epi["incid.gc"], epi["incid.rgc"] + epi["incid.ugc"] + epi["incid.pgc"])
+    assert np.allclose(epi["incid.rgc"], sum(epi[f"incid.{r}.rgc"] for r in "BHOW"))
+    assert np.allclose(epi["incid.gc"], sum(epi[k] for k in epi if re.search(r"(r|u|p)2", k)))      # 98_summarize_sims.r:75
+    assert np.allclose(epi["i.num.dx.B"], sum(epi[f"i.num.dx.B.age{a}"] for a in range(1, 6)))
+    # device target columns == sim0.0_setup.r pipeline (derived measures -> NA->0 -> tail mean) on the same series
+    tm = T.tail_means(T.derived_measures(epi), 52)
+    tg = dict(zip(T.device_target_names(), o.targets(69, 52)))
+    for k in ("num", "i.prev", "ir100.pop", "i.prev.dx.inf.B", "i.prev.dx.inf.age3", "cc.vsupp.W", "cc.vsupp.age2", "prepCov.H",
+              "prop.rect.tested", "prob.uGC.tested", "prev.gc", "prev.pgc", "ir100.rgc"):
+        assert tg[k] == pytest.approx(tm[k], rel=1e-12, abs=1e-15), k
+    # calculate_targets.r family on the same series
+    assert T.target_prob_prep_byrace(epi, 52)["prep.cov.W"] == pytest.approx(tm["prepCov.W"], rel=1e-9)
+    assert set(T.target_prop_anatsites_tested(epi, 52)) == {"prop.rect.tested", "prop.ureth.tested", "prop.phar.tested"}
+    assert set(T.target_prob_gcpos_tested_anatsites(epi, 52)) == {"prob.rGC.tested", "prob.uGC.tested", "prob.pGC.tested"}
+    assert T.target_prob_vls(epi, 52, "race")["prob.vsupp.B"] == pytest.approx(tm["cc.vsupp.B"])
+    d = T.get_absdiff("ct_hiv_prev", np.array([0.10, 0.124, 0.30]))
+    assert d["output_within_5pts"].tolist() == [1, 1, 0] and d["output_in_targcl"].tolist() == [0, 1, 0]
+    assert T.get_absdiff("ct_hiv_incid_per100pop", np.array([0.9]))["output_within_5pts"].tolist() == [1]
+    assert T.select_by_popsize(np.array([19100, 20900, 21100])).tolist() == [True, True, False]

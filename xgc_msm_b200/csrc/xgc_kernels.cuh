@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent1: aging_msm, departure_msm, hivtest_msm, hivtx_msm, hivprogress_msm, hivvl_msm (sim1_02_lhs.r:202-208)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+__global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   int n_slots = rp->n_slots;
@@ -118,7 +118,12 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
   bool live = i < n_slots;
   uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
   live = live && (c.y & DM_ACTIVE);
-  unsigned uid = c.x, demo = c.y, hiv = c.w;
+  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
+  if (snap) {       // start of week: remember the GC / PrEP bits that acts, condoms and hivtrans must see (they run before
+                    // prep / stirecov / stitx in the reference's module order)
+    gc = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
+    hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
+  }
   bool isnew = i >= n_pre;
   Aux ax; ax.age_ref = 0; ax.vl = 0; ax.ins_quot = 0;
   bool hivpos = live && (hiv & HV_STATUS);
@@ -215,7 +220,12 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
     if (ha_dirty) g.hck_a[idx] = ha;
     if (hb_dirty) g.hck_b[idx] = hb;
   }
-  if (demo != c.y || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; if (demo != c.y) q[0].y = demo; if (hiv != c.w) q[1].y = hiv; }
+  if (i < n_slots && (demo != c.y || gc != c.z || hiv != c.w)) {
+    uint2* q = (uint2*)&g.core[idx];
+    if (demo != c.y) q[0].y = demo;
+    if (gc != c.z) q[1].x = gc;
+    if (hiv != c.w) q[1].y = hiv;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -445,8 +455,7 @@ __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_agent2: prep_msm, stirecov_msm, stitx_msm (sim1_02_lhs.r:213, 215-216).  Takes the snapshot of the GC / PrEP bits
-// that hivtrans_msm and the lazily evaluated condom model must see (they run before these modules in the reference).
+// k_agent2: prep_msm, stirecov_msm, stitx_msm (sim1_02_lhs.r:213, 215-216).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.y;
@@ -465,8 +474,6 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
   int race = (int)DM_RACE(demo);
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
   if (live) {
-    gc = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
-    hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
     short4 tk = na4();
     bool ind_sti = false;
     // ---- stirecov

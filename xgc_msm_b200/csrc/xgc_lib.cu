@@ -437,8 +437,9 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
   LAUNCH(h, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
-  if (mask & (XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL))
-    LAUNCH(h, k_agent1, ga, TPB, g, inj, mask);
+  // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
+  if (zero_row || (mask & (XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL)))
+    LAUNCH(h, k_agent1, ga, TPB, g, inj, mask, zero_row);
   bool native = inj.u == nullptr;
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
   if (mask & XGC_M_RESIM_NETS) {
@@ -447,7 +448,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     LAUNCH(h, k_form, dim3(3, g.R), TPB, g, inj);
   }
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCH(h, k_edge1, ge, TPB, g, inj, mask);
-  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCH(h, k_agent2, ga, TPB, g, inj, mask);
+  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCH(h, k_agent2, ga, TPB, g, inj, mask);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCH(h, k_edge2, ge, TPB, g, inj, mask);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3, ga, TPB, g, inj, mask);
   return 0;

@@ -25,6 +25,8 @@ class SweepSpec:
     seed: int = 1971
     network_mode: str = "surrogate"
     weeks_between_compactions: int = 64
+    lhs: bool = True               # False: every replicate uses the prior-midpoint parameters (exchangeable replicates)
+    n_distinct: int = N_DISTINCT   # distinct starting populations
     n_cap: int = field(init=False)
     e_cap: list = field(init=False)
 
@@ -50,12 +52,14 @@ def _population(idx: int, n: int, seed: int):
 
 
 def replicate_params(spec: SweepSpec, rid: int) -> np.ndarray:
+    if not spec.lhs:
+        return P.params_from_env(P.prior_midpoint_env(), n_init=spec.n_agents)
     env = _lhs_block(rid // LHS_BLOCK, spec.seed)[rid % LHS_BLOCK]
     return P.params_from_env(env, n_init=spec.n_agents)
 
 
 def replicate_case(spec: SweepSpec, rid: int) -> dict:
-    a, els, starts = _population(rid % N_DISTINCT, spec.n_agents, spec.seed)
+    a, els, starts = _population(rid % spec.n_distinct, spec.n_agents, spec.seed)
     return dict(n=spec.n_agents, params=replicate_params(spec, rid), control=P.control_msm(network_mode=spec.network_mode).flags,
                 tables=synth.make_tables(), attrs=a, els=els, starts=starts, cap=spec.n_cap, e_cap=spec.e_cap, at0=1)
 
@@ -68,7 +72,7 @@ def load_sweep(h, spec: SweepSpec, rid0: int = 0):
     first = {}
     for r in range(R):
         rid = rid0 + r
-        idx = rid % N_DISTINCT
+        idx = rid % spec.n_distinct
         if idx not in first:
             a, els, starts = _population(idx, spec.n_agents, spec.seed)
             h.set_population(r, spec.n_agents, 1)
