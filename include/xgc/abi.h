@@ -107,12 +107,11 @@ enum xgc_module_bit {
 #define XGC_FORM_TRIES 4
 enum xgc_stream {
   /* agent streams */
-  XGC_S_DEPART = 0,    /* k0 natural mortality, k1 AIDS mortality                                                   */
-  XGC_S_HIVTEST,       /* k0 interval test                                                                          */
-  XGC_S_HIVTX,         /* k0 initiation, k1 halting, k2 re-initiation                                               */
-  XGC_S_PREP,          /* k0 start, k1 adherence class, k2 discontinuation                                          */
-  XGC_S_STIRECOV,      /* k0..2 untreated recovery r,u,p; k3..5 treated recovery r,u,p                              */
-  XGC_S_STITX,         /* k0..2 symptomatic care seeking r,u,p; k3 asymptomatic visit; k4..6 site tested r,u,p      */
+  XGC_S_AGENT1 = 0,    /* aging..hivvl pass: k0 natural mortality, k1 AIDS mortality, k2 HIV interval test,
+                          k3 HIV treatment transition (initiation | halting | re-initiation: mutually exclusive)            */
+  XGC_S_AGENT2,        /* prep/stirecov/stitx pass: k0 asymptomatic clinic visit, k1 PrEP start | discontinuation,
+                          k2 PrEP adherence class; k4..6 recovery r,u,p (treated | untreated: exclusive per site);
+                          k8..10 symptomatic care seeking r,u,p; k12..14 site tested r,u,p                                    */
   XGC_S_INFECT,        /* k0..2 symptomatic r,u,p; k3..5 Poisson duration r,u,p                                     */
   XGC_S_ARRIVE_ATTR,   /* k0 race, k1 role, k2 ins.quot, k3 circ, k4 late.tester, k5 tt.traj, k6 act.stopper, k7 risk.grp */
   /* replicate streams */
@@ -147,8 +146,7 @@ enum xgc_stream {
 static inline XGC_HD int xgc_stream_width(int s) {
   if (s < XGC_S_EDGE0) {
     switch (s) {
-      case XGC_S_DEPART: return 2;  case XGC_S_HIVTEST: return 1;  case XGC_S_HIVTX: return 3;
-      case XGC_S_PREP: return 3;    case XGC_S_STIRECOV: return 6; case XGC_S_STITX: return 7;
+      case XGC_S_AGENT1: return 4;  case XGC_S_AGENT2: return 16;
       case XGC_S_INFECT: return 6;  case XGC_S_ARRIVE_ATTR: return 8;
       case XGC_S_ARRIVE_N: return 64; case XGC_S_PATHORDER: return 6; case XGC_S_NET_N: return 3;
       default: return 2 * XGC_FORM_TRIES;      /* XGC_S_FORM + layer */
@@ -249,7 +247,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_M_AGING) X(XGC_M_DEPARTURE) X(XGC_M_ARRIVAL) X(XGC_M_HIVTEST) X(XGC_M_HIVTX) X(XGC_M_HIVPROGRESS) X(XGC_M_HIVVL) \
   X(XGC_M_RESIM_NETS) X(XGC_M_ACTS) X(XGC_M_CONDOMS) X(XGC_M_POSITION) X(XGC_M_PREP) X(XGC_M_HIVTRANS) X(XGC_M_STIRECOV) \
   X(XGC_M_STITX) X(XGC_M_STITRANS) X(XGC_M_PREV) X(XGC_M_ALL) \
-  X(XGC_S_DEPART) X(XGC_S_HIVTEST) X(XGC_S_HIVTX) X(XGC_S_PREP) X(XGC_S_STIRECOV) X(XGC_S_STITX) X(XGC_S_INFECT) \
+  X(XGC_S_AGENT1) X(XGC_S_AGENT2) X(XGC_S_INFECT) \
   X(XGC_S_ARRIVE_ATTR) X(XGC_S_ARRIVE_N) X(XGC_S_PATHORDER) X(XGC_S_NET_N) X(XGC_S_FORM) X(XGC_S_EDGE0) X(XGC_S_DISSOLVE) \
   X(XGC_S_ACTS) X(XGC_S_COND) X(XGC_S_POS) X(XGC_S_OIDIR) X(XGC_S_RIMDIR) X(XGC_S_HIVTRANS) X(XGC_S_GC_AI_A) X(XGC_S_GC_AI_B) \
   X(XGC_S_GC_OI_A) X(XGC_S_GC_OI_B) X(XGC_S_GC_RIM_A) X(XGC_S_GC_RIM_B) X(XGC_S_GC_KISS_A) X(XGC_S_GC_KISS_B) \

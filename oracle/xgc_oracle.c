@@ -293,9 +293,9 @@ static void departure_msm(orc_dat* d, int at) {
     if (ai < 0) ai = 0;
     if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
     double pm = d->tb[XGC_T_ASMR + ((int)d->a[A_RACE][i] - 1) * XGC_ASMR_AGES + ai];
-    int dg = orc_bern(UA(XGC_S_DEPART, i, 0), pm);
+    int dg = orc_bern(UA(XGC_S_AGENT1, i, 0), pm);
     int da = 0;
-    if ((int)d->a[A_STAGE][i] == 4) da = orc_bern(UA(XGC_S_DEPART, i, 1), d->p[XGC_P_aids_mr]);
+    if ((int)d->a[A_STAGE][i] == 4) da = orc_bern(UA(XGC_S_AGENT1, i, 1), d->p[XGC_P_aids_mr]);
     if (dg) c[XGC_K_DEP_GEN]++;
     if (da) c[XGC_K_DEP_AIDS]++;
     if (dg || da) { dead[i] = 1; any = 1; }
@@ -348,7 +348,7 @@ static void hivtest_msm(orc_dat* d, int at) {
     double tsl = (double)at - last;
     int tested = 0;
     if ((int)d->a[A_PREPSTAT][i] == 0 && (int)d->a[A_LATE][i] == 0 && tsl >= 2.0)
-      tested = orc_bern(UA(XGC_S_HIVTEST, i, 0), d->p[XGC_P_hiv_test_rate + race]);
+      tested = orc_bern(UA(XGC_S_AGENT1, i, 2), d->p[XGC_P_hiv_test_rate + race]);
     if ((int)d->a[A_STAGE][i] == 4 && tsl >= d->p[XGC_P_aids_test_int]) tested = 1;
     if ((int)d->a[A_PREPSTAT][i] == 1 && tsl >= d->p[XGC_P_prep_tst_int]) tested = 1;
     if (!tested) continue;
@@ -367,13 +367,13 @@ static void hivtx_msm(orc_dat* d, int at) {
     if ((int)d->a[A_DIAG][i] == 1) {
       int txs = (int)d->a[A_TXS][i]; double cumon = d->a[A_CUMON][i];
       if (txs == 0 && cumon == 0.0) {
-        if (orc_bern(UA(XGC_S_HIVTX, i, 0), d->p[XGC_P_tx_init_prob + race])) { d->a[A_TXS][i] = 1; d->a[A_TXINIT][i] = at; }
+        if (orc_bern(UA(XGC_S_AGENT1, i, 3), d->p[XGC_P_tx_init_prob + race])) { d->a[A_TXS][i] = 1; d->a[A_TXINIT][i] = at; }
       } else if (txs == 1) {
         double rr = traj == 2 ? d->p[XGC_P_tx_halt_full_rr + race] : traj == 3 ? d->p[XGC_P_tx_halt_dur_rr + race] : 1.0;
-        if (orc_bern(UA(XGC_S_HIVTX, i, 1), d->p[XGC_P_tx_halt_part_prob + race] * rr)) d->a[A_TXS][i] = 0;
+        if (orc_bern(UA(XGC_S_AGENT1, i, 3), d->p[XGC_P_tx_halt_part_prob + race] * rr)) d->a[A_TXS][i] = 0;
       } else {
         double rr = traj == 2 ? d->p[XGC_P_tx_reinit_full_rr + race] : traj == 3 ? d->p[XGC_P_tx_reinit_dur_rr + race] : 1.0;
-        if (orc_bern(UA(XGC_S_HIVTX, i, 2), d->p[XGC_P_tx_reinit_part_prob + race] * rr)) d->a[A_TXS][i] = 1;
+        if (orc_bern(UA(XGC_S_AGENT1, i, 3), d->p[XGC_P_tx_reinit_part_prob + race] * rr)) d->a[A_TXS][i] = 1;
       }
     }
     if ((int)d->a[A_TXS][i] == 1) d->a[A_CUMON][i] += 1.0; else d->a[A_CUMOFF][i] += 1.0;
@@ -636,15 +636,15 @@ static void prep_msm(orc_dat* d, int at) {
     if ((int)d->a[A_PREPSTAT][i] == 1) {
       int stop = 0;
       if (diag == 1) stop = 1;
-      else if (orc_bern(UA(XGC_S_PREP, i, 2), p[XGC_P_prep_discont_rate + race])) stop = 1;
+      else if (orc_bern(UA(XGC_S_AGENT2, i, 1), p[XGC_P_prep_discont_rate + race])) stop = 1;
       else if ((int)d->a[A_LNT][i] == at && (double)at - d->a[A_PREPLR][i] >= p[XGC_P_prep_reassess_int]) {
         if (!ind) stop = 1; else d->a[A_PREPLR][i] = at;
       }
       if (stop) { d->a[A_PREPSTAT][i] = 0; d->a[A_PREPCLASS][i] = 0; }
     } else if (diag == 0 && (double)at >= p[XGC_P_prep_start] && (int)d->a[A_LNT][i] == at && ind) {
-      if (orc_bern(UA(XGC_S_PREP, i, 0), p[XGC_P_prep_start_prob + race])) {
+      if (orc_bern(UA(XGC_S_AGENT2, i, 1), p[XGC_P_prep_start_prob + race])) {
         d->a[A_PREPSTAT][i] = 1; d->a[A_PREPSTART][i] = at; d->a[A_PREPLR][i] = at;
-        d->a[A_PREPCLASS][i] = 1 + categorical(UA(XGC_S_PREP, i, 1), p + XGC_P_prep_adhr_dist, 3);
+        d->a[A_PREPCLASS][i] = 1 + categorical(UA(XGC_S_AGENT2, i, 2), p + XGC_P_prep_adhr_dist, 3);
       }
     }
   }
@@ -697,9 +697,9 @@ static void stirecov_msm(orc_dat* d, int at) {
       int recov = 0;
       if ((int)d->a[A_GC_TX + s][i] == 1) {
         int k = at - (int)d->a[A_GC_TXT + s][i];
-        if (k >= 1) recov = orc_bern(UA(XGC_S_STIRECOV, i, 3 + s), p[txpr[s] + (k >= 3 ? 2 : k - 1)]);
+        if (k >= 1) recov = orc_bern(UA(XGC_S_AGENT2, i, 4 + s), p[txpr[s] + (k >= 3 ? 2 : k - 1)]);
       } else if (d->a[A_GC_INF + s][i] < (double)at) {
-        if (d->c[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = orc_bern(UA(XGC_S_STIRECOV, i, s), 1.0 / p[XGC_P_gc_ntx_int + s]);
+        if (d->c[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = orc_bern(UA(XGC_S_AGENT2, i, 4 + s), 1.0 / p[XGC_P_gc_ntx_int + s]);
         else recov = (double)at - d->a[A_GC_INF + s][i] >= d->a[A_GC_DUR + s][i];
       }
       if (recov) {
@@ -719,11 +719,11 @@ static void stitx_msm(orc_dat* d, int at) {
     for (int s = 0; s < 3; ++s)
       if ((int)d->a[A_GC + s][i] == 1 && (int)d->a[A_GC_SYM + s][i] == 1 && (int)d->a[A_GC_TX + s][i] == 0) {
         double rr = s == 0 ? p[XGC_P_rgc_sympt_seek_test_rr] : s == 2 ? p[XGC_P_pgc_sympt_seek_test_rr] : 1.0;
-        if (orc_bern(UA(XGC_S_STITX, i, s), p[XGC_P_ugc_sympt_seek_test_prob] * rr)) sv = 1;
+        if (orc_bern(UA(XGC_S_AGENT2, i, 8 + s), p[XGC_P_ugc_sympt_seek_test_prob] * rr)) sv = 1;
       }
     int ex = (int)d->a[A_EXPO][i];
     if (!sv) {
-      if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = orc_bern(UA(XGC_S_STITX, i, 3), p[XGC_P_gc_asympt_visit_prob]);
+      if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = orc_bern(UA(XGC_S_AGENT2, i, 0), p[XGC_P_gc_asympt_visit_prob]);
       else if (proto == XGC_SCREEN_CDC) {
         int active = (ex & 7) != 0 || (kissx && (ex & 8));
         int hr = (int)d->a[A_PREPSTAT][i] == 1 || (ex & 16);
@@ -739,7 +739,7 @@ static void stitx_msm(orc_dat* d, int at) {
       int exposed = (ex >> s) & 1; if (s == 2 && kissx && (ex & 8)) exposed = 1;
       if (proto == XGC_SCREEN_CDC && !symp && !exposed) tested = 0;
       else if (proto == XGC_SCREEN_UNIVERSAL) tested = 1;
-      else tested = orc_bern(UA(XGC_S_STITX, i, 4 + s), symp ? p[XGC_P_gc_sympt_prob_test + s] : p[XGC_P_gc_asympt_prob_test + s]);
+      else tested = orc_bern(UA(XGC_S_AGENT2, i, 12 + s), symp ? p[XGC_P_gc_sympt_prob_test + s] : p[XGC_P_gc_asympt_prob_test + s]);
       if (!tested) continue;
       c[XGC_K_TESTED + s]++;
       if (inf) {

@@ -131,8 +131,8 @@ def test_inject_layout_agrees_between_python_and_c():
     o = load_oracle(case, 1, 0)
     stride = abi.inject_size(case["cap"], case["e_cap"], 64)
     u = np.full(stride, 0.5)
-    off = sum(abi.stream_entities(s, case["cap"], case["e_cap"], 64) * abi.stream_width(s) for s in range(K.S_DEPART))
-    u[off + 17 * abi.stream_width(K.S_DEPART) + 0] = 1.0 - 1e-9              # uid 17, natural-mortality draw -> dies
+    off = sum(abi.stream_entities(s, case["cap"], case["e_cap"], 64) * abi.stream_width(s) for s in range(K.S_AGENT1))
+    u[off + 17 * abi.stream_width(K.S_AGENT1) + 0] = 1.0 - 1e-9              # uid 17, natural-mortality draw -> dies
     o.step(2, K.M_AGING | K.M_DEPARTURE, O.make_inject(u, stride, case["cap"], case["e_cap"], 64))
     gone = sorted(set(range(200)) - set(o.get_attr("uid").astype(int)))
     assert 17 in gone and all(g == 17 or case["attrs"]["age"][g] + 7 / 365 >= 65 for g in gone)   # others only by ageing out

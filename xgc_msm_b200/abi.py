@@ -114,7 +114,7 @@ def make_inject(u: Optional[np.ndarray], uid_cap: int, e_cap, form_cap: int) -> 
 
 def stream_width(s: int) -> int:
     if s < K.S_EDGE0:
-        return {K.S_DEPART: 2, K.S_HIVTEST: 1, K.S_HIVTX: 3, K.S_PREP: 3, K.S_STIRECOV: 6, K.S_STITX: 7, K.S_INFECT: 6,
+        return {K.S_AGENT1: 4, K.S_AGENT2: 16, K.S_INFECT: 6,
                 K.S_ARRIVE_ATTR: 8, K.S_ARRIVE_N: 64, K.S_PATHORDER: 6, K.S_NET_N: 3}.get(s, 2 * K.FORM_TRIES)
     s = (s - K.S_EDGE0) % K.EDGE_STREAMS + K.S_EDGE0
     return 1 if s == K.S_DISSOLVE else 4 if s == K.S_ACTS else K.MAX_ACTS

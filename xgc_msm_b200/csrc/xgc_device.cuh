@@ -51,6 +51,7 @@
 #define HV_PREPCLASS_MASK (3u << 7)
 #define HV_PREPELIG     (1u << 9)
 #define HV_PREP_PRE     (1u << 10)               // prepStat as acts/condoms saw it (before this week's prep module)
+#define HV_VSUPP        (1u << 11)              // diagnosed-independent: vl <= log10(200), maintained by hivvl / attribute upload
 #define HV_NEW          (1u << 31)
 
 struct __align__(16) Aux { double age_ref; float vl; float ins_quot; };
@@ -84,6 +85,7 @@ struct Dev {                 // everything a kernel needs; passed by value
   int* pos2slot;             // [R][n_cap] rank -> slot (built by k_rank)
   int4* edge;                // [R][e_stride]: layer l at e_off[l]
   Rep* rep; const double* params; const int* control; const double* tables;
+  const double* pois;        // [R][4][XGC_MAX_ACTS+1] Poisson CDF tables of the constant weekly rates: kiss main/casual, rim main/casual
   unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
   const int* at_ptr;
 };
@@ -100,14 +102,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-struct Draw {                // one stream of one entity; caches the Philox block of 4
-  const Inj* inj; size_t base; unsigned seed, rep, at, stream, e0, e1; int blk; uint4 v;
-  __device__ __forceinline__ Draw(const Inj& j, const Dev& g, int r, int at_, int stream_, unsigned e0_, unsigned e1_, size_t idx)
-      : inj(&j), seed(g.seed), rep((unsigned)(g.rep0 + r)), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
-    base = j.u ? (size_t)r * j.stride + j.off[stream_] + idx * (size_t)xgc_stream_width(stream_) : 0;
+// One stream of one entity; caches the Philox block of 4.  INJ = true reads the injected table instead (parity mode);
+// the native kernels are compiled without that path.
+template <bool INJ> struct DrawT {
+  const double* u; unsigned seed, rep, at, stream, e0, e1; int blk; uint4 v;
+  __device__ __forceinline__ DrawT(const Inj& j, const Dev& g, int r, int at_, int stream_, unsigned e0_, unsigned e1_, size_t idx)
+      : u(nullptr), seed(g.seed), rep((unsigned)(g.rep0 + r)), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
+    if (INJ) u = j.u + (size_t)r * j.stride + j.off[stream_] + idx * (size_t)xgc_stream_width(stream_);
   }
   __device__ __forceinline__ double operator()(int k) {
-    if (inj->u) return inj->u[base + k];
+    if (INJ) return u[k];
     int b = k >> 2;
     if (b != blk) { v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b; }
     unsigned x = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
@@ -145,6 +149,12 @@ __device__ __forceinline__ int xgc_pois(double u, double mu, int kmax) {
   double pr = xgc_exp(-mu), cdf = pr;
   int k = 0;
   while (u > cdf && k < kmax) { k++; pr = pr * mu / (double)k; cdf = cdf + pr; }
+  return k;
+}
+// same walk on a precomputed table tab[k] = cdf_k (built with the identical recurrence by k_derive): bit-identical result
+__device__ __forceinline__ int xgc_pois_tab(double u, const double* tab) {
+  int k = 0;
+  while (u > tab[k] && k < XGC_MAX_ACTS) k++;
   return k;
 }
 __device__ __forceinline__ int xgc_categorical(double u, const double* prob, int n) {

@@ -27,11 +27,25 @@ __device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
 }
 __device__ __forceinline__ short4 na4() { return make_short4(-1, -1, -1, -1); }
 
+// k_derive: per-replicate tables derived from the parameters (run whenever parameters change)
+__global__ void k_derive(const __grid_constant__ Dev g, double* pois) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.R * 4) return;
+  int r = t >> 2, w = t & 3;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  double mu = w == 0 ? P[XGC_P_kiss_rate_main] : w == 1 ? P[XGC_P_kiss_rate_casl] : w == 2 ? P[XGC_P_rim_rate_main] : P[XGC_P_rim_rate_casl];
+  double* tab = pois + (size_t)t * (XGC_MAX_ACTS + 1);
+  if (!(mu > 0.0)) { for (int k = 0; k <= XGC_MAX_ACTS; ++k) tab[k] = __longlong_as_double(0x7ff0000000000000LL); return; }
+  double pr = xgc_exp(-mu), cdf = pr;
+  tab[0] = cdf;
+  for (int k = 1; k <= XGC_MAX_ACTS; ++k) { pr = pr * mu / (double)k; cdf = cdf + pr; tab[k] = cdf; }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_begin: one warp per replicate.  Sets the week, zeroes its tally row, draws the pathway order, appends arrivals.
 // arrival_msm: /root/reference/burnin/cal/sim1_02_lhs.r:204, 63-66
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
+template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
   int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= g.R) return;
   Rep* rp = g.rep + r;
@@ -47,7 +61,7 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
     rp->n_slots_pre = n_slots;
     rp->t_age = t_age;
     if (mask & XGC_M_STITRANS) {          // weekly random pathway order (stitrans_msm_rand, ambiguity A2)
-      Draw d(inj, g, r, at, XGC_S_PATHORDER, 0u, 0u, 0);
+      DrawT<INJ> d(inj, g, r, at, XGC_S_PATHORDER, 0u, 0u, 0);
       int perm[XGC_NPATH];
       for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
       for (int i = XGC_NPATH - 1; i >= 1; --i) {
@@ -64,7 +78,7 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
   double muc = mu / (double)m;
   int nnew = 0;
   {
-    Draw d(inj, g, r, at, XGC_S_ARRIVE_N, 0u, 0u, 0);
+    DrawT<INJ> d(inj, g, r, at, XGC_S_ARRIVE_N, 0u, 0u, 0);
     for (int ch = lane; ch < m; ch += 32) nnew += xgc_pois(d(ch), muc, 255);
 #pragma unroll
     for (int o = 16; o; o >>= 1) nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
@@ -74,7 +88,7 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
   for (int j = lane; j < nnew; j += 32) {
     int i = n_slots + j; size_t idx = (size_t)r * g.n_cap + i;
     unsigned uid = (unsigned)(uid0 + j);
-    Draw d(inj, g, r, at, XGC_S_ARRIVE_ATTR, uid, 0u, uid);
+    DrawT<INJ> d(inj, g, r, at, XGC_S_ARRIVE_ATTR, uid, 0u, uid);
     int race = xgc_categorical(d(0), g.tables + XGC_T_RACE_PROP, 4);
     int role = xgc_categorical(d(1), g.tables + XGC_T_ROLE_PROB + race * 3, 3);
     float insq = role == 0 ? 1.0f : role == 1 ? 0.0f : (float)d(2);
@@ -88,7 +102,7 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
     double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
     unsigned demo = (unsigned)race | (xgc_age_group(age) << 2) | ((unsigned)role << 5) | ((unsigned)rg << 7) |
                     (circ ? DM_CIRC : 0u) | (late ? DM_LATE : 0u) | (traj << 12) | (stopper ? DM_STOPPER : 0u) | DM_ACTIVE;
-    g.core[idx] = make_uint4(uid, demo, 0u, 0u);
+    g.core[idx] = make_uint4(uid, demo, 0u, HV_VSUPP);
     g.aux[idx] = ax;
     g.gck_a[idx] = na4(); g.gck_b[idx] = na4(); g.gck_d[idx] = na4();
     g.hck_a[idx] = na4(); g.hck_b[idx] = make_short4(0, 0, -1, -1); g.tck[idx] = na4();
@@ -105,18 +119,28 @@ __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, co
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent1: aging_msm, departure_msm, hivtest_msm, hivtx_msm, hivprogress_msm, hivvl_msm (sim1_02_lhs.r:202-208)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// Agent kernels: each CTA walks `tpc` consecutive 256-slot tiles of one replicate.  The next tile's core word is loaded
+// (and its secondary planes prefetched into L2) before the current tile is processed, so every thread keeps two tiles
+// of loads in flight; fewer, longer CTAs also mean fewer flushes of the per-CTA tallies.
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
+  const size_t rbase = (size_t)r * g.n_cap;
+  uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];      // speculative: always inside the plane
   int n_slots = rp->n_slots;
-  if ((int)(blockIdx.x * TPB) >= n_slots) return;
-  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
+  if (t0 >= t1) return;
+  int at = g.at_ptr[r];
   int n_pre = rp->n_slots_pre, t_ref = rp->t_ref, t_age = rp->t_age;
-  size_t idx = (size_t)r * g.n_cap + i;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   unsigned* row = counter_row(g, r, at);
+  for (int t = t0; t < t1; ++t) {
+  int i = t * TPB + threadIdx.x;
+  size_t idx = rbase + i;
+  uint4 c = cn;
+  if (t + 1 < t1) { cn = g.core[idx + TPB]; prefetch_l2(g.aux + idx + TPB); prefetch_l2(g.tck + idx + TPB); }
   bool live = i < n_slots;
-  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
   live = live && (c.y & DM_ACTIVE);
   unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
   if (snap) {       // start of week: remember the GC / PrEP bits that acts, condoms and hivtrans must see (they run before
@@ -130,11 +154,11 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
   if (live && ((!isnew && (mask & (XGC_M_AGING | XGC_M_DEPARTURE))) || (hivpos && (mask & XGC_M_HIVVL)))) ax = g.aux[idx];
   double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
   int race = (int)DM_RACE(demo);
+  DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);       // the whole pass draws from ONE Philox block per agent
   if ((mask & XGC_M_AGING) && live && !isnew) demo = (demo & ~(7u << 2)) | (xgc_age_group(age) << 2);
   bool dep_g = false, dep_a = false;
   if ((mask & XGC_M_DEPARTURE) && live && !isnew) {
     int ai = (int)floor(age); if (ai < 0) ai = 0; if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
-    Draw d(inj, g, r, at, XGC_S_DEPART, uid, 0u, uid);
     dep_g = xgc_bern(d(0), g.tables[XGC_T_ASMR + race * XGC_ASMR_AGES + ai]);
     if (HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
   }
@@ -157,8 +181,7 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
     int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
     double tsl = (double)(at - last);
     if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) {
-      Draw d(inj, g, r, at, XGC_S_HIVTEST, uid, 0u, uid);
-      tested = xgc_bern(d(0), P[XGC_P_hiv_test_rate + race]);
+      tested = xgc_bern(d(2), P[XGC_P_hiv_test_rate + race]);
     }
     if (HV_STAGE(hiv) == 4 && tsl >= P[XGC_P_aids_test_int]) tested = true;
     if ((hiv & HV_PREP) && tsl >= P[XGC_P_prep_tst_int]) tested = true;
@@ -172,15 +195,14 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
     unsigned traj = DM_TTTRAJ(demo);
     if (mask & XGC_M_HIVTX) {
       if (hiv & HV_DIAG) {
-        Draw d(inj, g, r, at, XGC_S_HIVTX, uid, 0u, uid);
         if (!(hiv & HV_TX) && hb.x == 0) {
-          if (xgc_bern(d(0), P[XGC_P_tx_init_prob + race])) { hiv |= HV_TX; ha.w = (short)at; ha_dirty = true; }
+          if (xgc_bern(d(3), P[XGC_P_tx_init_prob + race])) { hiv |= HV_TX; ha.w = (short)at; ha_dirty = true; }
         } else if (hiv & HV_TX) {
           double rr = traj == 2 ? P[XGC_P_tx_halt_full_rr + race] : traj == 3 ? P[XGC_P_tx_halt_dur_rr + race] : 1.0;
-          if (xgc_bern(d(1), P[XGC_P_tx_halt_part_prob + race] * rr)) hiv &= ~HV_TX;
+          if (xgc_bern(d(3), P[XGC_P_tx_halt_part_prob + race] * rr)) hiv &= ~HV_TX;
         } else {
           double rr = traj == 2 ? P[XGC_P_tx_reinit_full_rr + race] : traj == 3 ? P[XGC_P_tx_reinit_dur_rr + race] : 1.0;
-          if (xgc_bern(d(2), P[XGC_P_tx_reinit_part_prob + race] * rr)) hiv |= HV_TX;
+          if (xgc_bern(d(3), P[XGC_P_tx_reinit_part_prob + race] * rr)) hiv |= HV_TX;
         }
       }
       if (hiv & HV_TX) hb.x++; else hb.y++;
@@ -216,6 +238,7 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
       }
       float vf = (float)v;
       if (vf != ax.vl) g.aux[idx].vl = vf;
+      hiv = (hiv & ~HV_VSUPP) | ((double)vf <= XGC_LOG10_200 ? HV_VSUPP : 0u);
     }
     if (ha_dirty) g.hck_a[idx] = ha;
     if (hb_dirty) g.hck_b[idx] = hb;
@@ -226,6 +249,7 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
     if (gc != c.z) q[1].x = gc;
     if (hiv != c.w) q[1].y = hiv;
   }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, c
 //   drops edges with a departed endpoint (tergmLite::delete_vertices semantics, departure_msm) and, in surrogate mode,
 //   dissolves edges with prob 1/duration (main, casual) or clears the layer (one-off).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
   int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne = rp->ne[l], at = g.at_ptr[r];
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(TPB) k_edges_resim(const __grid_constant__ Dev
       ed = E[e];
       uint4 ca = core[ed.x], cb = core[ed.y];
       keep = (ca.y & DM_ACTIVE) && (cb.y & DM_ACTIVE);
-      if (keep && surrogate) { Draw d(inj, g, r, at, es, ca.x, cb.x, (size_t)e); keep = !xgc_bern(d(0), pd); }
+      if (keep && surrogate) { DrawT<INJ> d(inj, g, r, at, es, ca.x, cb.x, (size_t)e); keep = !xgc_bern(d(0), pd); }
     }
     unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) wsum[w] = __popc(m);
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
 }
 
 // k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order
-__global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
@@ -310,7 +334,7 @@ __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, con
   double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
   double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
   double fl = floor(mu);
-  Draw dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
+  DrawT<INJ> dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
   int nform = (int)fl + (dn(l) < mu - fl);
   if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
   if (n < 2) nform = 0;
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, con
   for (int j0 = 0; j0 < nform; j0 += TPB) {
     int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
     if (j < nform) {
-      Draw d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+      DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
       for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
         int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
         int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
@@ -366,7 +390,7 @@ __device__ __forceinline__ double edge_cond_prob(const Dev& g, const double* P, 
   return pc;
 }
 // position of anal act k: 1 = p1 insertive
-__device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x, Draw& dpos, int k) {
+template <class D> __device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x, D& dpos, int k) {
   unsigned r1 = DM_ROLE(x.ca.y), r2 = DM_ROLE(x.cb.y);
   if (r1 == 0 || r2 == 1) return 1;
   if (r1 == 1 || r2 == 0) return 0;
@@ -376,7 +400,7 @@ __device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x, Draw& dpos, int k
 }
 
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
-__global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.z, l = blockIdx.y;
   const Rep* rp = g.rep + r;
   int ne = rp->ne[l];
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, co
       int ai = 0, oi = 0, ki = 0, ri = 0;
       if (!(act_stopped(x.ca.y, x.ca.z) || act_stopped(x.cb.y, x.cb.z))) {
         bool compat = roles_compatible(x.ca.y, x.cb.y);
-        Draw d(inj, g, r, at, x.base + (XGC_S_ACTS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        DrawT<INJ> d(inj, g, r, at, x.base + (XGC_S_ACTS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
         if (l < 2) {
           double dur = (double)(at - x.ed.z), ca = x.age_a + x.age_b;
           int hcp = (x.ca.w & HV_DIAG) && (x.cb.w & HV_DIAG);
@@ -409,8 +433,9 @@ __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, co
           double roi = xgc_exp(xgc_glm_eta(g.tables + XGC_T_GLM_OI, dur, l == 1, ca, hcp, 0, r1, r2)) / 52.0 * P[XGC_P_oi_acts_scale_mc];
           ai = compat ? xgc_pois(d(0), rai, XGC_MAX_ACTS) : 0;
           oi = xgc_pois(d(1), roi, XGC_MAX_ACTS);
-          ki = xgc_pois(d(2), l == 0 ? P[XGC_P_kiss_rate_main] : P[XGC_P_kiss_rate_casl], XGC_MAX_ACTS);
-          ri = xgc_pois(d(3), l == 0 ? P[XGC_P_rim_rate_main] : P[XGC_P_rim_rate_casl], XGC_MAX_ACTS);
+          const double* pt = g.pois + ((size_t)r * 4 + l) * (XGC_MAX_ACTS + 1);
+          ki = xgc_pois_tab(d(2), pt);
+          ri = xgc_pois_tab(d(3), pt + 2 * (XGC_MAX_ACTS + 1));
         } else {
           ai = compat ? 1 : 0;
           oi = xgc_bern(d(1), P[XGC_P_oi_prob_oo]);
@@ -440,7 +465,7 @@ __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, co
       if (ai > 0 && (ua || ub)) {
         bool uai = false;
         double pc = edge_cond_prob(g, P, x, false);
-        Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
         for (int k = 0; k < ai && !uai; ++k) uai = xgc_bern(dc(k), 1.0 - pc);
         short4* tck = g.tck + (size_t)r * g.n_cap;
         if (ua && (uai || (x.cb.w & HV_DIAG))) tck[x.ed.x].y = (short)at;
@@ -457,23 +482,30 @@ __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, co
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent2: prep_msm, stirecov_msm, stitx_msm (sim1_02_lhs.r:213, 215-216).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
+  const size_t rbase = (size_t)r * g.n_cap;
+  uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
   int n_slots = rp->n_slots;
-  if ((int)(blockIdx.x * TPB) >= n_slots) return;
-  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
-  size_t idx = (size_t)r * g.n_cap + i;
+  int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
+  if (t0 >= t1) return;
+  int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   unsigned* row = counter_row(g, r, at);
+  for (int t = t0; t < t1; ++t) {
+  int i = t * TPB + threadIdx.x;
+  size_t idx = rbase + i;
+  uint4 c = cn;
+  if (t + 1 < t1) { cn = g.core[idx + TPB]; prefetch_l2(g.tck + idx + TPB); }
   bool live = i < n_slots;
-  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
   live = live && (c.y & DM_ACTIVE);
   unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
   int race = (int)DM_RACE(demo);
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
   if (live) {
+    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);     // block 0 (visit, PrEP) is all most agents ever draw
     short4 tk = na4();
     bool ind_sti = false;
     // ---- stirecov
@@ -488,24 +520,21 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
       hiv = (hiv & ~HV_PREPELIG) | ((!diag && ind) ? HV_PREPELIG : 0u);
       if (hiv & HV_PREP) {
         bool stop = false;
-        Draw d(inj, g, r, at, XGC_S_PREP, uid, 0u, uid);
         if (diag) stop = true;
-        else if (xgc_bern(d(2), P[XGC_P_prep_discont_rate + race])) stop = true;
+        else if (xgc_bern(d(1), P[XGC_P_prep_discont_rate + race])) stop = true;
         else if ((int)tk.x == at && (double)(at - (int)tk.z) >= P[XGC_P_prep_reassess_int]) {
           if (!ind) stop = true; else g.tck[idx].z = (short)at;
         }
         if (stop) hiv &= ~(HV_PREP | HV_PREPCLASS_MASK);
       } else if (!diag && (double)at >= P[XGC_P_prep_start] && (int)tk.x == at && ind) {
-        Draw d(inj, g, r, at, XGC_S_PREP, uid, 0u, uid);
-        if (xgc_bern(d(0), P[XGC_P_prep_start_prob + race])) {
-          unsigned cl = 1 + xgc_categorical(d(1), P + XGC_P_prep_adhr_dist, 3);
+        if (xgc_bern(d(1), P[XGC_P_prep_start_prob + race])) {
+          unsigned cl = 1 + xgc_categorical(d(2), P + XGC_P_prep_adhr_dist, 3);
           hiv = (hiv & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
           short4* q = g.tck + idx; q->z = (short)at; q->w = (short)at;
         }
       }
     }
     if ((mask & XGC_M_STIRECOV) && (gc & 7u)) {
-      Draw d(inj, g, r, at, XGC_S_STIRECOV, uid, 0u, uid);
       const int txpr[3] = { XGC_P_rgc_tx_recov_pr, XGC_P_ugc_tx_recov_pr, XGC_P_pgc_tx_recov_pr };
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
@@ -515,9 +544,9 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
         bool recov = false;
         if (gc & GC_TX(s)) {
           int k = at - (int)txT;
-          if (k >= 1) recov = xgc_bern(d(3 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
+          if (k >= 1) recov = xgc_bern(d(4 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
         } else if ((int)infT < at) {
-          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(s), 1.0 / P[XGC_P_gc_ntx_int + s]);
+          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(4 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
           else recov = (at - (int)infT) >= (int)dur;
         }
         if (recov) {
@@ -530,17 +559,16 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
     }
     if (mask & XGC_M_STITX) {
       int proto = C[XGC_C_stiScreeningProtocol], kissx = C[XGC_C_cdcExposureSite_Kissing];
-      Draw d(inj, g, r, at, XGC_S_STITX, uid, 0u, uid);
       bool sv = false, av = false;
 #pragma unroll
       for (int s = 0; s < 3; ++s)
         if ((gc & GC_ST(s)) && (gc & GC_SY(s)) && !(gc & GC_TX(s))) {
           double rr = s == 0 ? P[XGC_P_rgc_sympt_seek_test_rr] : s == 2 ? P[XGC_P_pgc_sympt_seek_test_rr] : 1.0;
-          if (xgc_bern(d(s), P[XGC_P_ugc_sympt_seek_test_prob] * rr)) sv = true;
+          if (xgc_bern(d(8 + s), P[XGC_P_ugc_sympt_seek_test_prob] * rr)) sv = true;
         }
       unsigned ex = (gc >> GC_EXPO_SHIFT) & 0x1Fu;
       if (!sv) {
-        if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = xgc_bern(d(3), P[XGC_P_gc_asympt_visit_prob]);
+        if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = xgc_bern(d(0), P[XGC_P_gc_asympt_visit_prob]);
         else if (proto == XGC_SCREEN_CDC) {
           bool active = (ex & 7u) || (kissx && (ex & 8u));
           bool hr = (hiv & HV_PREP) || (ex & 16u);
@@ -559,7 +587,7 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
           bool exposed = (ex >> s) & 1u; if (s == 2 && kissx && (ex & 8u)) exposed = true;
           if (proto == XGC_SCREEN_CDC && !symp && !exposed) tested = false;
           else if (proto == XGC_SCREEN_UNIVERSAL) tested = true;
-          else tested = xgc_bern(d(4 + s), symp ? P[XGC_P_gc_sympt_prob_test + s] : P[XGC_P_gc_asympt_prob_test + s]);
+          else tested = xgc_bern(d(12 + s), symp ? P[XGC_P_gc_sympt_prob_test + s] : P[XGC_P_gc_asympt_prob_test + s]);
           if (!tested) continue;
           tst[s] = 1;
           if (inf) {
@@ -585,130 +613,176 @@ __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, c
 #pragma unroll
       for (int s = 0; s < 3; ++s) { warp_tally(row, XGC_K_TESTED + s, tst[s]); warp_tally(row, XGC_K_POS + s, pos[s]); warp_tally(row, XGC_K_TXSTART + s, txs[s]); }
     }
-  }
+  }  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_edge2: hivtrans_msm + stitrans_msm_rand over the site-/sero-discordant edges (sim1_02_lhs.r:214, 217).
 // Condom use and position of each act are evaluated lazily from their indexed draws (condoms_msm, position_msm).
 // New infections are OR-ed into the agents' core words; k_agent3 applies them (unique() semantics).
+//
+// Only a minority of edges is discordant and the per-act loops have different lengths per act type, so a
+// one-thread-per-edge loop runs at ~4 active lanes per warp instruction.  Instead each CTA
+//   1. classifies its 256 edges (record + two 128-bit endpoint gathers, staged in shared memory),
+//   2. ballot-compacts the (edge, act type) pairs that can transmit into a dense work queue, sorted by act type,
+//   3. lets consecutive threads take consecutive queue entries, so warps run one act type with all lanes busy.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_edge2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+__device__ __forceinline__ void e2_flag(uint4* core, const int4& ed, unsigned new_a, unsigned new_b, bool hiv_a, bool hiv_b) {
+  if (new_a) atomicOr(&core[ed.x].z, new_a << GC_NEW_SHIFT);
+  if (new_b) atomicOr(&core[ed.y].z, new_b << GC_NEW_SHIFT);
+  if (hiv_a) atomicOr(&core[ed.x].w, HV_NEW);
+  if (hiv_b) atomicOr(&core[ed.y].w, HV_NEW);
+}
+template <bool INJ> __device__ __noinline__ void e2_anal(const Dev& g, const Inj& inj, unsigned mask, int r, int l, int e, int at, const double* P,
+                                     const int4& ed, const uint4& ca, const uint4& cb, uint4* core, double dt) {
+  EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = ed; x.ca = ca; x.cb = cb; x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+  const Aux* aux = g.aux + (size_t)r * g.n_cap;
+  Aux aa = aux[ed.x], ab = aux[ed.y];
+  int ai = ed.w & 0xFF;
+  unsigned ga = ca.z & 7u, gb = cb.z & 7u;
+  bool hivdisc = (mask & XGC_M_HIVTRANS) && ((ca.w ^ cb.w) & HV_STATUS);
+  bool d_ai = (mask & XGC_M_STITRANS) && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
+                                          (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
+  x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
+  double pc = edge_cond_prob(g, P, x, true);
+  DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dh(inj, g, r, at, x.base + (XGC_S_HIVTRANS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dA(inj, g, r, at, x.base + (XGC_S_GC_AI_A - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dB(inj, g, r, at, x.base + (XGC_S_GC_AI_B - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  bool a_pos = ca.w & HV_STATUS;
+  uint4 cp = a_pos ? ca : cb, cn = a_pos ? cb : ca;
+  double vlf = 0.0; int nrace = (int)DM_RACE(cn.y);
+  if (hivdisc) vlf = xgc_exp(((double)(a_pos ? aa.vl : ab.vl) - 4.5) * XGC_LN_2_45);
+  unsigned gpre_n = (cn.z >> GC_PRE_SHIFT) & 7u;          // negative partner's GC status as hivtrans saw it
+  unsigned new_a = 0, new_b = 0; bool hiv_a = false, hiv_b = false;
+  for (int k = 0; k < ai; ++k) {
+    int uai = xgc_bern(dc(k), 1.0 - pc);
+    int p1ins = edge_ai_p1ins(x, dp, k);
+    if (hivdisc) {
+      bool pos_ins = (p1ins != 0) == a_pos;
+      double t;
+      if (pos_ins) { t = P[XGC_P_urai_prob] * vlf; if (gpre_n & 1u) t = t * P[XGC_P_hiv_rgc_rr]; }
+      else { t = P[XGC_P_uiai_prob] * vlf; if (cn.y & DM_CIRC) t = t * P[XGC_P_circ_rr]; if (gpre_n & 2u) t = t * P[XGC_P_hiv_ugc_rr]; }
+      if (!uai) t = t * (1.0 - P[XGC_P_cond_eff] * (1.0 - P[XGC_P_cond_fail + nrace]));
+      unsigned st = HV_STAGE(cp.w);
+      if (st == 1 || st == 2) t = t * P[XGC_P_acute_rr];
+      if (cn.w & HV_PREP) { unsigned cl = HV_PREPCLASS(cn.w); if (cl >= 1) t = t * P[XGC_P_prep_adhr_hr + cl - 1]; }
+      t = t * P[XGC_P_trans_scale + nrace];
+      if (t > 1.0) t = 1.0;
+      if (xgc_bern(dh(k), t)) { if (a_pos) hiv_b = true; else hiv_a = true; }
+    }
+    if (d_ai) {                                         // insertive partner's urethra <-> receptive partner's rectum
+      unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
+      bool ux = (gx >> 1) & 1u, ry = gy & 1u;
+      if (ux && !ry) {
+        double t = P[XGC_P_u2rgc_tprob];
+        if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? cb.y : ca.y)]));
+        if (xgc_bern(dA(k), t)) { if (p1ins) new_b |= 1u << XGC_PATH_U2R; else new_a |= 1u << XGC_PATH_U2R; }
+      }
+      if (ry && !ux) {
+        double t = P[XGC_P_r2ugc_tprob];
+        if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? ca.y : cb.y)]));
+        if (xgc_bern(dB(k), t)) { if (p1ins) new_a |= 1u << XGC_PATH_R2U; else new_b |= 1u << XGC_PATH_R2U; }
+      }
+    }
+  }
+  e2_flag(core, ed, new_a, new_b, hiv_a, hiv_b);
+}
+// oral (type 1: urethra <-> pharynx) and rimming (type 3: pharynx <-> rectum): direction per act ~ Bernoulli(0.5)
+template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, const Inj& inj, int type, int r, int l, int e, int at, const double* P,
+                                            const int4& ed, const uint4& ca, const uint4& cb, uint4* core) {
+  int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+  bool oral = type == 1;
+  int n = oral ? (ed.w >> 8) & 0xFF : (ed.w >> 24) & 0xFF;
+  unsigned ga = ca.z & 7u, gb = cb.z & 7u;
+  int sx = oral ? 1 : 2, sy = oral ? 2 : 0;                 // active partner's site, other partner's site
+  double tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob], tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
+  unsigned pA = oral ? XGC_PATH_U2P : XGC_PATH_P2R, pB = oral ? XGC_PATH_P2U : XGC_PATH_R2P;
+  DrawT<INJ> dd(inj, g, r, at, base + ((oral ? XGC_S_OIDIR : XGC_S_RIMDIR) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dA(inj, g, r, at, base + ((oral ? XGC_S_GC_OI_A : XGC_S_GC_RIM_A) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dB(inj, g, r, at, base + ((oral ? XGC_S_GC_OI_B : XGC_S_GC_RIM_B) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  unsigned new_a = 0, new_b = 0;
+  for (int k = 0; k < n; ++k) {
+    int p1act = xgc_bern(dd(k), 0.5);
+    unsigned gx = p1act ? ga : gb, gy = p1act ? gb : ga;
+    bool ix = (gx >> sx) & 1u, iy = (gy >> sy) & 1u;
+    if (ix && !iy && xgc_bern(dA(k), tA)) { if (p1act) new_b |= 1u << pA; else new_a |= 1u << pA; }
+    if (iy && !ix && xgc_bern(dB(k), tB)) { if (p1act) new_a |= 1u << pB; else new_b |= 1u << pB; }
+  }
+  e2_flag(core, ed, new_a, new_b, false, false);
+}
+template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const Inj& inj, int r, int l, int e, int at, const double* P,
+                                        const int4& ed, const uint4& ca, const uint4& cb, uint4* core) {
+  int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS, n = (ed.w >> 16) & 0xFF;
+  bool pa = (ca.z >> 2) & 1u;
+  DrawT<INJ> d(inj, g, r, at, base + ((pa ? XGC_S_GC_KISS_A : XGC_S_GC_KISS_B) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  double t = P[XGC_P_p2pgc_tprob];
+  bool hit = false;
+  for (int k = 0; k < n; ++k) hit |= (bool)xgc_bern(d(k), t);
+  if (hit) e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
+}
+
+template <bool INJ> __global__ void __launch_bounds__(TPB, 3) k_edge2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.z, l = blockIdx.y;
   const Rep* rp = g.rep + r;
   int ne = rp->ne[l];
   if ((int)(blockIdx.x * TPB) >= ne) return;
-  int e = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
-  if (e >= ne) return;
+  __shared__ int4 s_ed[TPB];
+  __shared__ uint4 s_ca[TPB], s_cb[TPB];
+  __shared__ unsigned short s_item[4 * TPB];
+  __shared__ unsigned short s_wc[4][TPB / 32];
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int e0 = blockIdx.x * TPB, e = e0 + tid, at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   uint4* core = g.core + (size_t)r * g.n_cap;
-  EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
-  if (x.ed.w == 0) return;
-  x.ca = core[x.ed.x]; x.cb = core[x.ed.y];
-  x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
-  int ai = x.ed.w & 0xFF, oi = (x.ed.w >> 8) & 0xFF, ki = (x.ed.w >> 16) & 0xFF, ri = (x.ed.w >> 24) & 0xFF;
-  unsigned ga = x.ca.z & 7u, gb = x.cb.z & 7u;              // current site status: bit0 r, bit1 u, bit2 p
-  bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((x.ca.w ^ x.cb.w) & HV_STATUS);
-  bool gct = mask & XGC_M_STITRANS;
-  // discordance per act type (either direction)
-  bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
-                                (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
-  bool d_oi = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
-                                (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
-  bool d_ri = gct && ri > 0 && C[XGC_C_transRoute_Rimming] &&
-              (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
-  bool d_ki = gct && ki > 0 && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
-  if (!(hivdisc || d_ai || d_oi || d_ri || d_ki)) return;
-  unsigned new_a = 0, new_b = 0; bool hiv_a = false, hiv_b = false;
-  if (hivdisc || d_ai) {
-    const Aux* aux = g.aux + (size_t)r * g.n_cap;
-    Aux aa = aux[x.ed.x], ab = aux[x.ed.y];
-    double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
-    x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
-    double pc = edge_cond_prob(g, P, x, true);
-    Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dh(inj, g, r, at, x.base + (XGC_S_HIVTRANS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_AI_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_AI_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    // HIV per-act probability pieces that do not depend on the act
-    bool a_pos = x.ca.w & HV_STATUS;
-    uint4 cp = a_pos ? x.ca : x.cb, cn = a_pos ? x.cb : x.ca;
-    double vlf = 0.0; int nrace = (int)DM_RACE(cn.y);
-    if (hivdisc) vlf = xgc_exp(((double)(a_pos ? aa.vl : ab.vl) - 4.5) * XGC_LN_2_45);
-    unsigned gpre_n = (cn.z >> GC_PRE_SHIFT) & 7u;          // negative partner's GC status as hivtrans saw it
-    for (int k = 0; k < ai; ++k) {
-      int uai = xgc_bern(dc(k), 1.0 - pc);
-      int p1ins = edge_ai_p1ins(x, dp, k);
-      if (hivdisc) {
-        bool pos_ins = (p1ins != 0) == a_pos;
-        double t;
-        if (pos_ins) { t = P[XGC_P_urai_prob] * vlf; if (gpre_n & 1u) t = t * P[XGC_P_hiv_rgc_rr]; }
-        else { t = P[XGC_P_uiai_prob] * vlf; if (cn.y & DM_CIRC) t = t * P[XGC_P_circ_rr]; if (gpre_n & 2u) t = t * P[XGC_P_hiv_ugc_rr]; }
-        if (!uai) t = t * (1.0 - P[XGC_P_cond_eff] * (1.0 - P[XGC_P_cond_fail + nrace]));
-        unsigned st = HV_STAGE(cp.w);
-        if (st == 1 || st == 2) t = t * P[XGC_P_acute_rr];
-        if (cn.w & HV_PREP) { unsigned cl = HV_PREPCLASS(cn.w); if (cl >= 1) t = t * P[XGC_P_prep_adhr_hr + cl - 1]; }
-        t = t * P[XGC_P_trans_scale + nrace];
-        if (t > 1.0) t = 1.0;
-        if (xgc_bern(dh(k), t)) { if (a_pos) hiv_b = true; else hiv_a = true; }
-      }
-      if (d_ai) {
-        // x = insertive (urethra), y = receptive (rectum)
-        unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
-        bool ux = (gx >> 1) & 1u, ry = gy & 1u;
-        if (ux && !ry) {
-          double t = P[XGC_P_u2rgc_tprob];
-          if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? x.cb.y : x.ca.y)]));
-          if (xgc_bern(dA(k), t)) { if (p1ins) new_b |= 1u << XGC_PATH_U2R; else new_a |= 1u << XGC_PATH_U2R; }
-        }
-        if (ry && !ux) {
-          double t = P[XGC_P_r2ugc_tprob];
-          if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? x.ca.y : x.cb.y)]));
-          if (xgc_bern(dB(k), t)) { if (p1ins) new_a |= 1u << XGC_PATH_R2U; else new_b |= 1u << XGC_PATH_R2U; }
-        }
-      }
+  // ---- 1. classify
+  bool f[4] = { false, false, false, false };
+  if (e < ne) {
+    int4 ed = E[e];
+    if (ed.w != 0) {
+      uint4 ca = core[ed.x], cb = core[ed.y];
+      s_ed[tid] = ed; s_ca[tid] = ca; s_cb[tid] = cb;
+      int ai = ed.w & 0xFF, oi = (ed.w >> 8) & 0xFF, ki = (ed.w >> 16) & 0xFF, ri = (ed.w >> 24) & 0xFF;
+      unsigned ga = ca.z & 7u, gb = cb.z & 7u;              // current site status: bit0 rect, bit1 ureth, bit2 phar
+      bool gct = mask & XGC_M_STITRANS;
+      bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((ca.w ^ cb.w) & HV_STATUS);
+      bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
+                                    (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
+      f[0] = hivdisc || d_ai;
+      f[1] = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
+                               (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
+      f[2] = gct && ki > 0 && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
+      f[3] = gct && ri > 0 && C[XGC_C_transRoute_Rimming] &&
+             (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
     }
   }
-  if (d_oi) {
-    Draw dd(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_OI_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_OI_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    for (int k = 0; k < oi; ++k) {
-      int p1ins = xgc_bern(dd(k), 0.5);
-      unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
-      bool ux = (gx >> 1) & 1u, py = (gy >> 2) & 1u;
-      if (ux && !py && xgc_bern(dA(k), P[XGC_P_u2pgc_tprob])) { if (p1ins) new_b |= 1u << XGC_PATH_U2P; else new_a |= 1u << XGC_PATH_U2P; }
-      if (py && !ux && xgc_bern(dB(k), P[XGC_P_p2ugc_tprob])) { if (p1ins) new_a |= 1u << XGC_PATH_P2U; else new_b |= 1u << XGC_PATH_P2U; }
-    }
+  // ---- 2. compact (edge, type) pairs into a queue sorted by type
+  unsigned b[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { b[t] = __ballot_sync(0xffffffffu, f[t]); if (lane == 0) s_wc[t][w] = (unsigned short)__popc(b[t]); }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < TPB / 32; ++k) { int c = s_wc[t][k]; all += c; if (k < w) before += c; }
+    if (f[t]) s_item[total + before + __popc(b[t] & ((1u << lane) - 1u))] = (unsigned short)((t << 8) | tid);
+    total += all;
   }
-  if (d_ri) {
-    Draw dd(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_RIM_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_RIM_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    for (int k = 0; k < ri; ++k) {
-      int p1rim = xgc_bern(dd(k), 0.5);
-      unsigned gx = p1rim ? ga : gb, gy = p1rim ? gb : ga;      // x = rimmer (pharynx), y = rimmee (rectum)
-      bool px = (gx >> 2) & 1u, ry = gy & 1u;
-      if (px && !ry && xgc_bern(dA(k), P[XGC_P_p2rgc_tprob])) { if (p1rim) new_b |= 1u << XGC_PATH_P2R; else new_a |= 1u << XGC_PATH_P2R; }
-      if (ry && !px && xgc_bern(dB(k), P[XGC_P_r2pgc_tprob])) { if (p1rim) new_a |= 1u << XGC_PATH_R2P; else new_b |= 1u << XGC_PATH_R2P; }
-    }
+  __syncthreads();
+  // ---- 3. dense processing
+  double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
+  for (int i = tid; i < total; i += TPB) {
+    int item = s_item[i], type = item >> 8, le = item & 0xFF;
+    int4 ed = s_ed[le]; uint4 ca = s_ca[le], cb = s_cb[le];
+    if (type == 0) e2_anal<INJ>(g, inj, mask, r, l, e0 + le, at, P, ed, ca, cb, core, dt);
+    else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e0 + le, at, P, ed, ca, cb, core);
+    else e2_directed<INJ>(g, inj, type, r, l, e0 + le, at, P, ed, ca, cb, core);
   }
-  if (d_ki) {
-    Draw dA(inj, g, r, at, x.base + (XGC_S_GC_KISS_A - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    Draw dB(inj, g, r, at, x.base + (XGC_S_GC_KISS_B - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-    bool pa = (ga >> 2) & 1u;
-    for (int k = 0; k < ki; ++k) {
-      if (pa) { if (xgc_bern(dA(k), P[XGC_P_p2pgc_tprob])) new_b |= 1u << XGC_PATH_P2P; }
-      else    { if (xgc_bern(dB(k), P[XGC_P_p2pgc_tprob])) new_a |= 1u << XGC_PATH_P2P; }
-    }
-  }
-  if (new_a) atomicOr(&core[x.ed.x].z, new_a << GC_NEW_SHIFT);
-  if (new_b) atomicOr(&core[x.ed.y].z, new_b << GC_NEW_SHIFT);
-  if (hiv_a) atomicOr(&core[x.ed.x].w, HV_NEW);
-  if (hiv_b) atomicOr(&core[x.ed.y].w, HV_NEW);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -716,29 +790,35 @@ __global__ void __launch_bounds__(TPB) k_edge2(const __grid_constant__ Dev g, co
 // prevalence_msm (sim1_02_lhs.r:218).  Per-CTA shared-memory histogram, one flush per CTA.
 // ---------------------------------------------------------------------------------------------------------------------
 #define A3_NHIST (XGC_K_NGROUP * XGC_NCELL + XGC_NPATH)
-__global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
+  const size_t rbase = (size_t)r * g.n_cap;
+  uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
   int n_slots = rp->n_slots;
-  if ((int)(blockIdx.x * TPB) >= n_slots) return;
+  int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
+  if (t0 >= t1) return;
   __shared__ unsigned hist[A3_NHIST];
   for (int k = threadIdx.x; k < A3_NHIST; k += TPB) hist[k] = 0u;
   __syncthreads();
-  int i = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
-  size_t idx = (size_t)r * g.n_cap + i;
+  int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  for (int t = t0; t < t1; ++t) {
+  int i = t * TPB + threadIdx.x;
+  size_t idx = rbase + i;
+  uint4 c = cn;
+  if (t + 1 < t1) cn = g.core[idx + TPB];
   bool live = i < n_slots;
-  uint4 c = live ? g.core[idx] : make_uint4(0, 0, 0, 0);
   live = live && (c.y & DM_ACTIVE);
+  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w, cell = DM_CELL(demo);
   if (live) {
-    unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w, cell = DM_CELL(demo);
     unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
     if (nm && (mask & XGC_M_STITRANS)) {
       short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
       bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
       if (pois) gd = g.gck_d[idx];
-      Draw d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
+      DrawT<INJ> d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
       const unsigned site_mask[3] = { (1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R), (1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U),
                                       (1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P) };
 #pragma unroll
@@ -760,7 +840,7 @@ __global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, c
     if (mask & XGC_M_STITRANS) gc &= ~GC_NEW_MASK;
     if ((hiv & HV_NEW) && (mask & XGC_M_HIVTRANS)) {
       if (!(hiv & HV_STATUS)) {
-        hiv = (hiv & ~(HV_STAGE_MASK | HV_DIAG | HV_TX)) | HV_STATUS | (1u << 1);
+        hiv = (hiv & ~(HV_STAGE_MASK | HV_DIAG | HV_TX)) | HV_STATUS | HV_VSUPP | (1u << 1);
         short4 ha = g.hck_a[idx]; ha.x = (short)at; ha.z = (short)at; g.hck_a[idx] = ha;
         short4 hb = g.hck_b[idx]; hb.x = 0; hb.y = 0; g.hck_b[idx] = hb;
         g.aux[idx].vl = 0.f;
@@ -769,21 +849,26 @@ __global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, c
     }
     if (mask & XGC_M_HIVTRANS) hiv &= ~HV_NEW;
     if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
-    if (mask & XGC_M_PREV) {
-      atomicAdd(&hist[XGC_K_NUM * XGC_NCELL + cell], 1u);
-      if (hiv & HV_STATUS) atomicAdd(&hist[XGC_K_INUM * XGC_NCELL + cell], 1u);
-      if (hiv & HV_DIAG) {
-        atomicAdd(&hist[XGC_K_INUM_DX * XGC_NCELL + cell], 1u);
-        if ((double)g.aux[idx].vl <= XGC_LOG10_200) atomicAdd(&hist[XGC_K_VSUPP * XGC_NCELL + cell], 1u);
-      }
-      if (hiv & HV_PREPELIG) atomicAdd(&hist[XGC_K_PREPELIG * XGC_NCELL + cell], 1u);
-      if (hiv & HV_PREP) atomicAdd(&hist[XGC_K_PREPCURR * XGC_NCELL + cell], 1u);
-      if (gc & 7u) {
-        atomicAdd(&hist[XGC_K_INUM_GC * XGC_NCELL + cell], 1u);
-#pragma unroll
-        for (int s = 0; s < 3; ++s) if (gc & GC_ST(s)) atomicAdd(&hist[(XGC_K_INUM_RGC + s) * XGC_NCELL + cell], 1u);
-      }
-    }
+  }
+  if (mask & XGC_M_PREV) {
+    // warp-aggregated tallies: lanes of the same (race, age group) cell vote, one shared-memory add per cell and series
+    unsigned lane = threadIdx.x & 31;
+    unsigned grp = __match_any_sync(0xffffffffu, live ? cell : 31u);
+    bool leader = live && lane == (unsigned)(__ffs(grp) - 1);
+#define A3_TALLY(group, pred) { unsigned m_ = __ballot_sync(0xffffffffu, live && (pred)) & grp; \
+                                if (leader && m_) atomicAdd(&hist[(group) * XGC_NCELL + cell], (unsigned)__popc(m_)); }
+    A3_TALLY(XGC_K_NUM, true)
+    A3_TALLY(XGC_K_INUM, hiv & HV_STATUS)
+    A3_TALLY(XGC_K_INUM_DX, hiv & HV_DIAG)
+    A3_TALLY(XGC_K_VSUPP, (hiv & HV_DIAG) && (hiv & HV_VSUPP))
+    A3_TALLY(XGC_K_PREPELIG, hiv & HV_PREPELIG)
+    A3_TALLY(XGC_K_PREPCURR, hiv & HV_PREP)
+    A3_TALLY(XGC_K_INUM_GC, gc & 7u)
+    A3_TALLY(XGC_K_INUM_RGC, gc & 1u)
+    A3_TALLY(XGC_K_INUM_UGC, gc & 2u)
+    A3_TALLY(XGC_K_INUM_PGC, gc & 4u)
+#undef A3_TALLY
+  }
   }
   __syncthreads();
   unsigned* row = counter_row(g, r, at);
@@ -897,7 +982,7 @@ __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ D
 }
 
 // k_actlist: materialise dat$temp$al for one replicate (debug / parity of condoms_msm + position_msm)
-__global__ void k_actlist(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* al, int cap, int* n_out) {
+template <bool INJ> __global__ void k_actlist(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* al, int cap, int* n_out) {
   // single thread: tiny test-only kernel, rows must come out in (layer, edge, type, k) order
   if (blockIdx.x || threadIdx.x) return;
   const Rep* rp = g.rep + r;
@@ -915,10 +1000,10 @@ __global__ void k_actlist(const __grid_constant__ Dev g, const __grid_constant__
       x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
       int cnt[4] = { x.ed.w & 0xFF, (x.ed.w >> 8) & 0xFF, (x.ed.w >> 16) & 0xFF, (x.ed.w >> 24) & 0xFF };
       double pc = cnt[0] > 0 ? edge_cond_prob(g, P, x, false) : 0.0;
-      Draw dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      Draw dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      Draw doi(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      Draw dri(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> doi(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> dri(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
       for (int type = 0; type < 4; ++type)
         for (int k = 0; k < cnt[type]; ++k) {
           int uai = 0, p1 = 0;

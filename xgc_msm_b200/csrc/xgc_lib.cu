@@ -33,7 +33,7 @@ struct xgc_handle {
   int last_at = -1;
   HostRep cache;
   double* d_inj = nullptr; size_t d_inj_cap = 0;
-  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr;
+  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
   bool profiling = false;
@@ -111,9 +111,10 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &dp, (size_t)g.R * XGC_NPARAM); rc |= dalloc(h, &dc, (size_t)g.R * XGC_NCONTROL);
   rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
   rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
+  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
-  g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat;
+  g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat; g.pois = h->d_pois;
   // defaults: parameter defaults from params.def, kissing/rimming routes on
   std::vector<double> P(XGC_NPARAM);
 #define XGC_PARAM(name, count, v) for (int k = 0; k < (count); ++k) P[XGC_P_##name + k] = (v);
@@ -145,19 +146,26 @@ extern "C" int xgc_stream_ptr(xgc_handle* h, void** s) { *s = (void*)h->stream; 
 // --------------------------------------------------------------------------------------------------------------------
 // configuration
 // --------------------------------------------------------------------------------------------------------------------
+static int derive(xgc_handle* h) {       // per-replicate tables that depend on the parameters
+  int n = h->g.R * 4;
+  k_derive<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_pois);
+  CU(h, cudaGetLastError());
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
 extern "C" int xgc_set_params(xgc_handle* h, int r, const double* p) {
   CU(h, cudaSetDevice(h->cfg.device));
   if (r >= h->cfg.n_replicates) FAIL(h, 2, "replicate out of range");
   CU(h, cudaStreamSynchronize(h->stream));
   for (int k = r < 0 ? 0 : r; k < (r < 0 ? h->cfg.n_replicates : r + 1); ++k)
     CU(h, cudaMemcpy((double*)h->g.params + (size_t)k * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM, cudaMemcpyHostToDevice));
-  return 0;
+  return derive(h);
 }
 extern "C" int xgc_set_params_all(xgc_handle* h, const double* p /*[R][XGC_NPARAM]*/) {
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemcpy((double*)h->g.params, p, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates, cudaMemcpyHostToDevice));
-  return 0;
+  return derive(h);
 }
 extern "C" int xgc_get_params(xgc_handle* h, int r, double* p) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
@@ -278,7 +286,7 @@ static std::vector<AttrDef> build_attrs() {
   A.push_back({"cuml.time.on.tx", [](const HostRep& c, int i) { return (double)c.hck_b[i].x; }, [](HostRep& c, int i, double v) { c.hck_b[i].x = S16(v); }});
   A.push_back({"cuml.time.off.tx", [](const HostRep& c, int i) { return (double)c.hck_b[i].y; }, [](HostRep& c, int i, double v) { c.hck_b[i].y = S16(v); }});
   A.push_back({"tx.init.time", [](const HostRep& c, int i) { return (double)c.hck_a[i].w; }, [](HostRep& c, int i, double v) { c.hck_a[i].w = S16(v); }});
-  A.push_back({"vl", [](const HostRep& c, int i) { return (double)c.aux[i].vl; }, [](HostRep& c, int i, double v) { c.aux[i].vl = (float)v; }});
+  A.push_back({"vl", [](const HostRep& c, int i) { return (double)c.aux[i].vl; }, [](HostRep& c, int i, double v) { c.aux[i].vl = (float)v; setbits(c.core[i].w, 1u, 11, (double)((double)(float)v <= XGC_LOG10_200)); }});
   A.push_back({"prepStat", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 6) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 6, v); }});
   A.push_back({"prepClass", [](const HostRep& c, int i) { return (double)HV_PREPCLASS(c.core[i].w); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 3u, 7, v); }});
   A.push_back({"prepElig", [](const HostRep& c, int i) { return (double)((c.core[i].w >> 9) & 1u); }, [](HostRep& c, int i, double v) { setbits(c.core[i].w, 1u, 9, v); }});
@@ -309,7 +317,7 @@ extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
   short4 na = make_short4(-1, -1, -1, -1);
   c.gck_a.assign(n, na); c.gck_b.assign(n, na); c.gck_d.assign(n, na); c.hck_a.assign(n, na);
   c.hck_b.assign(n, make_short4(0, 0, -1, -1)); c.tck.assign(n, na); c.arr_t.assign(n, at);
-  for (int i = 0; i < n; ++i) c.core[i] = make_uint4((unsigned)i, DM_ACTIVE | (2u << 12), 0u, 0u);
+  for (int i = 0; i < n; ++i) c.core[i] = make_uint4((unsigned)i, DM_ACTIVE | (2u << 12), 0u, HV_VSUPP);
   for (int l = 0; l < 3; ++l) c.edge[l].clear();
   rebuild_maps(c);
   c.r = r; c.dirty = true;
@@ -429,28 +437,35 @@ static void prof_begin(xgc_handle* h, const char* name) {
 }
 static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream); }
 #define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
+// kernels that draw: native instantiation unless an injected table is attached
+#define LAUNCHD(h, inj, kern, grid, block, ...) do { prof_begin(h, #kern); \
+  if ((inj).u) kern<true><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); else kern<false><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); \
+  prof_end(h); (h)->launches++; } while (0)
 
 // enqueue one week.  at_host < 0: week = previous + 1 (graph replay).
 static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& inj, int zero_row) {
   const Dev& g = h->g;
-  dim3 ga((g.n_cap + TPB - 1) / TPB, g.R);
+  // agent kernels: tiles per CTA chosen so the grid stays a few waves of the 148 SMs
+  int tiles = (g.n_cap + TPB - 1) / TPB;
+  int tpc = std::max(1, std::min(tiles, (int)(((long long)tiles * g.R) / (148 * 16))));
+  dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
-  LAUNCH(h, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
+  LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   if (zero_row || (mask & (XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL)))
-    LAUNCH(h, k_agent1, ga, TPB, g, inj, mask, zero_row);
+    LAUNCHD(h, inj, k_agent1, ga, TPB, g, inj, mask, zero_row, tpc);
   bool native = inj.u == nullptr;
-  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
+  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
   if (mask & XGC_M_RESIM_NETS) {
-    LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, inj, 1);
+    LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 1);
     LAUNCH(h, k_rank, g.R, TPB, g);
-    LAUNCH(h, k_form, dim3(3, g.R), TPB, g, inj);
+    LAUNCHD(h, inj, k_form, dim3(3, g.R), TPB, g, inj);
   }
-  if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCH(h, k_edge1, ge, TPB, g, inj, mask);
-  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCH(h, k_agent2, ga, TPB, g, inj, mask);
-  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCH(h, k_edge2, ge, TPB, g, inj, mask);
-  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3, ga, TPB, g, inj, mask);
+  if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, ge, TPB, g, inj, mask);
+  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2, ga, TPB, g, inj, mask, tpc);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCHD(h, inj, k_edge2, ge, TPB, g, inj, mask);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCHD(h, inj, k_agent3, ga, TPB, g, inj, mask, tpc);
   return 0;
 }
 
@@ -472,7 +487,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
-  LAUNCH(h, k_edges_resim, dim3(3, g.R), TPB, g, make_inj(h, nullptr, nullptr), 0);   // no dangling endpoints before re-numbering
+  { Inj inj = make_inj(h, nullptr, nullptr); LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0); }   // no dangling endpoints before re-numbering
   LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
   LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
   CU(h, cudaGetLastError());
@@ -548,7 +563,7 @@ extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int ca
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
   int* d_al; CU(h, cudaMalloc((void**)&d_al, sizeof(int) * 6 * (size_t)std::max(cap, 1)));
   CU(h, cudaMemcpyAsync((int*)h->g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(h, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
+  LAUNCHD(h, j, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
   int n = 0;
   cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t e2 = cudaStreamSynchronize(h->stream);
@@ -729,7 +744,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
   h->last_at = -1;
-  return 0;
+  return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   CHECK_R(src, sr); CHECK_R(dst, dr);
