@@ -109,8 +109,8 @@ enum xgc_stream {
   /* agent streams */
   XGC_S_AGENT1 = 0,    /* aging..hivvl pass: k0 natural mortality, k1 AIDS mortality, k2 HIV interval test,
                           k3 HIV treatment transition (initiation | halting | re-initiation: mutually exclusive)            */
-  XGC_S_AGENT2,        /* prep/stirecov/stitx pass: k0 asymptomatic clinic visit, k1 PrEP start | discontinuation,
-                          k2 PrEP adherence class; k4..6 recovery r,u,p (treated | untreated: exclusive per site);
+  XGC_S_AGENT2,        /* prep/stirecov/stitx pass: k0 asymptomatic clinic visit, k1..3 recovery r,u,p (treated |
+                          untreated: exclusive per site); k4 PrEP start | discontinuation, k5 PrEP adherence class;
                           k8..10 symptomatic care seeking r,u,p; k12..14 site tested r,u,p                                    */
   XGC_S_INFECT,        /* k0..2 symptomatic r,u,p; k3..5 Poisson duration r,u,p                                     */
   XGC_S_ARRIVE_ATTR,   /* k0 race, k1 role, k2 ins.quot, k3 circ, k4 late.tester, k5 tt.traj, k6 act.stopper, k7 risk.grp */
@@ -204,7 +204,7 @@ enum xgc_counter_scalar {
   XGC_K_NNEW,
   XGC_K_HIVTESTS,
   XGC_K_NEDGES,                    /* [3] edges per layer after resim                                               */
-  XGC_K_NACTS = XGC_K_NEDGES + 3,  /* [4] total anal, oral, kissing, rimming acts                                   */
+  XGC_K_NACTS = XGC_K_NEDGES + 3,  /* [4] total anal, oral acts; [2],[3] reserved (kissing / rimming are evaluated lazily)   */
   XGC_NCOUNTER_RAW = XGC_K_NACTS + 4
 };
 #define XGC_NCOUNTER ((XGC_NCOUNTER_RAW + 3) & ~3)
@@ -299,6 +299,8 @@ int  xgc_attr_names   (const char** names, int cap);           /* returns the nu
 int  xgc_set_edgelist (xgc_handle* h, int r, int layer, const int32_t* el /*[E,2] col-major, 1-based*/, int n_edges,
                        const int32_t* start_time /*[E] or NULL -> current week*/);
 int  xgc_get_edgelist (xgc_handle* h, int r, int layer, int32_t* el, int cap, int* n_edges, int32_t* start_time);
+/* dat$temp$el act counts of the current week; defined from acts_msm to the end of that week (kissing / rimming counts are
+ * evaluated lazily on the hot path and materialised by this call). */
 int  xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts /*[E,4] col-major: ai,oi,kiss,rim*/, int cap,
                        int* n_edges);
 /* materialise the act list of week `at` (dat$temp$al): rows (layer, edge index, act type 0 ai/1 oi/2 kiss/3 rim,

@@ -126,10 +126,14 @@ int orc_bern(double u, double p) {
 
 /* single-uniform Poisson by CDF walk, truncated at kmax (own definition) */
 int orc_pois(double u, double mu, int kmax) {
+  /* p_k = p_{k-1} * mu * (1/k) with correctly rounded reciprocal constants for k <= 32, a true division beyond */
+  static const double INVK[33] = { 0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+    1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24,
+    1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32 };
   if (!(mu > 0.0)) return 0;
   double pr = orc_exp(-mu), cdf = pr;
   int k = 0;
-  while (u > cdf && k < kmax) { k++; pr = pr * mu / (double)k; cdf = cdf + pr; }
+  while (u > cdf && k < kmax) { k++; pr = k <= 32 ? pr * mu * INVK[k] : pr * mu / (double)k; cdf = cdf + pr; }
   return k;
 }
 
@@ -519,8 +523,7 @@ static void acts_msm(orc_dat* d, int at) {
           g->rim = orc_bern(U(d, at, es, ua, ub, (size_t)e, 3), p[XGC_P_rim_prob_oo]);
         }
       }
-      c[XGC_K_NACTS] += (uint32_t)g->ai; c[XGC_K_NACTS + 1] += (uint32_t)g->oi;
-      c[XGC_K_NACTS + 2] += (uint32_t)g->kiss; c[XGC_K_NACTS + 3] += (uint32_t)g->rim;
+      c[XGC_K_NACTS] += (uint32_t)g->ai; c[XGC_K_NACTS + 1] += (uint32_t)g->oi;     /* kissing / rimming are not tallied */
       /* exposure history for the CDC screening protocol (ambiguity A4) */
       for (int side = 0; side < 2; ++side) {
         int i = side ? b : a, role = (int)d->a[A_ROLE][i], ex = (int)d->a[A_EXPO][i];
@@ -636,15 +639,15 @@ static void prep_msm(orc_dat* d, int at) {
     if ((int)d->a[A_PREPSTAT][i] == 1) {
       int stop = 0;
       if (diag == 1) stop = 1;
-      else if (orc_bern(UA(XGC_S_AGENT2, i, 1), p[XGC_P_prep_discont_rate + race])) stop = 1;
+      else if (orc_bern(UA(XGC_S_AGENT2, i, 4), p[XGC_P_prep_discont_rate + race])) stop = 1;
       else if ((int)d->a[A_LNT][i] == at && (double)at - d->a[A_PREPLR][i] >= p[XGC_P_prep_reassess_int]) {
         if (!ind) stop = 1; else d->a[A_PREPLR][i] = at;
       }
       if (stop) { d->a[A_PREPSTAT][i] = 0; d->a[A_PREPCLASS][i] = 0; }
     } else if (diag == 0 && (double)at >= p[XGC_P_prep_start] && (int)d->a[A_LNT][i] == at && ind) {
-      if (orc_bern(UA(XGC_S_AGENT2, i, 1), p[XGC_P_prep_start_prob + race])) {
+      if (orc_bern(UA(XGC_S_AGENT2, i, 4), p[XGC_P_prep_start_prob + race])) {
         d->a[A_PREPSTAT][i] = 1; d->a[A_PREPSTART][i] = at; d->a[A_PREPLR][i] = at;
-        d->a[A_PREPCLASS][i] = 1 + categorical(UA(XGC_S_AGENT2, i, 2), p + XGC_P_prep_adhr_dist, 3);
+        d->a[A_PREPCLASS][i] = 1 + categorical(UA(XGC_S_AGENT2, i, 5), p + XGC_P_prep_adhr_dist, 3);
       }
     }
   }
@@ -697,9 +700,9 @@ static void stirecov_msm(orc_dat* d, int at) {
       int recov = 0;
       if ((int)d->a[A_GC_TX + s][i] == 1) {
         int k = at - (int)d->a[A_GC_TXT + s][i];
-        if (k >= 1) recov = orc_bern(UA(XGC_S_AGENT2, i, 4 + s), p[txpr[s] + (k >= 3 ? 2 : k - 1)]);
+        if (k >= 1) recov = orc_bern(UA(XGC_S_AGENT2, i, 1 + s), p[txpr[s] + (k >= 3 ? 2 : k - 1)]);
       } else if (d->a[A_GC_INF + s][i] < (double)at) {
-        if (d->c[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = orc_bern(UA(XGC_S_AGENT2, i, 4 + s), 1.0 / p[XGC_P_gc_ntx_int + s]);
+        if (d->c[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = orc_bern(UA(XGC_S_AGENT2, i, 1 + s), 1.0 / p[XGC_P_gc_ntx_int + s]);
         else recov = (double)at - d->a[A_GC_INF + s][i] >= d->a[A_GC_DUR + s][i];
       }
       if (recov) {

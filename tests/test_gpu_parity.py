@@ -47,7 +47,7 @@ def test_full_step_native_draws(recov, protocol, kiss):
     h = load_handle(cases, SEED, replicate_offset=40)
     orcs = [load_oracle(c, SEED, 40 + r) for r, c in enumerate(cases)]
     for r, o in enumerate(orcs):
-        compare_state(h, r, o, 1, f"after upload r={r}")
+        compare_state(h, r, o, 1, f"after upload r={r}", acts=False)
     for at in range(2, 2 + weeks):
         h.step(at)
         for r, o in enumerate(orcs):
@@ -65,7 +65,7 @@ def test_full_step_native_draws(recov, protocol, kiss):
              "rectal infections": tot[K.K_INCID_RGC * G:(K.K_INCID_RGC + 1) * G].sum(), "urethral infections": tot[K.K_INCID_UGC * G:(K.K_INCID_UGC + 1) * G].sum(),
              "pharyngeal infections": tot[K.K_INCID_PGC * G:(K.K_INCID_PGC + 1) * G].sum(), "visits": tot[K.K_VISITS],
              "positives": tot[K.K_POS:K.K_POS + 3].sum(), "treatments": tot[K.K_TXSTART:K.K_TXSTART + 3].sum(),
-             "anal acts": tot[K.K_NACTS], "kissing acts": tot[K.K_NACTS + 2], "edges": tot[K.K_NEDGES:K.K_NEDGES + 3].min()}
+             "anal acts": tot[K.K_NACTS], "oral acts": tot[K.K_NACTS + 1], "edges": tot[K.K_NEDGES:K.K_NEDGES + 3].min()}
     for p in range(K.NPATH):
         fired[f"pathway {p}"] = tot[K.K_PATH + p]
     assert all(v > 0 for v in fired.values()), fired
@@ -82,7 +82,7 @@ def test_module_by_module_contract():
             bit = P.MODULE_BIT[name]
             h.step(at, bit)
             o.step(at, bit)
-            compare_state(h, 0, o, at, f"week {at} after {name}")
+            compare_state(h, 0, o, at, f"week {at} after {name}", acts=P.MODULE_ORDER.index(name) >= P.MODULE_ORDER.index("acts"))
 
 
 def test_injected_draws_bit_exact():

@@ -86,6 +86,8 @@ struct Dev {                 // everything a kernel needs; passed by value
   int4* edge;                // [R][e_stride]: layer l at e_off[l]
   Rep* rep; const double* params; const int* control; const double* tables;
   const double* pois;        // [R][4][XGC_MAX_ACTS+1] Poisson CDF tables of the constant weekly rates: kiss main/casual, rim main/casual
+  unsigned* q_items;         // [R][4][e_stride] work queue of k_edge2: (layer << 28 | edge index) per act type
+  unsigned* q_count;         // [R][4]
   unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
   const int* at_ptr;
 };
@@ -144,11 +146,19 @@ __device__ __forceinline__ double xgc_exp(double x) {
   return q * __longlong_as_double((k + 1023) << 52);
 }
 __device__ __forceinline__ int xgc_bern(double u, double p) { return p <= 0.5 ? (u >= 1.0 - p) : (u < p); }
+// pr_k = pr_{k-1} * mu * (1/k): the reciprocals 1/1..1/32 are correctly rounded constants (no division in the hot loop);
+// beyond 32 (arrival counts only) a true division is used.  The oracle does exactly the same.
+__constant__ double XGC_INVK[33] = { 0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12,
+                                     1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23,
+                                     1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32 };
+__device__ __forceinline__ double xgc_pois_next(double pr, double mu, int k) {
+  return k <= 32 ? pr * mu * XGC_INVK[k] : pr * mu / (double)k;
+}
 __device__ __forceinline__ int xgc_pois(double u, double mu, int kmax) {
   if (!(mu > 0.0)) return 0;
   double pr = xgc_exp(-mu), cdf = pr;
   int k = 0;
-  while (u > cdf && k < kmax) { k++; pr = pr * mu / (double)k; cdf = cdf + pr; }
+  while (u > cdf && k < kmax) { k++; pr = xgc_pois_next(pr, mu, k); cdf = cdf + pr; }
   return k;
 }
 // same walk on a precomputed table tab[k] = cdf_k (built with the identical recurrence by k_derive): bit-identical result

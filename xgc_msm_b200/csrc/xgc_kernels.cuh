@@ -38,7 +38,7 @@ __global__ void k_derive(const __grid_constant__ Dev g, double* pois) {
   if (!(mu > 0.0)) { for (int k = 0; k <= XGC_MAX_ACTS; ++k) tab[k] = __longlong_as_double(0x7ff0000000000000LL); return; }
   double pr = xgc_exp(-mu), cdf = pr;
   tab[0] = cdf;
-  for (int k = 1; k <= XGC_MAX_ACTS; ++k) { pr = pr * mu / (double)k; cdf = cdf + pr; tab[k] = cdf; }
+  for (int k = 1; k <= XGC_MAX_ACTS; ++k) { pr = xgc_pois_next(pr, mu, k); cdf = cdf + pr; tab[k] = cdf; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -56,6 +56,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   int n_slots = rp->n_slots, t_ref = rp->t_ref;
   int t_age = (mask & XGC_M_AGING) ? at : rp->t_age;
   __syncwarp();
+  if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
   if (lane == 0) {
     ((int*)g.at_ptr)[r] = at;
     rp->n_slots_pre = n_slots;
@@ -399,6 +400,34 @@ template <class D> __device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x
   return xgc_bern(dpos(k), pi);
 }
 
+// kissing / rimming counts of one edge-week: constant-rate Poisson (main, casual) or Bernoulli (one-off), gated by the
+// act-stopper rule on the START-of-week symptom / treatment bits (acts_msm runs before stirecov / stitx).
+// tab = g.pois + (r*4 + layer)*33: kissing CDF at tab, rimming CDF at tab + 2*33.
+__device__ __forceinline__ int pois_count(double u, const double* tab) {
+  int k = 0;
+#pragma unroll 1
+  for (int j = 0; j < XGC_MAX_ACTS; j += 8) {
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c += u > tab[j + q];
+    k += c;
+    if (c < 8) break;
+  }
+  return k;
+}
+template <class D> __device__ __forceinline__ void edge_kiss_rim(const double* P, int l, const uint4& ca, const uint4& cb, D& dacts,
+                                                                 const double* tab, bool want_k, bool want_r, int& ki, int& ri) {
+  ki = ri = 0;
+  if (act_stopped(ca.y, ca.z >> GC_PRE_SHIFT) || act_stopped(cb.y, cb.z >> GC_PRE_SHIFT)) return;
+  if (l < 2) {
+    if (want_k) ki = pois_count(dacts(2), tab);
+    if (want_r) ri = pois_count(dacts(3), tab + 2 * (XGC_MAX_ACTS + 1));
+  } else {
+    if (want_k) ki = xgc_bern(dacts(2), P[XGC_P_kiss_prob_oo]);
+    if (want_r) ri = xgc_bern(dacts(3), P[XGC_P_rim_prob_oo]);
+  }
+}
+
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.z, l = blockIdx.y;
@@ -412,7 +441,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_
   uint4* core = g.core + (size_t)r * g.n_cap;
   const Aux* aux = g.aux + (size_t)r * g.n_cap;
   bool live = e < ne;
-  unsigned nai = 0, noi = 0, nki = 0, nri = 0;
+  unsigned nai = 0, noi = 0;
   if (live) {
     EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
     x.ca = core[x.ed.x]; x.cb = core[x.ed.y];
@@ -433,9 +462,11 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_
           double roi = xgc_exp(xgc_glm_eta(g.tables + XGC_T_GLM_OI, dur, l == 1, ca, hcp, 0, r1, r2)) / 52.0 * P[XGC_P_oi_acts_scale_mc];
           ai = compat ? xgc_pois(d(0), rai, XGC_MAX_ACTS) : 0;
           oi = xgc_pois(d(1), roi, XGC_MAX_ACTS);
+          // kissing / rimming: only "any act this week" is needed here (exposure history); the counts are evaluated
+          // lazily by k_edge2 for the edges where they can transmit (same indexed draws, same table)
           const double* pt = g.pois + ((size_t)r * 4 + l) * (XGC_MAX_ACTS + 1);
-          ki = xgc_pois_tab(d(2), pt);
-          ri = xgc_pois_tab(d(3), pt + 2 * (XGC_MAX_ACTS + 1));
+          ki = d(2) > pt[0];
+          ri = d(3) > pt[2 * (XGC_MAX_ACTS + 1)];
         } else {
           ai = compat ? 1 : 0;
           oi = xgc_bern(d(1), P[XGC_P_oi_prob_oo]);
@@ -443,9 +474,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_
           ri = xgc_bern(d(3), P[XGC_P_rim_prob_oo]);
         }
       }
-      x.ed.w = ai | (oi << 8) | (ki << 16) | (ri << 24);
+      x.ed.w = ai | (oi << 8);
       E[e].w = x.ed.w;
-      nai = ai; noi = oi; nki = ki; nri = ri;
+      nai = ai; noi = oi;
       // exposure history for the CDC screening protocol (ambiguity A4)
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
@@ -475,7 +506,6 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_
   }
   if (mask & XGC_M_ACTS) {
     warp_tally_n(row, XGC_K_NACTS, nai); warp_tally_n(row, XGC_K_NACTS + 1, noi);
-    warp_tally_n(row, XGC_K_NACTS + 2, nki); warp_tally_n(row, XGC_K_NACTS + 3, nri);
   }
 }
 
@@ -505,7 +535,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
   int race = (int)DM_RACE(demo);
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
   if (live) {
-    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);     // block 0 (visit, PrEP) is all most agents ever draw
+    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);     // block 0 (clinic visit, recovery r,u,p) is all most agents ever draw
     short4 tk = na4();
     bool ind_sti = false;
     // ---- stirecov
@@ -521,14 +551,14 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
       if (hiv & HV_PREP) {
         bool stop = false;
         if (diag) stop = true;
-        else if (xgc_bern(d(1), P[XGC_P_prep_discont_rate + race])) stop = true;
+        else if (xgc_bern(d(4), P[XGC_P_prep_discont_rate + race])) stop = true;
         else if ((int)tk.x == at && (double)(at - (int)tk.z) >= P[XGC_P_prep_reassess_int]) {
           if (!ind) stop = true; else g.tck[idx].z = (short)at;
         }
         if (stop) hiv &= ~(HV_PREP | HV_PREPCLASS_MASK);
       } else if (!diag && (double)at >= P[XGC_P_prep_start] && (int)tk.x == at && ind) {
-        if (xgc_bern(d(1), P[XGC_P_prep_start_prob + race])) {
-          unsigned cl = 1 + xgc_categorical(d(2), P + XGC_P_prep_adhr_dist, 3);
+        if (xgc_bern(d(4), P[XGC_P_prep_start_prob + race])) {
+          unsigned cl = 1 + xgc_categorical(d(5), P + XGC_P_prep_adhr_dist, 3);
           hiv = (hiv & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
           short4* q = g.tck + idx; q->z = (short)at; q->w = (short)at;
         }
@@ -544,9 +574,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
         bool recov = false;
         if (gc & GC_TX(s)) {
           int k = at - (int)txT;
-          if (k >= 1) recov = xgc_bern(d(4 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
+          if (k >= 1) recov = xgc_bern(d(1 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
         } else if ((int)infT < at) {
-          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(4 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
+          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(1 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
           else recov = (at - (int)infT) >= (int)dur;
         }
         if (recov) {
@@ -691,10 +721,15 @@ template <bool INJ> __device__ __noinline__ void e2_anal(const Dev& g, const Inj
 }
 // oral (type 1: urethra <-> pharynx) and rimming (type 3: pharynx <-> rectum): direction per act ~ Bernoulli(0.5)
 template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, const Inj& inj, int type, int r, int l, int e, int at, const double* P,
-                                            const int4& ed, const uint4& ca, const uint4& cb, uint4* core) {
+                                            const int4& ed, const uint4& ca, const uint4& cb, uint4* core, const double* tab) {
   int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
   bool oral = type == 1;
-  int n = oral ? (ed.w >> 8) & 0xFF : (ed.w >> 24) & 0xFF;
+  int n = (ed.w >> 8) & 0xFF;
+  if (!oral) {                                              // this week's rimming count, evaluated only here
+    int dummy;
+    DrawT<INJ> da(inj, g, r, at, base + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+    edge_kiss_rim(P, l, ca, cb, da, tab, false, true, dummy, n);
+  }
   unsigned ga = ca.z & 7u, gb = cb.z & 7u;
   int sx = oral ? 1 : 2, sy = oral ? 2 : 0;                 // active partner's site, other partner's site
   double tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob], tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
@@ -713,8 +748,11 @@ template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, co
   e2_flag(core, ed, new_a, new_b, false, false);
 }
 template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const Inj& inj, int r, int l, int e, int at, const double* P,
-                                        const int4& ed, const uint4& ca, const uint4& cb, uint4* core) {
-  int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS, n = (ed.w >> 16) & 0xFF;
+                                                            const int4& ed, const uint4& ca, const uint4& cb, uint4* core, const double* tab) {
+  int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS, n, dummy;
+  DrawT<INJ> da(inj, g, r, at, base + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  edge_kiss_rim(P, l, ca, cb, da, tab, true, false, n, dummy);       // this week's kissing count, evaluated only here
+  if (n == 0) return;
   bool pa = (ca.z >> 2) & 1u;
   DrawT<INJ> d(inj, g, r, at, base + ((pa ? XGC_S_GC_KISS_A : XGC_S_GC_KISS_B) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
   double t = P[XGC_P_p2pgc_tprob];
@@ -723,66 +761,76 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
   if (hit) e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
 }
 
-template <bool INJ> __global__ void __launch_bounds__(TPB, 3) k_edge2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+// k_edge2a: classify every edge and append the (edge, act type) pairs that can transmit to the replicate's per-type
+// work queues (one atomicAdd per CTA and type).  No draws here.
+__global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, unsigned mask) {
   int r = blockIdx.z, l = blockIdx.y;
   const Rep* rp = g.rep + r;
   int ne = rp->ne[l];
   if ((int)(blockIdx.x * TPB) >= ne) return;
-  __shared__ int4 s_ed[TPB];
-  __shared__ uint4 s_ca[TPB], s_cb[TPB];
-  __shared__ unsigned short s_item[4 * TPB];
   __shared__ unsigned short s_wc[4][TPB / 32];
+  __shared__ unsigned s_base[4];
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int e0 = blockIdx.x * TPB, e = e0 + tid, at = g.at_ptr[r];
-  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  int e = blockIdx.x * TPB + tid;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
-  uint4* core = g.core + (size_t)r * g.n_cap;
-  // ---- 1. classify
+  const uint4* core = g.core + (size_t)r * g.n_cap;
   bool f[4] = { false, false, false, false };
   if (e < ne) {
     int4 ed = E[e];
-    if (ed.w != 0) {
-      uint4 ca = core[ed.x], cb = core[ed.y];
-      s_ed[tid] = ed; s_ca[tid] = ca; s_cb[tid] = cb;
-      int ai = ed.w & 0xFF, oi = (ed.w >> 8) & 0xFF, ki = (ed.w >> 16) & 0xFF, ri = (ed.w >> 24) & 0xFF;
-      unsigned ga = ca.z & 7u, gb = cb.z & 7u;              // current site status: bit0 rect, bit1 ureth, bit2 phar
-      bool gct = mask & XGC_M_STITRANS;
-      bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((ca.w ^ cb.w) & HV_STATUS);
-      bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
-                                    (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
-      f[0] = hivdisc || d_ai;
-      f[1] = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
-                               (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
-      f[2] = gct && ki > 0 && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
-      f[3] = gct && ri > 0 && C[XGC_C_transRoute_Rimming] &&
-             (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
-    }
+    uint4 ca = core[ed.x], cb = core[ed.y];
+    int ai = ed.w & 0xFF, oi = (ed.w >> 8) & 0xFF;
+    unsigned ga = ca.z & 7u, gb = cb.z & 7u;              // current site status: bit0 rect, bit1 ureth, bit2 phar
+    bool gct = mask & XGC_M_STITRANS;
+    bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((ca.w ^ cb.w) & HV_STATUS);
+    bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
+                                  (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
+    f[0] = hivdisc || d_ai;
+    f[1] = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
+                             (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
+    // kissing / rimming: queued on site discordance; their counts are drawn in k_edge2b
+    bool stopped = act_stopped(ca.y, ca.z >> GC_PRE_SHIFT) || act_stopped(cb.y, cb.z >> GC_PRE_SHIFT);
+    f[2] = gct && !stopped && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
+    f[3] = gct && !stopped && C[XGC_C_transRoute_Rimming] &&
+           (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
   }
-  // ---- 2. compact (edge, type) pairs into a queue sorted by type
   unsigned b[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) { b[t] = __ballot_sync(0xffffffffu, f[t]); if (lane == 0) s_wc[t][w] = (unsigned short)__popc(b[t]); }
   __syncthreads();
-  int total = 0;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    int before = 0, all = 0;
-#pragma unroll
-    for (int k = 0; k < TPB / 32; ++k) { int c = s_wc[t][k]; all += c; if (k < w) before += c; }
-    if (f[t]) s_item[total + before + __popc(b[t] & ((1u << lane) - 1u))] = (unsigned short)((t << 8) | tid);
-    total += all;
+  if (tid < 4) {
+    unsigned all = 0;
+    for (int k = 0; k < TPB / 32; ++k) all += s_wc[tid][k];
+    s_base[tid] = all ? atomicAdd(g.q_count + (size_t)r * 4 + tid, all) : 0u;
   }
   __syncthreads();
-  // ---- 3. dense processing
-  double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
-  for (int i = tid; i < total; i += TPB) {
-    int item = s_item[i], type = item >> 8, le = item & 0xFF;
-    int4 ed = s_ed[le]; uint4 ca = s_ca[le], cb = s_cb[le];
-    if (type == 0) e2_anal<INJ>(g, inj, mask, r, l, e0 + le, at, P, ed, ca, cb, core, dt);
-    else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e0 + le, at, P, ed, ca, cb, core);
-    else e2_directed<INJ>(g, inj, type, r, l, e0 + le, at, P, ed, ca, cb, core);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (!f[t]) continue;
+    unsigned before = 0;
+    for (int k = 0; k < w; ++k) before += s_wc[t][k];
+    g.q_items[((size_t)r * 4 + t) * g.e_stride + s_base[t] + before + __popc(b[t] & ((1u << lane) - 1u))] = ((unsigned)l << 28) | (unsigned)e;
   }
+}
+
+// k_edge2b: dense processing of the work queues; blockIdx.y = act type, so every warp runs one act type with all lanes busy.
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.z, type = blockIdx.y;
+  unsigned n = g.q_count[(size_t)r * 4 + type];
+  unsigned i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  unsigned item = g.q_items[((size_t)r * 4 + type) * g.e_stride + i];
+  int l = (int)(item >> 28), e = (int)(item & 0x0FFFFFFFu);
+  const Rep* rp = g.rep + r;
+  int at = g.at_ptr[r];
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  uint4* core = g.core + (size_t)r * g.n_cap;
+  int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
+  uint4 ca = core[ed.x], cb = core[ed.y];
+  const double* tab = g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1);
+  if (type == 0) e2_anal<INJ>(g, inj, mask, r, l, e, at, P, ed, ca, cb, core, (double)(rp->t_age - rp->t_ref) * XGC_WEEK);
+  else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e, at, P, ed, ca, cb, core, tab);
+  else e2_directed<INJ>(g, inj, type, r, l, e, at, P, ed, ca, cb, core, tab);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -979,6 +1027,24 @@ __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ D
   int4 ed = E[e];
   ed.x = RM[ed.x]; ed.y = RM[ed.y];
   E[e] = ed;
+}
+
+// k_actcounts: materialise the lazily evaluated kissing / rimming counts of one replicate into the edge records
+// (xgc_get_actcounts / dat$temp$el parity); the hot path never needs them for non-discordant edges.
+template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r) {
+  int l = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.rep[r].ne[l]) return;
+  int at = g.at_ptr[r];
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  int4 ed = E[e];
+  uint4 ca = core[ed.x], cb = core[ed.y];
+  const double* tab = g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1);
+  int ki, ri;
+  DrawT<INJ> da(inj, g, r, at, XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  edge_kiss_rim(P, l, ca, cb, da, tab, true, true, ki, ri);
+  E[e].w = (ed.w & 0xFFFF) | (ki << 16) | (ri << 24);
 }
 
 // k_actlist: materialise dat$temp$al for one replicate (debug / parity of condoms_msm + position_msm)

@@ -36,6 +36,8 @@ struct xgc_handle {
   int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
+  bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
+  Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -91,6 +93,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return 1; }
   xgc_handle* h = new xgc_handle();
   h->cfg = *cfg;
+  memset(&h->last_inj, 0, sizeof(Inj));
   if (h->cfg.compact_every <= 0) h->cfg.compact_every = 64;
   auto fail = [&](int code) { g_create_error = h->err; xgc_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(3); }
@@ -111,6 +114,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &dp, (size_t)g.R * XGC_NPARAM); rc |= dalloc(h, &dc, (size_t)g.R * XGC_NCONTROL);
   rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
   rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
+  rc |= dalloc(h, &g.q_items, (size_t)g.R * 4 * g.e_stride); rc |= dalloc(h, &g.q_count, (size_t)g.R * 4);
   rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
@@ -326,7 +330,7 @@ extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemset(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap));
   CU(h, cudaMemcpy((int*)g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice));
-  h->last_at = -1;
+  h->last_at = -1; h->acts_valid = false;
   return cache_flush(h);
 }
 extern "C" int xgc_num_agents(xgc_handle* h, int r, int* n) {
@@ -379,7 +383,7 @@ extern "C" int xgc_set_edgelist(xgc_handle* h, int r, int layer, const int32_t* 
     if (a < 1 || a > n || b < 1 || b > n || a == b) FAIL(h, 7, "layer %d edge %d: node ids (%d,%d) outside 1..%d", layer, e, a, b, n);
     E[e] = make_int4(c.pos2slot[a - 1], c.pos2slot[b - 1], start ? start[e] : c.rep.t_age, 0);
   }
-  c.edge[layer] = E; c.dirty = true;
+  c.edge[layer] = E; c.dirty = true; h->acts_valid = false;
   return 0;
 }
 extern "C" int xgc_get_edgelist(xgc_handle* h, int r, int layer, int32_t* el, int cap, int* n_edges, int32_t* start) {
@@ -396,20 +400,6 @@ extern "C" int xgc_get_edgelist(xgc_handle* h, int r, int layer, int32_t* el, in
   }
   return 0;
 }
-extern "C" int xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts, int cap, int* n_edges) {
-  CHECK_R(h, r);
-  if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
-  int rc = cache_load(h, r); if (rc) return rc;
-  const HostRep& c = h->cache; int ne = (int)c.edge[layer].size();
-  if (n_edges) *n_edges = ne;
-  if (cap < ne) FAIL(h, 6, "buffer too small");
-  for (int e = 0; e < ne; ++e) {
-    int w = c.edge[layer][e].w;
-    counts[e] = w & 0xFF; counts[ne + e] = (w >> 8) & 0xFF; counts[2 * ne + e] = (w >> 16) & 0xFF; counts[3 * ne + e] = (w >> 24) & 0xFF;
-  }
-  return 0;
-}
-
 // --------------------------------------------------------------------------------------------------------------------
 // the step
 // --------------------------------------------------------------------------------------------------------------------
@@ -464,7 +454,10 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   }
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, ge, TPB, g, inj, mask);
   if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2, ga, TPB, g, inj, mask, tpc);
-  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCHD(h, inj, k_edge2, ge, TPB, g, inj, mask);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
+    LAUNCH(h, k_edge2a, ge, TPB, g, mask);
+    LAUNCHD(h, inj, k_edge2b, dim3((unsigned)((g.e_stride + TPB - 1) / TPB), 4, g.R), TPB, g, inj, mask);
+  }
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCHD(h, inj, k_agent3, ga, TPB, g, inj, mask, tpc);
   return 0;
 }
@@ -475,6 +468,9 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
+  h->last_inj = j;
+  if (at != h->last_at) h->acts_valid = false;          // a new week: last week's act counts are history
+  if (mask & XGC_M_ACTS) h->acts_valid = true;
   int zero_row = at != h->last_at; h->last_at = at;
   rc = enqueue_week(h, at, mask, j, zero_row); if (rc) return rc;
   CU(h, cudaGetLastError());
@@ -520,7 +516,7 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
     h->launches += h->graph_launches;
     if (at % h->cfg.compact_every == 0) { rc = xgc_compact(h); if (rc) return rc; }
   }
-  h->last_at = at1;
+  h->last_at = at1; h->acts_valid = true; memset(&h->last_inj, 0, sizeof(Inj));
   CU(h, cudaGetLastError());
   return 0;
 }
@@ -556,6 +552,31 @@ extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
   *status = rp.status; return 0;
 }
 
+static int materialise_actcounts(xgc_handle* h, int r, const Inj& j) {      // kissing / rimming counts are lazy on the hot path
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const Dev& g = h->g;
+  int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
+  LAUNCHD(h, j, k_actcounts, dim3((emax + TPB - 1) / TPB, 3), TPB, g, j, r);
+  CU(h, cudaGetLastError());
+  return 0;
+}
+extern "C" int xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts, int cap, int* n_edges) {
+  CHECK_R(h, r);
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
+  int rc = 0;
+  if (h->acts_valid && (h->cache.r != r || !h->cache.dirty)) { rc = materialise_actcounts(h, r, h->last_inj); if (rc) return rc; }
+  rc = cache_load(h, r); if (rc) return rc;
+  const HostRep& c = h->cache; int ne = (int)c.edge[layer].size();
+  if (n_edges) *n_edges = ne;
+  if (cap < ne) FAIL(h, 6, "buffer too small");
+  for (int e = 0; e < ne; ++e) {
+    int w = c.edge[layer][e].w;
+    counts[e] = w & 0xFF; counts[ne + e] = (w >> 8) & 0xFF; counts[2 * ne + e] = (w >> 16) & 0xFF; counts[3 * ne + e] = (w >> 24) & 0xFF;
+  }
+  return 0;
+}
+
 extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int cap, int* n_acts, const xgc_inject* inj) {
   CHECK_R(h, r);
   int rc = cache_drop(h); if (rc) return rc;
@@ -563,6 +584,7 @@ extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int ca
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
   int* d_al; CU(h, cudaMalloc((void**)&d_al, sizeof(int) * 6 * (size_t)std::max(cap, 1)));
   CU(h, cudaMemcpyAsync((int*)h->g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  { int rc2 = materialise_actcounts(h, r, j); if (rc2) { cudaFree(d_al); return rc2; } }
   LAUNCHD(h, j, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
   int n = 0;
   cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -743,7 +765,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
-  h->last_at = -1;
+  h->last_at = -1; h->acts_valid = false;
   return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {

@@ -16,7 +16,7 @@ def kernel_bytes(stats: dict) -> dict:
     Returns {kernel: algorithmic bytes per launch}."""
     n, e = stats["n"], stats["edges"]
     f_hiv, f_dx, f_gc = stats["f_hiv"], stats["f_dx"], stats["f_gc"]
-    f_disc = stats.get("f_disc", 0.15)
+    f_disc = stats.get("f_disc", 0.6)        # discordant (edge, act type) pairs per edge (measured: queue lengths / edges)
     return {
         # core R + aux R (age for aging/mortality) + tck R (last.neg.test, undiagnosed) + HIV+: hck_a R, hck_b R+W
         "k_agent1": n * (16 + 16 + 8 * (1 - f_dx) + f_hiv * (8 + 8 + 8)),
@@ -26,8 +26,10 @@ def kernel_bytes(stats: dict) -> dict:
         "k_agent3": n * (16 + f_dx * 16),
         # edge record R + acts W(4) + 2 endpoints x (core + aux)
         "k_edge1": e * (16 + 4 + 2 * 32),
-        # edge record R + 2 endpoints x core; discordant edges also gather aux
-        "k_edge2": e * (16 + 2 * 16 + f_disc * 2 * 16),
+        # classify: edge record R + 2 endpoints x core (+ 4 B queue entry per discordant (edge, type) pair)
+        "k_edge2a": e * (16 + 2 * 16 + f_disc * 4),
+        # dense queue: per pair 4 B item + edge record + 2 x core (+ aux for anal pairs, ~1/4 of the pairs)
+        "k_edge2b": e * f_disc * (4 + 16 + 2 * 16 + 0.25 * 2 * 16),
         # in-place stable compaction: record R, survivors W, endpoint core gathers
         "k_edges_resim": e * (16 + 16 + 2 * 16),
     }
