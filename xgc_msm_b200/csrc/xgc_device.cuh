@@ -112,6 +112,11 @@ template <bool INJ> struct DrawT {
       : u(nullptr), seed(g.seed), rep((unsigned)(g.rep0 + r)), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
     if (INJ) u = j.u + (size_t)r * j.stride + j.off[stream_] + idx * (size_t)xgc_stream_width(stream_);
   }
+  // compute block b now, while the warp is still converged (later uses of its 4 draws are then free of divergent copies)
+  __device__ __forceinline__ void prime(int b) {
+    if (INJ) return;
+    v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b;
+  }
   __device__ __forceinline__ double operator()(int k) {
     if (INJ) return u[k];
     int b = k >> 2;

@@ -129,6 +129,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];      // speculative: always inside the plane
+  Aux axn = g.aux[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
+  short lntn = g.tck[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x].x;
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
@@ -139,8 +141,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
   for (int t = t0; t < t1; ++t) {
   int i = t * TPB + threadIdx.x;
   size_t idx = rbase + i;
-  uint4 c = cn;
-  if (t + 1 < t1) { cn = g.core[idx + TPB]; prefetch_l2(g.aux + idx + TPB); prefetch_l2(g.tck + idx + TPB); }
+  uint4 c = cn; Aux ax = axn; short lnt = lntn;
+  if (t + 1 < t1) { cn = g.core[idx + TPB]; axn = g.aux[idx + TPB]; lntn = g.tck[idx + TPB].x; }
   bool live = i < n_slots;
   live = live && (c.y & DM_ACTIVE);
   unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
@@ -150,9 +152,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
     hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
   }
   bool isnew = i >= n_pre;
-  Aux ax; ax.age_ref = 0; ax.vl = 0; ax.ins_quot = 0;
   bool hivpos = live && (hiv & HV_STATUS);
-  if (live && ((!isnew && (mask & (XGC_M_AGING | XGC_M_DEPARTURE))) || (hivpos && (mask & XGC_M_HIVVL)))) ax = g.aux[idx];
   double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
   int race = (int)DM_RACE(demo);
   DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);       // the whole pass draws from ONE Philox block per agent
@@ -178,7 +178,6 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
   bool ha_dirty = false, hb_dirty = false;
   if (hivpos && (mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL))) { ha = g.hck_a[idx]; hb = g.hck_b[idx]; }
   if ((mask & XGC_M_HIVTEST) && live && !(hiv & HV_DIAG)) {
-    short lnt = g.tck[idx].x;
     int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
     double tsl = (double)(at - last);
     if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) {
@@ -250,6 +249,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
     if (gc != c.z) q[1].x = gc;
     if (hiv != c.w) q[1].y = hiv;
   }
+  if (t + 1 < t1 && (cn.w & HV_STATUS)) { prefetch_l2(g.hck_a + idx + TPB); prefetch_l2(g.hck_b + idx + TPB); }
   }
 }
 
@@ -517,6 +517,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
+  short4 tkn = g.tck[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
@@ -527,8 +528,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
   for (int t = t0; t < t1; ++t) {
   int i = t * TPB + threadIdx.x;
   size_t idx = rbase + i;
-  uint4 c = cn;
-  if (t + 1 < t1) { cn = g.core[idx + TPB]; prefetch_l2(g.tck + idx + TPB); }
+  uint4 c = cn; short4 tk0 = tkn;
+  if (t + 1 < t1) { cn = g.core[idx + TPB]; tkn = g.tck[idx + TPB]; }
   bool live = i < n_slots;
   live = live && (c.y & DM_ACTIVE);
   unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
@@ -536,7 +537,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
   if (live) {
     DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);     // block 0 (clinic visit, recovery r,u,p) is all most agents ever draw
-    short4 tk = na4();
+    d.prime(0);
+    short4 tk = tk0;
     bool ind_sti = false;
     // ---- stirecov
     short4 ga = na4(), gb = na4(), gd = na4(); bool g_loaded = false, ga_dirty = false, gb_dirty = false, gd_dirty = false;
@@ -544,7 +546,6 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
       if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS) gd = g.gck_d[idx]; }
     // prep first (reference order: prep, hivtrans, stirecov, stitx)
     if (mask & XGC_M_PREP) {
-      tk = g.tck[idx];
       bool diag = hiv & HV_DIAG;
       bool ind = tk.y != XGC_NA16 && (double)tk.y >= (double)at - P[XGC_P_prep_risk_int];
       hiv = (hiv & ~HV_PREPELIG) | ((!diag && ind) ? HV_PREPELIG : 0u);
@@ -636,6 +637,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
     if (gd_dirty) g.gck_d[idx] = gd;
     if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
   }
+  // the next tile's core word has arrived by now: start fetching the GC clocks of its infected agents
+  if (t + 1 < t1 && (cn.z & 7u)) { prefetch_l2(g.gck_a + idx + TPB); prefetch_l2(g.gck_b + idx + TPB); }
   if (mask & XGC_M_STITX) {
     unsigned any = __ballot_sync(0xffffffffu, visit != 0);
     if (any) {
@@ -663,7 +666,7 @@ __device__ __forceinline__ void e2_flag(uint4* core, const int4& ed, unsigned ne
   if (hiv_a) atomicOr(&core[ed.x].w, HV_NEW);
   if (hiv_b) atomicOr(&core[ed.y].w, HV_NEW);
 }
-template <bool INJ> __device__ __noinline__ void e2_anal(const Dev& g, const Inj& inj, unsigned mask, int r, int l, int e, int at, const double* P,
+template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const Inj& inj, unsigned mask, int r, int l, int e, int at, const double* P,
                                      const int4& ed, const uint4& ca, const uint4& cb, uint4* core, double dt) {
   EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = ed; x.ca = ca; x.cb = cb; x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
   const Aux* aux = g.aux + (size_t)r * g.n_cap;
@@ -814,8 +817,8 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
 }
 
 // k_edge2b: dense processing of the work queues; blockIdx.y = act type, so every warp runs one act type with all lanes busy.
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
-  int r = blockIdx.z, type = blockIdx.y;
+template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 : 4) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.z, type = ANAL ? 0 : 1 + blockIdx.y;
   unsigned n = g.q_count[(size_t)r * 4 + type];
   unsigned i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
@@ -828,7 +831,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge2b(const __grid
   int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
   uint4 ca = core[ed.x], cb = core[ed.y];
   const double* tab = g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1);
-  if (type == 0) e2_anal<INJ>(g, inj, mask, r, l, e, at, P, ed, ca, cb, core, (double)(rp->t_age - rp->t_ref) * XGC_WEEK);
+  if (ANAL) e2_anal<INJ>(g, inj, mask, r, l, e, at, P, ed, ca, cb, core, (double)(rp->t_age - rp->t_ref) * XGC_WEEK);
   else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e, at, P, ed, ca, cb, core, tab);
   else e2_directed<INJ>(g, inj, type, r, l, e, at, P, ed, ca, cb, core, tab);
 }

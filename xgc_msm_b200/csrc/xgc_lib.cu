@@ -456,7 +456,13 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2, ga, TPB, g, inj, mask, tpc);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
     LAUNCH(h, k_edge2a, ge, TPB, g, mask);
-    LAUNCHD(h, inj, k_edge2b, dim3((unsigned)((g.e_stride + TPB - 1) / TPB), 4, g.R), TPB, g, inj, mask);
+    unsigned qb = (unsigned)((g.e_stride + TPB - 1) / TPB);
+    prof_begin(h, "k_edge2b_anal");
+    if (inj.u) k_edge2b<true, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask);
+    prof_end(h); h->launches++;
+    prof_begin(h, "k_edge2b_oral_kiss_rim");
+    if (inj.u) k_edge2b<true, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask);
+    prof_end(h); h->launches++;
   }
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCHD(h, inj, k_agent3, ga, TPB, g, inj, mask, tpc);
   return 0;

@@ -29,7 +29,8 @@ def kernel_bytes(stats: dict) -> dict:
         # classify: edge record R + 2 endpoints x core (+ 4 B queue entry per discordant (edge, type) pair)
         "k_edge2a": e * (16 + 2 * 16 + f_disc * 4),
         # dense queue: per pair 4 B item + edge record + 2 x core (+ aux for anal pairs, ~1/4 of the pairs)
-        "k_edge2b": e * f_disc * (4 + 16 + 2 * 16 + 0.25 * 2 * 16),
+        "k_edge2b_anal": e * f_disc * 0.25 * (4 + 16 + 2 * 16 + 2 * 16),
+        "k_edge2b_oral_kiss_rim": e * f_disc * 0.75 * (4 + 16 + 2 * 16),
         # in-place stable compaction: record R, survivors W, endpoint core gathers
         "k_edges_resim": e * (16 + 16 + 2 * 16),
     }
