@@ -185,3 +185,16 @@ def test_edge_cases_empty_and_ragged():
         ob.step(at, K.M_ALL); os_.step(at, K.M_ALL)
         compare_state(h, 0, ob, at, f"big week {at}")
         compare_state(h, 1, os_, at, f"small/no-edge week {at}")
+
+
+def test_large_population_100k_plus():
+    """BASELINE configs[3]/[4] shape: a 170k-agent replicate (k_rank / pos2slot path of the surrogate network, long
+    per-layer edge loops) next to a second replicate, 3 weeks, bit-exact vs the oracle."""
+    case = make_case(170000, 77, network_mode="surrogate")
+    h = load_handle([case, case], SEED, t_cap=8, replicate_offset=5)
+    orcs = [load_oracle(case, SEED, 5 + r, t_cap=8) for r in range(2)]
+    for at in (2, 3, 4):
+        h.step(at)
+        for r, o in enumerate(orcs):
+            o.step(at, K.M_ALL)
+            compare_state(h, r, o, at, f"170k agents week {at} r={r}")

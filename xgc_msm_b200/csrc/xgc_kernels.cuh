@@ -293,34 +293,36 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const _
   if (tid == 0) rp->ne[l] = base;
 }
 
-// k_rank: pos2slot[r][rank] = slot, from the alive bitmap (one CTA per replicate)
+// k_rank: pos2slot[r][rank] = slot, from the alive bitmap.  grid (slot tiles, R): each CTA sums the bitmap words before its
+// tile (<= n_cap/32 words, a block reduction) and ranks its own 256 slots with popcounts.
 __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
-  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int nw = (g.rep[r].n_slots + 31) >> 5;
+  int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int n_slots = g.rep[r].n_slots;
+  int i0 = blockIdx.x * TPB;
+  if (i0 >= n_slots) return;
   const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
   int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   __shared__ int wsum[TPB / 32];
-  __shared__ int base;
-  if (tid == 0) base = 0;
-  __syncthreads();
-  for (int w0 = 0; w0 < nw; w0 += TPB) {
-    unsigned bits = w0 + tid < nw ? A[w0 + tid] : 0u;
-    int cnt = __popc(bits), inc = cnt;
+  __shared__ unsigned tilebits[TPB / 32];
+  int w0 = i0 >> 5, acc = 0;
+  for (int k = tid; k < w0; k += TPB) acc += __popc(A[k]);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    int off = base + inc - cnt;
-    for (int k = 0; k < w; ++k) off += wsum[k];
-    while (bits) { int b = __ffs(bits) - 1; bits &= bits - 1; P2S[off++] = ((w0 + tid) << 5) + b; }
-    __syncthreads();
-    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
-    __syncthreads();
-  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) wsum[w] = acc;
+  if (tid < TPB / 32) tilebits[tid] = A[w0 + tid];
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int k = 0; k < TPB / 32; ++k) base += wsum[k];
+  for (int k = 0; k < w; ++k) base += __popc(tilebits[k]);
+  unsigned bits = tilebits[w];
+  if ((bits >> lane) & 1u) P2S[base + __popc(bits & ((1u << lane) - 1u))] = i0 + tid;
 }
 
-// k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+// k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order.
+// R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
+// directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
+template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
@@ -328,8 +330,37 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_form(const __grid_c
   int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  extern __shared__ unsigned dyn[];
+  unsigned* bm = dyn; int* pre = (int*)(dyn + g.n_cap / 32);
   __shared__ int wsum[TPB / 32];
   __shared__ int base;
+  int nw = (rp->n_slots + 31) >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  if (SMEM) {
+    const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+    for (int w0 = 0; w0 < nw; w0 += TPB) {
+      unsigned bits = w0 + tid < nw ? A[w0 + tid] : 0u;
+      int cnt = __popc(bits), inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      if (lane == 31) wsum[w] = inc;
+      __syncthreads();
+      int off = base + inc - cnt;
+      for (int k = 0; k < w; ++k) off += wsum[k];
+      if (w0 + tid < nw) { bm[w0 + tid] = bits; pre[w0 + tid] = off; }
+      __syncthreads();
+      if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+      __syncthreads();
+    }
+  }
+  auto slot_of = [&](int pos) -> int {
+    if (!SMEM) return P2S[pos];
+    int lo = 0, hi = nw - 1;                      // largest word index with pre[w] <= pos
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (pre[mid] <= pos) lo = mid; else hi = mid - 1; }
+    return (lo << 5) + (int)__fns(bm[lo], 0, pos - pre[lo] + 1);
+  };
+  __syncthreads();
   if (tid == 0) base = ne;
   __syncthreads();
   double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
@@ -348,7 +379,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_form(const __grid_c
         int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
         int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
         if (b >= a) b++;
-        int sa = P2S[a < b ? a : b], sb = P2S[a < b ? b : a];
+        int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);
         if (roles_compatible(core[sa].y, core[sb].y)) { ok = true; ed.x = sa; ed.y = sb; }
       }
     }
@@ -429,7 +460,7 @@ template <class D> __device__ __forceinline__ void edge_kiss_rim(const double* P
 }
 
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.z, l = blockIdx.y;
   const Rep* rp = g.rep + r;
   int ne = rp->ne[l];

@@ -449,8 +449,17 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
   if (mask & XGC_M_RESIM_NETS) {
     LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 1);
-    LAUNCH(h, k_rank, g.R, TPB, g);
-    LAUNCHD(h, inj, k_form, dim3(3, g.R), TPB, g, inj);
+    size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
+    if (form_smem <= 40 * 1024) {
+      prof_begin(h, "k_form");
+      if (inj.u) k_form<true, true><<<dim3(3, g.R), TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true><<<dim3(3, g.R), TPB, form_smem, h->stream>>>(g, inj);
+      prof_end(h); h->launches++;
+    } else {
+      LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+      prof_begin(h, "k_form");
+      if (inj.u) k_form<true, false><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj); else k_form<false, false><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj);
+      prof_end(h); h->launches++;
+    }
   }
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, ge, TPB, g, inj, mask);
   if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2, ga, TPB, g, inj, mask, tpc);
@@ -827,7 +836,7 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   CU(h, cudaMemcpyAsync(d_el, el, R * cap * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (start) CU(h, cudaMemcpyAsync(d_start, start, R * cap * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(h, k_rank, g.R, TPB, g);
+  LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
   LAUNCH(h, k_edges_upload, dim3((unsigned)((cap + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr);
   CU(h, cudaGetLastError());
   return 0;
