@@ -88,6 +88,8 @@ struct Dev {                 // everything a kernel needs; passed by value
   const double* pois;        // [R][4][XGC_MAX_ACTS+1] Poisson CDF tables of the constant weekly rates: kiss main/casual, rim main/casual
   unsigned* q_items;         // [R][4][e_stride] work queue of k_edge2: (layer << 28 | edge index) per act type
   unsigned* q_count;         // [R][4]
+  unsigned* qa_items;        // [R][n_cap] work queue of k_agent2b: slot | asymptomatic-visit draw << 31
+  unsigned* qa_count;        // [R]
   unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
   const int* at_ptr;
 };

@@ -4,7 +4,8 @@
 //   k_agent1  (1 thread / slot)       aging, departure, hivtest, hivtx, hivprogress, hivvl        [reads core+aux]
 //   k_edges_prune / k_rank / k_form   edge deletion for departed agents; surrogate for simnet_msm
 //   k_edge1   (1 thread / edge)       acts (+ exposure history, PrEP risk history)                [gathers core+aux]
-//   k_agent2  (1 thread / slot)       prep, stirecov, stitx                                       [reads core+clocks]
+//   k_agent2a (1 thread / slot)       prep; queue agents with GC work                              [reads core+tck]
+//   k_agent2b (1 thread / queued)     stirecov, stitx                                              [reads core+clocks]
 //   k_edge2   (1 thread / edge)       condoms + position (lazily per act), hivtrans, stitrans     [gathers core]
 //   k_agent3  (1 thread / slot)       apply new infections, prevalence tallies                    [reads core]
 // Module semantics follow DESIGN.md §3; reference call sites are cited there and in include/xgc/abi.h.
@@ -57,6 +58,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   int t_age = (mask & XGC_M_AGING) ? at : rp->t_age;
   __syncwarp();
   if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
+  if (lane == 4) g.qa_count[r] = 0u;
   if (lane == 0) {
     ((int*)g.at_ptr)[r] = at;
     rp->n_slots_pre = n_slots;
@@ -543,7 +545,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __gr
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent2: prep_msm, stirecov_msm, stitx_msm (sim1_02_lhs.r:213, 215-216).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
+// k_agent2a: prep_msm for every agent + classification: agents with GC work this week (an infected site, a clinic visit)
+// are appended to the replicate's work queue; k_agent2b runs stirecov_msm / stitx_msm on the queue with all lanes busy.
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -552,51 +556,84 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
+  int at = g.at_ptr[r], lane = threadIdx.x & 31;
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  int proto = C[XGC_C_stiScreeningProtocol], kissx = C[XGC_C_cdcExposureSite_Kissing];
+  unsigned* Q = g.qa_items + rbase;
+  for (int t = t0; t < t1; ++t) {
+    int i = t * TPB + threadIdx.x;
+    size_t idx = rbase + i;
+    uint4 c = cn; short4 tk = tkn;
+    if (t + 1 < t1) { cn = g.core[idx + TPB]; tkn = g.tck[idx + TPB]; }
+    bool live = i < n_slots && (c.y & DM_ACTIVE);
+    unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
+    int race = (int)DM_RACE(demo);
+    bool queue = false, avd = false;
+    if (live) {
+      DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);
+      if ((mask & XGC_M_STITX) && (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL))
+        avd = xgc_bern(d(0), P[XGC_P_gc_asympt_visit_prob]);           // asymptomatic clinic-visit draw (used unless a symptomatic visit happens)
+      if (mask & XGC_M_PREP) {                                           // prep_msm (sim1_02_lhs.r:213)
+        bool diag = hiv & HV_DIAG;
+        bool ind = tk.y != XGC_NA16 && (double)tk.y >= (double)at - P[XGC_P_prep_risk_int];
+        hiv = (hiv & ~HV_PREPELIG) | ((!diag && ind) ? HV_PREPELIG : 0u);
+        if (hiv & HV_PREP) {
+          bool stop = false;
+          if (diag) stop = true;
+          else if (xgc_bern(d(4), P[XGC_P_prep_discont_rate + race])) stop = true;
+          else if ((int)tk.x == at && (double)(at - (int)tk.z) >= P[XGC_P_prep_reassess_int]) {
+            if (!ind) stop = true; else g.tck[idx].z = (short)at;
+          }
+          if (stop) hiv &= ~(HV_PREP | HV_PREPCLASS_MASK);
+        } else if (!diag && (double)at >= P[XGC_P_prep_start] && (int)tk.x == at && ind) {
+          if (xgc_bern(d(4), P[XGC_P_prep_start_prob + race])) {
+            unsigned cl = 1 + xgc_categorical(d(5), P + XGC_P_prep_adhr_dist, 3);
+            hiv = (hiv & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
+            short4* q = g.tck + idx; q->z = (short)at; q->w = (short)at;
+          }
+        }
+        if (hiv != c.w) ((uint2*)&g.core[idx])[1].y = hiv;
+      }
+      unsigned ex = (gc >> GC_EXPO_SHIFT) & 0x1Fu;
+      bool cdc_active = proto == XGC_SCREEN_CDC && ((ex & 7u) || (kissx && (ex & 8u)));
+      queue = (mask & (XGC_M_STIRECOV | XGC_M_STITX)) && ((gc & 7u) || ((mask & XGC_M_STITX) && (avd || cdc_active)));
+    }
+    unsigned m = __ballot_sync(0xffffffffu, queue);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(g.qa_count + r, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (avd ? 0x80000000u : 0u);
+    }
+  }
+}
+
+// k_agent2b: stirecov_msm, stitx_msm (sim1_02_lhs.r:215-216) over the queued agents
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  unsigned n = g.qa_count[r];
+  if (blockIdx.x * TPB >= n) return;
+  unsigned qi = blockIdx.x * TPB + threadIdx.x;
+  const size_t rbase = (size_t)r * g.n_cap;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   unsigned* row = counter_row(g, r, at);
-  for (int t = t0; t < t1; ++t) {
-  int i = t * TPB + threadIdx.x;
-  size_t idx = rbase + i;
-  uint4 c = cn; short4 tk0 = tkn;
-  if (t + 1 < t1) { cn = g.core[idx + TPB]; tkn = g.tck[idx + TPB]; }
-  bool live = i < n_slots;
-  live = live && (c.y & DM_ACTIVE);
-  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
-  int race = (int)DM_RACE(demo);
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
-  if (live) {
-    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);     // block 0 (clinic visit, recovery r,u,p) is all most agents ever draw
-    d.prime(0);
-    short4 tk = tk0;
-    bool ind_sti = false;
-    // ---- stirecov
-    short4 ga = na4(), gb = na4(), gd = na4(); bool g_loaded = false, ga_dirty = false, gb_dirty = false, gd_dirty = false;
-    if ((gc & 7u) && (mask & (XGC_M_STIRECOV | XGC_M_STITX))) { ga = g.gck_a[idx]; gb = g.gck_b[idx]; g_loaded = true;
-      if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS) gd = g.gck_d[idx]; }
-    // prep first (reference order: prep, hivtrans, stirecov, stitx)
-    if (mask & XGC_M_PREP) {
-      bool diag = hiv & HV_DIAG;
-      bool ind = tk.y != XGC_NA16 && (double)tk.y >= (double)at - P[XGC_P_prep_risk_int];
-      hiv = (hiv & ~HV_PREPELIG) | ((!diag && ind) ? HV_PREPELIG : 0u);
-      if (hiv & HV_PREP) {
-        bool stop = false;
-        if (diag) stop = true;
-        else if (xgc_bern(d(4), P[XGC_P_prep_discont_rate + race])) stop = true;
-        else if ((int)tk.x == at && (double)(at - (int)tk.z) >= P[XGC_P_prep_reassess_int]) {
-          if (!ind) stop = true; else g.tck[idx].z = (short)at;
-        }
-        if (stop) hiv &= ~(HV_PREP | HV_PREPCLASS_MASK);
-      } else if (!diag && (double)at >= P[XGC_P_prep_start] && (int)tk.x == at && ind) {
-        if (xgc_bern(d(4), P[XGC_P_prep_start_prob + race])) {
-          unsigned cl = 1 + xgc_categorical(d(5), P + XGC_P_prep_adhr_dist, 3);
-          hiv = (hiv & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
-          short4* q = g.tck + idx; q->z = (short)at; q->w = (short)at;
-        }
-      }
-    }
+  if (qi < n) {
+    unsigned item = g.qa_items[rbase + qi];
+    bool avd = item >> 31;
+    size_t idx = rbase + (item & 0x7FFFFFFFu);
+    uint4 c = g.core[idx];
+    unsigned uid = c.x, gc = c.z, hiv = c.w;
+    bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
+    short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
+    if (pois && (gc & 7u)) gd = g.gck_d[idx];
+    bool ga_dirty = false, gb_dirty = false, gd_dirty = false, ind_sti = false;
+    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT2, uid, 0u, uid);
     if ((mask & XGC_M_STIRECOV) && (gc & 7u)) {
+      d.prime(0);                                                        // recovery draws r,u,p live in block 0
       const int txpr[3] = { XGC_P_rgc_tx_recov_pr, XGC_P_ugc_tx_recov_pr, XGC_P_pgc_tx_recov_pr };
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
@@ -608,14 +645,14 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
           int k = at - (int)txT;
           if (k >= 1) recov = xgc_bern(d(1 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
         } else if ((int)infT < at) {
-          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_GEOM) recov = xgc_bern(d(1 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
+          if (!pois) recov = xgc_bern(d(1 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
           else recov = (at - (int)infT) >= (int)dur;
         }
         if (recov) {
           gc &= ~(GC_ST(s) | GC_SY(s) | GC_TX(s));
           if (s == 0) { ga.x = -1; gb.x = -1; gd.x = -1; } else if (s == 1) { ga.y = -1; gb.y = -1; gd.y = -1; } else { ga.z = -1; gb.z = -1; gd.z = -1; }
           ga_dirty = gb_dirty = true;
-          if (C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS) gd_dirty = true; else (&g.gck_d[idx].x)[s] = -1;
+          if (pois) gd_dirty = true; else (&g.gck_d[idx].x)[s] = -1;
         }
       }
     }
@@ -630,19 +667,17 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
         }
       unsigned ex = (gc >> GC_EXPO_SHIFT) & 0x1Fu;
       if (!sv) {
-        if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = xgc_bern(d(0), P[XGC_P_gc_asympt_visit_prob]);
+        if (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL) av = avd;       // drawn by k_agent2a (AGENT2 k0)
         else if (proto == XGC_SCREEN_CDC) {
           bool active = (ex & 7u) || (kissx && (ex & 8u));
           bool hr = (hiv & HV_PREP) || (ex & 16u);
           double interval = (hr ? P[XGC_P_cdc_sti_hr_int] : P[XGC_P_cdc_sti_int]) * (52.0 / 12.0);
-          short ls = g_loaded ? ga.w : g.gck_a[idx].w;
-          bool due = ls == XGC_NA16 || (double)(at - (int)ls) >= interval;
+          bool due = ga.w == XGC_NA16 || (double)(at - (int)ga.w) >= interval;
           av = active && due;
         }
       }
       if (sv || av) {
         visit = 1; svisit = sv;
-        if (!g_loaded) { ga = g.gck_a[idx]; gb = g.gck_b[idx]; g_loaded = true; }
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           bool inf = gc & GC_ST(s), symp = inf && (gc & GC_SY(s)), tested;
@@ -666,10 +701,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
     if (ga_dirty) g.gck_a[idx] = ga;
     if (gb_dirty) g.gck_b[idx] = gb;
     if (gd_dirty) g.gck_d[idx] = gd;
-    if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
+    if (gc != c.z) ((uint2*)&g.core[idx])[1].x = gc;
   }
-  // the next tile's core word has arrived by now: start fetching the GC clocks of its infected agents
-  if (t + 1 < t1 && (cn.z & 7u)) { prefetch_l2(g.gck_a + idx + TPB); prefetch_l2(g.gck_b + idx + TPB); }
   if (mask & XGC_M_STITX) {
     unsigned any = __ballot_sync(0xffffffffu, visit != 0);
     if (any) {
@@ -677,7 +710,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2(const __grid
 #pragma unroll
       for (int s = 0; s < 3; ++s) { warp_tally(row, XGC_K_TESTED + s, tst[s]); warp_tally(row, XGC_K_POS + s, pos[s]); warp_tally(row, XGC_K_TXSTART + s, txs[s]); }
     }
-  }  }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

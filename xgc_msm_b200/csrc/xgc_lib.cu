@@ -115,6 +115,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
   rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
   rc |= dalloc(h, &g.q_items, (size_t)g.R * 4 * g.e_stride); rc |= dalloc(h, &g.q_count, (size_t)g.R * 4);
+  rc |= dalloc(h, &g.qa_items, NA); rc |= dalloc(h, &g.qa_count, (size_t)g.R);
   rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
@@ -462,7 +463,8 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     }
   }
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, ge, TPB, g, inj, mask);
-  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2, ga, TPB, g, inj, mask, tpc);
+  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2a, ga, TPB, g, inj, mask, tpc);
+  if (mask & (XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2b, dim3(tiles, g.R), TPB, g, inj, mask);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
     LAUNCH(h, k_edge2a, ge, TPB, g, mask);
     unsigned qb = (unsigned)((g.e_stride + TPB - 1) / TPB);

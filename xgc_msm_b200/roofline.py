@@ -20,8 +20,10 @@ def kernel_bytes(stats: dict) -> dict:
     return {
         # core R + aux R (age for aging/mortality) + tck R (last.neg.test, undiagnosed) + HIV+: hck_a R, hck_b R+W
         "k_agent1": n * (16 + 16 + 8 * (1 - f_dx) + f_hiv * (8 + 8 + 8)),
-        # core R + tck R (prep indications) + infected: gck_a R, gck_b R
-        "k_agent2": n * (16 + 8 + f_gc * 16),
+        # prep + classification: core R + tck R (+ 4 B queue entry for agents with GC work)
+        "k_agent2a": n * (16 + 8 + f_gc * 4),
+        # queued agents (infected or visiting): item + core + gck_a + gck_b
+        "k_agent2b": n * f_gc * (4 + 16 + 8 + 8),
         # core R + diagnosed: aux R (viral load for cc.vsupp)
         "k_agent3": n * (16 + f_dx * 16),
         # edge record R + acts W(4) + 2 endpoints x (core + aux)
