@@ -83,3 +83,24 @@ def test_statistical_equivalence_1000_replicates():
     # and the same seed gives the same numbers exactly (counter-based RNG): one replicate, CPU vs GPU
     c0 = cpu_bench.run_targets(N, 2, WEEKS, TAIL, 1971, K.M_ALL, kw, philox_seed=1971, cores=2)
     assert np.array_equal(c0.view(np.uint64), g[:2].view(np.uint64))
+
+
+def test_screening_scenario_grid():
+    """BASELINE configs[2]: burn-in -> fork into the five screening arms -> NIA / PIA / NTIA (99_analyze.r:146-208)."""
+    from xgc_msm_b200 import scenarios, workload
+    from xgc_msm_b200.abi import Handle
+    from xgc_msm_b200.params import control_msm
+    R, N, BURN, CONT = 6, 2500, 26, 30
+    spec = workload.SweepSpec(n_agents=N, seed=1971, lhs=False, n_distinct=1)
+    h = Handle(R, spec.n_cap, spec.e_cap, BURN + CONT + 4, seed=1971)
+    workload.load_sweep(h, spec)
+    h.run(2, BURN + 1)
+    res = scenarios.run_screening_grid(h, BURN + 1, CONT, control_msm(network_mode="surrogate"))
+    assert set(res) == {"base", "symp", "cdc1", "cdc2", "univ"}
+    assert np.all(res["base"]["nia_gc"] == 0) and np.all(res["symp"]["asympt_visits"] == 0)
+    assert np.all(res["base"]["asympt_visits"] > 0) and np.all(res["cdc1"]["asympt_visits"] > 0)
+    assert res["cdc2"]["sum_num.pgc.test"].sum() > 0.9 * res["cdc1"]["sum_num.pgc.test"].sum()   # kissing as an extra pharyngeal exposure
+    assert res["univ"]["sum_num.gc.test"].sum() > res["base"]["sum_num.gc.test"].sum()
+    assert res["symp"]["sum_num.gc.test"].sum() < res["base"]["sum_num.gc.test"].sum()        # symptomatic-only testing tests least
+    for k in ("nia_gc", "pia_rgc", "ntia_pgc", "sum_incid.ugc"):
+        assert res["cdc1"][k].shape == (R,)
