@@ -32,7 +32,7 @@ METRIC, UNIT = "agent-weeks/sec", "agent-weeks/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=52)
+    ap.add_argument("--steps", type=int, default=260)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="xgc", choices=["xgc", "reference"])
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU")
@@ -103,7 +103,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None

@@ -29,7 +29,10 @@ def scale(k, v):
     return v
 agg = collections.OrderedDict()
 for r in data:
-    name = r[ki].split("(")[0]
+    name = r[ki].split("(")[0].replace("void ", "")
+    if name.startswith("k_edge2b<"):
+        name = "k_edge2b_anal" if name.rstrip(">").split(",")[-1].strip() in ("1", "true") else "k_edge2b_oral_kiss_rim"
+    name = name.split("<")[0]
     a = agg.setdefault(name, collections.defaultdict(list))
     for k in ix:
         try: a[k].append(scale(k, r[ix[k]]))
