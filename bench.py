@@ -151,14 +151,14 @@ def host_network_pool(R, e_cap, n_lo, rng, torch):
     """Pinned host edge lists standing for what host-side simnet_msm returns each week: [R][2][e_cap] 1-based positions."""
     bufs = []
     for l in range(3):
-        ne = int(e_cap[l] / 1.35) - 100
-        a = rng.integers(1, n_lo, size=(R, e_cap[l]), dtype=np.int32)
-        b = rng.integers(1, n_lo - 1, size=(R, e_cap[l]), dtype=np.int32)
+        ne = int(e_cap[l] / 1.35) - 100                # the layer's equilibrium edge count; buffers hold exactly ne edges
+        a = rng.integers(1, n_lo, size=(R, ne), dtype=np.int32)
+        b = rng.integers(1, n_lo - 1, size=(R, ne), dtype=np.int32)
         b = np.where(b >= a, b + 1, b)
         el = np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1).astype(np.int32)          # [R,2,e_cap]
         t_el = torch.from_numpy(el).pin_memory()
         t_ne = torch.full((R,), ne, dtype=torch.int32).pin_memory()
-        t_st = torch.from_numpy((1 - rng.geometric(1 / 100.0, size=(R, e_cap[l]))).astype(np.int32)).pin_memory()
+        t_st = torch.from_numpy((1 - rng.geometric(1 / 100.0, size=(R, ne))).astype(np.int32)).pin_memory()
         bufs.append((t_el, t_ne, t_st, ne))
     return bufs
 
@@ -259,8 +259,8 @@ def run_xgc(args, rank, world, local_rank):
     def e2e_week(t):
         h.step(t, pre)
         h.num_agents_all(n_host.numpy())
-        for l, (t_el, t_ne, t_st, _) in enumerate(pool):
-            h.set_edgelists_all(l, t_el.data_ptr(), t_ne.data_ptr(), t_st.data_ptr())
+        for l, (t_el, t_ne, t_st, _ne) in enumerate(pool):
+            h.set_edgelists_all(l, t_el.data_ptr(), t_ne.data_ptr(), t_st.data_ptr(), stride=t_el.shape[2])
         h.step(t, post)
         h.counters_all(t, c_host.numpy().view(np.uint32))
         return float(c_host[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum())

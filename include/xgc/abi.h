@@ -330,8 +330,8 @@ int  xgc_fork    (xgc_handle* src, int src_r, xgc_handle* dst, int dst_r);   /* 
 
 /* e2e helpers with caller-owned pinned host buffers: one call moves every replicate's edge lists in, or the week's
  * counters out (the two transfers the weekly R<->device contract needs; DESIGN.md "boundary cost"). */
-int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][e_cap] 1-based positions*/,
-                           const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][e_cap] or NULL*/);
+int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][stride] 1-based positions*/,
+                           const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][stride] or NULL*/, int stride);
 int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);
 int  xgc_num_agents_all   (xgc_handle* h, int32_t* out /*[R]*/);   /* living agents per replicate (what simnet_msm needs) */
 

@@ -36,6 +36,7 @@ struct xgc_handle {
   int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
+  bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
@@ -222,7 +223,7 @@ static int cache_flush(xgc_handle* h) {
     if (!c.edge[l].empty()) CU(h, cudaMemcpy(g.edge + (size_t)c.r * g.e_stride + g.e_off[l], c.edge[l].data(), c.edge[l].size() * sizeof(int4), cudaMemcpyHostToDevice));
   }
   CU(h, cudaMemcpy(g.rep + c.r, &c.rep, sizeof(Rep), cudaMemcpyHostToDevice));
-  c.dirty = false;
+  c.dirty = false; h->rank_fresh = false;
   return 0;
 }
 static int cache_load(xgc_handle* h, int r) {
@@ -485,7 +486,7 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
-  h->last_inj = j;
+  h->last_inj = j; h->rank_fresh = false;
   if (at != h->last_at) h->acts_valid = false;          // a new week: last week's act counts are history
   if (mask & XGC_M_ACTS) h->acts_valid = true;
   int zero_row = at != h->last_at; h->last_at = at;
@@ -501,6 +502,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   { Inj inj = make_inj(h, nullptr, nullptr); LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0); }   // no dangling endpoints before re-numbering
+  h->rank_fresh = false;
   LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
   LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
   CU(h, cudaGetLastError());
@@ -533,7 +535,7 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
     h->launches += h->graph_launches;
     if (at % h->cfg.compact_every == 0) { rc = xgc_compact(h); if (rc) return rc; }
   }
-  h->last_at = at1; h->acts_valid = true; memset(&h->last_inj, 0, sizeof(Inj));
+  h->last_at = at1; h->rank_fresh = false; h->acts_valid = true; memset(&h->last_inj, 0, sizeof(Inj));
   CU(h, cudaGetLastError());
   return 0;
 }
@@ -782,7 +784,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
-  h->last_at = -1; h->acts_valid = false;
+  h->last_at = -1; h->acts_valid = false; h->rank_fresh = false;
   return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
@@ -811,35 +813,37 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
 // --------------------------------------------------------------------------------------------------------------------
 // bulk edge-list upload for the weekly host<->device contract (host network resimulation)
 // --------------------------------------------------------------------------------------------------------------------
-__global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el /*[R][2][e_cap]*/, const int* ne /*[R]*/, const int* start /*[R][e_cap] or null*/) {
+__global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el /*[R][2][stride]*/, const int* ne /*[R]*/, const int* start /*[R][stride] or null*/, int stride) {
   int r = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
-  int n = ne[r], cap = g.e_cap[l];
+  int n = ne[r], cap = g.e_cap[l] < stride ? g.e_cap[l] : stride;
   if (e == 0) { g.rep[r].ne[l] = n < cap ? n : cap; if (n > cap) atomicOr(&g.rep[r].status, XGC_ST_EDGE_OVERFLOW); }
   if (e >= n || e >= cap) return;
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   int na = g.rep[r].n_alive;
-  int a = el[((size_t)r * 2 + 0) * cap + e], b = el[((size_t)r * 2 + 1) * cap + e];
+  int a = el[((size_t)r * 2 + 0) * stride + e], b = el[((size_t)r * 2 + 1) * stride + e];
   if (a < 1 || a > na || b < 1 || b > na) { atomicOr(&g.rep[r].status, XGC_ST_BAD_EDGE); a = b = 1; }
-  g.edge[(size_t)r * g.e_stride + g.e_off[l] + e] = make_int4(P2S[a - 1], P2S[b - 1], start ? start[(size_t)r * cap + e] : g.at_ptr[r], 0);
+  g.edge[(size_t)r * g.e_stride + g.e_off[l] + e] = make_int4(P2S[a - 1], P2S[b - 1], start ? start[(size_t)r * stride + e] : g.at_ptr[r], 0);
 }
-extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el, const int32_t* n_edges, const int32_t* start) {
+extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el, const int32_t* n_edges, const int32_t* start, int stride) {
   if (layer < 0 || layer > 2) FAIL(h, 2, "layer out of range");
+  if (stride < 1) FAIL(h, 2, "stride must be >= 1");
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
-  const Dev& g = h->g; size_t cap = g.e_cap[layer], R = g.R;
-  size_t need = R * cap * 3 + R;
+  const Dev& g = h->g; size_t st = (size_t)stride, R = g.R;
+  size_t need = R * st * 3 + R;
   if (need > h->el_stage_cap) {
     if (h->d_el_stage) cudaFree(h->d_el_stage);
     h->d_el_stage = nullptr; h->el_stage_cap = 0;
     CU(h, cudaMalloc((void**)&h->d_el_stage, need * sizeof(int)));
     h->el_stage_cap = need;
   }
-  int* d_el = h->d_el_stage; int* d_start = d_el + R * cap * 2; int* d_ne = d_start + R * cap;
-  CU(h, cudaMemcpyAsync(d_el, el, R * cap * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  if (start) CU(h, cudaMemcpyAsync(d_start, start, R * cap * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  int* d_el = h->d_el_stage; int* d_start = d_el + R * st * 2; int* d_ne = d_start + R * st;
+  CU(h, cudaMemcpyAsync(d_el, el, R * st * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (start) CU(h, cudaMemcpyAsync(d_start, start, R * st * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
-  LAUNCH(h, k_edges_upload, dim3((unsigned)((cap + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr);
+  if (!h->rank_fresh) { LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g); h->rank_fresh = true; }
+  LAUNCH(h, k_edges_upload, dim3((unsigned)((st + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr, stride);
+  h->acts_valid = false;
   CU(h, cudaGetLastError());
   return 0;
 }
