@@ -124,7 +124,9 @@ template <bool INJ> struct DrawT {
     int b = k >> 2;
     if (b != blk) { v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b; }
     unsigned x = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
-    return ((double)x + 0.5) * (1.0 / 4294967296.0);
+    // ((double)x + 0.5) * 2^-32 without an int->fp64 conversion (XU pipe): 1.x with x in the top 32 mantissa bits is
+    // 1 + x * 2^-32 exactly; subtracting 1 (Sterbenz) and adding 2^-33 are both exact, so the value is bit-identical.
+    return (__hiloint2double((int)(0x3FF00000u | (x >> 12)), (int)(x << 20)) - 1.0) + (1.0 / 8589934592.0);
   }
 };
 
@@ -149,8 +151,9 @@ __device__ __forceinline__ double xgc_exp(double x) {
   q = q * r + 0.5;
   q = q * r + 1.0;
   q = q * r + 1.0;
-  long long k = (long long)kf;
-  return q * __longlong_as_double((k + 1023) << 52);
+  // kf is an integer-valued double in [-1011, 1011]: its two's-complement value sits in the low word of kf + 1.5 * 2^52
+  int k = __double2loint(kf + 6755399441055744.0);
+  return q * __hiloint2double((k + 1023) << 20, 0);
 }
 __device__ __forceinline__ int xgc_bern(double u, double p) { return p <= 0.5 ? (u >= 1.0 - p) : (u < p); }
 // pr_k = pr_{k-1} * mu * (1/k): the reciprocals 1/1..1/32 are correctly rounded constants (no division in the hot loop);
@@ -183,16 +186,17 @@ __device__ __forceinline__ unsigned xgc_age_group(double age) {   // age.grp - 1
   return (unsigned)((age >= 25.0) + (age >= 35.0) + (age >= 45.0) + (age >= 55.0));
 }
 __device__ __forceinline__ double xgc_glm_eta(const double* b, double dur, int casual, double ca, int hcp, int prep, int r1, int r2) {
+  // indicator covariates enter as selects instead of int->fp64 conversions: b * 1.0 == b and eta + b * 0.0 == eta
   double eta = b[XGC_G_B0];
   eta = eta + b[XGC_G_DUR] * dur;
   eta = eta + b[XGC_G_DUR2] * (dur * dur);
   eta = eta + b[XGC_G_RC + r1 * 4 + r2];
-  eta = eta + b[XGC_G_PT2] * (double)casual;
-  eta = eta + b[XGC_G_DUR_PT2] * (dur * (double)casual);
+  eta = eta + (casual ? b[XGC_G_PT2] : 0.0);
+  eta = eta + (casual ? b[XGC_G_DUR_PT2] * dur : 0.0);
   eta = eta + b[XGC_G_CA] * ca;
   eta = eta + b[XGC_G_CA2] * (ca * ca);
-  eta = eta + b[XGC_G_HCP] * (double)hcp;
-  eta = eta + b[XGC_G_PREP] * (double)prep;
+  eta = eta + (hcp ? b[XGC_G_HCP] : 0.0);
+  eta = eta + (prep ? b[XGC_G_PREP] : 0.0);
   return eta;
 }
 __device__ __forceinline__ bool roles_compatible(unsigned da, unsigned db) {
