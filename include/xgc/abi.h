@@ -124,19 +124,13 @@ enum xgc_stream {
   XGC_S_EDGE0 = XGC_S_FORM + 3,
   XGC_S_DISSOLVE = XGC_S_EDGE0, /* k0 (surrogate network)                                                           */
   XGC_S_ACTS,          /* k0 anal, k1 oral, k2 kissing, k3 rimming counts                                           */
-  XGC_S_COND,          /* k = anal act index: condom                                                                */
-  XGC_S_POS,           /* k = anal act index: position (versatile pairs)                                            */
-  XGC_S_OIDIR,         /* k = oral act index: direction                                                             */
-  XGC_S_RIMDIR,        /* k = rimming act index: direction                                                          */
-  XGC_S_HIVTRANS,      /* k = anal act index                                                                        */
-  XGC_S_GC_AI_A,       /* k = act index; A = insertive->receptive (u2r), B = receptive->insertive (r2u)             */
-  XGC_S_GC_AI_B,
-  XGC_S_GC_OI_A,       /* u2p / p2u                                                                                 */
-  XGC_S_GC_OI_B,
-  XGC_S_GC_RIM_A,      /* p2r / r2p                                                                                 */
-  XGC_S_GC_RIM_B,
-  XGC_S_GC_KISS_A,     /* p1->p2 / p2->p1                                                                           */
-  XGC_S_GC_KISS_B,
+  XGC_S_ANAL,          /* k = 4*act + {0 condom, 1 position (versatile pairs), 2 HIV transmission, 3 GC transmission:
+                          insertive->receptive (u2r) or receptive->insertive (r2u), at most one is possible per act}:
+                          one Philox block per anal act                                                               */
+  XGC_S_ORAL,          /* k0 = direction word: act j is "p1 insertive" iff bit (31-j) of floor(u * 2^32) is set;
+                          k = 1 + act: GC transmission (u2p or p2u, exclusive)                                        */
+  XGC_S_RIM,           /* same layout: k0 direction word (p1 is the rimmer), k = 1 + act: p2r or r2p                 */
+  XGC_S_KISS,          /* k = act: p2p from whichever partner is infected                                             */
   XGC_S_EDGE_END
 };
 #define XGC_EDGE_STREAMS (XGC_S_EDGE_END - XGC_S_EDGE0)
@@ -155,7 +149,9 @@ static inline XGC_HD int xgc_stream_width(int s) {
   s = (s - XGC_S_EDGE0) % XGC_EDGE_STREAMS + XGC_S_EDGE0;
   if (s == XGC_S_DISSOLVE) return 1;
   if (s == XGC_S_ACTS) return 4;
-  return XGC_MAX_ACTS;
+  if (s == XGC_S_ANAL) return 4 * XGC_MAX_ACTS;
+  if (s == XGC_S_KISS) return XGC_MAX_ACTS;
+  return 1 + XGC_MAX_ACTS;
 }
 
 /* Injected-draw table for ONE replicate and ONE week.  Layout: for each stream s in increasing order, a block of
@@ -249,8 +245,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_M_STITX) X(XGC_M_STITRANS) X(XGC_M_PREV) X(XGC_M_ALL) \
   X(XGC_S_AGENT1) X(XGC_S_AGENT2) X(XGC_S_INFECT) \
   X(XGC_S_ARRIVE_ATTR) X(XGC_S_ARRIVE_N) X(XGC_S_PATHORDER) X(XGC_S_NET_N) X(XGC_S_FORM) X(XGC_S_EDGE0) X(XGC_S_DISSOLVE) \
-  X(XGC_S_ACTS) X(XGC_S_COND) X(XGC_S_POS) X(XGC_S_OIDIR) X(XGC_S_RIMDIR) X(XGC_S_HIVTRANS) X(XGC_S_GC_AI_A) X(XGC_S_GC_AI_B) \
-  X(XGC_S_GC_OI_A) X(XGC_S_GC_OI_B) X(XGC_S_GC_RIM_A) X(XGC_S_GC_RIM_B) X(XGC_S_GC_KISS_A) X(XGC_S_GC_KISS_B) \
+  X(XGC_S_ACTS) X(XGC_S_ANAL) X(XGC_S_ORAL) X(XGC_S_RIM) X(XGC_S_KISS) \
   X(XGC_K_NUM) X(XGC_K_INUM) X(XGC_K_INUM_DX) X(XGC_K_VSUPP) X(XGC_K_INCID_HIV) X(XGC_K_PREPELIG) X(XGC_K_PREPCURR) \
   X(XGC_K_INUM_GC) X(XGC_K_INUM_RGC) X(XGC_K_INUM_UGC) X(XGC_K_INUM_PGC) X(XGC_K_INCID_RGC) X(XGC_K_INCID_UGC) X(XGC_K_INCID_PGC) \
   X(XGC_K_NGROUP) X(XGC_K_PATH) X(XGC_K_VISITS) X(XGC_K_VISITS_SYMPT) X(XGC_K_TESTED) X(XGC_K_POS) X(XGC_K_TXSTART) \

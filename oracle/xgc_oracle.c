@@ -570,7 +570,7 @@ static void condoms_msm(orc_dat* d, int at) {
       for (int type = 0; type < 4; ++type)
         for (int k = 0; k < cnts[type]; ++k) {
           orc_act r = { l, e, type, k, 0, 0 };
-          if (type == 0) r.uai = orc_bern(U(d, at, base + (XGC_S_COND - XGC_S_EDGE0), ua, ub, (size_t)e, k), 1.0 - pc);
+          if (type == 0) r.uai = orc_bern(U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), ua, ub, (size_t)e, 4 * k), 1.0 - pc);
           al_push(d, r);
         }
     }
@@ -590,10 +590,14 @@ static void position_msm(orc_dat* d, int at) {
       else {
         double q1 = d->a[A_INSQ][g->p1], q2 = d->a[A_INSQ][g->p2];
         double pi = q1 + q2 > 0.0 ? q1 / (q1 + q2) : 0.5;
-        r->p1act = orc_bern(U(d, at, base + (XGC_S_POS - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), pi);
+        r->p1act = orc_bern(U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), ua, ub, (size_t)r->e, 4 * r->k + 1), pi);
       }
-    } else if (r->type == 1) r->p1act = orc_bern(U(d, at, base + (XGC_S_OIDIR - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), 0.5);
-    else if (r->type == 3) r->p1act = orc_bern(U(d, at, base + (XGC_S_RIMDIR - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), 0.5);
+    } else if (r->type == 1 || r->type == 3) {
+      /* direction of oral / rimming act j: bit (31 - j) of the 32-bit direction word floor(u * 2^32) (draw k0) */
+      double u = U(d, at, base + ((r->type == 1 ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0), ua, ub, (size_t)r->e, 0);
+      uint32_t w = (uint32_t)(u * 4294967296.0);
+      r->p1act = (int)((w >> (31 - r->k)) & 1u);
+    }
   }
   d->al_has_pos = 1;
 }
@@ -678,7 +682,7 @@ static void hivtrans_msm(orc_dat* d, int at) {
     t = t * p[XGC_P_trans_scale + nrace];
     if (t > 1.0) t = 1.0;
     int base = XGC_S_EDGE0 + r->layer * XGC_EDGE_STREAMS;
-    double u = U(d, at, base + (XGC_S_HIVTRANS - XGC_S_EDGE0), (uint32_t)d->a[A_UID][g->p1], (uint32_t)d->a[A_UID][g->p2], (size_t)r->e, r->k);
+    double u = U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), (uint32_t)d->a[A_UID][g->p1], (uint32_t)d->a[A_UID][g->p2], (size_t)r->e, 4 * r->k + 2);
     if (orc_bern(u, t)) d->newmask[neg] |= 1u << 7;
   }
   uint32_t* c = CNT(d, at);
@@ -765,26 +769,27 @@ static void stitrans_msm_rand(orc_dat* d, int at) {
     const orc_edge* g = &d->el[r->layer][r->e];
     int base = XGC_S_EDGE0 + r->layer * XGC_EDGE_STREAMS;
     uint32_t ua = (uint32_t)d->a[A_UID][g->p1], ub = (uint32_t)d->a[A_UID][g->p2];
-    int x, y, sx, sy, pathA, pathB, sA, sB; double tA, tB;
-    /* x = active partner (insertive / rimmer / p1), y = the other; A: x's site sx -> y's site sy; B: reverse */
-    if (r->type == 0)      { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 0; pathA = XGC_PATH_U2R; pathB = XGC_PATH_R2U; tA = p[XGC_P_u2rgc_tprob]; tB = p[XGC_P_r2ugc_tprob]; sA = XGC_S_GC_AI_A; sB = XGC_S_GC_AI_B; }
-    else if (r->type == 1) { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 2; pathA = XGC_PATH_U2P; pathB = XGC_PATH_P2U; tA = p[XGC_P_u2pgc_tprob]; tB = p[XGC_P_p2ugc_tprob]; sA = XGC_S_GC_OI_A; sB = XGC_S_GC_OI_B; }
+    int x, y, sx, sy, pathA, pathB, st, kk; double tA, tB;
+    /* x = active partner (insertive / rimmer / p1), y = the other; A: x's site sx -> y's site sy; B: reverse.
+       A and B exclude each other (each needs exactly one of the two sites infected), so they share one draw per act. */
+    if (r->type == 0)      { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 0; pathA = XGC_PATH_U2R; pathB = XGC_PATH_R2U; tA = p[XGC_P_u2rgc_tprob]; tB = p[XGC_P_r2ugc_tprob]; st = XGC_S_ANAL; kk = 4 * r->k + 3; }
+    else if (r->type == 1) { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 2; pathA = XGC_PATH_U2P; pathB = XGC_PATH_P2U; tA = p[XGC_P_u2pgc_tprob]; tB = p[XGC_P_p2ugc_tprob]; st = XGC_S_ORAL; kk = 1 + r->k; }
     else if (r->type == 3) { if (!d->c[XGC_C_transRoute_Rimming]) continue;
-                             x = r->p1act ? g->p1 : g->p2; sx = 2; sy = 0; pathA = XGC_PATH_P2R; pathB = XGC_PATH_R2P; tA = p[XGC_P_p2rgc_tprob]; tB = p[XGC_P_r2pgc_tprob]; sA = XGC_S_GC_RIM_A; sB = XGC_S_GC_RIM_B; }
+                             x = r->p1act ? g->p1 : g->p2; sx = 2; sy = 0; pathA = XGC_PATH_P2R; pathB = XGC_PATH_R2P; tA = p[XGC_P_p2rgc_tprob]; tB = p[XGC_P_r2pgc_tprob]; st = XGC_S_RIM; kk = 1 + r->k; }
     else                   { if (!d->c[XGC_C_transRoute_Kissing]) continue;
-                             x = g->p1; sx = 2; sy = 2; pathA = XGC_PATH_P2P; pathB = XGC_PATH_P2P; tA = p[XGC_P_p2pgc_tprob]; tB = tA; sA = XGC_S_GC_KISS_A; sB = XGC_S_GC_KISS_B; }
+                             x = g->p1; sx = 2; sy = 2; pathA = XGC_PATH_P2P; pathB = XGC_PATH_P2P; tA = p[XGC_P_p2pgc_tprob]; tB = tA; st = XGC_S_KISS; kk = r->k; }
     y = x == g->p1 ? g->p2 : g->p1;
     int gx = (int)d->a[A_GC + sx][x] == 1, gy = (int)d->a[A_GC + sy][y] == 1;
     int condom = r->type == 0 && !r->uai;
     if (gx && !gy && d->a[A_GC_INF + sx][x] < (double)at) {
       double t = tA;
       if (condom) t = t * (1.0 - p[XGC_P_sti_cond_eff] * (1.0 - p[XGC_P_sti_cond_fail + (int)d->a[A_RACE][y] - 1]));
-      if (orc_bern(U(d, at, base + (sA - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), t)) d->newmask[y] |= 1u << pathA;
+      if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[y] |= 1u << pathA;
     }
     if (gy && !gx && d->a[A_GC_INF + sy][y] < (double)at) {
       double t = tB;
       if (condom) t = t * (1.0 - p[XGC_P_sti_cond_eff] * (1.0 - p[XGC_P_sti_cond_fail + (int)d->a[A_RACE][x] - 1]));
-      if (orc_bern(U(d, at, base + (sB - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), t)) d->newmask[x] |= 1u << pathB;
+      if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[x] |= 1u << pathB;
     }
   }
   /* "_rand": weekly random order of the 7 pathways decides which pathway a multiply-hit site is attributed to */

@@ -117,7 +117,8 @@ def stream_width(s: int) -> int:
         return {K.S_AGENT1: 4, K.S_AGENT2: 16, K.S_INFECT: 6,
                 K.S_ARRIVE_ATTR: 8, K.S_ARRIVE_N: 64, K.S_PATHORDER: 6, K.S_NET_N: 3}.get(s, 2 * K.FORM_TRIES)
     s = (s - K.S_EDGE0) % K.EDGE_STREAMS + K.S_EDGE0
-    return 1 if s == K.S_DISSOLVE else 4 if s == K.S_ACTS else K.MAX_ACTS
+    return (1 if s == K.S_DISSOLVE else 4 if s == K.S_ACTS else 4 * K.MAX_ACTS if s == K.S_ANAL else
+            K.MAX_ACTS if s == K.S_KISS else 1 + K.MAX_ACTS)
 
 
 def stream_entities(s: int, uid_cap: int, e_cap, form_cap: int) -> int:

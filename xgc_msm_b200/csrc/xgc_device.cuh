@@ -119,6 +119,13 @@ template <bool INJ> struct DrawT {
     if (INJ) return;
     v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b;
   }
+  // the 32-bit word behind draw k (direction bits of oral / rimming acts): floor(u * 2^32)
+  __device__ __forceinline__ unsigned bits32(int k) {
+    if (INJ) return (unsigned)(u[k] * 4294967296.0);
+    int b = k >> 2;
+    if (b != blk) { v = philox4x32_10(make_uint4(at, (stream << 16) | (unsigned)b, e0, e1), make_uint2(seed, rep)); blk = b; }
+    return (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+  }
   __device__ __forceinline__ double operator()(int k) {
     if (INJ) return u[k];
     int b = k >> 2;

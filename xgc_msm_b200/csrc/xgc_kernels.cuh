@@ -430,7 +430,7 @@ template <class D> __device__ __forceinline__ int edge_ai_p1ins(const EdgeCtx& x
   if (r1 == 1 || r2 == 0) return 0;
   double q1 = (double)x.insq_a, q2 = (double)x.insq_b;
   double pi = q1 + q2 > 0.0 ? q1 / (q1 + q2) : 0.5;
-  return xgc_bern(dpos(k), pi);
+  return xgc_bern(dpos(4 * k + 1), pi);
 }
 
 // kissing / rimming counts of one edge-week: constant-rate Poisson (main, casual) or Bernoulli (one-off), gated by the
@@ -529,8 +529,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __gr
       if (ai > 0 && (ua || ub)) {
         bool uai = false;
         double pc = edge_cond_prob(g, P, x, false);
-        DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-        for (int k = 0; k < ai && !uai; ++k) uai = xgc_bern(dc(k), 1.0 - pc);
+        DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_ANAL - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        for (int k = 0; k < ai && !uai; ++k) uai = xgc_bern(dc(4 * k), 1.0 - pc);
         short4* tck = g.tck + (size_t)r * g.n_cap;
         if (ua && (uai || (x.cb.w & HV_DIAG))) tck[x.ed.x].y = (short)at;
         if (ub && (uai || (x.ca.w & HV_DIAG))) tck[x.ed.y].y = (short)at;
@@ -742,11 +742,7 @@ template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const 
                                           (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
   x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
   double pc = edge_cond_prob(g, P, x, true);
-  DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dh(inj, g, r, at, x.base + (XGC_S_HIVTRANS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dA(inj, g, r, at, x.base + (XGC_S_GC_AI_A - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dB(inj, g, r, at, x.base + (XGC_S_GC_AI_B - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> da(inj, g, r, at, x.base + (XGC_S_ANAL - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);     // one Philox block per act
   bool a_pos = ca.w & HV_STATUS;
   uint4 cp = a_pos ? ca : cb, cn = a_pos ? cb : ca;
   double vlf = 0.0; int nrace = (int)DM_RACE(cn.y);
@@ -754,8 +750,8 @@ template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const 
   unsigned gpre_n = (cn.z >> GC_PRE_SHIFT) & 7u;          // negative partner's GC status as hivtrans saw it
   unsigned new_a = 0, new_b = 0; bool hiv_a = false, hiv_b = false;
   for (int k = 0; k < ai; ++k) {
-    int uai = xgc_bern(dc(k), 1.0 - pc);
-    int p1ins = edge_ai_p1ins(x, dp, k);
+    int uai = xgc_bern(da(4 * k), 1.0 - pc);
+    int p1ins = edge_ai_p1ins(x, da, k);
     if (hivdisc) {
       bool pos_ins = (p1ins != 0) == a_pos;
       double t;
@@ -767,7 +763,7 @@ template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const 
       if (cn.w & HV_PREP) { unsigned cl = HV_PREPCLASS(cn.w); if (cl >= 1) t = t * P[XGC_P_prep_adhr_hr + cl - 1]; }
       t = t * P[XGC_P_trans_scale + nrace];
       if (t > 1.0) t = 1.0;
-      if (xgc_bern(dh(k), t)) { if (a_pos) hiv_b = true; else hiv_a = true; }
+      if (xgc_bern(da(4 * k + 2), t)) { if (a_pos) hiv_b = true; else hiv_a = true; }
     }
     if (d_ai) {                                         // insertive partner's urethra <-> receptive partner's rectum
       unsigned gx = p1ins ? ga : gb, gy = p1ins ? gb : ga;
@@ -775,12 +771,12 @@ template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const 
       if (ux && !ry) {
         double t = P[XGC_P_u2rgc_tprob];
         if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? cb.y : ca.y)]));
-        if (xgc_bern(dA(k), t)) { if (p1ins) new_b |= 1u << XGC_PATH_U2R; else new_a |= 1u << XGC_PATH_U2R; }
+        if (xgc_bern(da(4 * k + 3), t)) { if (p1ins) new_b |= 1u << XGC_PATH_U2R; else new_a |= 1u << XGC_PATH_U2R; }
       }
       if (ry && !ux) {
         double t = P[XGC_P_r2ugc_tprob];
         if (!uai) t = t * (1.0 - P[XGC_P_sti_cond_eff] * (1.0 - P[XGC_P_sti_cond_fail + (int)DM_RACE(p1ins ? ca.y : cb.y)]));
-        if (xgc_bern(dB(k), t)) { if (p1ins) new_a |= 1u << XGC_PATH_R2U; else new_b |= 1u << XGC_PATH_R2U; }
+        if (xgc_bern(da(4 * k + 3), t)) { if (p1ins) new_a |= 1u << XGC_PATH_R2U; else new_b |= 1u << XGC_PATH_R2U; }
       }
     }
   }
@@ -801,16 +797,15 @@ template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, co
   int sx = oral ? 1 : 2, sy = oral ? 2 : 0;                 // active partner's site, other partner's site
   double tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob], tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
   unsigned pA = oral ? XGC_PATH_U2P : XGC_PATH_P2R, pB = oral ? XGC_PATH_P2U : XGC_PATH_R2P;
-  DrawT<INJ> dd(inj, g, r, at, base + ((oral ? XGC_S_OIDIR : XGC_S_RIMDIR) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dA(inj, g, r, at, base + ((oral ? XGC_S_GC_OI_A : XGC_S_GC_RIM_A) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  DrawT<INJ> dB(inj, g, r, at, base + ((oral ? XGC_S_GC_OI_B : XGC_S_GC_RIM_B) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> dd(inj, g, r, at, base + ((oral ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  unsigned dirword = n > 0 ? dd.bits32(0) : 0u;             // act j: p1 is the active partner iff bit (31 - j) is set
   unsigned new_a = 0, new_b = 0;
   for (int k = 0; k < n; ++k) {
-    int p1act = xgc_bern(dd(k), 0.5);
+    int p1act = (dirword >> (31 - k)) & 1u;
     unsigned gx = p1act ? ga : gb, gy = p1act ? gb : ga;
     bool ix = (gx >> sx) & 1u, iy = (gy >> sy) & 1u;
-    if (ix && !iy && xgc_bern(dA(k), tA)) { if (p1act) new_b |= 1u << pA; else new_a |= 1u << pA; }
-    if (iy && !ix && xgc_bern(dB(k), tB)) { if (p1act) new_a |= 1u << pB; else new_b |= 1u << pB; }
+    if (ix && !iy) { if (xgc_bern(dd(1 + k), tA)) { if (p1act) new_b |= 1u << pA; else new_a |= 1u << pA; } }
+    else if (iy && !ix) { if (xgc_bern(dd(1 + k), tB)) { if (p1act) new_a |= 1u << pB; else new_b |= 1u << pB; } }
   }
   e2_flag(core, ed, new_a, new_b, false, false);
 }
@@ -821,7 +816,7 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
   edge_kiss_rim(P, l, ca, cb, da, tab, true, false, n, dummy);       // this week's kissing count, evaluated only here
   if (n == 0) return;
   bool pa = (ca.z >> 2) & 1u;
-  DrawT<INJ> d(inj, g, r, at, base + ((pa ? XGC_S_GC_KISS_A : XGC_S_GC_KISS_B) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  DrawT<INJ> d(inj, g, r, at, base + (XGC_S_KISS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
   double t = P[XGC_P_p2pgc_tprob];
   bool hit = false;
   for (int k = 0; k < n; ++k) hit |= (bool)xgc_bern(d(k), t);
@@ -1133,16 +1128,15 @@ template <bool INJ> __global__ void k_actlist(const __grid_constant__ Dev g, con
       x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
       int cnt[4] = { x.ed.w & 0xFF, (x.ed.w >> 8) & 0xFF, (x.ed.w >> 16) & 0xFF, (x.ed.w >> 24) & 0xFF };
       double pc = cnt[0] > 0 ? edge_cond_prob(g, P, x, false) : 0.0;
-      DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_COND - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      DrawT<INJ> dp(inj, g, r, at, x.base + (XGC_S_POS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      DrawT<INJ> doi(inj, g, r, at, x.base + (XGC_S_OIDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-      DrawT<INJ> dri(inj, g, r, at, x.base + (XGC_S_RIMDIR - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_ANAL - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> doi(inj, g, r, at, x.base + (XGC_S_ORAL - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+      DrawT<INJ> dri(inj, g, r, at, x.base + (XGC_S_RIM - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
       for (int type = 0; type < 4; ++type)
         for (int k = 0; k < cnt[type]; ++k) {
           int uai = 0, p1 = 0;
-          if (type == 0) { uai = xgc_bern(dc(k), 1.0 - pc); p1 = edge_ai_p1ins(x, dp, k); }
-          else if (type == 1) p1 = xgc_bern(doi(k), 0.5);
-          else if (type == 3) p1 = xgc_bern(dri(k), 0.5);
+          if (type == 0) { uai = xgc_bern(dc(4 * k), 1.0 - pc); p1 = edge_ai_p1ins(x, dc, k); }
+          else if (type == 1) p1 = (doi.bits32(0) >> (31 - k)) & 1u;
+          else if (type == 3) p1 = (dri.bits32(0) >> (31 - k)) & 1u;
           if (n < cap) { al[n] = l; al[cap + n] = e; al[2 * cap + n] = type; al[3 * cap + n] = k; al[4 * cap + n] = uai; al[5 * cap + n] = p1; }
           n++;
         }
