@@ -90,6 +90,8 @@ struct Dev {                 // everything a kernel needs; passed by value
   unsigned* q_count;         // [R][4]
   unsigned* qa_items;        // [R][n_cap] work queue of k_agent2b: slot | asymptomatic-visit draw << 31
   unsigned* qa_count;        // [R]
+  unsigned* qh_items;        // [R][n_cap] work queue of k_agent1b (HIV-positive agents): slot | tested << 31 | died << 30
+  unsigned* qh_count;        // [R]
   unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
   const int* at_ptr;
 };

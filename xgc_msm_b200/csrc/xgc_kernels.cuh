@@ -1,7 +1,8 @@
 // Hand-written sm_100a kernels of the weekly epidemic step.  No tensor cores: the path is scan / gather / compaction
 // work bound by HBM bandwidth.  One week =
 //   k_begin   (1 warp / replicate)    week bookkeeping, arrivals (arrival_msm), pathway order
-//   k_agent1  (1 thread / slot)       aging, departure, hivtest, hivtx, hivprogress, hivvl        [reads core+aux]
+//   k_agent1a (1 thread / slot)       aging, natural mortality, HIV test draw; queue HIV-positives  [reads core+aux+tck]
+//   k_agent1b (1 thread / queued)     AIDS mortality, test result, hivtx, hivprogress, hivvl        [reads core+HIV clocks]
 //   k_edges_prune / k_rank / k_form   edge deletion for departed agents; surrogate for simnet_msm
 //   k_edge1   (1 thread / edge)       acts (+ exposure history, PrEP risk history)                [gathers core+aux]
 //   k_agent2a (1 thread / slot)       prep; queue agents with GC work                              [reads core+tck]
@@ -59,6 +60,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   __syncwarp();
   if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
   if (lane == 4) g.qa_count[r] = 0u;
+  if (lane == 5) g.qh_count[r] = 0u;
   if (lane == 0) {
     ((int*)g.at_ptr)[r] = at;
     rp->n_slots_pre = n_slots;
@@ -126,7 +128,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // Agent kernels: each CTA walks `tpc` consecutive 256-slot tiles of one replicate.  The next tile's core word is loaded
 // (and its secondary planes prefetched into L2) before the current tile is processed, so every thread keeps two tiles
 // of loads in flight; fewer, longer CTAs also mean fewer flushes of the per-CTA tallies.
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap, int tpc) {
+// k_agent1a: everything every agent goes through: start-of-week snapshot bits, aging, natural mortality, the HIV
+// interval-test draw.  HIV-positive agents (a minority, with long divergent code paths: AIDS mortality, test result,
+// treatment, progression, viral load) are appended to the replicate's work queue and finished densely by k_agent1b.
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -136,122 +141,164 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1(const __grid
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
-  int at = g.at_ptr[r];
-  int n_pre = rp->n_slots_pre, t_ref = rp->t_ref, t_age = rp->t_age;
+  int at = g.at_ptr[r], lane = threadIdx.x & 31;
+  int n_pre = rp->n_slots_pre;
+  const double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   unsigned* row = counter_row(g, r, at);
+  unsigned* Q = g.qh_items + rbase;
+  const bool hivmods = mask & (XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL);
   for (int t = t0; t < t1; ++t) {
-  int i = t * TPB + threadIdx.x;
-  size_t idx = rbase + i;
-  uint4 c = cn; Aux ax = axn; short lnt = lntn;
-  if (t + 1 < t1) { cn = g.core[idx + TPB]; axn = g.aux[idx + TPB]; lntn = g.tck[idx + TPB].x; }
-  bool live = i < n_slots;
-  live = live && (c.y & DM_ACTIVE);
-  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
-  if (snap) {       // start of week: remember the GC / PrEP bits that acts, condoms and hivtrans must see (they run before
+    int i = t * TPB + threadIdx.x;
+    size_t idx = rbase + i;
+    uint4 c = cn; Aux ax = axn; short lnt = lntn;
+    if (t + 1 < t1) { cn = g.core[idx + TPB]; axn = g.aux[idx + TPB]; lntn = g.tck[idx + TPB].x; }
+    bool live = i < n_slots && (c.y & DM_ACTIVE);
+    unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
+    if (snap) {     // start of week: remember the GC / PrEP bits that acts, condoms and hivtrans must see (they run before
                     // prep / stirecov / stitx in the reference's module order)
-    gc = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
-    hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
+      gc = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
+      hiv = (hiv & ~HV_PREP_PRE) | ((hiv & HV_PREP) ? HV_PREP_PRE : 0u);
+    }
+    bool isnew = i >= n_pre;
+    bool hivpos = live && (hiv & HV_STATUS);
+    double age = ax.age_ref + dt;
+    int race = (int)DM_RACE(demo);
+    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);     // k0 natural mortality and k2 interval test: one Philox block
+    if ((mask & XGC_M_AGING) && live && !isnew) demo = (demo & ~(7u << 2)) | (xgc_age_group(age) << 2);
+    bool dep_g = false;
+    if ((mask & XGC_M_DEPARTURE) && live && !isnew) {
+      int ai = (int)floor(age); if (ai < 0) ai = 0; if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
+      dep_g = xgc_bern(d(0), g.tables[XGC_T_ASMR + race * XGC_ASMR_AGES + ai]);
+    }
+    if (mask & XGC_M_DEPARTURE) {
+      unsigned dm = __ballot_sync(0xffffffffu, dep_g);
+      if (dm && lane == 0) {
+        atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~dm);
+        atomicSub((int*)&rp->n_alive, __popc(dm));
+        atomicAdd(row + XGC_K_DEP_GEN, (unsigned)__popc(dm));
+      }
+    }
+    if (dep_g) demo &= ~DM_ACTIVE;
+    // hivtest_msm: who gets tested this week (the result of a positive's test is settled in k_agent1b)
+    bool tested = false;
+    if ((mask & XGC_M_HIVTEST) && live && !dep_g && !(hiv & HV_DIAG)) {
+      int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
+      double tsl = (double)(at - last);
+      if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) tested = xgc_bern(d(2), P[XGC_P_hiv_test_rate + race]);
+      if (HV_STAGE(hiv) == 4 && tsl >= P[XGC_P_aids_test_int]) tested = true;
+      if ((hiv & HV_PREP) && tsl >= P[XGC_P_prep_tst_int]) tested = true;
+      if (tested && !(hiv & HV_STATUS)) g.tck[idx].x = (short)at;
+    }
+    if (mask & XGC_M_HIVTEST) warp_tally(row, XGC_K_HIVTESTS, tested);
+    if (i < n_slots && (demo != c.y || gc != c.z || hiv != c.w)) {
+      uint2* q = (uint2*)&g.core[idx];
+      if (demo != c.y) q[0].y = demo;
+      if (gc != c.z || hiv != c.w) q[1] = make_uint2(gc, hiv);
+    }
+    // queue the HIV-positive agents (also those who just died of natural causes: their AIDS-mortality draw is still tallied)
+    bool queue = hivmods && hivpos && !isnew;
+    unsigned m = __ballot_sync(0xffffffffu, queue);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(g.qh_count + r, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (tested ? 0x80000000u : 0u) | (dep_g ? 0x40000000u : 0u);
+    }
   }
-  bool isnew = i >= n_pre;
-  bool hivpos = live && (hiv & HV_STATUS);
-  double age = ax.age_ref + (double)(t_age - t_ref) * XGC_WEEK;
-  int race = (int)DM_RACE(demo);
-  DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);       // the whole pass draws from ONE Philox block per agent
-  if ((mask & XGC_M_AGING) && live && !isnew) demo = (demo & ~(7u << 2)) | (xgc_age_group(age) << 2);
-  bool dep_g = false, dep_a = false;
-  if ((mask & XGC_M_DEPARTURE) && live && !isnew) {
-    int ai = (int)floor(age); if (ai < 0) ai = 0; if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
-    dep_g = xgc_bern(d(0), g.tables[XGC_T_ASMR + race * XGC_ASMR_AGES + ai]);
-    if (HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
+}
+
+// k_agent1b: AIDS mortality, HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued HIV-positive agents
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  unsigned n = g.qh_count[r];
+  if (blockIdx.x * TPB >= n) return;
+  unsigned qi = blockIdx.x * TPB + threadIdx.x;
+  Rep* rp = g.rep + r;
+  const size_t rbase = (size_t)r * g.n_cap;
+  int at = g.at_ptr[r];
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  unsigned* row = counter_row(g, r, at);
+  bool dep_a = false, dead_before = false;
+  if (qi < n) {
+    unsigned item = g.qh_items[rbase + qi];
+    bool tested = item >> 31; dead_before = (item >> 30) & 1u;
+    int i = (int)(item & 0x3FFFFFFFu);
+    size_t idx = rbase + i;
+    uint4 c = g.core[idx];
+    unsigned uid = c.x, demo = c.y, hiv = c.w;
+    int race = (int)DM_RACE(demo);
+    unsigned traj = DM_TTTRAJ(demo);
+    DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);
+    if ((mask & XGC_M_DEPARTURE) && HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
+    if (dep_a && !dead_before) {
+      atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~(1u << (i & 31)));
+      ((uint2*)&g.core[idx])[0].y = demo & ~DM_ACTIVE;
+    }
+    if (!dep_a && !dead_before) {
+      short4 ha = g.hck_a[idx], hb = g.hck_b[idx];
+      bool ha_dirty = false, hb_dirty = false;
+      if ((mask & XGC_M_HIVTEST) && tested) {
+        if ((double)(at - (int)ha.x) >= P[XGC_P_test_window_int]) { hiv |= HV_DIAG; ha.y = (short)at; ha_dirty = true; }
+        else g.tck[idx].x = (short)at;
+      }
+      if (mask & XGC_M_HIVTX) {
+        if (hiv & HV_DIAG) {
+          if (!(hiv & HV_TX) && hb.x == 0) {
+            if (xgc_bern(d(3), P[XGC_P_tx_init_prob + race])) { hiv |= HV_TX; ha.w = (short)at; ha_dirty = true; }
+          } else if (hiv & HV_TX) {
+            double rr = traj == 2 ? P[XGC_P_tx_halt_full_rr + race] : traj == 3 ? P[XGC_P_tx_halt_dur_rr + race] : 1.0;
+            if (xgc_bern(d(3), P[XGC_P_tx_halt_part_prob + race] * rr)) hiv &= ~HV_TX;
+          } else {
+            double rr = traj == 2 ? P[XGC_P_tx_reinit_full_rr + race] : traj == 3 ? P[XGC_P_tx_reinit_dur_rr + race] : 1.0;
+            if (xgc_bern(d(3), P[XGC_P_tx_reinit_part_prob + race] * rr)) hiv |= HV_TX;
+          }
+        }
+        if (hiv & HV_TX) hb.x++; else hb.y++;
+        hb_dirty = true;
+      }
+      double tsi = (double)(at - (int)ha.x);
+      if (mask & XGC_M_HIVPROGRESS) {
+        unsigned stage = HV_STAGE(hiv);
+        if (stage == 1 && tsi >= P[XGC_P_vl_acute_rise_int]) { stage = 2; ha.z = (short)at; ha_dirty = true; }
+        if (stage == 2 && tsi >= P[XGC_P_vl_acute_rise_int] + P[XGC_P_vl_acute_fall_int]) { stage = 3; ha.z = (short)at; ha_dirty = true; }
+        if (stage == 3) {
+          bool aids = false; double on = (double)hb.x, off = (double)hb.y;
+          if (on == 0.0 && tsi >= P[XGC_P_vl_aids_onset_int]) aids = true;
+          if (traj == 1 && on > 0.0 && off / P[XGC_P_max_time_off_tx_part_int] + on / P[XGC_P_max_time_on_tx_part_int] >= 1.0) aids = true;
+          if (traj >= 2 && !(hiv & HV_TX) && on > 0.0 && off >= P[XGC_P_max_time_off_tx_full_int]) aids = true;
+          if (aids) { stage = 4; ha.z = (short)at; ha_dirty = true; }
+        }
+        hiv = (hiv & ~HV_STAGE_MASK) | (stage << 1);
+      }
+      if (mask & XGC_M_HIVVL) {
+        unsigned stage = HV_STAGE(hiv);
+        float vl0 = g.aux[idx].vl;
+        double v, vl = (double)vl0, peak = P[XGC_P_vl_acute_peak], sp = P[XGC_P_vl_set_point];
+        if (!(hiv & HV_TX)) {
+          if (stage == 1) { v = peak * (tsi / P[XGC_P_vl_acute_rise_int]); if (v > peak) v = peak; }
+          else if (stage == 2) { v = peak - (peak - sp) * ((tsi - P[XGC_P_vl_acute_rise_int]) / P[XGC_P_vl_acute_fall_int]); if (v < sp) v = sp; }
+          else if (stage == 3) { if (hb.x == 0) v = sp; else { v = vl + P[XGC_P_vl_tx_up_slope]; if (v > sp) v = sp; } }
+          else { double tsa = (double)(at - (int)ha.z);
+                 v = sp + (tsa / P[XGC_P_vl_aids_int]) * (P[XGC_P_vl_aids_peak] - sp); if (v > P[XGC_P_vl_aids_peak]) v = P[XGC_P_vl_aids_peak]; }
+        } else {
+          double target = traj == 1 ? P[XGC_P_vl_part_supp] : P[XGC_P_vl_full_supp];
+          double slope = stage == 4 ? P[XGC_P_vl_tx_aids_down_slope] : P[XGC_P_vl_tx_down_slope];
+          v = vl - slope; if (v < target) v = target;
+        }
+        float vf = (float)v;
+        if (vf != vl0) g.aux[idx].vl = vf;
+        hiv = (hiv & ~HV_VSUPP) | ((double)vf <= XGC_LOG10_200 ? HV_VSUPP : 0u);
+      }
+      if (ha_dirty) g.hck_a[idx] = ha;
+      if (hb_dirty) g.hck_b[idx] = hb;
+      if (hiv != c.w) ((uint2*)&g.core[idx])[1].y = hiv;
+    }
   }
   if (mask & XGC_M_DEPARTURE) {
-    warp_tally(row, XGC_K_DEP_GEN, dep_g); warp_tally(row, XGC_K_DEP_AIDS, dep_a);
-    unsigned dm = __ballot_sync(0xffffffffu, dep_g || dep_a);
-    if (dm && (threadIdx.x & 31) == 0) {
-      g.alive[(size_t)r * (g.n_cap / 32) + (i >> 5)] &= ~dm;
-      atomicSub((int*)&rp->n_alive, __popc(dm));
-    }
-  }
-  if (dep_g || dep_a) { demo &= ~DM_ACTIVE; live = false; hivpos = false; }
-  // ---- HIV care cascade
-  bool tested = false;
-  short4 ha = na4(), hb = make_short4(0, 0, -1, -1);
-  bool ha_dirty = false, hb_dirty = false;
-  if (hivpos && (mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL))) { ha = g.hck_a[idx]; hb = g.hck_b[idx]; }
-  if ((mask & XGC_M_HIVTEST) && live && !(hiv & HV_DIAG)) {
-    int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
-    double tsl = (double)(at - last);
-    if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) {
-      tested = xgc_bern(d(2), P[XGC_P_hiv_test_rate + race]);
-    }
-    if (HV_STAGE(hiv) == 4 && tsl >= P[XGC_P_aids_test_int]) tested = true;
-    if ((hiv & HV_PREP) && tsl >= P[XGC_P_prep_tst_int]) tested = true;
-    if (tested) {
-      if ((hiv & HV_STATUS) && (double)(at - (int)ha.x) >= P[XGC_P_test_window_int]) { hiv |= HV_DIAG; ha.y = (short)at; ha_dirty = true; }
-      else g.tck[idx].x = (short)at;
-    }
-  }
-  if (mask & XGC_M_HIVTEST) warp_tally(row, XGC_K_HIVTESTS, tested);
-  if (hivpos) {
-    unsigned traj = DM_TTTRAJ(demo);
-    if (mask & XGC_M_HIVTX) {
-      if (hiv & HV_DIAG) {
-        if (!(hiv & HV_TX) && hb.x == 0) {
-          if (xgc_bern(d(3), P[XGC_P_tx_init_prob + race])) { hiv |= HV_TX; ha.w = (short)at; ha_dirty = true; }
-        } else if (hiv & HV_TX) {
-          double rr = traj == 2 ? P[XGC_P_tx_halt_full_rr + race] : traj == 3 ? P[XGC_P_tx_halt_dur_rr + race] : 1.0;
-          if (xgc_bern(d(3), P[XGC_P_tx_halt_part_prob + race] * rr)) hiv &= ~HV_TX;
-        } else {
-          double rr = traj == 2 ? P[XGC_P_tx_reinit_full_rr + race] : traj == 3 ? P[XGC_P_tx_reinit_dur_rr + race] : 1.0;
-          if (xgc_bern(d(3), P[XGC_P_tx_reinit_part_prob + race] * rr)) hiv |= HV_TX;
-        }
-      }
-      if (hiv & HV_TX) hb.x++; else hb.y++;
-      hb_dirty = true;
-    }
-    double tsi = (double)(at - (int)ha.x);
-    if (mask & XGC_M_HIVPROGRESS) {
-      unsigned stage = HV_STAGE(hiv);
-      if (stage == 1 && tsi >= P[XGC_P_vl_acute_rise_int]) { stage = 2; ha.z = (short)at; ha_dirty = true; }
-      if (stage == 2 && tsi >= P[XGC_P_vl_acute_rise_int] + P[XGC_P_vl_acute_fall_int]) { stage = 3; ha.z = (short)at; ha_dirty = true; }
-      if (stage == 3) {
-        bool aids = false; double on = (double)hb.x, off = (double)hb.y;
-        if (on == 0.0 && tsi >= P[XGC_P_vl_aids_onset_int]) aids = true;
-        if (traj == 1 && on > 0.0 && off / P[XGC_P_max_time_off_tx_part_int] + on / P[XGC_P_max_time_on_tx_part_int] >= 1.0) aids = true;
-        if (traj >= 2 && !(hiv & HV_TX) && on > 0.0 && off >= P[XGC_P_max_time_off_tx_full_int]) aids = true;
-        if (aids) { stage = 4; ha.z = (short)at; ha_dirty = true; }
-      }
-      hiv = (hiv & ~HV_STAGE_MASK) | (stage << 1);
-    }
-    if (mask & XGC_M_HIVVL) {
-      unsigned stage = HV_STAGE(hiv);
-      double v, vl = (double)ax.vl, peak = P[XGC_P_vl_acute_peak], sp = P[XGC_P_vl_set_point];
-      if (!(hiv & HV_TX)) {
-        if (stage == 1) { v = peak * (tsi / P[XGC_P_vl_acute_rise_int]); if (v > peak) v = peak; }
-        else if (stage == 2) { v = peak - (peak - sp) * ((tsi - P[XGC_P_vl_acute_rise_int]) / P[XGC_P_vl_acute_fall_int]); if (v < sp) v = sp; }
-        else if (stage == 3) { if (hb.x == 0) v = sp; else { v = vl + P[XGC_P_vl_tx_up_slope]; if (v > sp) v = sp; } }
-        else { double tsa = (double)(at - (int)ha.z);
-               v = sp + (tsa / P[XGC_P_vl_aids_int]) * (P[XGC_P_vl_aids_peak] - sp); if (v > P[XGC_P_vl_aids_peak]) v = P[XGC_P_vl_aids_peak]; }
-      } else {
-        double target = traj == 1 ? P[XGC_P_vl_part_supp] : P[XGC_P_vl_full_supp];
-        double slope = stage == 4 ? P[XGC_P_vl_tx_aids_down_slope] : P[XGC_P_vl_tx_down_slope];
-        v = vl - slope; if (v < target) v = target;
-      }
-      float vf = (float)v;
-      if (vf != ax.vl) g.aux[idx].vl = vf;
-      hiv = (hiv & ~HV_VSUPP) | ((double)vf <= XGC_LOG10_200 ? HV_VSUPP : 0u);
-    }
-    if (ha_dirty) g.hck_a[idx] = ha;
-    if (hb_dirty) g.hck_b[idx] = hb;
-  }
-  if (i < n_slots && (demo != c.y || gc != c.z || hiv != c.w)) {
-    uint2* q = (uint2*)&g.core[idx];
-    if (demo != c.y) q[0].y = demo;
-    if (gc != c.z) q[1].x = gc;
-    if (hiv != c.w) q[1].y = hiv;
-  }
-  if (t + 1 < t1 && (cn.w & HV_STATUS)) { prefetch_l2(g.hck_a + idx + TPB); prefetch_l2(g.hck_b + idx + TPB); }
+    warp_tally(row, XGC_K_DEP_AIDS, dep_a);
+    unsigned dm = __ballot_sync(0xffffffffu, dep_a && !dead_before);
+    if (dm && (threadIdx.x & 31) == 0) atomicSub((int*)&rp->n_alive, __popc(dm));
   }
 }
 

@@ -117,6 +117,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
   rc |= dalloc(h, &g.q_items, (size_t)g.R * 4 * g.e_stride); rc |= dalloc(h, &g.q_count, (size_t)g.R * 4);
   rc |= dalloc(h, &g.qa_items, NA); rc |= dalloc(h, &g.qa_count, (size_t)g.R);
+  rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
   rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
@@ -445,8 +446,9 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
   LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
-  if (zero_row || (mask & (XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL)))
-    LAUNCHD(h, inj, k_agent1, ga, TPB, g, inj, mask, zero_row, tpc);
+  const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
+  if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
+  if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(tiles, g.R), TPB, g, inj, mask);
   bool native = inj.u == nullptr;
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
   if (mask & XGC_M_RESIM_NETS) {

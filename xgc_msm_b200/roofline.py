@@ -18,8 +18,10 @@ def kernel_bytes(stats: dict) -> dict:
     f_hiv, f_dx, f_gc = stats["f_hiv"], stats["f_dx"], stats["f_gc"]
     f_disc = stats.get("f_disc", 0.6)        # discordant (edge, act type) pairs per edge (measured: queue lengths / edges)
     return {
-        # core R + aux R (age for aging/mortality) + tck R (last.neg.test, undiagnosed) + HIV+: hck_a R, hck_b R+W
-        "k_agent1": n * (16 + 16 + 8 * (1 - f_dx) + f_hiv * (8 + 8 + 8)),
+        # core R + aux R (age for aging/mortality) + tck R (last.neg.test, undiagnosed) (+ 4 B queue entry per HIV-positive)
+        "k_agent1a": n * (16 + 16 + 8 * (1 - f_dx) + f_hiv * 4),
+        # queued HIV-positive agents: item + core + aux (vl) + hck_a R + hck_b R+W
+        "k_agent1b": n * f_hiv * (4 + 16 + 16 + 8 + 8 + 8),
         # prep + classification: core R + tck R (+ 4 B queue entry for agents with GC work)
         "k_agent2a": n * (16 + 8 + f_gc * 4),
         # queued agents (infected or visiting): item + core + gck_a + gck_b
