@@ -889,19 +889,20 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
     int4 ed = E[e];
     uint4 ca = core[ed.x], cb = core[ed.y];
     int ai = ed.w & 0xFF, oi = (ed.w >> 8) & 0xFF;
-    unsigned ga = ca.z & 7u, gb = cb.z & 7u;              // current site status: bit0 rect, bit1 ureth, bit2 phar
+    unsigned x = ca.z & 7u, y = cb.z & 7u;                // current site status: bit0 rect, bit1 ureth, bit2 phar
     bool gct = mask & XGC_M_STITRANS;
     bool hivdisc = (mask & XGC_M_HIVTRANS) && ai > 0 && ((ca.w ^ cb.w) & HV_STATUS);
-    bool d_ai = gct && ai > 0 && ((((ga >> 1) & 1u) && !(gb & 1u)) || ((gb & 1u) && !((ga >> 1) & 1u)) ||
-                                  (((gb >> 1) & 1u) && !(ga & 1u)) || ((ga & 1u) && !((gb >> 1) & 1u)));
-    f[0] = hivdisc || d_ai;
-    f[1] = gct && oi > 0 && ((((ga >> 1) & 1u) && !(gb & 4u)) || ((gb & 4u) && !((ga >> 1) & 1u)) ||
-                             (((gb >> 1) & 1u) && !(ga & 4u)) || ((ga & 4u) && !((gb >> 1) & 1u)));
+    // a pathway pair (site s of one partner, site t of the other) can transmit iff exactly one of the two is infected
+    bool d_ai = (((x >> 1) ^ y) | ((y >> 1) ^ x)) & 1u;                    // urethra <-> rectum
+    bool d_oi = (((x >> 1) ^ (y >> 2)) | ((y >> 1) ^ (x >> 2))) & 1u;      // urethra <-> pharynx
+    bool d_ri = (((x >> 2) ^ y) | ((y >> 2) ^ x)) & 1u;                    // pharynx <-> rectum
+    bool d_ki = ((x ^ y) >> 2) & 1u;                                       // pharynx <-> pharynx
+    f[0] = hivdisc || (gct && ai > 0 && d_ai);
+    f[1] = gct && oi > 0 && d_oi;
     // kissing / rimming: queued on site discordance; their counts are drawn in k_edge2b
     bool stopped = act_stopped(ca.y, ca.z >> GC_PRE_SHIFT) || act_stopped(cb.y, cb.z >> GC_PRE_SHIFT);
-    f[2] = gct && !stopped && C[XGC_C_transRoute_Kissing] && (((ga ^ gb) & 4u) != 0);
-    f[3] = gct && !stopped && C[XGC_C_transRoute_Rimming] &&
-           (((ga & 4u) && !(gb & 1u)) || ((gb & 1u) && !(ga & 4u)) || ((gb & 4u) && !(ga & 1u)) || ((ga & 1u) && !(gb & 4u)));
+    f[2] = gct && !stopped && C[XGC_C_transRoute_Kissing] && d_ki;
+    f[3] = gct && !stopped && C[XGC_C_transRoute_Rimming] && d_ri;
   }
   unsigned b[4];
 #pragma unroll
