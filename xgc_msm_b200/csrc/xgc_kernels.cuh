@@ -314,6 +314,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const _
   int surrogate = dissolve && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1;
   int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
+  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);          // 1 bit per slot: no 16-byte gathers just to see who is alive
   __shared__ int wsum[TPB / 32];
   __shared__ int base;
   if (tid == 0) base = 0;
@@ -325,16 +326,19 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const _
     int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
     if (e < ne) {
       ed = E[e];
-      uint4 ca = core[ed.x], cb = core[ed.y];
-      keep = (ca.y & DM_ACTIVE) && (cb.y & DM_ACTIVE);
-      if (keep && surrogate) { DrawT<INJ> d(inj, g, r, at, es, ca.x, cb.x, (size_t)e); keep = !xgc_bern(d(0), pd); }
+      keep = ((A[ed.x >> 5] >> (ed.x & 31)) & 1u) && ((A[ed.y >> 5] >> (ed.y & 31)) & 1u);
+      if (keep && surrogate) {
+        if (!INJ && (((unsigned)ed.w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep = !((unsigned)ed.w >> 31);   // drawn ahead by k_edge1
+        else { DrawT<INJ> d(inj, g, r, at, es, core[ed.x].x, core[ed.y].x, (size_t)e); keep = !xgc_bern(d(0), pd); }
+      }
     }
     unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) wsum[w] = __popc(m);
     __syncthreads();
     int off = base;
     for (int k = 0; k < w; ++k) off += wsum[k];
-    if (keep) E[off + __popc(m & ((1u << lane) - 1u))] = ed;
+    off += __popc(m & ((1u << lane) - 1u));
+    if (keep && off != e) E[off] = ed;
     __syncthreads();
     if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
     __syncthreads();
@@ -554,7 +558,15 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __gr
           ri = xgc_bern(d(3), P[XGC_P_rim_prob_oo]);
         }
       }
-      x.ed.w = ai | (oi << 8);
+      // surrogate network: next week's dissolution draw of this tie is a pure function of (uids, at + 1); drawing it here,
+      // where the endpoint uids are already gathered, lets k_edges_resim compact next week without touching the agents.
+      unsigned tag = 0x7FFFu, dis = 0u;
+      if (!INJ && l < 2 && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1) {
+        DrawT<INJ> dd(inj, g, r, at + 1, x.base + (XGC_S_DISSOLVE - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        dis = xgc_bern(dd(0), 1.0 / g.tables[XGC_T_NET_DUR + l]);
+        tag = (unsigned)(at + 1) & 0x7FFFu;
+      }
+      x.ed.w = (int)((unsigned)ai | ((unsigned)oi << 8) | (tag << 16) | (dis << 31));
       E[e].w = x.ed.w;
       nai = ai; noi = oi;
       // exposure history for the CDC screening protocol (ambiguity A4)
@@ -1141,12 +1153,12 @@ __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ D
 
 // k_actcounts: materialise the lazily evaluated kissing / rimming counts of one replicate into the edge records
 // (xgc_get_actcounts / dat$temp$el parity); the hot path never needs them for non-discordant edges.
-template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r) {
+template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* out /*[3][emax]: ki | ri << 8*/, int emax) {
   int l = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.rep[r].ne[l]) return;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
-  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
   int4 ed = E[e];
   uint4 ca = core[ed.x], cb = core[ed.y];
@@ -1154,7 +1166,7 @@ template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, c
   int ki, ri;
   DrawT<INJ> da(inj, g, r, at, XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
   edge_kiss_rim(P, l, ca, cb, da, tab, true, true, ki, ri);
-  E[e].w = (ed.w & 0xFFFF) | (ki << 16) | (ri << 24);
+  out[(size_t)l * emax + e] = ki | (ri << 8);
 }
 
 // k_actlist: materialise dat$temp$al for one replicate (debug / parity of condoms_msm + position_msm)
@@ -1174,7 +1186,11 @@ template <bool INJ> __global__ void k_actlist(const __grid_constant__ Dev g, con
       x.ca = core[x.ed.x]; x.cb = core[x.ed.y]; x.base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
       Aux aa = aux[x.ed.x], ab = aux[x.ed.y];
       x.age_a = aa.age_ref + dt; x.age_b = ab.age_ref + dt; x.insq_a = aa.ins_quot; x.insq_b = ab.ins_quot;
-      int cnt[4] = { x.ed.w & 0xFF, (x.ed.w >> 8) & 0xFF, (x.ed.w >> 16) & 0xFF, (x.ed.w >> 24) & 0xFF };
+      int cnt[4] = { x.ed.w & 0xFF, (x.ed.w >> 8) & 0xFF, 0, 0 };
+      {
+        DrawT<INJ> dacts(inj, g, r, at, x.base + (XGC_S_ACTS - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
+        edge_kiss_rim(P, l, x.ca, x.cb, dacts, g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1), true, true, cnt[2], cnt[3]);
+      }
       double pc = cnt[0] > 0 ? edge_cond_prob(g, P, x, false) : 0.0;
       DrawT<INJ> dc(inj, g, r, at, x.base + (XGC_S_ANAL - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
       DrawT<INJ> doi(inj, g, r, at, x.base + (XGC_S_ORAL - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);

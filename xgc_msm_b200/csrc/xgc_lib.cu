@@ -21,6 +21,7 @@ struct HostRep {                      // host mirror of one replicate (cache for
   std::vector<uint4> core; std::vector<Aux> aux;
   std::vector<short4> gck_a, gck_b, gck_d, hck_a, hck_b, tck; std::vector<int> arr_t;
   std::vector<int4> edge[3];
+  std::vector<int> lazy[3];            // materialised kissing | rimming << 8 counts (xgc_get_actcounts)
   std::vector<int> pos2slot, slot2pos;
 };
 
@@ -242,6 +243,7 @@ static int cache_load(xgc_handle* h, int r) {
   for (int l = 0; l < 3; ++l) rc |= pull(h, c.edge[l], g.edge + (size_t)r * g.e_stride + g.e_off[l], (size_t)c.rep.ne[l]);
   if (rc) return rc;
   rebuild_maps(c);
+  for (int l = 0; l < 3; ++l) c.lazy[l].clear();
   c.r = r; c.dirty = false;
   return 0;
 }
@@ -578,26 +580,35 @@ static int materialise_actcounts(xgc_handle* h, int r, const Inj& j) {      // k
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
-  LAUNCHD(h, j, k_actcounts, dim3((emax + TPB - 1) / TPB, 3), TPB, g, j, r);
-  CU(h, cudaGetLastError());
+  int* d_out; CU(h, cudaMalloc((void**)&d_out, sizeof(int) * 3 * (size_t)emax));
+  cudaMemsetAsync(d_out, 0, sizeof(int) * 3 * (size_t)emax, h->stream);
+  LAUNCHD(h, j, k_actcounts, dim3((emax + TPB - 1) / TPB, 3), TPB, g, j, r, d_out, emax);
+  std::vector<int> all(3 * (size_t)emax);
+  cudaError_t e = cudaMemcpyAsync(all.data(), d_out, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) FAIL(h, 100 + (int)e, "xgc_get_actcounts: %s", cudaGetErrorString(e));
+  rc = cache_load(h, r); if (rc) return rc;
+  for (int l = 0; l < 3; ++l) h->cache.lazy[l].assign(all.begin() + (size_t)l * emax, all.begin() + (size_t)l * emax + h->cache.edge[l].size());
   return 0;
 }
 extern "C" int xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts, int cap, int* n_edges) {
   CHECK_R(h, r);
   if (layer < 0 || layer > 2) FAIL(h, 2, "layer %d out of range", layer);
   int rc = 0;
-  if (h->acts_valid && (h->cache.r != r || !h->cache.dirty)) { rc = materialise_actcounts(h, r, h->last_inj); if (rc) return rc; }
+  bool lazy_ok = h->cache.r == r && h->cache.lazy[layer].size() == h->cache.edge[layer].size() && !h->cache.edge[layer].empty();
+  if (h->acts_valid && !lazy_ok && !(h->cache.r == r && h->cache.dirty)) { rc = materialise_actcounts(h, r, h->last_inj); if (rc) return rc; }
   rc = cache_load(h, r); if (rc) return rc;
   const HostRep& c = h->cache; int ne = (int)c.edge[layer].size();
   if (n_edges) *n_edges = ne;
   if (cap < ne) FAIL(h, 6, "buffer too small");
+  bool have = h->acts_valid && c.lazy[layer].size() == (size_t)ne;
   for (int e = 0; e < ne; ++e) {
-    int w = c.edge[layer][e].w;
-    counts[e] = w & 0xFF; counts[ne + e] = (w >> 8) & 0xFF; counts[2 * ne + e] = (w >> 16) & 0xFF; counts[3 * ne + e] = (w >> 24) & 0xFF;
+    int w = c.edge[layer][e].w, z = have ? c.lazy[layer][e] : 0;
+    counts[e] = w & 0xFF; counts[ne + e] = (w >> 8) & 0xFF; counts[2 * ne + e] = z & 0xFF; counts[3 * ne + e] = (z >> 8) & 0xFF;
   }
   return 0;
 }
-
 extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int cap, int* n_acts, const xgc_inject* inj) {
   CHECK_R(h, r);
   int rc = cache_drop(h); if (rc) return rc;
@@ -605,7 +616,6 @@ extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int ca
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
   int* d_al; CU(h, cudaMalloc((void**)&d_al, sizeof(int) * 6 * (size_t)std::max(cap, 1)));
   CU(h, cudaMemcpyAsync((int*)h->g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  { int rc2 = materialise_actcounts(h, r, j); if (rc2) { cudaFree(d_al); return rc2; } }
   LAUNCHD(h, j, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
   int n = 0;
   cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
