@@ -376,11 +376,10 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
 // R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
 template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
-  int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // one CTA per replicate, the three layers in turn
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
-  int at = g.at_ptr[r], n = rp->n_alive, ne = rp->ne[l];
-  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  int at = g.at_ptr[r], n = rp->n_alive;
   const uint4* core = g.core + (size_t)r * g.n_cap;
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   extern __shared__ unsigned dyn[];
@@ -390,7 +389,7 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
   int nw = (rp->n_slots + 31) >> 5;
   if (tid == 0) base = 0;
   __syncthreads();
-  if (SMEM) {
+  if (SMEM) {                                   // alive bitmap + exclusive popcount prefix of this replicate, built once
     const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
     for (int w0 = 0; w0 < nw; w0 += TPB) {
       unsigned bits = w0 + tid < nw ? A[w0 + tid] : 0u;
@@ -413,45 +412,48 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (pre[mid] <= pos) lo = mid; else hi = mid - 1; }
     return (lo << 5) + (int)__fns(bm[lo], 0, pos - pre[lo] + 1);
   };
-  __syncthreads();
-  if (tid == 0) base = ne;
-  __syncthreads();
-  double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
-  double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
-  double fl = floor(mu);
   DrawT<INJ> dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
-  int nform = (int)fl + (dn(l) < mu - fl);
-  if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
-  if (n < 2) nform = 0;
-  bool overflow = false;
-  for (int j0 = 0; j0 < nform; j0 += TPB) {
-    int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
-    if (j < nform) {
-      DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
-      for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
-        int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
-        int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
-        if (b >= a) b++;
-        int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);
-        if (roles_compatible(core[sa].y, core[sb].y)) { ok = true; ed.x = sa; ed.y = sb; }
+  for (int l = 0; l < 3; ++l) {
+    int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+    __syncthreads();
+    if (tid == 0) base = rp->ne[l];
+    __syncthreads();
+    double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
+    double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
+    double fl = floor(mu);
+    int nform = (int)fl + (dn(l) < mu - fl);
+    if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
+    if (n < 2) nform = 0;
+    bool overflow = false;
+    for (int j0 = 0; j0 < nform; j0 += TPB) {
+      int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
+      if (j < nform) {
+        DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+        for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
+          int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
+          int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+          if (b >= a) b++;
+          int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);
+          if (roles_compatible(core[sa].y, core[sb].y)) { ok = true; ed.x = sa; ed.y = sb; }
+        }
       }
+      unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) wsum[w] = __popc(m);
+      __syncthreads();
+      int off = base;
+      for (int k = 0; k < w; ++k) off += wsum[k];
+      off += __popc(m & ((1u << lane) - 1u));
+      if (ok) { if (off < g.e_cap[l]) E[off] = ed; else overflow = true; }
+      __syncthreads();
+      if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+      __syncthreads();
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) wsum[w] = __popc(m);
-    __syncthreads();
-    int off = base;
-    for (int k = 0; k < w; ++k) off += wsum[k];
-    off += __popc(m & ((1u << lane) - 1u));
-    if (ok) { if (off < g.e_cap[l]) E[off] = ed; else overflow = true; }
-    __syncthreads();
-    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
-    __syncthreads();
-  }
-  if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);
-  if (tid == 0) {
-    int nn = base < g.e_cap[l] ? base : g.e_cap[l];
-    rp->ne[l] = nn;
-    counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)nn;
+    if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);
+    if (tid == 0) {
+      int nn = base < g.e_cap[l] ? base : g.e_cap[l];
+      rp->ne[l] = nn;
+      counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)nn;
+    }
   }
 }
 

@@ -458,12 +458,12 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 40 * 1024) {
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, true><<<dim3(3, g.R), TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true><<<dim3(3, g.R), TPB, form_smem, h->stream>>>(g, inj);
+      if (inj.u) k_form<true, true><<<g.R, TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true><<<g.R, TPB, form_smem, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, false><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj); else k_form<false, false><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj);
+      if (inj.u) k_form<true, false><<<g.R, TPB, 0, h->stream>>>(g, inj); else k_form<false, false><<<g.R, TPB, 0, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     }
   }
