@@ -80,6 +80,7 @@ struct Inj {                 // injected-draw table (device copy), u == nullptr 
 struct Dev {                 // everything a kernel needs; passed by value
   int R, n_cap, t_cap, rep0; int e_cap[3]; size_t e_off[3]; size_t e_stride;
   unsigned seed;
+  double inv_dur[2];         // 1 / mean duration of main, casual ties (surrogate dissolution probability), set with the tables
   uint4* core; Aux* aux; short4 *gck_a, *gck_b, *gck_d, *hck_a, *hck_b, *tck; int* arr_t;
   unsigned* alive;           // [R][n_cap/32] bitmap of living slots
   int* pos2slot;             // [R][n_cap] rank -> slot (built by k_rank)

@@ -320,7 +320,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const _
   if (tid == 0) base = 0;
   __syncthreads();
   if (surrogate && l == 2) ne = 0;
-  double pd = surrogate && l < 2 ? 1.0 / g.tables[XGC_T_NET_DUR + l] : 0.0;
+  double pd = surrogate && l < 2 ? g.inv_dur[l] : 0.0;
   int es = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_DISSOLVE - XGC_S_EDGE0);
   for (int e0 = 0; e0 < ne; e0 += TPB) {
     int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
@@ -565,7 +565,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __gr
       unsigned tag = 0x7FFFu, dis = 0u;
       if (!INJ && l < 2 && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1) {
         DrawT<INJ> dd(inj, g, r, at + 1, x.base + (XGC_S_DISSOLVE - XGC_S_EDGE0), x.ca.x, x.cb.x, (size_t)e);
-        dis = xgc_bern(dd(0), 1.0 / g.tables[XGC_T_NET_DUR + l]);
+        dis = xgc_bern(dd(0), g.inv_dur[l]);
         tag = (unsigned)(at + 1) & 0x7FFFu;
       }
       x.ed.w = (int)((unsigned)ai | ((unsigned)oi << 8) | (tag << 16) | (dis << 31));

@@ -191,6 +191,8 @@ extern "C" int xgc_set_control(xgc_handle* h, int r, const int32_t* c) {
 extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
+  for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];       // same IEEE division the oracle performs
+  if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }   // kernel arguments changed
   return 0;
 }
 
@@ -797,6 +799,9 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
   h->last_at = -1; h->acts_valid = false; h->rank_fresh = false;
+  { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
+    for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
+    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; } }
   return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
