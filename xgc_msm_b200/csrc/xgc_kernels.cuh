@@ -307,7 +307,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
 //   drops edges with a departed endpoint (tergmLite::delete_vertices semantics, departure_msm) and, in surrogate mode,
 //   dissolves edges with prob 1/duration (main, casual) or clears the layer (one-off).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
+// NT threads, IPT edges per thread and iteration: <256,1> for calibration-size layers, <1024,4> for the 100k..1M-agent
+// configs where one CTA walks a whole layer (4096 edges per iteration keeps the sequential part short).
+template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
   int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne = rp->ne[l], at = g.at_ptr[r];
@@ -315,32 +317,41 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim(const _
   int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
   const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);          // 1 bit per slot: no 16-byte gathers just to see who is alive
-  __shared__ int wsum[TPB / 32];
+  __shared__ int wsum[IPT][NT / 32];
   __shared__ int base;
   if (tid == 0) base = 0;
   __syncthreads();
   if (surrogate && l == 2) ne = 0;
   double pd = surrogate && l < 2 ? g.inv_dur[l] : 0.0;
   int es = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_DISSOLVE - XGC_S_EDGE0);
-  for (int e0 = 0; e0 < ne; e0 += TPB) {
-    int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
-    if (e < ne) {
-      ed = E[e];
-      keep = ((A[ed.x >> 5] >> (ed.x & 31)) & 1u) && ((A[ed.y >> 5] >> (ed.y & 31)) & 1u);
-      if (keep && surrogate) {
-        if (!INJ && (((unsigned)ed.w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep = !((unsigned)ed.w >> 31);   // drawn ahead by k_edge1
-        else { DrawT<INJ> d(inj, g, r, at, es, core[ed.x].x, core[ed.y].x, (size_t)e); keep = !xgc_bern(d(0), pd); }
+  for (int e0 = 0; e0 < ne; e0 += NT * IPT) {
+    int4 ed[IPT]; bool keep[IPT]; unsigned m[IPT];
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {                 // item q of this iteration: edges e0 + q*NT .. e0 + (q+1)*NT - 1 (stable order)
+      int e = e0 + q * NT + tid; keep[q] = false; ed[q] = make_int4(0, 0, 0, 0);
+      if (e < ne) {
+        ed[q] = E[e];
+        keep[q] = ((A[ed[q].x >> 5] >> (ed[q].x & 31)) & 1u) && ((A[ed[q].y >> 5] >> (ed[q].y & 31)) & 1u);
+        if (keep[q] && surrogate) {
+          if (!INJ && (((unsigned)ed[q].w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep[q] = !((unsigned)ed[q].w >> 31);   // drawn ahead by k_edge1
+          else { DrawT<INJ> d(inj, g, r, at, es, core[ed[q].x].x, core[ed[q].y].x, (size_t)e); keep[q] = !xgc_bern(d(0), pd); }
+        }
       }
+      m[q] = __ballot_sync(0xffffffffu, keep[q]);
+      if (lane == 0) wsum[q][w] = __popc(m[q]);
     }
-    unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) wsum[w] = __popc(m);
     __syncthreads();
-    int off = base;
-    for (int k = 0; k < w; ++k) off += wsum[k];
-    off += __popc(m & ((1u << lane) - 1u));
-    if (keep && off != e) E[off] = ed;
+    int run = base;
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+      int off = run, tot = 0;
+      for (int k = 0; k < NT / 32; ++k) { int c = wsum[q][k]; tot += c; if (k < w) off += c; }
+      off += __popc(m[q] & ((1u << lane) - 1u));
+      if (keep[q] && off != e0 + q * NT + tid) E[off] = ed[q];
+      run += tot;
+    }
     __syncthreads();
-    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    if (tid == 0) base = run;
     __syncthreads();
   }
   if (tid == 0) rp->ne[l] = base;
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
 // k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order.
 // R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
-template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // one CTA per replicate, the three layers in turn
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
@@ -384,14 +395,14 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   extern __shared__ unsigned dyn[];
   unsigned* bm = dyn; int* pre = (int*)(dyn + g.n_cap / 32);
-  __shared__ int wsum[TPB / 32];
+  __shared__ int wsum[NT / 32];
   __shared__ int base;
   int nw = (rp->n_slots + 31) >> 5;
   if (tid == 0) base = 0;
   __syncthreads();
   if (SMEM) {                                   // alive bitmap + exclusive popcount prefix of this replicate, built once
     const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
-    for (int w0 = 0; w0 < nw; w0 += TPB) {
+    for (int w0 = 0; w0 < nw; w0 += NT) {
       unsigned bits = w0 + tid < nw ? A[w0 + tid] : 0u;
       int cnt = __popc(bits), inc = cnt;
 #pragma unroll
@@ -402,7 +413,7 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
       for (int k = 0; k < w; ++k) off += wsum[k];
       if (w0 + tid < nw) { bm[w0 + tid] = bits; pre[w0 + tid] = off; }
       __syncthreads();
-      if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+      if (tid == 0) { int t = 0; for (int k = 0; k < NT / 32; ++k) t += wsum[k]; base += t; }
       __syncthreads();
     }
   }
@@ -425,7 +436,7 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
     if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
     if (n < 2) nform = 0;
     bool overflow = false;
-    for (int j0 = 0; j0 < nform; j0 += TPB) {
+    for (int j0 = 0; j0 < nform; j0 += NT) {
       int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
       if (j < nform) {
         DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
@@ -445,7 +456,7 @@ template <bool INJ, bool SMEM> __global__ void __launch_bounds__(TPB) k_form(con
       off += __popc(m & ((1u << lane) - 1u));
       if (ok) { if (off < g.e_cap[l]) E[off] = ed; else overflow = true; }
       __syncthreads();
-      if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+      if (tid == 0) { int t = 0; for (int k = 0; k < NT / 32; ++k) t += wsum[k]; base += t; }
       __syncthreads();
     }
     if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);

@@ -439,6 +439,21 @@ static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.
   if ((inj).u) kern<true><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); else kern<false><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); \
   prof_end(h); (h)->launches++; } while (0)
 
+// stable in-place edge compaction: small CTAs for calibration-size layers, 1024 x 4 for very long layers
+static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve) {
+  const Dev& g = h->g;
+  int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
+  prof_begin(h, "k_edges_resim");
+  if (emax > 16384) {
+    if (inj.u) k_edges_resim<true, 1024, 4><<<dim3(3, g.R), 1024, 0, h->stream>>>(g, inj, dissolve);
+    else k_edges_resim<false, 1024, 4><<<dim3(3, g.R), 1024, 0, h->stream>>>(g, inj, dissolve);
+  } else {
+    if (inj.u) k_edges_resim<true, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
+    else k_edges_resim<false, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
+  }
+  prof_end(h); h->launches++;
+}
+
 // enqueue one week.  at_host < 0: week = previous + 1 (graph replay).
 static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& inj, int zero_row) {
   const Dev& g = h->g;
@@ -454,18 +469,18 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
   if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(tiles, g.R), TPB, g, inj, mask);
   bool native = inj.u == nullptr;
-  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0);
+  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0);
   if (mask & XGC_M_RESIM_NETS) {
-    LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 1);
+    launch_resim(h, inj, 1);
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 40 * 1024) {
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, true><<<g.R, TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true><<<g.R, TPB, form_smem, h->stream>>>(g, inj);
+      if (inj.u) k_form<true, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, false><<<g.R, TPB, 0, h->stream>>>(g, inj); else k_form<false, false><<<g.R, TPB, 0, h->stream>>>(g, inj);
+      if (inj.u) k_form<true, false, 1024><<<g.R, 1024, 0, h->stream>>>(g, inj); else k_form<false, false, 1024><<<g.R, 1024, 0, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     }
   }
@@ -507,7 +522,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
-  { Inj inj = make_inj(h, nullptr, nullptr); LAUNCHD(h, inj, k_edges_resim, dim3(3, g.R), TPB, g, inj, 0); }   // no dangling endpoints before re-numbering
+  launch_resim(h, make_inj(h, nullptr, nullptr), 0);          // no dangling endpoints before re-numbering
   h->rank_fresh = false;
   LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
   LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
