@@ -70,7 +70,8 @@ struct Rep {                 // per-replicate scalars
   int ne[3];
   unsigned status;
   int path_rank[XGC_NPATH];  // this week's pathway order (stitrans_msm_rand)
-  int pad;
+  unsigned lb_epoch[3];      // launch counter of the look-back edge compaction, per layer (stale tile status words never match)
+  int pad[2];
 };
 
 struct Inj {                 // injected-draw table (device copy), u == nullptr -> native Philox
@@ -93,6 +94,9 @@ struct Dev {                 // everything a kernel needs; passed by value
   unsigned* qa_count;        // [R]
   unsigned* qh_items;        // [R][n_cap] work queue of k_agent1b (HIV-positive agents): slot | tested << 31 | died << 30
   unsigned* qh_count;        // [R]
+  unsigned long long* lb_status;   // [R][3][lb_tiles] decoupled look-back tile status of the multi-CTA edge compaction
+  unsigned* lb_ticket;       // [R][3] tile tickets (reset every week by k_begin)
+  int lb_tiles;
   unsigned* counters;        // [R][t_cap][XGC_NCOUNTER]
   const int* at_ptr;
 };

@@ -61,6 +61,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
   if (lane == 4) g.qa_count[r] = 0u;
   if (lane == 5) g.qh_count[r] = 0u;
+  if (lane >= 8 && lane < 11) g.lb_ticket[r * 3 + lane - 8] = 0u;
   if (lane == 0) {
     ((int*)g.at_ptr)[r] = at;
     rp->n_slots_pre = n_slots;
@@ -355,6 +356,84 @@ template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edg
     __syncthreads();
   }
   if (tid == 0) rp->ne[l] = base;
+}
+
+// k_edges_resim_lb: the same stable in-place compaction for very long layers (100k..1M-agent replicates), many CTAs per
+// layer.  Single pass with decoupled look-back: every CTA takes a tile ticket, loads its 1024 records, publishes its
+// keep-count, sums the counts of the tiles before it (spinning only on tiles that have not published yet) and writes its
+// survivors.  In place is safe: a tile publishes only after it has loaded its records, and tile t only writes below
+// (t+1)*1024, i.e. into source ranges whose owners have already loaded.  Status word = epoch << 34 | state << 32 | count
+// (state 1 = tile count, 2 = inclusive prefix); the epoch is a per-layer launch counter kept on the device (bumped by the
+// last tile), so status words of earlier launches never match.
+#define LB_TILE 1024
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve, int kind) {
+  int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Rep* rp = g.rep + r;
+  int at = g.at_ptr[r];
+  int ne = *(volatile int*)&rp->ne[l];               // read BEFORE taking the ticket (the last tile overwrites both)
+  unsigned epoch = *(volatile unsigned*)&rp->lb_epoch[l];
+  __shared__ int s_tile, s_base;
+  __shared__ int wsum[4][TPB / 32];
+  if (tid == 0) s_tile = (int)(atomicAdd(g.lb_ticket + r * 3 + l, 1u) % (unsigned)g.lb_tiles);
+  __syncthreads();
+  int tile = s_tile;
+  int surrogate = dissolve && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1;
+  if (surrogate && l == 2) { if (tile == 0 && tid == 0) rp->ne[l] = 0; return; }
+  int ntiles = (ne + LB_TILE - 1) / LB_TILE;
+  if (tile >= ntiles) return;
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  double pd = surrogate && l < 2 ? g.inv_dur[l] : 0.0;
+  int es = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS + (XGC_S_DISSOLVE - XGC_S_EDGE0);
+  int e0 = tile * LB_TILE;
+  int4 ed[4]; bool keep[4]; unsigned m[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int e = e0 + q * TPB + tid; keep[q] = false; ed[q] = make_int4(0, 0, 0, 0);
+    if (e < ne) {
+      ed[q] = E[e];
+      keep[q] = ((A[ed[q].x >> 5] >> (ed[q].x & 31)) & 1u) && ((A[ed[q].y >> 5] >> (ed[q].y & 31)) & 1u);
+      if (keep[q] && surrogate) {
+        if (!INJ && (((unsigned)ed[q].w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep[q] = !((unsigned)ed[q].w >> 31);
+        else { DrawT<INJ> d(inj, g, r, at, es, core[ed[q].x].x, core[ed[q].y].x, (size_t)e); keep[q] = !xgc_bern(d(0), pd); }
+      }
+    }
+    m[q] = __ballot_sync(0xffffffffu, keep[q]);
+    if (lane == 0) wsum[q][w] = __popc(m[q]);
+  }
+  __syncthreads();
+  int off[4], run = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int o = run, tot = 0;
+    for (int k = 0; k < TPB / 32; ++k) { int c = wsum[q][k]; tot += c; if (k < w) o += c; }
+    off[q] = o + __popc(m[q] & ((1u << lane) - 1u));
+    run += tot;
+  }
+  if (tid == 0) {
+    unsigned long long* S = g.lb_status + ((size_t)r * 3 + l) * g.lb_tiles;
+    unsigned long long ep = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
+    int base = 0;
+    if (tile > 0) {
+      atomicExch(S + tile, ep | (1ull << 32) | (unsigned)run);
+      for (int p = tile - 1; p >= 0; --p) {
+        unsigned long long v;
+        do { v = *(volatile unsigned long long*)(S + p); } while ((v >> 34) != (ep >> 34) || ((v >> 32) & 3ull) == 0);
+        base += (int)(unsigned)v;
+        if (((v >> 32) & 3ull) == 2) break;
+      }
+    }
+    atomicExch(S + tile, ep | (2ull << 32) | (unsigned)(base + run));
+    s_base = base;
+    if (tile == ntiles - 1) { rp->ne[l] = base + run; rp->lb_epoch[l] = epoch + 1u; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int dst = s_base + off[q];
+    if (keep[q] && dst != e0 + q * TPB + tid) E[dst] = ed[q];
+  }
 }
 
 // k_rank: pos2slot[r][rank] = slot, from the alive bitmap.  grid (slot tiles, R): each CTA sums the bitmap words before its

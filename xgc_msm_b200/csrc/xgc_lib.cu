@@ -119,6 +119,8 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.q_items, (size_t)g.R * 4 * g.e_stride); rc |= dalloc(h, &g.q_count, (size_t)g.R * 4);
   rc |= dalloc(h, &g.qa_items, NA); rc |= dalloc(h, &g.qa_count, (size_t)g.R);
   rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
+  g.lb_tiles = (std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2])) + 1023) / 1024;
+  rc |= dalloc(h, &g.lb_status, (size_t)g.R * 3 * g.lb_tiles); rc |= dalloc(h, &g.lb_ticket, (size_t)g.R * 3);
   rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
@@ -440,13 +442,14 @@ static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.
   prof_end(h); (h)->launches++; } while (0)
 
 // stable in-place edge compaction: small CTAs for calibration-size layers, 1024 x 4 for very long layers
-static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve) {
+static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve, int kind) {
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   prof_begin(h, "k_edges_resim");
-  if (emax > 16384) {
-    if (inj.u) k_edges_resim<true, 1024, 4><<<dim3(3, g.R), 1024, 0, h->stream>>>(g, inj, dissolve);
-    else k_edges_resim<false, 1024, 4><<<dim3(3, g.R), 1024, 0, h->stream>>>(g, inj, dissolve);
+  if (emax > 16384) {           // very long layers: many CTAs per layer, decoupled look-back
+    dim3 grid(g.lb_tiles, 3, g.R);
+    if (inj.u) k_edges_resim_lb<true><<<grid, TPB, 0, h->stream>>>(g, inj, dissolve, kind);
+    else k_edges_resim_lb<false><<<grid, TPB, 0, h->stream>>>(g, inj, dissolve, kind);
   } else {
     if (inj.u) k_edges_resim<true, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
     else k_edges_resim<false, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
@@ -469,9 +472,9 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
   if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(tiles, g.R), TPB, g, inj, mask);
   bool native = inj.u == nullptr;
-  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0);
+  if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0, 0);
   if (mask & XGC_M_RESIM_NETS) {
-    launch_resim(h, inj, 1);
+    launch_resim(h, inj, 1, 1);
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 40 * 1024) {
       prof_begin(h, "k_form");
@@ -522,7 +525,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
-  launch_resim(h, make_inj(h, nullptr, nullptr), 0);          // no dangling endpoints before re-numbering
+  launch_resim(h, make_inj(h, nullptr, nullptr), 0, 2);       // no dangling endpoints before re-numbering
   h->rank_fresh = false;
   LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
   LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
