@@ -447,8 +447,9 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
   int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   __shared__ int wsum[TPB / 32];
   __shared__ unsigned tilebits[TPB / 32];
-  int w0 = i0 >> 5, acc = 0;
-  for (int k = tid; k < w0; k += TPB) acc += __popc(A[k]);
+  int w0 = i0 >> 5, acc = 0;                       // w0 is a multiple of 8: sum the earlier words with 128-bit loads
+  const uint4* A4 = (const uint4*)A;
+  for (int k = tid; k < (w0 >> 2); k += TPB) { uint4 v = A4[k]; acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) wsum[w] = acc;
@@ -544,6 +545,90 @@ template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_f
       rp->ne[l] = nn;
       counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)nn;
     }
+  }
+}
+
+// k_form_lb: the same formation for large replicates, many CTAs per (replicate, layer): each CTA draws 1024 candidate
+// ties, the accepted ones are appended in draw order through the decoupled look-back prefix (shares the tile tickets /
+// status words / epoch with k_edges_resim_lb; launches are serialised on the stream).  Needs pos2slot (k_rank).
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+  int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Rep* rp = g.rep + r;
+  int ne0 = *(volatile int*)&rp->ne[l];
+  unsigned epoch = *(volatile unsigned*)&rp->lb_epoch[l];
+  __shared__ int s_tile, s_base;
+  __shared__ int wsum[4][TPB / 32];
+  if (tid == 0) s_tile = (int)(atomicAdd(g.lb_ticket + r * 3 + l, 1u) % (unsigned)g.lb_tiles);
+  __syncthreads();
+  int tile = s_tile;
+  if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
+  int at = g.at_ptr[r], n = rp->n_alive;
+  double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
+  double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
+  double fl = floor(mu);
+  DrawT<INJ> dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
+  int nform = (int)fl + (dn(l) < mu - fl);
+  if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
+  if (n < 2) nform = 0;
+  int ntiles = (nform + LB_TILE - 1) / LB_TILE;
+  if (ntiles == 0) { if (tile == 0 && tid == 0) counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)ne0; return; }
+  if (tile >= ntiles) return;
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  const uint4* core = g.core + (size_t)r * g.n_cap;
+  const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  int4 ed[4]; bool ok[4]; unsigned m[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int j = tile * LB_TILE + q * TPB + tid; ok[q] = false; ed[q] = make_int4(0, 0, at, 0);
+    if (j < nform) {
+      DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+      for (int t = 0; t < XGC_FORM_TRIES && !ok[q]; ++t) {
+        int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
+        int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+        if (b >= a) b++;
+        int sa = P2S[a < b ? a : b], sb = P2S[a < b ? b : a];
+        if (roles_compatible(core[sa].y, core[sb].y)) { ok[q] = true; ed[q].x = sa; ed[q].y = sb; }
+      }
+    }
+    m[q] = __ballot_sync(0xffffffffu, ok[q]);
+    if (lane == 0) wsum[q][w] = __popc(m[q]);
+  }
+  __syncthreads();
+  int off[4], run = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int o = run, tot = 0;
+    for (int k = 0; k < TPB / 32; ++k) { int c = wsum[q][k]; tot += c; if (k < w) o += c; }
+    off[q] = o + __popc(m[q] & ((1u << lane) - 1u));
+    run += tot;
+  }
+  if (tid == 0) {
+    unsigned long long* S = g.lb_status + ((size_t)r * 3 + l) * g.lb_tiles;
+    unsigned long long ep = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
+    int base = 0;
+    if (tile > 0) {
+      atomicExch(S + tile, ep | (1ull << 32) | (unsigned)run);
+      for (int p = tile - 1; p >= 0; --p) {
+        unsigned long long v;
+        do { v = *(volatile unsigned long long*)(S + p); } while ((v >> 34) != (ep >> 34) || ((v >> 32) & 3ull) == 0);
+        base += (int)(unsigned)v;
+        if (((v >> 32) & 3ull) == 2) break;
+      }
+    }
+    atomicExch(S + tile, ep | (2ull << 32) | (unsigned)(base + run));
+    s_base = ne0 + base;
+    if (tile == ntiles - 1) {
+      int total = ne0 + base + run;
+      if (total > g.e_cap[l]) { atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW); total = g.e_cap[l]; }
+      rp->ne[l] = total; rp->lb_epoch[l] = epoch + 1u;
+      counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)total;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int dst = s_base + off[q];
+    if (ok[q] && dst < g.e_cap[l]) E[dst] = ed[q];
   }
 }
 

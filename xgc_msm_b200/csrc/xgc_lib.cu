@@ -476,14 +476,14 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if (mask & XGC_M_RESIM_NETS) {
     launch_resim(h, inj, 1, 1);
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
-    if (form_smem <= 40 * 1024) {
+    if (form_smem <= 8 * 1024) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
       prof_begin(h, "k_form");
       if (inj.u) k_form<true, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, false, 1024><<<g.R, 1024, 0, h->stream>>>(g, inj); else k_form<false, false, 1024><<<g.R, 1024, 0, h->stream>>>(g, inj);
+      if (inj.u) k_form_lb<true><<<dim3(g.lb_tiles, 3, g.R), TPB, 0, h->stream>>>(g, inj); else k_form_lb<false><<<dim3(g.lb_tiles, 3, g.R), TPB, 0, h->stream>>>(g, inj);
       prof_end(h); h->launches++;
     }
   }
