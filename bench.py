@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU")
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-groups", type=int, default=8, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -243,11 +244,24 @@ def run_xgc(args, rank, world, local_rank):
 
     # ---- end to end through the C ABI with HOST buffers: the weekly R <-> device contract with simnet_msm on the host
     #      (pre-network modules -> living counts to host -> three edge lists from pinned host memory -> remaining
-    #       modules -> the week's tallies back to host)
+    #       modules -> the week's tallies back to host).  The replicates of this GPU are served as `--e2e-groups` handles
+    #      (each with its own stream and host thread), so the edge-list upload of one group overlaps the kernels of the
+    #      others; every group still goes through the full serial contract every week.
     from xgc_msm_b200.params import control_msm
-    h.set_control(control_msm(network_mode="host").flags)
+    Ge = max(1, min(args.e2e_groups, R))
+    while R % Ge:
+        Ge -= 1
+    Rg = R // Ge
+    groups = []
+    for gi in range(Ge):
+        hg = Handle(Rg, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rank * R + gi * Rg,
+                    compact_every=spec.weeks_between_compactions)
+        workload.load_sweep(hg, spec, rid0=rank * R + gi * Rg)
+        hg.run(2, at - 1)                                   # same point of the epidemic as the kernel-resident arm
+        hg.set_control(control_msm(network_mode="host").flags)
+        groups.append(hg)
     rng = np.random.default_rng(args.seed + rank)
-    nmin = int(h.num_agents_all().min())
+    nmin = min(int(hg.num_agents_all().min()) for hg in groups)
     pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch)
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
@@ -255,30 +269,64 @@ def run_xgc(args, rank, world, local_rank):
     c_host = torch.empty((R, K.NCOUNTER), dtype=torch.int32).pin_memory()
     h2d = sum(t_el.numel() * 4 + t_ne.numel() * 4 + t_st.numel() * 4 for t_el, t_ne, t_st, _ in pool)
     d2h = n_host.numel() * 4 + c_host.numel() * 4
+    n_np, c_np = n_host.numpy(), c_host.numpy().view(np.uint32)
 
-    def e2e_week(t):
-        h.step(t, pre)
-        h.num_agents_all(n_host.numpy())
+    def e2e_week(gi, t):
+        """One week of the contract for group gi (what one host-side simnet_msm loop does); returns living agents."""
+        hg, r0 = groups[gi], gi * Rg
+        hg.step(t, pre)
+        hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
         for l, (t_el, t_ne, t_st, _ne) in enumerate(pool):
-            h.set_edgelists_all(l, t_el.data_ptr(), t_ne.data_ptr(), t_st.data_ptr(), stride=t_el.shape[2])
-        h.step(t, post)
-        h.counters_all(t, c_host.numpy().view(np.uint32))
-        return float(c_host[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
+            hg.set_edgelists_all(l, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), t_st[r0:r0 + Rg].data_ptr(),
+                                 stride=t_el.shape[2])
+        hg.step(t, post)
+        hg.counters_all(t, c_np[r0:r0 + Rg])
+        return float(c_np[r0:r0 + Rg, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
 
-    for _ in range(3):
-        e2e_week(at); at += 1
+    # one host thread per group, like the independent host processes of the reference's job array; ctypes drops the GIL
+    # inside every ABI call, so one group's blocking device->host read does not stall the others' uploads and launches
+    import threading
+    aw_g = [0.0] * Ge
+    errs = []
+
+    def drive(gi, t_first, n_weeks):
+        try:
+            torch.cuda.set_device(local_rank)
+            acc = 0.0
+            for t in range(t_first, t_first + n_weeks):
+                acc += e2e_week(gi, t)
+            aw_g[gi] = acc
+        except Exception as ex:                               # surface in the main thread
+            errs.append(ex)
+
+    def run_weeks(t_first, n_weeks):
+        th = [threading.Thread(target=drive, args=(gi, t_first, n_weeks)) for gi in range(Ge)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+        return sum(aw_g)
+
+    run_weeks(at, 3); at += 3
     barrier()
     t0 = time.perf_counter()
-    aw_e = 0.0
-    for _ in range(En):
-        aw_e += e2e_week(at); at += 1
+    aw_e = run_weeks(at, En); at += En
     barrier()
     dt_e = time.perf_counter() - t0
     if world > 1:
         tt = torch.tensor([dt_e], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt_e = float(tt.item())
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
-           "ms_per_step": dt_e / En * 1e3, "path": "xgc_step(pre) -> xgc_num_agents_all -> 3x xgc_set_edgelists_all (pinned) -> xgc_step(post) -> xgc_get_counters_all"}
+           "ms_per_step": dt_e / En * 1e3, "groups": Ge,
+           "path": f"{Ge} handles x {Rg} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 3x xgc_set_edgelists_all (pinned) -> "
+                   "xgc_step(post) -> xgc_get_counters_all"}
+    e2e_status = 0
+    for hg in groups:
+        e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, Rg, max(Rg // 8, 1))]))
+        hg.close()
+    e2e["status_sample_or"] = e2e_status
 
     # ---- final exchange of the path: gather the [R x K] targets matrix (NCCL all_gather), outside the timed regions
     tg = torch.from_numpy(h.targets(t_last, min(Kt, 52))).cuda()
