@@ -315,6 +315,10 @@ int  xgc_status (xgc_handle* h, int r, uint32_t* status); /* XGC_ST_* bits */
 int  xgc_get_counters(xgc_handle* h, int r, int at0, int at1, uint32_t* out /*[at1-at0+1][XGC_NCOUNTER]*/);
 int  xgc_get_epi     (xgc_handle* h, int r, const char* var, double* out, int at0, int at1);
 int  xgc_epi_names   (const char** names, int cap);
+/* Many series of one replicate with ONE device->host read of its weekly tallies: out[k * (at1 - at0 + 1) + (at - at0)] =
+ * series vars[k] at week `at`.  This is the `as.data.table(sim$epi)` table that inst/cal/sim_clean.r:55-64 builds per
+ * simulation file (columns = epi names, rows = weeks) before it stacks them with a `simid` column. */
+int  xgc_get_epi_table(xgc_handle* h, int r, const char* const* vars, int n_vars, double* out, int at0, int at1);
 int  xgc_targets     (xgc_handle* h, int at_last, int tailn, double* out /*[n_replicates][XGC_NTARGET]*/);
 
 /* checkpoint / scenario fork (02.00_epi.r:40-76,292,296: burn-in output reused as the start of 5 screening arms). */

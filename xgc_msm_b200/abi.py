@@ -52,6 +52,7 @@ def _load() -> C.CDLL:
         "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
         "xgc_compact": [vp], "xgc_status": [vp, ci, pu],
         "xgc_get_counters": [vp, ci, ci, ci, pu], "xgc_get_epi": [vp, ci, C.c_char_p, pd, ci, ci],
+        "xgc_get_epi_table": [vp, ci, C.POINTER(C.c_char_p), ci, pd, ci, ci],
         "xgc_targets": [vp, ci, ci, pd],
         "xgc_snapshot_size": [vp, C.POINTER(C.c_size_t)], "xgc_snapshot": [vp, vp, C.c_size_t],
         "xgc_restore": [vp, vp, C.c_size_t], "xgc_fork": [vp, ci, vp, ci],
@@ -271,6 +272,14 @@ class Handle:
     def epi(self, r: int, var: str, at0: int, at1: int) -> np.ndarray:
         out = np.empty(at1 - at0 + 1)
         self._ck(lib.xgc_get_epi(self._h, r, var.encode(), _ptr(out, C.c_double), at0, at1))
+        return out
+
+    def epi_table(self, r: int, names, at0: int, at1: int) -> np.ndarray:
+        """[len(names), at1 - at0 + 1] series of replicate r with one device->host read (xgc_get_epi_table)."""
+        names = list(names)
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        out = np.empty((len(names), at1 - at0 + 1))
+        self._ck(lib.xgc_get_epi_table(self._h, r, arr, len(names), _ptr(out, C.c_double), at0, at1))
         return out
 
     def targets(self, at_last: int, tailn: int) -> np.ndarray:

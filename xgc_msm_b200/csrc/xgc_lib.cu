@@ -743,6 +743,20 @@ extern "C" int xgc_get_epi(xgc_handle* h, int r, const char* var, double* out, i
     if (!epi_eval(c.data() + (size_t)(at - at0) * XGC_NCOUNTER, var, out + (at - at0))) FAIL(h, 5, "unknown epi variable '%s'", var);
   return 0;
 }
+extern "C" int xgc_get_epi_table(xgc_handle* h, int r, const char* const* vars, int n_vars, double* out, int at0, int at1) {
+  CHECK_R(h, r);
+  if (at0 < 0 || at1 >= h->cfg.t_cap || at1 < at0) FAIL(h, 2, "bad week range");
+  if (n_vars < 0 || (n_vars > 0 && !vars)) FAIL(h, 2, "bad variable list");
+  size_t T = (size_t)(at1 - at0 + 1);
+  std::vector<uint32_t> c(T * XGC_NCOUNTER);
+  int rc = xgc_get_counters(h, r, at0, at1, c.data()); if (rc) return rc;
+  for (int k = 0; k < n_vars; ++k) {
+    std::string v(vars[k]);
+    for (size_t t = 0; t < T; ++t)
+      if (!epi_eval(c.data() + t * XGC_NCOUNTER, v, out + (size_t)k * T + t)) FAIL(h, 5, "unknown epi variable '%s'", vars[k]);
+  }
+  return 0;
+}
 static std::vector<std::string> build_epi_names() {
   std::vector<std::string> N;
   const char* R[4] = { "B", "H", "O", "W" };
