@@ -328,7 +328,12 @@ int  xgc_restore (xgc_handle* h, const void* buf, size_t bytes);
 int  xgc_fork    (xgc_handle* src, int src_r, xgc_handle* dst, int dst_r);   /* device-to-device copy of one replicate */
 
 /* e2e helpers with caller-owned pinned host buffers: one call moves every replicate's edge lists in, or the week's
- * counters out (the two transfers the weekly R<->device contract needs; DESIGN.md "boundary cost"). */
+ * counters out (the two transfers the weekly R<->device contract needs; DESIGN.md "boundary cost").
+ * xgc_set_edgelists_all is asynchronous on the handle's stream: with page-locked buffers the caller must leave `el`,
+ * `n_edges` and `start_time` unchanged until the next synchronising call on this handle (xgc_sync, any xgc_get_* /
+ * xgc_num_agents_all); pageable buffers are staged before the call returns.  Positions outside 1..living agents set
+ * XGC_ST_BAD_EDGE in that replicate's status word (the edge is replaced by (1,1)); lists longer than the layer's
+ * capacity are truncated and set XGC_ST_EDGE_OVERFLOW. */
 int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][stride] 1-based positions*/,
                            const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][stride] or NULL*/, int stride);
 int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);

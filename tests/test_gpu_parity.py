@@ -198,3 +198,56 @@ def test_large_population_100k_plus():
         for r, o in enumerate(orcs):
             o.step(at, K.M_ALL)
             compare_state(h, r, o, at, f"170k agents week {at} r={r}")
+
+
+def test_host_network_weekly_contract_all_replicates():
+    """The end-to-end contract bench.py's e2e arm times (INTEGRATION.md "weekly host <-> device traffic"): pre-network
+    modules -> living counts to the host -> three ragged edge lists for EVERY replicate in one call each (1-based
+    positions among the living, as tergmLite returns them) -> remaining modules -> the week's tallies for every replicate.
+    Bit-exact against the oracle driven through its per-replicate edge-list setter."""
+    n, weeks, R = 2500, 8, 4
+    cases = [make_case(n, 300 + r, midcourse=True, network_mode="host", stiScreeningProtocol="cdc" if r == 1 else "base") for r in range(R)]
+    h = load_handle(cases, SEED, replicate_offset=7)
+    orcs = [load_oracle(c, SEED, 7 + r) for r, c in enumerate(cases)]
+    pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
+    post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
+    rng = np.random.default_rng(5)
+    e_cap = cases[0]["e_cap"]
+    for at in range(2, 2 + weeks):
+        h.step(at, pre)
+        for o in orcs:
+            o.step(at, pre)
+        alive = h.num_agents_all()
+        assert alive.tolist() == [o.num_agents() for o in orcs]
+        for l in range(3):
+            ne = rng.integers(e_cap[l] // 3, e_cap[l] // 2, size=R).astype(np.int32)
+            if at == 4:
+                ne[2] = 0                                   # an empty layer in one replicate
+            if at == 5 and l == 2:
+                ne[0] = e_cap[l]                            # a layer at capacity
+            stride = int(ne.max()) + 3                      # ragged: rows longer than any list
+            el = np.zeros((R, 2, stride), dtype=np.int32)
+            st = np.zeros((R, stride), dtype=np.int32)
+            use_start = not (at == 6 and l == 1)            # NULL start weeks = "formed this week"
+            for r in range(R):
+                a = rng.integers(1, alive[r] + 1, size=ne[r]); b = rng.integers(1, alive[r], size=ne[r])
+                b = np.where(b >= a, b + 1, b)
+                el[r, 0, :ne[r]] = np.minimum(a, b); el[r, 1, :ne[r]] = np.maximum(a, b)
+                st[r, :ne[r]] = at - rng.integers(0, 150, size=ne[r])
+                orcs[r].set_edgelist(l, el[r, :, :ne[r]].T, st[r, :ne[r]] if use_start else None)
+            h.set_edgelists_all(l, el.ctypes.data, ne.ctypes.data, st.ctypes.data if use_start else 0, stride=stride)
+            h.sync()                                        # el / st are reused next iteration
+        h.step(at, post)
+        call = h.counters_all(at)
+        for r, o in enumerate(orcs):
+            o.step(at, post)
+            compare_state(h, r, o, at, f"host network week {at} r={r}")
+            assert np.array_equal(call[r], o.counters(at))
+    for r, o in enumerate(orcs):
+        assert h.status(r) == o.status() == 0
+    tot = h.counters(1, 2, 1 + weeks).astype(np.int64).sum(0)
+    assert tot[K.K_NACTS] > 0 and tot[K.K_PATH:K.K_PATH + K.NPATH].sum() > 0 and tot[K.K_VISITS] > 0
+    # a position outside 1..n_alive is reported, not dereferenced
+    bad = np.zeros((R, 2, 4), dtype=np.int32); bad[:, 0, :] = 1; bad[:, 1, :] = 2; bad[1, 1, 2] = int(alive[1]) + 50
+    h.set_edgelists_all(0, bad.ctypes.data, np.full(R, 4, np.int32).ctypes.data, 0, stride=4); h.sync()
+    assert h.status(1) & K.ST_BAD_EDGE and not (h.status(0) & K.ST_BAD_EDGE)
