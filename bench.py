@@ -144,7 +144,8 @@ def week_stats(h, K, at):
     G = K.NCELL
     grp = lambda g: c[g * G:(g + 1) * G].sum()
     n = grp(K.K_NUM)
-    return {"n": n, "f_hiv": grp(K.K_INUM) / n, "f_dx": grp(K.K_INUM_DX) / n, "f_gc": grp(K.K_INUM_GC) / n,
+    incid = grp(K.K_INCID_RGC) + grp(K.K_INCID_UGC) + grp(K.K_INCID_PGC) + grp(K.K_INCID_HIV)
+    return {"n": n, "f_hiv": grp(K.K_INUM) / n, "f_dx": grp(K.K_INUM_DX) / n, "f_gc": grp(K.K_INUM_GC) / n, "f_new": incid / n,
             "edges": float(c[K.K_NEDGES:K.K_NEDGES + 3].sum())}
 
 

@@ -92,6 +92,7 @@ struct Dev {                 // everything a kernel needs; passed by value
   unsigned* q_count;         // [R][4]
   unsigned* qa_items;        // [R][n_cap] work queue of k_agent2b: slot | asymptomatic-visit draw << 31
   unsigned* qa_count;        // [R]
+  unsigned* q3_count;        // [R] agents with new-infection flags this week (queue of k_agent3b; items reuse qa_items)
   unsigned* qh_items;        // [R][n_cap] work queue of k_agent1b (HIV-positive agents): slot | tested << 31 | died << 30
   unsigned* qh_count;        // [R]
   unsigned long long* lb_status;   // [R][3][lb_tiles] decoupled look-back tile status of the multi-CTA edge compaction

@@ -61,6 +61,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
   if (lane == 4) g.qa_count[r] = 0u;
   if (lane == 5) g.qh_count[r] = 0u;
+  if (lane == 6) g.q3_count[r] = 0u;
   if (lane >= 8 && lane < 11) g.lb_ticket[r * 3 + lane - 8] = 0u;
   if (lane == 0) {
     ((int*)g.at_ptr)[r] = at;
@@ -214,12 +215,15 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
   int r = blockIdx.y;
   unsigned n = g.qh_count[r];
   if (blockIdx.x * TPB >= n) return;
-  unsigned qi = blockIdx.x * TPB + threadIdx.x;
   Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   unsigned* row = counter_row(g, r, at);
+  // queue kernels run a few CTAs per replicate that stride over the replicate's queue (grid.x is sized by the host for
+  // ~2 waves of the GPU, not for the longest possible queue: no tens of thousands of empty CTAs)
+  for (unsigned qbase = blockIdx.x * TPB; qbase < n; qbase += gridDim.x * TPB) {
+  unsigned qi = qbase + threadIdx.x;
   bool dep_a = false, dead_before = false;
   if (qi < n) {
     unsigned item = g.qh_items[rbase + qi];
@@ -300,6 +304,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
     warp_tally(row, XGC_K_DEP_AIDS, dep_a);
     unsigned dm = __ballot_sync(0xffffffffu, dep_a && !dead_before);
     if (dm && (threadIdx.x & 31) == 0) atomicSub((int*)&rp->n_alive, __popc(dm));
+  }
   }
 }
 
@@ -690,18 +695,24 @@ template <class D> __device__ __forceinline__ void edge_kiss_rim(const double* P
 }
 
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
-template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
-  int r = blockIdx.z, l = blockIdx.y;
+template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
   const Rep* rp = g.rep + r;
-  int ne = rp->ne[l];
-  if ((int)(blockIdx.x * TPB) >= ne) return;
-  int e = blockIdx.x * TPB + threadIdx.x, at = g.at_ptr[r];
+  // the three layers of the replicate are walked as one index space [0, ne0 + ne1 + ne2): full tiles except the last,
+  // a few CTAs per replicate striding over it
+  const int ne0 = rp->ne[0], ne01 = ne0 + rp->ne[1], ne_all = ne01 + rp->ne[2];
+  if ((int)(blockIdx.x * TPB) >= ne_all) return;
+  const int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   unsigned* row = counter_row(g, r, at);
-  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   uint4* core = g.core + (size_t)r * g.n_cap;
   const Aux* aux = g.aux + (size_t)r * g.n_cap;
-  bool live = e < ne;
+  for (int fbase = blockIdx.x * TPB; fbase < ne_all; fbase += gridDim.x * TPB) {
+  const int f = fbase + threadIdx.x;
+  const bool live = f < ne_all;
+  const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0;
+  const int e = f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   unsigned nai = 0, noi = 0;
   if (live) {
     EdgeCtx x; x.r = r; x.l = l; x.e = e; x.at = at; x.ed = E[e];
@@ -775,6 +786,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 5) k_edge1(const __gr
   }
   if (mask & XGC_M_ACTS) {
     warp_tally_n(row, XGC_K_NACTS, nai); warp_tally_n(row, XGC_K_NACTS + 1, noi);
+  }
   }
 }
 
@@ -850,12 +862,13 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __gri
   int r = blockIdx.y;
   unsigned n = g.qa_count[r];
   if (blockIdx.x * TPB >= n) return;
-  unsigned qi = blockIdx.x * TPB + threadIdx.x;
   const size_t rbase = (size_t)r * g.n_cap;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   unsigned* row = counter_row(g, r, at);
+  for (unsigned qbase = blockIdx.x * TPB; qbase < n; qbase += gridDim.x * TPB) {
+  unsigned qi = qbase + threadIdx.x;
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
   if (qi < n) {
     unsigned item = g.qa_items[rbase + qi];
@@ -946,6 +959,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __gri
 #pragma unroll
       for (int s = 0; s < 3; ++s) { warp_tally(row, XGC_K_TESTED + s, tst[s]); warp_tally(row, XGC_K_POS + s, pos[s]); warp_tally(row, XGC_K_TXSTART + s, txs[s]); }
     }
+  }
   }
 }
 
@@ -1062,19 +1076,22 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
 // k_edge2a: classify every edge and append the (edge, act type) pairs that can transmit to the replicate's per-type
 // work queues (one atomicAdd per CTA and type).  No draws here.
 __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, unsigned mask) {
-  int r = blockIdx.z, l = blockIdx.y;
+  int r = blockIdx.y;
   const Rep* rp = g.rep + r;
-  int ne = rp->ne[l];
-  if ((int)(blockIdx.x * TPB) >= ne) return;
+  const int ne0 = rp->ne[0], ne01 = ne0 + rp->ne[1], ne_all = ne01 + rp->ne[2];     // one index space over the three layers
+  if ((int)(blockIdx.x * TPB) >= ne_all) return;
   __shared__ unsigned short s_wc[4][TPB / 32];
   __shared__ unsigned s_base[4];
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int e = blockIdx.x * TPB + tid;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
-  const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
+  for (int fbase = blockIdx.x * TPB; fbase < ne_all; fbase += gridDim.x * TPB) {
+  const int fi = fbase + tid;
+  const int l = fi >= ne01 ? 2 : fi >= ne0 ? 1 : 0;
+  const int e = fi - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+  const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   bool f[4] = { false, false, false, false };
-  if (e < ne) {
+  if (fi < ne_all) {
     int4 ed = E[e];
     uint4 ca = core[ed.x], cb = core[ed.y];
     int ai = ed.w & 0xFF, oi = (ed.w >> 8) & 0xFF;
@@ -1110,34 +1127,43 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
     for (int k = 0; k < w; ++k) before += s_wc[t][k];
     g.q_items[((size_t)r * 4 + t) * g.e_stride + s_base[t] + before + __popc(b[t] & ((1u << lane) - 1u))] = ((unsigned)l << 28) | (unsigned)e;
   }
+  __syncthreads();                 // s_wc / s_base are reused by the next tile
+  }
 }
 
 // k_edge2b: dense processing of the work queues; blockIdx.y = act type, so every warp runs one act type with all lanes busy.
 template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 : 4) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   int r = blockIdx.z, type = ANAL ? 0 : 1 + blockIdx.y;
   unsigned n = g.q_count[(size_t)r * 4 + type];
-  unsigned i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  unsigned item = g.q_items[((size_t)r * 4 + type) * g.e_stride + i];
-  int l = (int)(item >> 28), e = (int)(item & 0x0FFFFFFFu);
+  if (blockIdx.x * TPB >= n) return;
   const Rep* rp = g.rep + r;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   uint4* core = g.core + (size_t)r * g.n_cap;
-  int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
-  uint4 ca = core[ed.x], cb = core[ed.y];
-  const double* tab = g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1);
-  if (ANAL) e2_anal<INJ>(g, inj, mask, r, l, e, at, P, ed, ca, cb, core, (double)(rp->t_age - rp->t_ref) * XGC_WEEK);
-  else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e, at, P, ed, ca, cb, core, tab);
-  else e2_directed<INJ>(g, inj, type, r, l, e, at, P, ed, ca, cb, core, tab);
+  for (unsigned i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    unsigned item = g.q_items[((size_t)r * 4 + type) * g.e_stride + i];
+    int l = (int)(item >> 28), e = (int)(item & 0x0FFFFFFFu);
+    int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
+    uint4 ca = core[ed.x], cb = core[ed.y];
+    const double* tab = g.pois + ((size_t)r * 4 + (l < 2 ? l : 0)) * (XGC_MAX_ACTS + 1);
+    if (ANAL) e2_anal<INJ>(g, inj, mask, r, l, e, at, P, ed, ca, cb, core, (double)(rp->t_age - rp->t_ref) * XGC_WEEK);
+    else if (type == 2) e2_kiss<INJ>(g, inj, r, l, e, at, P, ed, ca, cb, core, tab);
+    else e2_directed<INJ>(g, inj, type, r, l, e, at, P, ed, ca, cb, core, tab);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent3: apply this week's new infections (unique ids; pathway attribution by the weekly random order) and tally
-// prevalence_msm (sim1_02_lhs.r:218).  Per-CTA shared-memory histogram, one flush per CTA.
+// prevalence_msm (sim1_02_lhs.r:218).
+// k_agent3a reads every agent once: it tallies the prevalence series on the status the agent WILL have once its flagged
+// infections are applied (a flagged site that is not yet infected becomes infected, whatever the draws say), and queues
+// the flagged agents; it writes nothing to the agent planes.  k_agent3b applies the infections of the queued agents
+// (a few per cent) with all lanes busy: symptom draw, Poisson duration, clocks, incidence and pathway tallies.
 // ---------------------------------------------------------------------------------------------------------------------
-#define A3_NHIST (XGC_K_NGROUP * XGC_NCELL + XGC_NPATH)
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
+#define A3_NHIST (XGC_K_NGROUP * XGC_NCELL)
+#define A3_SITE_MASK(s) ((s) == 0 ? ((1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R)) : (s) == 1 ? ((1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U)) \
+                                  : ((1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P)))
+__global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, unsigned mask, int tpc) {
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -1149,79 +1175,110 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3(const __grid
   for (int k = threadIdx.x; k < A3_NHIST; k += TPB) hist[k] = 0u;
   __syncthreads();
   int at = g.at_ptr[r];
-  const double* P = g.params + (size_t)r * XGC_NPARAM;
-  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  unsigned lane = threadIdx.x & 31;
+  unsigned* Q = g.qa_items + rbase;
+  const bool gct = mask & XGC_M_STITRANS, hvt = mask & XGC_M_HIVTRANS;
   for (int t = t0; t < t1; ++t) {
-  int i = t * TPB + threadIdx.x;
-  size_t idx = rbase + i;
-  uint4 c = cn;
-  if (t + 1 < t1) cn = g.core[idx + TPB];
-  bool live = i < n_slots;
-  live = live && (c.y & DM_ACTIVE);
-  unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w, cell = DM_CELL(demo);
-  if (live) {
-    unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
-    if (nm && (mask & XGC_M_STITRANS)) {
-      short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
-      bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
-      if (pois) gd = g.gck_d[idx];
-      DrawT<INJ> d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
-      const unsigned site_mask[3] = { (1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R), (1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U),
-                                      (1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P) };
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        unsigned cand = nm & site_mask[s];
-        if (!cand || (gc & GC_ST(s))) continue;
-        int win = -1, wr = 99;
-        for (int k = 0; k < XGC_NPATH; ++k) if ((cand >> k) & 1u) { int rk = rp->path_rank[k]; if (rk < wr) { wr = rk; win = k; } }
-        gc = (gc | GC_ST(s)) & ~(GC_SY(s) | GC_TX(s));
-        if (xgc_bern(d(s), P[XGC_P_gc_sympt_prob + s])) gc |= GC_SY(s);
-        short du = -1;
-        if (pois) { int q = xgc_pois(d(3 + s), P[XGC_P_gc_ntx_int + s], 255); du = (short)(q < 1 ? 1 : q); }
-        if (s == 0) { ga.x = (short)at; gb.x = -1; gd.x = du; } else if (s == 1) { ga.y = (short)at; gb.y = -1; gd.y = du; } else { ga.z = (short)at; gb.z = -1; gd.z = du; }
-        atomicAdd(&hist[(XGC_K_INCID_RGC + s) * XGC_NCELL + cell], 1u);
-        atomicAdd(&hist[XGC_K_NGROUP * XGC_NCELL + win], 1u);
-      }
-      g.gck_a[idx] = ga; g.gck_b[idx] = gb; if (pois) g.gck_d[idx] = gd;
+    int i = t * TPB + threadIdx.x;
+    uint4 c = cn;
+    if (t + 1 < t1) cn = g.core[rbase + i + TPB];
+    bool live = i < n_slots && (c.y & DM_ACTIVE);
+    unsigned gc = c.z, hiv = c.w, cell = DM_CELL(c.y);
+    unsigned nm = gct ? (gc >> GC_NEW_SHIFT) & 0x7Fu : 0u;
+    bool hnew = hvt && (hiv & HV_NEW);
+    bool queue = live && (nm || hnew);
+    if (queue) {      // status after k_agent3b: flagged susceptible sites become infected; a flagged HIV-negative becomes positive
+      if (nm & A3_SITE_MASK(0)) gc |= GC_ST(0);
+      if (nm & A3_SITE_MASK(1)) gc |= GC_ST(1);
+      if (nm & A3_SITE_MASK(2)) gc |= GC_ST(2);
+      if (hnew) hiv |= HV_STATUS;
     }
-    if (mask & XGC_M_STITRANS) gc &= ~GC_NEW_MASK;
-    if ((hiv & HV_NEW) && (mask & XGC_M_HIVTRANS)) {
-      if (!(hiv & HV_STATUS)) {
-        hiv = (hiv & ~(HV_STAGE_MASK | HV_DIAG | HV_TX)) | HV_STATUS | HV_VSUPP | (1u << 1);
-        short4 ha = g.hck_a[idx]; ha.x = (short)at; ha.z = (short)at; g.hck_a[idx] = ha;
-        short4 hb = g.hck_b[idx]; hb.x = 0; hb.y = 0; g.hck_b[idx] = hb;
-        g.aux[idx].vl = 0.f;
-        atomicAdd(&hist[XGC_K_INCID_HIV * XGC_NCELL + cell], 1u);
-      }
+    unsigned m = __ballot_sync(0xffffffffu, queue);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(g.q3_count + r, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i;
     }
-    if (mask & XGC_M_HIVTRANS) hiv &= ~HV_NEW;
-    if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
-  }
-  if (mask & XGC_M_PREV) {
-    // warp-aggregated tallies: lanes of the same (race, age group) cell vote, one shared-memory add per cell and series
-    unsigned lane = threadIdx.x & 31;
-    unsigned grp = __match_any_sync(0xffffffffu, live ? cell : 31u);
-    bool leader = live && lane == (unsigned)(__ffs(grp) - 1);
+    if (mask & XGC_M_PREV) {
+      // warp-aggregated tallies: lanes of the same (race, age group) cell vote, one shared-memory add per cell and series
+      unsigned grp = __match_any_sync(0xffffffffu, live ? cell : 31u);
+      bool leader = live && lane == (unsigned)(__ffs(grp) - 1);
 #define A3_TALLY(group, pred) { unsigned m_ = __ballot_sync(0xffffffffu, live && (pred)) & grp; \
                                 if (leader && m_) atomicAdd(&hist[(group) * XGC_NCELL + cell], (unsigned)__popc(m_)); }
-    A3_TALLY(XGC_K_NUM, true)
-    A3_TALLY(XGC_K_INUM, hiv & HV_STATUS)
-    A3_TALLY(XGC_K_INUM_DX, hiv & HV_DIAG)
-    A3_TALLY(XGC_K_VSUPP, (hiv & HV_DIAG) && (hiv & HV_VSUPP))
-    A3_TALLY(XGC_K_PREPELIG, hiv & HV_PREPELIG)
-    A3_TALLY(XGC_K_PREPCURR, hiv & HV_PREP)
-    A3_TALLY(XGC_K_INUM_GC, gc & 7u)
-    A3_TALLY(XGC_K_INUM_RGC, gc & 1u)
-    A3_TALLY(XGC_K_INUM_UGC, gc & 2u)
-    A3_TALLY(XGC_K_INUM_PGC, gc & 4u)
+      A3_TALLY(XGC_K_NUM, true)
+      A3_TALLY(XGC_K_INUM, hiv & HV_STATUS)
+      A3_TALLY(XGC_K_INUM_DX, hiv & HV_DIAG)
+      A3_TALLY(XGC_K_VSUPP, (hiv & HV_DIAG) && (hiv & HV_VSUPP))
+      A3_TALLY(XGC_K_PREPELIG, hiv & HV_PREPELIG)
+      A3_TALLY(XGC_K_PREPCURR, hiv & HV_PREP)
+      A3_TALLY(XGC_K_INUM_GC, gc & 7u)
+      A3_TALLY(XGC_K_INUM_RGC, gc & 1u)
+      A3_TALLY(XGC_K_INUM_UGC, gc & 2u)
+      A3_TALLY(XGC_K_INUM_PGC, gc & 4u)
 #undef A3_TALLY
+    }
   }
-  }
+  if (!(mask & XGC_M_PREV)) return;
   __syncthreads();
   unsigned* row = counter_row(g, r, at);
+  // the incidence groups are tallied by k_agent3b; only the series above can be non-zero here
   for (int k = threadIdx.x; k < A3_NHIST; k += TPB) {
     unsigned v = hist[k];
-    if (v) atomicAdd(row + (k < XGC_K_NGROUP * XGC_NCELL ? k : XGC_K_PATH + (k - XGC_K_NGROUP * XGC_NCELL)), v);
+    if (v) atomicAdd(row + k, v);
+  }
+}
+
+template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  int r = blockIdx.y;
+  unsigned n = g.q3_count[r];
+  if (blockIdx.x * TPB >= n) return;
+  const Rep* rp = g.rep + r;
+  const size_t rbase = (size_t)r * g.n_cap;
+  int at = g.at_ptr[r];
+  const double* P = g.params + (size_t)r * XGC_NPARAM;
+  const int* C = g.control + (size_t)r * XGC_NCONTROL;
+  unsigned* row = counter_row(g, r, at);
+  for (unsigned qi = blockIdx.x * TPB + threadIdx.x; qi < n; qi += gridDim.x * TPB) {
+  size_t idx = rbase + g.qa_items[rbase + qi];
+  uint4 c = g.core[idx];
+  unsigned uid = c.x, gc = c.z, hiv = c.w, cell = DM_CELL(c.y);
+  unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
+  if (nm && (mask & XGC_M_STITRANS)) {
+    short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
+    bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
+    if (pois) gd = g.gck_d[idx];
+    DrawT<INJ> d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      unsigned cand = nm & A3_SITE_MASK(s);
+      if (!cand || (gc & GC_ST(s))) continue;
+      int win = -1, wr = 99;
+      for (int k = 0; k < XGC_NPATH; ++k) if ((cand >> k) & 1u) { int rk = rp->path_rank[k]; if (rk < wr) { wr = rk; win = k; } }
+      gc = (gc | GC_ST(s)) & ~(GC_SY(s) | GC_TX(s));
+      if (xgc_bern(d(s), P[XGC_P_gc_sympt_prob + s])) gc |= GC_SY(s);
+      short du = -1;
+      if (pois) { int q = xgc_pois(d(3 + s), P[XGC_P_gc_ntx_int + s], 255); du = (short)(q < 1 ? 1 : q); }
+      if (s == 0) { ga.x = (short)at; gb.x = -1; gd.x = du; } else if (s == 1) { ga.y = (short)at; gb.y = -1; gd.y = du; } else { ga.z = (short)at; gb.z = -1; gd.z = du; }
+      atomicAdd(row + (XGC_K_INCID_RGC + s) * XGC_NCELL + cell, 1u);
+      atomicAdd(row + XGC_K_PATH + win, 1u);
+      any = true;
+    }
+    if (any) { g.gck_a[idx] = ga; g.gck_b[idx] = gb; if (pois) g.gck_d[idx] = gd; }
+  }
+  if (mask & XGC_M_STITRANS) gc &= ~GC_NEW_MASK;
+  if ((hiv & HV_NEW) && (mask & XGC_M_HIVTRANS)) {
+    if (!(hiv & HV_STATUS)) {
+      hiv = (hiv & ~(HV_STAGE_MASK | HV_DIAG | HV_TX)) | HV_STATUS | HV_VSUPP | (1u << 1);
+      short4 ha = g.hck_a[idx]; ha.x = (short)at; ha.z = (short)at; g.hck_a[idx] = ha;
+      short4 hb = g.hck_b[idx]; hb.x = 0; hb.y = 0; g.hck_b[idx] = hb;
+      g.aux[idx].vl = 0.f;
+      atomicAdd(row + XGC_K_INCID_HIV * XGC_NCELL + cell, 1u);
+    }
+  }
+  if (mask & XGC_M_HIVTRANS) hiv &= ~HV_NEW;
+  if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
   }
 }
 

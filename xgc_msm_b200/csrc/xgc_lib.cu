@@ -117,7 +117,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
   rc |= dalloc(h, &g.counters, (size_t)g.R * g.t_cap * XGC_NCOUNTER);
   rc |= dalloc(h, &g.q_items, (size_t)g.R * 4 * g.e_stride); rc |= dalloc(h, &g.q_count, (size_t)g.R * 4);
-  rc |= dalloc(h, &g.qa_items, NA); rc |= dalloc(h, &g.qa_count, (size_t)g.R);
+  rc |= dalloc(h, &g.qa_items, NA); rc |= dalloc(h, &g.qa_count, (size_t)g.R); rc |= dalloc(h, &g.q3_count, (size_t)g.R);
   rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
   g.lb_tiles = (std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2])) + 1023) / 1024;
   rc |= dalloc(h, &g.lb_status, (size_t)g.R * 3 * g.lb_tiles); rc |= dalloc(h, &g.lb_ticket, (size_t)g.R * 3);
@@ -466,11 +466,13 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
+  // queue kernels: a few CTAs per replicate striding over its queue, ~2 waves of the GPU in total
+  auto qgrid = [&](int max_tiles) { return (unsigned)std::max(1, std::min(max_tiles, (148 * 16 + g.R - 1) / g.R)); };
   LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
   if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
-  if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(tiles, g.R), TPB, g, inj, mask);
+  if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
   bool native = inj.u == nullptr;
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0, 0);
   if (mask & XGC_M_RESIM_NETS) {
@@ -487,12 +489,15 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
       prof_end(h); h->launches++;
     }
   }
-  if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, ge, TPB, g, inj, mask);
+  // edge kernels: the three layers as one index space, a few CTAs per replicate striding over it
+  int etiles = (int)((g.e_stride + TPB - 1) / TPB);
+  dim3 gef((unsigned)std::max(1, std::min(etiles, (148 * 32 + g.R - 1) / g.R)), g.R);
+  if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, gef, TPB, g, inj, mask);
   if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2a, ga, TPB, g, inj, mask, tpc);
-  if (mask & (XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2b, dim3(tiles, g.R), TPB, g, inj, mask);
+  if (mask & (XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
-    LAUNCH(h, k_edge2a, ge, TPB, g, mask);
-    unsigned qb = (unsigned)((g.e_stride + TPB - 1) / TPB);
+    LAUNCH(h, k_edge2a, gef, TPB, g, mask);
+    unsigned qb = qgrid((int)((g.e_stride + TPB - 1) / TPB));
     prof_begin(h, "k_edge2b_anal");
     if (inj.u) k_edge2b<true, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask);
     prof_end(h); h->launches++;
@@ -500,7 +505,8 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     if (inj.u) k_edge2b<true, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask);
     prof_end(h); h->launches++;
   }
-  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCHD(h, inj, k_agent3, ga, TPB, g, inj, mask, tpc);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3a, ga, TPB, g, mask, tpc);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCHD(h, inj, k_agent3b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
   return 0;
 }
 

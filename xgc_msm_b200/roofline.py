@@ -26,8 +26,10 @@ def kernel_bytes(stats: dict) -> dict:
         "k_agent2a": n * (16 + 8 + f_gc * 4),
         # queued agents (infected or visiting): item + core + gck_a + gck_b
         "k_agent2b": n * f_gc * (4 + 16 + 8 + 8),
-        # core R + diagnosed: aux R (viral load for cc.vsupp)
-        "k_agent3": n * (16 + f_dx * 16),
+        # tally pass: core R (+ 4 B queue entry per agent with a new infection)
+        "k_agent3a": n * (16 + stats.get("f_new", 0.0) * 4),
+        # queued agents: item + core R+W (8 B of it) + gck_a / gck_b R+W
+        "k_agent3b": n * stats.get("f_new", 0.0) * (4 + 16 + 8 + 4 * 8),
         # edge record R + acts W(4) + 2 endpoints x (core + aux)
         "k_edge1": e * (16 + 4 + 2 * 32),
         # classify: edge record R + 2 endpoints x core (+ 4 B queue entry per discordant (edge, type) pair)
