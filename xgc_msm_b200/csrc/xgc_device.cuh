@@ -145,6 +145,14 @@ template <bool INJ> struct DrawT {
   }
 };
 
+// Programmatic dependent launch: first statement of every weekly kernel.  launch_dependents lets the next kernel's CTAs
+// become resident as soon as every CTA of this grid has started; wait blocks until the previous grid has completed and
+// its writes are visible (a no-op for a kernel launched without the attribute).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- arithmetic contract (mirrors the oracle operation for operation; no FMA)
 __device__ __forceinline__ double xgc_exp(double x) {
   if (x < -700.0) x = -700.0;

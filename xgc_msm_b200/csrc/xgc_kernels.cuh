@@ -48,6 +48,7 @@ __global__ void k_derive(const __grid_constant__ Dev g, double* pois) {
 // arrival_msm: /root/reference/burnin/cal/sim1_02_lhs.r:204, 63-66
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
+  pdl_prologue();
   int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= g.R) return;
   Rep* rp = g.rep + r;
@@ -134,6 +135,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // interval-test draw.  HIV-positive agents (a minority, with long divergent code paths: AIDS mortality, test result,
 // treatment, progression, viral load) are appended to the replicate's work queue and finished densely by k_agent1b.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap, int tpc) {
+  pdl_prologue();
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -212,6 +214,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
 
 // k_agent1b: AIDS mortality, HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued HIV-positive agents
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.y;
   unsigned n = g.qh_count[r];
   if (blockIdx.x * TPB >= n) return;
@@ -316,6 +319,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
 // NT threads, IPT edges per thread and iteration: <256,1> for calibration-size layers, <1024,4> for the 100k..1M-agent
 // configs where one CTA walks a whole layer (4096 edges per iteration keeps the sequential part short).
 template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
+  pdl_prologue();
   int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne = rp->ne[l], at = g.at_ptr[r];
@@ -372,6 +376,7 @@ template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edg
 // last tile), so status words of earlier launches never match.
 #define LB_TILE 1024
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve, int kind) {
+  pdl_prologue();
   int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int at = g.at_ptr[r];
@@ -444,6 +449,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(cons
 // k_rank: pos2slot[r][rank] = slot, from the alive bitmap.  grid (slot tiles, R): each CTA sums the bitmap words before its
 // tile (<= n_cap/32 words, a block reduction) and ranks its own 256 slots with popcounts.
 __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
+  pdl_prologue();
   int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int n_slots = g.rep[r].n_slots;
   int i0 = blockIdx.x * TPB;
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
 // R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
 template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+  pdl_prologue();
   int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // one CTA per replicate, the three layers in turn
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
@@ -557,6 +564,7 @@ template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_f
 // ties, the accepted ones are appended in draw order through the decoupled look-back prefix (shares the tile tickets /
 // status words / epoch with k_edges_resim_lb; launches are serialised on the stream).  Needs pos2slot (k_rank).
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+  pdl_prologue();
   int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne0 = *(volatile int*)&rp->ne[l];
@@ -696,6 +704,7 @@ template <class D> __device__ __forceinline__ void edge_kiss_rim(const double* P
 
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
 template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   // the three layers of the replicate are walked as one index space [0, ne0 + ne1 + ne2): full tiles except the last,
@@ -796,6 +805,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __gr
 // k_agent2a: prep_msm for every agent + classification: agents with GC work this week (an infected site, a clinic visit)
 // are appended to the replicate's work queue; k_agent2b runs stirecov_msm / stitx_msm on the queue with all lanes busy.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
+  pdl_prologue();
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -859,6 +869,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __gri
 
 // k_agent2b: stirecov_msm, stitx_msm (sim1_02_lhs.r:215-216) over the queued agents
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.y;
   unsigned n = g.qa_count[r];
   if (blockIdx.x * TPB >= n) return;
@@ -1076,6 +1087,7 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
 // k_edge2a: classify every edge and append the (edge, act type) pairs that can transmit to the replicate's per-type
 // work queues (one atomicAdd per CTA and type).  No draws here.
 __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const int ne0 = rp->ne[0], ne01 = ne0 + rp->ne[1], ne_all = ne01 + rp->ne[2];     // one index space over the three layers
@@ -1133,6 +1145,7 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
 
 // k_edge2b: dense processing of the work queues; blockIdx.y = act type, so every warp runs one act type with all lanes busy.
 template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 : 4) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.z, type = ANAL ? 0 : 1 + blockIdx.y;
   unsigned n = g.q_count[(size_t)r * 4 + type];
   if (blockIdx.x * TPB >= n) return;
@@ -1164,6 +1177,7 @@ template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 :
 #define A3_SITE_MASK(s) ((s) == 0 ? ((1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R)) : (s) == 1 ? ((1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U)) \
                                   : ((1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P)))
 __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, unsigned mask, int tpc) {
+  pdl_prologue();
   int r = blockIdx.y;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -1230,6 +1244,7 @@ __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, 
 }
 
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
+  pdl_prologue();
   int r = blockIdx.y;
   unsigned n = g.q3_count[r];
   if (blockIdx.x * TPB >= n) return;
@@ -1322,6 +1337,7 @@ __device__ double target_week(const unsigned* c, int k) {
   return gsum(c, XGC_K_INCID_RGC + s, ALL) / (num - gsum(c, XGC_K_INUM_RGC + s, ALL)) * 5200.0;
 }
 __global__ void k_targets(const __grid_constant__ Dev g, int at_last, int tailn, double* out) {
+  pdl_prologue();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.R * XGC_NTARGET) return;
   int r = t / XGC_NTARGET, k = t % XGC_NTARGET;
@@ -1334,6 +1350,7 @@ __global__ void k_targets(const __grid_constant__ Dev g, int at_last, int tailn,
 // k_compact: squeeze tombstones out of one replicate (stable, in place, one CTA per replicate) and re-number edges.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ Dev g, int* remap /*[R][n_cap] old slot -> new slot*/) {
+  pdl_prologue();
   int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int n_slots = rp->n_slots;
@@ -1374,6 +1391,7 @@ __global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ 
   if (tid == 0) { rp->n_slots = n; rp->n_slots_pre = n; rp->n_alive = n; }
 }
 __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ Dev g, const int* remap) {
+  pdl_prologue();
   int r = blockIdx.z, l = blockIdx.y;
   int ne = g.rep[r].ne[l];
   int e = blockIdx.x * TPB + threadIdx.x;

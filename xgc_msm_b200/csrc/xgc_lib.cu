@@ -41,6 +41,7 @@ struct xgc_handle {
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
+  bool pdl = true;            // programmatic dependent launch of the weekly kernels (XGC_PDL=0 turns it off)
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<void*> allocs;
@@ -99,6 +100,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   if (h->cfg.compact_every <= 0) h->cfg.compact_every = 64;
   auto fail = [&](int code) { g_create_error = h->err; xgc_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(3); }
+  { const char* e = getenv("XGC_PDL"); if (e && e[0] == '0') h->pdl = false; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return fail(3); }
   Dev& g = h->g; memset(&g, 0, sizeof g);
   g.R = cfg->n_replicates; g.n_cap = cfg->n_cap; g.t_cap = cfg->t_cap; g.rep0 = cfg->replicate_offset; g.seed = (unsigned)cfg->seed;
@@ -435,10 +437,22 @@ static void prof_begin(xgc_handle* h, const char* name) {
   h->prof.push_back(r);
 }
 static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.back().b, h->stream); }
-#define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
+// Every weekly kernel is launched with programmatic stream serialization (PDL): the next kernel's CTAs become resident while
+// the previous kernel drains and block in griddepcontrol.wait (first statement of every kernel) until it has completed
+// and flushed, so the launch ramp overlaps the tail.  Captured into the week graph as programmatic edges.
+template <class... KArgs, class... Args>
+static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kl(h, kern, grid, block, 0, __VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
 // kernels that draw: native instantiation unless an injected table is attached
 #define LAUNCHD(h, inj, kern, grid, block, ...) do { prof_begin(h, #kern); \
-  if ((inj).u) kern<true><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); else kern<false><<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); \
+  if ((inj).u) kl(h, kern<true>, grid, block, 0, __VA_ARGS__); else kl(h, kern<false>, grid, block, 0, __VA_ARGS__); \
   prof_end(h); (h)->launches++; } while (0)
 
 // stable in-place edge compaction: small CTAs for calibration-size layers, 1024 x 4 for very long layers
@@ -448,11 +462,11 @@ static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve, int kind) 
   prof_begin(h, "k_edges_resim");
   if (emax > 16384) {           // very long layers: many CTAs per layer, decoupled look-back
     dim3 grid(g.lb_tiles, 3, g.R);
-    if (inj.u) k_edges_resim_lb<true><<<grid, TPB, 0, h->stream>>>(g, inj, dissolve, kind);
-    else k_edges_resim_lb<false><<<grid, TPB, 0, h->stream>>>(g, inj, dissolve, kind);
+    if (inj.u) kl(h, k_edges_resim_lb<true>, grid, TPB, 0, g, inj, dissolve, kind);
+    else kl(h, k_edges_resim_lb<false>, grid, TPB, 0, g, inj, dissolve, kind);
   } else {
-    if (inj.u) k_edges_resim<true, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
-    else k_edges_resim<false, TPB, 1><<<dim3(3, g.R), TPB, 0, h->stream>>>(g, inj, dissolve);
+    if (inj.u) kl(h, k_edges_resim<true, TPB, 1>, dim3(3, g.R), TPB, 0, g, inj, dissolve);
+    else kl(h, k_edges_resim<false, TPB, 1>, dim3(3, g.R), TPB, 0, g, inj, dissolve);
   }
   prof_end(h); h->launches++;
 }
@@ -480,12 +494,12 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 8 * 1024) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
       prof_begin(h, "k_form");
-      if (inj.u) k_form<true, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj); else k_form<false, true, TPB><<<g.R, TPB, form_smem, h->stream>>>(g, inj);
+      if (inj.u) kl(h, k_form<true, true, TPB>, g.R, TPB, form_smem, g, inj); else kl(h, k_form<false, true, TPB>, g.R, TPB, form_smem, g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
       prof_begin(h, "k_form");
-      if (inj.u) k_form_lb<true><<<dim3(g.lb_tiles, 3, g.R), TPB, 0, h->stream>>>(g, inj); else k_form_lb<false><<<dim3(g.lb_tiles, 3, g.R), TPB, 0, h->stream>>>(g, inj);
+      if (inj.u) kl(h, k_form_lb<true>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj); else kl(h, k_form_lb<false>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj);
       prof_end(h); h->launches++;
     }
   }
@@ -499,10 +513,10 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     LAUNCH(h, k_edge2a, gef, TPB, g, mask);
     unsigned qb = qgrid((int)((g.e_stride + TPB - 1) / TPB));
     prof_begin(h, "k_edge2b_anal");
-    if (inj.u) k_edge2b<true, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, true><<<dim3(qb, 1, g.R), TPB, 0, h->stream>>>(g, inj, mask);
+    if (inj.u) kl(h, k_edge2b<true, true>, dim3(qb, 1, g.R), TPB, 0, g, inj, mask); else kl(h, k_edge2b<false, true>, dim3(qb, 1, g.R), TPB, 0, g, inj, mask);
     prof_end(h); h->launches++;
     prof_begin(h, "k_edge2b_oral_kiss_rim");
-    if (inj.u) k_edge2b<true, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask); else k_edge2b<false, false><<<dim3(qb, 3, g.R), TPB, 0, h->stream>>>(g, inj, mask);
+    if (inj.u) kl(h, k_edge2b<true, false>, dim3(qb, 3, g.R), TPB, 0, g, inj, mask); else kl(h, k_edge2b<false, false>, dim3(qb, 3, g.R), TPB, 0, g, inj, mask);
     prof_end(h); h->launches++;
   }
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3a, ga, TPB, g, mask, tpc);
