@@ -128,13 +128,23 @@ enum xgc_stream {
                           insertive->receptive (u2r) or receptive->insertive (r2u), at most one is possible per act}:
                           one Philox block per anal act                                                               */
   XGC_S_ORAL,          /* k0 = direction word: act j is "p1 insertive" iff bit (31-j) of floor(u * 2^32) is set;
-                          k = 1 + act: GC transmission (u2p or p2u, exclusive)                                        */
-  XGC_S_RIM,           /* same layout: k0 direction word (p1 is the rimmer), k = 1 + act: p2r or r2p                 */
-  XGC_S_KISS,          /* k = act: p2p from whichever partner is infected                                             */
+                          k1 = GC transmission over ALL of the week's acts with p1 insertive, k2 = with p2 insertive
+                          (u2p or p2u, exclusive per direction): n iid per-act Bernoulli(t) trials whose only observable
+                          is "any success" are drawn as ONE Bernoulli(1 - (1-t)^n)                     */
+  XGC_S_RIM,           /* same layout: k0 direction word (p1 is the rimmer), k1 / k2: p2r or r2p                     */
+  XGC_S_KISS,          /* k0: p2p from whichever partner is infected, over all of the week's kissing acts            */
   XGC_S_EDGE_END
 };
 #define XGC_EDGE_STREAMS (XGC_S_EDGE_END - XGC_S_EDGE0)
 #define XGC_NSTREAM (XGC_S_EDGE0 + 3 * XGC_EDGE_STREAMS)
+
+/* P(at least one of n iid Bernoulli(t) trials succeeds) = 1 - (1-t)^n, the power by binary exponentiation in a fixed
+ * operation order (n <= 63) so that the device and the oracle round identically. */
+static inline XGC_HD double xgc_any_of_n(double t, int n) {
+  double q = 1.0, b = 1.0 - t;
+  for (int i = 0; i < 6; ++i) { if (n & 1) q = q * b; b = b * b; n >>= 1; }
+  return 1.0 - q;
+}
 
 /* Draws per entity for each stream (table width in injected mode). */
 static inline XGC_HD int xgc_stream_width(int s) {
@@ -150,8 +160,8 @@ static inline XGC_HD int xgc_stream_width(int s) {
   if (s == XGC_S_DISSOLVE) return 1;
   if (s == XGC_S_ACTS) return 4;
   if (s == XGC_S_ANAL) return 4 * XGC_MAX_ACTS;
-  if (s == XGC_S_KISS) return XGC_MAX_ACTS;
-  return 1 + XGC_MAX_ACTS;
+  if (s == XGC_S_KISS) return 1;
+  return 3;                                        /* XGC_S_ORAL, XGC_S_RIM */
 }
 
 /* Injected-draw table for ONE replicate and ONE week.  Layout: for each stream s in increasing order, a block of
@@ -255,6 +265,8 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_F64) X(XGC_I32)
 int  xgc_constant(const char* name, int64_t* value);          /* 0 if found */
 int  xgc_param_index(const char* name, int* offset, int* count);   /* params.def lookup */
+int  xgc_inject_stream_width(int stream);                       /* = xgc_stream_width() for bindings that cannot include this header */
+size_t xgc_inject_table_size(const xgc_inject* d);               /* = xgc_inject_size()                                                */
 
 typedef struct xgc_config {
   int32_t  abi_version;        /* XGC_ABI_VERSION                                                                   */

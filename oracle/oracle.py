@@ -51,6 +51,7 @@ def _load():
     lib.orc_status.argtypes = [vp]; lib.orc_status.restype = C.c_uint32
     lib.orc_philox4x32_10.argtypes = [pu, pu, pu]; lib.orc_philox4x32_10.restype = None
     lib.orc_exp.argtypes = [C.c_double]; lib.orc_exp.restype = C.c_double
+    lib.orc_any_of_n.argtypes = [C.c_double, C.c_int]; lib.orc_any_of_n.restype = C.c_double
     lib.orc_bern.argtypes = [C.c_double, C.c_double]; lib.orc_bern.restype = ci
     lib.orc_pois.argtypes = [C.c_double, C.c_double, ci]; lib.orc_pois.restype = ci
     lib.orc_uniform.argtypes = [vp, ci, ci, C.c_uint32, C.c_uint32, ci]; lib.orc_uniform.restype = C.c_double

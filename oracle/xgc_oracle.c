@@ -118,6 +118,8 @@ double orc_exp(double x) {
   return q * s.f;
 }
 
+double orc_any_of_n(double t, int n) { return xgc_any_of_n(t, n); }
+
 /* rbinom(1, 1, p) by inversion, as base R does it */
 int orc_bern(double u, double p) {
   if (p <= 0.5) return u >= 1.0 - p;
@@ -764,34 +766,67 @@ static void stitrans_msm_rand(orc_dat* d, int at) {
   ensure_al(d, at);
   const double* p = d->p;
   memset(d->newmask, 0, sizeof(uint32_t) * (size_t)d->n);
+  /* Anal acts: one draw per act (condom use and position are per-act attributes shared with hivtrans and the PrEP risk
+     history).  Oral, rimming and kissing acts carry no per-act attribute besides the direction, site status is constant
+     within the week and only "any transmission" is observable, so the m acts of one (edge, type, direction) are ONE
+     Bernoulli(1 - (1-t)^m) trial; the act list supplies m. */
+  int* cnt[3];                       /* per layer: [e][type 1..3][direction p1 active / p2 active] */
+  for (int l = 0; l < 3; ++l) cnt[l] = (int*)calloc((size_t)(d->ne[l] + 1) * 6, sizeof(int));
   for (int j = 0; j < d->nal; ++j) {
     const orc_act* r = &d->al[j];
+    if (r->type != 0) { cnt[r->layer][(size_t)r->e * 6 + (r->type - 1) * 2 + (r->type == 2 ? 0 : (r->p1act ? 0 : 1))]++; continue; }
     const orc_edge* g = &d->el[r->layer][r->e];
     int base = XGC_S_EDGE0 + r->layer * XGC_EDGE_STREAMS;
     uint32_t ua = (uint32_t)d->a[A_UID][g->p1], ub = (uint32_t)d->a[A_UID][g->p2];
-    int x, y, sx, sy, pathA, pathB, st, kk; double tA, tB;
-    /* x = active partner (insertive / rimmer / p1), y = the other; A: x's site sx -> y's site sy; B: reverse.
-       A and B exclude each other (each needs exactly one of the two sites infected), so they share one draw per act. */
-    if (r->type == 0)      { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 0; pathA = XGC_PATH_U2R; pathB = XGC_PATH_R2U; tA = p[XGC_P_u2rgc_tprob]; tB = p[XGC_P_r2ugc_tprob]; st = XGC_S_ANAL; kk = 4 * r->k + 3; }
-    else if (r->type == 1) { x = r->p1act ? g->p1 : g->p2; sx = 1; sy = 2; pathA = XGC_PATH_U2P; pathB = XGC_PATH_P2U; tA = p[XGC_P_u2pgc_tprob]; tB = p[XGC_P_p2ugc_tprob]; st = XGC_S_ORAL; kk = 1 + r->k; }
-    else if (r->type == 3) { if (!d->c[XGC_C_transRoute_Rimming]) continue;
-                             x = r->p1act ? g->p1 : g->p2; sx = 2; sy = 0; pathA = XGC_PATH_P2R; pathB = XGC_PATH_R2P; tA = p[XGC_P_p2rgc_tprob]; tB = p[XGC_P_r2pgc_tprob]; st = XGC_S_RIM; kk = 1 + r->k; }
-    else                   { if (!d->c[XGC_C_transRoute_Kissing]) continue;
-                             x = g->p1; sx = 2; sy = 2; pathA = XGC_PATH_P2P; pathB = XGC_PATH_P2P; tA = p[XGC_P_p2pgc_tprob]; tB = tA; st = XGC_S_KISS; kk = r->k; }
-    y = x == g->p1 ? g->p2 : g->p1;
-    int gx = (int)d->a[A_GC + sx][x] == 1, gy = (int)d->a[A_GC + sy][y] == 1;
-    int condom = r->type == 0 && !r->uai;
-    if (gx && !gy && d->a[A_GC_INF + sx][x] < (double)at) {
-      double t = tA;
+    /* x = insertive partner, y = receptive; A: x's urethra -> y's rectum; B: reverse.  A and B exclude each other
+       (each needs exactly one of the two sites infected), so they share one draw per act. */
+    int x = r->p1act ? g->p1 : g->p2, y = x == g->p1 ? g->p2 : g->p1;
+    int gx = (int)d->a[A_GC + 1][x] == 1, gy = (int)d->a[A_GC + 0][y] == 1;
+    int condom = !r->uai, kk = 4 * r->k + 3;
+    if (gx && !gy && d->a[A_GC_INF + 1][x] < (double)at) {
+      double t = p[XGC_P_u2rgc_tprob];
       if (condom) t = t * (1.0 - p[XGC_P_sti_cond_eff] * (1.0 - p[XGC_P_sti_cond_fail + (int)d->a[A_RACE][y] - 1]));
-      if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[y] |= 1u << pathA;
+      if (orc_bern(U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[y] |= 1u << XGC_PATH_U2R;
     }
-    if (gy && !gx && d->a[A_GC_INF + sy][y] < (double)at) {
-      double t = tB;
+    if (gy && !gx && d->a[A_GC_INF + 0][y] < (double)at) {
+      double t = p[XGC_P_r2ugc_tprob];
       if (condom) t = t * (1.0 - p[XGC_P_sti_cond_eff] * (1.0 - p[XGC_P_sti_cond_fail + (int)d->a[A_RACE][x] - 1]));
-      if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[x] |= 1u << pathB;
+      if (orc_bern(U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), ua, ub, (size_t)r->e, kk), t)) d->newmask[x] |= 1u << XGC_PATH_R2U;
     }
   }
+  for (int l = 0; l < 3; ++l) {
+    int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
+    for (int e = 0; e < d->ne[l]; ++e) {
+      const orc_edge* g = &d->el[l][e];
+      const int* c = cnt[l] + (size_t)e * 6;
+      uint32_t ua = (uint32_t)d->a[A_UID][g->p1], ub = (uint32_t)d->a[A_UID][g->p2];
+      for (int type = 1; type <= 3; ++type) {
+        if (type == 2) {                                     /* kissing: pharynx <-> pharynx, no direction */
+          int m = c[2];
+          if (!m || !d->c[XGC_C_transRoute_Kissing]) continue;
+          int ga = (int)d->a[A_GC + 2][g->p1] == 1, gb = (int)d->a[A_GC + 2][g->p2] == 1;
+          if (ga == gb) continue;
+          if (orc_bern(U(d, at, base + (XGC_S_KISS - XGC_S_EDGE0), ua, ub, (size_t)e, 0), xgc_any_of_n(p[XGC_P_p2pgc_tprob], m)))
+            d->newmask[ga ? g->p2 : g->p1] |= 1u << XGC_PATH_P2P;
+          continue;
+        }
+        if (type == 3 && !d->c[XGC_C_transRoute_Rimming]) continue;
+        int sx = type == 1 ? 1 : 2, sy = type == 1 ? 2 : 0, st = type == 1 ? XGC_S_ORAL : XGC_S_RIM;
+        int pathA = type == 1 ? XGC_PATH_U2P : XGC_PATH_P2R, pathB = type == 1 ? XGC_PATH_P2U : XGC_PATH_R2P;
+        double tA = type == 1 ? p[XGC_P_u2pgc_tprob] : p[XGC_P_p2rgc_tprob], tB = type == 1 ? p[XGC_P_p2ugc_tprob] : p[XGC_P_r2pgc_tprob];
+        for (int dir = 0; dir < 2; ++dir) {                  /* dir 0: p1 active (draw k1), dir 1: p2 active (draw k2) */
+          int m = c[(type - 1) * 2 + dir];
+          if (!m) continue;
+          int x = dir == 0 ? g->p1 : g->p2, y = dir == 0 ? g->p2 : g->p1;
+          int gx = (int)d->a[A_GC + sx][x] == 1, gy = (int)d->a[A_GC + sy][y] == 1;
+          if (gx == gy) continue;
+          if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)e, 1 + dir), xgc_any_of_n(gx ? tA : tB, m)))
+            d->newmask[gx ? y : x] |= 1u << (gx ? pathA : pathB);
+        }
+      }
+    }
+  }
+  for (int l = 0; l < 3; ++l) free(cnt[l]);
   /* "_rand": weekly random order of the 7 pathways decides which pathway a multiply-hit site is attributed to */
   int perm[XGC_NPATH], rank[XGC_NPATH];
   for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;

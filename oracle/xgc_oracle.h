@@ -55,6 +55,7 @@ uint32_t orc_status(const orc_dat* d);
 /* building blocks exposed for unit tests */
 void     orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double   orc_exp(double x);
+double   orc_any_of_n(double t, int n);    /* xgc_any_of_n of include/xgc/abi.h */
 int      orc_bern(double u, double p);
 int      orc_pois(double u, double mu, int kmax);
 double   orc_uniform(const orc_dat* d, int at, int stream, uint32_t e0, uint32_t e1, int k);

@@ -57,6 +57,23 @@ def test_poisson_cdf_walk_matches_scipy():
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "caltargets.json")))
 
 
+def test_any_of_n_is_the_distribution_of_n_per_act_draws():
+    """one Bernoulli(1 - (1-t)^n) stands for n per-act Bernoulli(t) draws of which only "any success" is
+    observed.  Closed form within a few ulp, exact at the edges, and the frequency of "any of n uniforms < t" matches."""
+    rng = np.random.default_rng(3)
+    for t in (0.0, 1e-6, 0.01, 0.25, 0.5, 0.9, 1.0):
+        for n in (0, 1, 2, 3, 7, 16, 31, 32, 63):
+            got = O.lib.orc_any_of_n(t, n)
+            want = 1.0 - (1.0 - t) ** n
+            assert abs(got - want) <= 1e-14, (t, n, got, want)
+    assert O.lib.orc_any_of_n(0.3, 0) == 0.0 and O.lib.orc_any_of_n(0.3, 1) == 1.0 - (1.0 - 0.3)
+    t, n, N = 0.07, 9, 400000
+    per_act = (rng.random((N, n)) < t).any(axis=1).mean()
+    one_draw = np.mean([O.lib.orc_bern(float(u), O.lib.orc_any_of_n(t, n)) for u in rng.random(20000)])
+    p = 1.0 - (1.0 - t) ** n
+    assert abs(per_act - p) < 4 * np.sqrt(p * (1 - p) / N) and abs(one_draw - p) < 4 * np.sqrt(p * (1 - p) / 20000)
+
+
 def test_caltargets_match_reference_literals():
     got = {(t, s): (v, lo, hi) for t, v, s, lo, hi in T.caltargets()}
     assert len(got) == len(GOLD["rows"]) == 30

@@ -61,6 +61,7 @@ def _load() -> C.CDLL:
         "xgc_profile_read": [vp, C.POINTER(C.c_char_p), pd, C.POINTER(C.c_uint64), ci], "xgc_num_agents_all": [vp, vp], "xgc_stream_ptr": [vp, C.POINTER(vp)],
         "xgc_debug_exp": [pd, pd, ci, ci], "xgc_debug_philox": [cu, cu, pu, pu, ci, ci],
         "xgc_constant": [C.c_char_p, C.POINTER(C.c_int64)], "xgc_param_index": [C.c_char_p, pi, pi],
+        "xgc_inject_stream_width": [ci],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -114,12 +115,11 @@ def make_inject(u: Optional[np.ndarray], uid_cap: int, e_cap, form_cap: int) -> 
 
 
 def stream_width(s: int) -> int:
-    if s < K.S_EDGE0:
-        return {K.S_AGENT1: 4, K.S_AGENT2: 16, K.S_INFECT: 6,
-                K.S_ARRIVE_ATTR: 8, K.S_ARRIVE_N: 64, K.S_PATHORDER: 6, K.S_NET_N: 3}.get(s, 2 * K.FORM_TRIES)
-    s = (s - K.S_EDGE0) % K.EDGE_STREAMS + K.S_EDGE0
-    return (1 if s == K.S_DISSOLVE else 4 if s == K.S_ACTS else 4 * K.MAX_ACTS if s == K.S_ANAL else
-            K.MAX_ACTS if s == K.S_KISS else 1 + K.MAX_ACTS)
+    """Draws per entity of stream s (the C header's xgc_stream_width, through the library so the two cannot drift)."""
+    w = lib.xgc_inject_stream_width(int(s))
+    if w < 0:
+        raise ValueError(f"no such stream {s}")
+    return w
 
 
 def stream_entities(s: int, uid_cap: int, e_cap, form_cap: int) -> int:

@@ -1043,7 +1043,10 @@ template <bool INJ> __device__ __forceinline__ void e2_anal(const Dev& g, const 
   }
   e2_flag(core, ed, new_a, new_b, hiv_a, hiv_b);
 }
-// oral (type 1: urethra <-> pharynx) and rimming (type 3: pharynx <-> rectum): direction per act ~ Bernoulli(0.5)
+// oral (type 1: urethra <-> pharynx) and rimming (type 3: pharynx <-> rectum): direction per act ~ Bernoulli(0.5) from
+// the direction word.  Site status does not change within the week, so all acts of one direction share one transmission
+// channel (active partner's site sx <-> other partner's site sy) and only "did any of them transmit" is observable:
+// one Bernoulli(1 - (1-t)^m) per direction instead of m per-act draws -- no per-act loop, no divergence.
 template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, const Inj& inj, int type, int r, int l, int e, int at, const double* P,
                                             const int4& ed, const uint4& ca, const uint4& cb, uint4* core, const double* tab) {
   int base = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
@@ -1054,19 +1057,26 @@ template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, co
     DrawT<INJ> da(inj, g, r, at, base + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
     edge_kiss_rim(P, l, ca, cb, da, tab, false, true, dummy, n);
   }
+  if (n == 0) return;
   unsigned ga = ca.z & 7u, gb = cb.z & 7u;
   int sx = oral ? 1 : 2, sy = oral ? 2 : 0;                 // active partner's site, other partner's site
   double tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob], tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
   unsigned pA = oral ? XGC_PATH_U2P : XGC_PATH_P2R, pB = oral ? XGC_PATH_P2U : XGC_PATH_R2P;
   DrawT<INJ> dd(inj, g, r, at, base + ((oral ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  unsigned dirword = n > 0 ? dd.bits32(0) : 0u;             // act j: p1 is the active partner iff bit (31 - j) is set
+  unsigned dirword = dd.bits32(0);                          // act j: p1 is the active partner iff bit (31 - j) is set
+  int m1 = __popc(dirword >> (32 - n)), m0 = n - m1;        // acts with p1 / p2 active (n in 1..32)
   unsigned new_a = 0, new_b = 0;
-  for (int k = 0; k < n; ++k) {
-    int p1act = (dirword >> (31 - k)) & 1u;
-    unsigned gx = p1act ? ga : gb, gy = p1act ? gb : ga;
-    bool ix = (gx >> sx) & 1u, iy = (gy >> sy) & 1u;
-    if (ix && !iy) { if (xgc_bern(dd(1 + k), tA)) { if (p1act) new_b |= 1u << pA; else new_a |= 1u << pA; } }
-    else if (iy && !ix) { if (xgc_bern(dd(1 + k), tB)) { if (p1act) new_a |= 1u << pB; else new_b |= 1u << pB; } }
+  {                                                         // p1 active: x = p1, y = p2
+    bool ix = (ga >> sx) & 1u, iy = (gb >> sy) & 1u;
+    if (m1 > 0 && ix != iy) {
+      if (xgc_bern(dd(1), xgc_any_of_n(ix ? tA : tB, m1))) { if (ix) new_b |= 1u << pA; else new_a |= 1u << pB; }
+    }
+  }
+  {                                                         // p2 active: x = p2, y = p1
+    bool ix = (gb >> sx) & 1u, iy = (ga >> sy) & 1u;
+    if (m0 > 0 && ix != iy) {
+      if (xgc_bern(dd(2), xgc_any_of_n(ix ? tA : tB, m0))) { if (ix) new_a |= 1u << pA; else new_b |= 1u << pB; }
+    }
   }
   e2_flag(core, ed, new_a, new_b, false, false);
 }
@@ -1076,12 +1086,11 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
   DrawT<INJ> da(inj, g, r, at, base + (XGC_S_ACTS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
   edge_kiss_rim(P, l, ca, cb, da, tab, true, false, n, dummy);       // this week's kissing count, evaluated only here
   if (n == 0) return;
-  bool pa = (ca.z >> 2) & 1u;
+  bool pa = (ca.z >> 2) & 1u, pb = (cb.z >> 2) & 1u;
+  if (pa == pb) return;
   DrawT<INJ> d(inj, g, r, at, base + (XGC_S_KISS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  double t = P[XGC_P_p2pgc_tprob];
-  bool hit = false;
-  for (int k = 0; k < n; ++k) hit |= (bool)xgc_bern(d(k), t);
-  if (hit) e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
+  if (xgc_bern(d(0), xgc_any_of_n(P[XGC_P_p2pgc_tprob], n)))
+    e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
 }
 
 // k_edge2a: classify every edge and append the (edge, act type) pairs that can transmit to the replicate's per-type

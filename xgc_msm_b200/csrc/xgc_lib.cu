@@ -75,6 +75,8 @@ extern "C" int xgc_constant(const char* name, int64_t* value) {
 #undef X
   return 1;
 }
+extern "C" int xgc_inject_stream_width(int stream) { return stream >= 0 && stream < XGC_NSTREAM ? xgc_stream_width(stream) : -1; }
+extern "C" size_t xgc_inject_table_size(const xgc_inject* d) { return d ? xgc_inject_size(d) : 0; }
 extern "C" int xgc_param_index(const char* name, int* offset, int* count) {
 #define XGC_PARAM(n, c, v) if (!strcmp(name, #n)) { *offset = XGC_P_##n; *count = (c); return 0; }
 #include "xgc/params.def"
