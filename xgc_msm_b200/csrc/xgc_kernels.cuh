@@ -1101,8 +1101,9 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
   const Rep* rp = g.rep + r;
   const int ne0 = rp->ne[0], ne01 = ne0 + rp->ne[1], ne_all = ne01 + rp->ne[2];     // one index space over the three layers
   if ((int)(blockIdx.x * TPB) >= ne_all) return;
+  static_assert(TPB == 256, "queue offsets assume 8 warps per CTA");
   __shared__ unsigned short s_wc[4][TPB / 32];
-  __shared__ unsigned s_base[4];
+  __shared__ unsigned s_off[4][TPB / 32];
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   const uint4* core = g.core + (size_t)r * g.n_cap;
@@ -1135,20 +1136,22 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
 #pragma unroll
   for (int t = 0; t < 4; ++t) { b[t] = __ballot_sync(0xffffffffu, f[t]); if (lane == 0) s_wc[t][w] = (unsigned short)__popc(b[t]); }
   __syncthreads();
-  if (tid < 4) {
-    unsigned all = 0;
-    for (int k = 0; k < TPB / 32; ++k) all += s_wc[tid][k];
-    s_base[tid] = all ? atomicAdd(g.q_count + (size_t)r * 4 + tid, all) : 0u;
+  // one warp turns the 4 x 8 per-warp counts into queue offsets: lane = type * 8 + warp; exclusive prefix over the 8
+  // warps of a type by shuffles, plus the type's base from one atomicAdd per CTA and type
+  if (tid < 32) {
+    unsigned cnt = s_wc[tid >> 3][tid & 7], inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o, 8); if ((tid & 7) >= o) inc += v; }
+    unsigned total = __shfl_sync(0xffffffffu, inc, 7, 8), base = 0;
+    if ((tid & 7) == 0 && total) base = atomicAdd(g.q_count + (size_t)r * 4 + (tid >> 3), total);
+    base = __shfl_sync(0xffffffffu, base, 0, 8);
+    s_off[tid >> 3][tid & 7] = base + inc - cnt;
   }
   __syncthreads();
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    if (!f[t]) continue;
-    unsigned before = 0;
-    for (int k = 0; k < w; ++k) before += s_wc[t][k];
-    g.q_items[((size_t)r * 4 + t) * g.e_stride + s_base[t] + before + __popc(b[t] & ((1u << lane) - 1u))] = ((unsigned)l << 28) | (unsigned)e;
-  }
-  __syncthreads();                 // s_wc / s_base are reused by the next tile
+  for (int t = 0; t < 4; ++t)
+    if (f[t]) g.q_items[((size_t)r * 4 + t) * g.e_stride + s_off[t][w] + __popc(b[t] & ((1u << lane) - 1u))] = ((unsigned)l << 28) | (unsigned)e;
+  // (no barrier needed before the next tile: s_wc is rewritten only after this tile's second barrier, s_off only after the next tile's first)
   }
 }
 
