@@ -189,15 +189,20 @@ def test_edge_cases_empty_and_ragged():
 
 def test_large_population_100k_plus():
     """BASELINE configs[3]/[4] shape: a 170k-agent replicate (k_rank / pos2slot path of the surrogate network, long
-    per-layer edge loops) next to a second replicate, 3 weeks, bit-exact vs the oracle."""
+    per-layer edge loops, parallel slot compaction) next to a second replicate, 4 weeks, bit-exact vs the oracle."""
     case = make_case(170000, 77, network_mode="surrogate")
     h = load_handle([case, case], SEED, t_cap=8, replicate_offset=5)
     orcs = [load_oracle(case, SEED, 5 + r, t_cap=8) for r in range(2)]
-    for at in (2, 3, 4):
+    for at in (2, 3, 4, 5):
         h.step(at)
         for r, o in enumerate(orcs):
             o.step(at, K.M_ALL)
             compare_state(h, r, o, at, f"170k agents week {at} r={r}")
+        if at == 3:
+            # slot compaction of a large replicate (parallel gathers through pos2slot) is invisible in R positions
+            h.compact()
+            for r, o in enumerate(orcs):
+                compare_state(h, r, o, at, f"170k agents after compaction r={r}", acts=False)
 
 
 def test_host_network_weekly_contract_all_replicates():

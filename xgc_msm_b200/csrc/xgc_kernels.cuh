@@ -1186,6 +1186,7 @@ template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 :
 // (a few per cent) with all lanes busy: symptom draw, Poisson duration, clocks, incidence and pathway tallies.
 // ---------------------------------------------------------------------------------------------------------------------
 #define A3_NHIST (XGC_K_NGROUP * XGC_NCELL)
+#define A3B_NHIST (4 * XGC_NCELL + XGC_NPATH)      /* incid r,u,p by cell; incid HIV by cell; pathway winners */
 #define A3_SITE_MASK(s) ((s) == 0 ? ((1u << XGC_PATH_U2R) | (1u << XGC_PATH_P2R)) : (s) == 1 ? ((1u << XGC_PATH_R2U) | (1u << XGC_PATH_P2U)) \
                                   : ((1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P)))
 __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, unsigned mask, int tpc) {
@@ -1266,6 +1267,11 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __gri
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   unsigned* row = counter_row(g, r, at);
+  // incidence tallies go through a per-CTA histogram: with few replicates on the device (1M-agent configs) direct global
+  // atomics from every queued agent would all land on the same counter row
+  __shared__ unsigned hist[A3B_NHIST];
+  for (int k = threadIdx.x; k < A3B_NHIST; k += TPB) hist[k] = 0u;
+  __syncthreads();
   for (unsigned qi = blockIdx.x * TPB + threadIdx.x; qi < n; qi += gridDim.x * TPB) {
   size_t idx = rbase + g.qa_items[rbase + qi];
   uint4 c = g.core[idx];
@@ -1288,8 +1294,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __gri
       short du = -1;
       if (pois) { int q = xgc_pois(d(3 + s), P[XGC_P_gc_ntx_int + s], 255); du = (short)(q < 1 ? 1 : q); }
       if (s == 0) { ga.x = (short)at; gb.x = -1; gd.x = du; } else if (s == 1) { ga.y = (short)at; gb.y = -1; gd.y = du; } else { ga.z = (short)at; gb.z = -1; gd.z = du; }
-      atomicAdd(row + (XGC_K_INCID_RGC + s) * XGC_NCELL + cell, 1u);
-      atomicAdd(row + XGC_K_PATH + win, 1u);
+      atomicAdd(&hist[s * XGC_NCELL + cell], 1u);
+      atomicAdd(&hist[4 * XGC_NCELL + win], 1u);
       any = true;
     }
     if (any) { g.gck_a[idx] = ga; g.gck_b[idx] = gb; if (pois) g.gck_d[idx] = gd; }
@@ -1301,11 +1307,18 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __gri
       short4 ha = g.hck_a[idx]; ha.x = (short)at; ha.z = (short)at; g.hck_a[idx] = ha;
       short4 hb = g.hck_b[idx]; hb.x = 0; hb.y = 0; g.hck_b[idx] = hb;
       g.aux[idx].vl = 0.f;
-      atomicAdd(row + XGC_K_INCID_HIV * XGC_NCELL + cell, 1u);
+      atomicAdd(&hist[3 * XGC_NCELL + cell], 1u);
     }
   }
   if (mask & XGC_M_HIVTRANS) hiv &= ~HV_NEW;
   if (gc != c.z || hiv != c.w) { uint2* q = (uint2*)&g.core[idx]; q[1] = make_uint2(gc, hiv); }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < A3B_NHIST; k += TPB) {
+    unsigned v = hist[k];
+    if (!v) continue;
+    int grp = k / XGC_NCELL, cell = k % XGC_NCELL;
+    atomicAdd(row + (grp < 3 ? (XGC_K_INCID_RGC + grp) * XGC_NCELL + cell : grp == 3 ? XGC_K_INCID_HIV * XGC_NCELL + cell : XGC_K_PATH + (k - 4 * XGC_NCELL)), v);
   }
 }
 
@@ -1401,6 +1414,47 @@ __global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ 
     A[wd] = n >= lo + 32 ? 0xFFFFFFFFu : n <= lo ? 0u : ((1u << (n - lo)) - 1u);
   }
   if (tid == 0) { rp->n_slots = n; rp->n_slots_pre = n; rp->n_alive = n; }
+}
+// Large replicates (one CTA per replicate would walk ~4000 tiles of a 1M-agent replicate one after the other): the same
+// stable compaction as k_compact_agents, as massively parallel gathers through k_rank's position -> slot plane.
+//   k_compact_remap    RM[slot] = new slot (edges are re-numbered with it afterwards)
+//   k_compact_gather   scratch[j] = plane[P2S[j]]   for every living position j, one plane at a time (out of place)
+//   k_compact_putback  plane[j] = scratch[j]
+//   k_compact_finish   clears the freed tail, rebuilds the alive bitmap, resets the slot counters
+__global__ void __launch_bounds__(TPB) k_compact_remap(const __grid_constant__ Dev g, int* remap) {
+  pdl_prologue();
+  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  if (j >= g.rep[r].n_alive) return;
+  size_t o = (size_t)r * g.n_cap;
+  remap[o + g.pos2slot[o + j]] = j;
+}
+template <class T> __global__ void __launch_bounds__(TPB) k_compact_gather(const __grid_constant__ Dev g, const T* plane, T* scratch) {
+  pdl_prologue();
+  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  if (j >= g.rep[r].n_alive) return;
+  size_t o = (size_t)r * g.n_cap;
+  scratch[o + j] = plane[o + g.pos2slot[o + j]];
+}
+template <class T> __global__ void __launch_bounds__(TPB) k_compact_putback(const __grid_constant__ Dev g, T* plane, const T* scratch) {
+  pdl_prologue();
+  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  if (j >= g.rep[r].n_alive) return;
+  size_t o = (size_t)r * g.n_cap;
+  plane[o + j] = scratch[o + j];
+}
+__global__ void __launch_bounds__(TPB) k_compact_finish(const __grid_constant__ Dev g, int stage) {
+  pdl_prologue();
+  int r = blockIdx.y, i = blockIdx.x * TPB + threadIdx.x;
+  Rep* rp = g.rep + r;
+  size_t o = (size_t)r * g.n_cap;
+  int n = rp->n_alive;
+  if (stage == 0) {                      // n_slots is still the old extent here
+    if (i >= n && i < rp->n_slots) g.core[o + i] = make_uint4(0, 0, 0, 0);
+    if (i < g.n_cap / 32) {
+      int lo = i * 32;
+      g.alive[(size_t)r * (g.n_cap / 32) + i] = n >= lo + 32 ? 0xFFFFFFFFu : n <= lo ? 0u : ((1u << (n - lo)) - 1u);
+    }
+  } else if (i == 0) { rp->n_slots = n; rp->n_slots_pre = n; }
 }
 __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ Dev g, const int* remap) {
   pdl_prologue();

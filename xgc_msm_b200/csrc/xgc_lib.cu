@@ -9,6 +9,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "xgc/abi.h"
 #include "xgc_kernels.cuh"
@@ -34,6 +35,7 @@ struct xgc_handle {
   int last_at = -1;
   HostRep cache;
   double* d_inj = nullptr; size_t d_inj_cap = 0;
+  void* d_cscratch = nullptr;   // 16 B per slot, large-replicate compaction only
   int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
@@ -41,6 +43,7 @@ struct xgc_handle {
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
+  bool launch_err = false;
   bool pdl = true;            // programmatic dependent launch of the weekly kernels (XGC_PDL=0 turns it off)
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -86,6 +89,27 @@ extern "C" int xgc_param_index(const char* name, int* offset, int* count) {
 extern "C" int xgc_abi_version(void) { return XGC_ABI_VERSION; }
 extern "C" const char* xgc_last_error(const xgc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// CUDA loads kernels lazily, on their first launch (tens of ms for a large image): touch every native-draw kernel once per
+// process at create time so that no week of a run pays for it (the compaction kernels first run at week 64).
+__global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el, const int* ne, const int* start, int stride);
+static void preload_kernels() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncAttributes a;
+#define PRELOAD(k) cudaFuncGetAttributes(&a, k)
+  PRELOAD(k_derive); PRELOAD(k_begin<false>); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
+  PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank);
+  PRELOAD((k_form<false, true, TPB>)); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
+  PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
+  PRELOAD(k_agent3a); PRELOAD(k_agent3b<false>); PRELOAD(k_targets); PRELOAD(k_compact_agents); PRELOAD(k_compact_edges);
+  PRELOAD(k_compact_remap); PRELOAD(k_compact_finish); PRELOAD(k_edges_upload);
+  PRELOAD(k_compact_gather<uint4>); PRELOAD(k_compact_gather<uint2>); PRELOAD(k_compact_gather<int>);
+  PRELOAD(k_compact_putback<uint4>); PRELOAD(k_compact_putback<uint2>); PRELOAD(k_compact_putback<int>);
+#undef PRELOAD
+  cudaGetLastError();
+}
+
 extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return 1; }
   if (cfg->abi_version != XGC_ABI_VERSION) { g_create_error = "ABI version mismatch"; return 1; }
@@ -103,6 +127,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   auto fail = [&](int code) { g_create_error = h->err; xgc_destroy(h); return code; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(3); }
   { const char* e = getenv("XGC_PDL"); if (e && e[0] == '0') h->pdl = false; }
+  preload_kernels();
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return fail(3); }
   Dev& g = h->g; memset(&g, 0, sizeof g);
   g.R = cfg->n_replicates; g.n_cap = cfg->n_cap; g.t_cap = cfg->t_cap; g.rep0 = cfg->replicate_offset; g.seed = (unsigned)cfg->seed;
@@ -114,6 +139,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.gck_a, NA); rc |= dalloc(h, &g.gck_b, NA); rc |= dalloc(h, &g.gck_d, NA);
   rc |= dalloc(h, &g.hck_a, NA); rc |= dalloc(h, &g.hck_b, NA); rc |= dalloc(h, &g.tck, NA); rc |= dalloc(h, &g.arr_t, NA);
   rc |= dalloc(h, &g.alive, NA / 32); rc |= dalloc(h, &g.pos2slot, NA);
+  if (g.n_cap > 32768) { uint4* cs = nullptr; rc |= dalloc(h, &cs, NA); h->d_cscratch = cs; }     // parallel slot compaction, 16 B per slot
   rc |= dalloc(h, &g.edge, (size_t)g.R * g.e_stride);
   rc |= dalloc(h, &g.rep, (size_t)g.R);
   double* dp; int* dc; double* dt; int* dat;
@@ -449,7 +475,12 @@ static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling) ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  if (e != cudaSuccess && !h->launch_err) {          // remembered for xgc_last_error; the caller's cudaGetLastError() reports it
+    h->launch_err = true;
+    fprintf(stderr, "xgc: kernel launch failed (%s): grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", cudaGetErrorString(e),
+            grid.x, grid.y, grid.z, block.x, block.y, block.z, smem);
+  }
 }
 #define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kl(h, kern, grid, block, 0, __VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
 // kernels that draw: native instantiation unless an injected table is attached
@@ -549,7 +580,23 @@ extern "C" int xgc_compact(xgc_handle* h) {
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   launch_resim(h, make_inj(h, nullptr, nullptr), 0, 2);       // no dangling endpoints before re-numbering
   h->rank_fresh = false;
-  LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);
+  if (g.n_cap <= 32768) {
+    LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);       // one CTA walks the replicate's ~40 tiles
+  } else {                                                      // 100k .. 1M-agent replicates: parallel gathers through pos2slot
+    size_t NA = h->n_agent();
+    dim3 gp((g.n_cap + TPB - 1) / TPB, g.R);
+    LAUNCH(h, k_rank, gp, TPB, g);
+    LAUNCH(h, k_compact_remap, gp, TPB, g, h->d_remap);
+    auto move = [&](auto* plane) {
+      using T = std::remove_pointer_t<decltype(plane)>;
+      LAUNCH(h, k_compact_gather<T>, gp, TPB, g, (const T*)plane, (T*)h->d_cscratch);
+      LAUNCH(h, k_compact_putback<T>, gp, TPB, g, plane, (const T*)h->d_cscratch);
+    };
+    move(g.core); move((uint4*)g.aux); move((uint2*)g.gck_a); move((uint2*)g.gck_b); move((uint2*)g.gck_d);
+    move((uint2*)g.hck_a); move((uint2*)g.hck_b); move((uint2*)g.tck); move(g.arr_t);
+    LAUNCH(h, k_compact_finish, gp, TPB, g, 0);
+    LAUNCH(h, k_compact_finish, dim3(1, g.R), TPB, g, 1);
+  }
   LAUNCH(h, k_compact_edges, dim3((emax + TPB - 1) / TPB, 3, g.R), TPB, g, h->d_remap);
   CU(h, cudaGetLastError());
   return 0;
