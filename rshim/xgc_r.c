@@ -77,6 +77,16 @@ SEXP xgcR_epi(SEXP p, SEXP r, SEXP var, SEXP at0, SEXP at1) {         /* dat$epi
   if (rc) Rf_error("xgc error %d: %s", rc, xgc_last_error(H(p)));
   return out;
 }
+SEXP xgcR_epi_table(SEXP p, SEXP r, SEXP vars, SEXP at0, SEXP at1) { /* as.matrix(as.data.frame(dat$epi)[at0:at1, vars]): one device read */
+  int a = Rf_asInteger(at0), b = Rf_asInteger(at1), n = LENGTH(vars), T = b - a + 1;
+  const char** names = (const char**)R_alloc((size_t)(n > 0 ? n : 1), sizeof(char*));
+  for (int k = 0; k < n; ++k) names[k] = CHAR(STRING_ELT(vars, k));
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, T, n));                  /* column k = series k: the library's [n_vars][T] layout */
+  int rc = xgc_get_epi_table(H(p), Rf_asInteger(r), names, n, REAL(out), a, b);
+  UNPROTECT(1);
+  if (rc) Rf_error("xgc error %d: %s", rc, xgc_last_error(H(p)));
+  return out;
+}
 SEXP xgcR_targets(SEXP p, SEXP nrep, SEXP at_last, SEXP tailn) {      /* [nsims x XGC_NTARGET], row-major from the library */
   int R_ = Rf_asInteger(nrep);
   double* buf = (double*)R_alloc((size_t)R_ * XGC_NTARGET, sizeof(double));

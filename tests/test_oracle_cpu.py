@@ -231,3 +231,24 @@ def test_epi_series_and_target_pipeline():
     assert d["output_within_5pts"].tolist() == [1, 1, 0] and d["output_in_targcl"].tolist() == [0, 1, 0]
     assert T.get_absdiff("ct_hiv_incid_per100pop", np.array([0.9]))["output_within_5pts"].tolist() == [1]
     assert T.select_by_popsize(np.array([19100, 20900, 21100])).tolist() == [True, True, False]
+
+
+def test_r_shim_compiles_against_the_r_api_and_binds_only_declared_symbols():
+    """rshim/xgc_r.c (the .Call binding a maintainer of the reference would build with `R CMD SHLIB`) cannot be built
+    here (no R), so it is syntax-checked against a stub of the R API, and every xgc_* function it calls must be
+    declared in include/xgc/abi.h."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(root, "tests", "stubs"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "rshim", "xgc_r.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(root, "rshim", "xgc_r.c")).read()
+    hdr = open(os.path.join(root, "include", "xgc", "abi.h")).read()
+    used = set(re.findall(r"\b(xgc_[a-z_]+)\s*\(", src))
+    declared = set(re.findall(r"\b(xgc_[a-z_]+)\s*\(", hdr))
+    assert used and used <= declared, used - declared
+    mods = open(os.path.join(root, "rshim", "modules.R")).read()
+    calls = set(re.findall(r'\.Call\("(xgcR_[a-z_]+)"', mods))
+    defined = set(re.findall(r"^SEXP (xgcR_[a-z_]+)\(", src, flags=re.M))
+    assert calls and calls <= defined, calls - defined
