@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU")
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=12)
-    ap.add_argument("--e2e-groups", type=int, default=8, help="handles (streams) the e2e arm splits this GPU's replicates into")
+    ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -98,10 +98,32 @@ def run_reference(args, rank):
 # helpers for the CUDA arm
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an in-process NVML sampling thread (one sample taken
+    synchronously at start and at stop, so even a very short region has some), nvidia-smi polling as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.p = self.th = self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.dev = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            except Exception:
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self._sample()
+            import threading
+            self._stop = threading.Event()
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(gpu_index)],
@@ -109,32 +131,54 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))); self.mx.append(self.max_sm)
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+        except Exception:
+            bits = 0
+        for bit, name in self.REASONS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.wait(0.01):
+            try:
+                self._sample()
+            except Exception:
+                return
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f:
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        if self.nv is not None:
+            self._stop.set(); self.th.join(timeout=2)
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, c[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+                self._sample()
+            except Exception:
+                pass
+        elif self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush(); self.f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1])); self.mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, c[5:9]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nm)
+            os.unlink(self.f.name)
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.mx)), reasons=sorted(self.reasons), samples=len(self.sm))
         return out
 
 
@@ -195,7 +239,11 @@ def run_xgc(args, rank, world, local_rank):
     at = 2
     h.run(at, at + W - 1); at += W
     barrier()
-    clocks = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)      # robust to CUDA_VISIBLE_DEVICES remapping
+    except Exception:
+        uuid = None
+    clocks = ClockSampler(local_rank, uuid)
     l0 = h.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -249,7 +297,9 @@ def run_xgc(args, rank, world, local_rank):
     #      (each with its own stream and host thread), so the edge-list upload of one group overlaps the kernels of the
     #      others; every group still goes through the full serial contract every week.
     from xgc_msm_b200.params import control_msm
-    Ge = max(1, min(args.e2e_groups, R))
+    # default: 8 host threads per GPU, fewer when the ranks of this node would oversubscribe its cores
+    Ge = args.e2e_groups if args.e2e_groups > 0 else min(8, max(2, (os.cpu_count() or 8) // max(world, 1)))
+    Ge = max(1, min(Ge, R))
     while R % Ge:
         Ge -= 1
     Rg = R // Ge
