@@ -151,7 +151,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   unsigned* row = counter_row(g, r, at);
   unsigned* Q = g.qh_items + rbase;
-  const bool hivmods = mask & (XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL);
+  const bool hivmods = mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL);
   for (int t = t0; t < t1; ++t) {
     int i = t * TPB + threadIdx.x;
     size_t idx = rbase + i;
@@ -170,23 +170,32 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
     int race = (int)DM_RACE(demo);
     DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);     // k0 natural mortality and k2 interval test: one Philox block
     if ((mask & XGC_M_AGING) && live && !isnew) demo = (demo & ~(7u << 2)) | (xgc_age_group(age) << 2);
-    bool dep_g = false;
+    bool dep_g = false, dep_a = false;
     if ((mask & XGC_M_DEPARTURE) && live && !isnew) {
       int ai = (int)floor(age); if (ai < 0) ai = 0; if (ai > XGC_ASMR_AGES - 1) ai = XGC_ASMR_AGES - 1;
       dep_g = xgc_bern(d(0), g.tables[XGC_T_ASMR + race * XGC_ASMR_AGES + ai]);
+      // AIDS-stage mortality: drawn (and tallied) for every stage-4 agent, from the same Philox block.  Settling every
+      // departure here means nothing after this kernel touches the alive bitmap: the HIV-positive queue (k_agent1b) and
+      // the network kernels are independent and run concurrently.
+      if (hivpos && HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
     }
+    const bool dead = dep_g || dep_a;
     if (mask & XGC_M_DEPARTURE) {
-      unsigned dm = __ballot_sync(0xffffffffu, dep_g);
-      if (dm && lane == 0) {
-        atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~dm);
-        atomicSub((int*)&rp->n_alive, __popc(dm));
-        atomicAdd(row + XGC_K_DEP_GEN, (unsigned)__popc(dm));
+      unsigned dm = __ballot_sync(0xffffffffu, dead);
+      if (dm) {
+        unsigned mg = __ballot_sync(0xffffffffu, dep_g), ma = __ballot_sync(0xffffffffu, dep_a);
+        if (lane == 0) {
+          atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~dm);
+          atomicSub((int*)&rp->n_alive, __popc(dm));
+          if (mg) atomicAdd(row + XGC_K_DEP_GEN, (unsigned)__popc(mg));
+          if (ma) atomicAdd(row + XGC_K_DEP_AIDS, (unsigned)__popc(ma));
+        }
       }
     }
-    if (dep_g) demo &= ~DM_ACTIVE;
+    if (dead) demo &= ~DM_ACTIVE;
     // hivtest_msm: who gets tested this week (the result of a positive's test is settled in k_agent1b)
     bool tested = false;
-    if ((mask & XGC_M_HIVTEST) && live && !dep_g && !(hiv & HV_DIAG)) {
+    if ((mask & XGC_M_HIVTEST) && live && !dead && !(hiv & HV_DIAG)) {
       int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
       double tsl = (double)(at - last);
       if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) tested = xgc_bern(d(2), P[XGC_P_hiv_test_rate + race]);
@@ -200,25 +209,25 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
       if (demo != c.y) q[0].y = demo;
       if (gc != c.z || hiv != c.w) q[1] = make_uint2(gc, hiv);
     }
-    // queue the HIV-positive agents (also those who just died of natural causes: their AIDS-mortality draw is still tallied)
-    bool queue = hivmods && hivpos && !isnew;
+    // queue the surviving HIV-positive agents
+    bool queue = hivmods && hivpos && !isnew && !dead;
     unsigned m = __ballot_sync(0xffffffffu, queue);
     if (m) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(g.qh_count + r, (unsigned)__popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (tested ? 0x80000000u : 0u) | (dep_g ? 0x40000000u : 0u);
+      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (tested ? 0x80000000u : 0u);
     }
   }
 }
 
-// k_agent1b: AIDS mortality, HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued HIV-positive agents
+// k_agent1b: HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued (surviving) HIV-positive agents.
+// Touches only HIV fields of the queued agents: independent of the network kernels that follow k_agent1a.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
   int r = blockIdx.y;
   unsigned n = g.qh_count[r];
   if (blockIdx.x * TPB >= n) return;
-  Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   int at = g.at_ptr[r];
   const double* P = g.params + (size_t)r * XGC_NPARAM;
@@ -227,23 +236,17 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
   // ~2 waves of the GPU, not for the longest possible queue: no tens of thousands of empty CTAs)
   for (unsigned qbase = blockIdx.x * TPB; qbase < n; qbase += gridDim.x * TPB) {
   unsigned qi = qbase + threadIdx.x;
-  bool dep_a = false, dead_before = false;
   if (qi < n) {
     unsigned item = g.qh_items[rbase + qi];
-    bool tested = item >> 31; dead_before = (item >> 30) & 1u;
-    int i = (int)(item & 0x3FFFFFFFu);
+    bool tested = item >> 31;
+    int i = (int)(item & 0x7FFFFFFFu);
     size_t idx = rbase + i;
     uint4 c = g.core[idx];
     unsigned uid = c.x, demo = c.y, hiv = c.w;
     int race = (int)DM_RACE(demo);
     unsigned traj = DM_TTTRAJ(demo);
     DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);
-    if ((mask & XGC_M_DEPARTURE) && HV_STAGE(hiv) == 4) dep_a = xgc_bern(d(1), P[XGC_P_aids_mr]);
-    if (dep_a && !dead_before) {
-      atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~(1u << (i & 31)));
-      ((uint2*)&g.core[idx])[0].y = demo & ~DM_ACTIVE;
-    }
-    if (!dep_a && !dead_before) {
+    {
       short4 ha = g.hck_a[idx], hb = g.hck_b[idx];
       bool ha_dirty = false, hb_dirty = false;
       if ((mask & XGC_M_HIVTEST) && tested) {
@@ -302,11 +305,6 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
       if (hb_dirty) g.hck_b[idx] = hb;
       if (hiv != c.w) ((uint2*)&g.core[idx])[1].y = hiv;
     }
-  }
-  if (mask & XGC_M_DEPARTURE) {
-    warp_tally(row, XGC_K_DEP_AIDS, dep_a);
-    unsigned dm = __ballot_sync(0xffffffffu, dep_a && !dead_before);
-    if (dm && (threadIdx.x & 31) == 0) atomicSub((int*)&rp->n_alive, __popc(dm));
   }
   }
 }

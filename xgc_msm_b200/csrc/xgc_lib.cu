@@ -44,6 +44,10 @@ struct xgc_handle {
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
   bool launch_err = false;
+  cudaStream_t stream2 = nullptr;        // side branch for kernels that are independent of the main chain
+  cudaEvent_t ev_fork[2] = { nullptr, nullptr }, ev_join[2] = { nullptr, nullptr };
+  cudaStream_t cur = nullptr;            // stream the next kl() launches on (main stream unless inside a side branch)
+  bool overlap = true;                   // XGC_OVERLAP=0 keeps everything on one stream
   bool pdl = true;            // programmatic dependent launch of the weekly kernels (XGC_PDL=0 turns it off)
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -128,7 +132,14 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(3); }
   { const char* e = getenv("XGC_PDL"); if (e && e[0] == '0') h->pdl = false; }
   preload_kernels();
+  { const char* e = getenv("XGC_OVERLAP"); if (e && e[0] == '0') h->overlap = false; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return fail(3); }
+  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return fail(3); }
+  for (int k = 0; k < 2; ++k)
+    if (cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
+      h->err = "cudaEventCreate failed"; return fail(3);
+    }
+  h->cur = h->stream;
   Dev& g = h->g; memset(&g, 0, sizeof g);
   g.R = cfg->n_replicates; g.n_cap = cfg->n_cap; g.t_cap = cfg->t_cap; g.rep0 = cfg->replicate_offset; g.seed = (unsigned)cfg->seed;
   size_t eo = 0;
@@ -174,6 +185,8 @@ extern "C" int xgc_destroy(xgc_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_inj) cudaFree(h->d_inj);
   if (h->d_el_stage) cudaFree(h->d_el_stage);
+  for (int k = 0; k < 2; ++k) { if (h->ev_fork[k]) cudaEventDestroy(h->ev_fork[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -471,7 +484,7 @@ static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.
 template <class... KArgs, class... Args>
 static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->cur ? h->cur : h->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling) ? 1 : 0;
@@ -482,6 +495,18 @@ static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
             grid.x, grid.y, grid.z, block.x, block.y, block.z, smem);
   }
 }
+// Side branch: kernels launched between branch_begin and branch_end go to the second stream and depend only on what
+// preceded branch_begin; branch_join makes the main stream wait for them.  Captured into the week graph as a fork / join.
+// Per-kernel profiling keeps everything on one stream (the events would serialise the branches anyway).
+static bool branch_begin(xgc_handle* h, int k) {
+  if (!h->overlap || h->profiling) return false;
+  cudaEventRecord(h->ev_fork[k], h->stream);
+  cudaStreamWaitEvent(h->stream2, h->ev_fork[k], 0);
+  h->cur = h->stream2;
+  return true;
+}
+static void branch_end(xgc_handle* h, int k, bool on) { if (on) { cudaEventRecord(h->ev_join[k], h->stream2); h->cur = h->stream; } }
+static void branch_join(xgc_handle* h, int k, bool on) { if (on) cudaStreamWaitEvent(h->stream, h->ev_join[k], 0); }
 #define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kl(h, kern, grid, block, 0, __VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
 // kernels that draw: native instantiation unless an injected table is attached
 #define LAUNCHD(h, inj, kern, grid, block, ...) do { prof_begin(h, #kern); \
@@ -519,7 +544,13 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
   if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
-  if (mask & (a1mods & ~XGC_M_AGING)) LAUNCHD(h, inj, k_agent1b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
+  // the HIV-positive queue touches only HIV fields of its agents: side branch, joined before the kernels that read them
+  bool br0 = false;
+  if (mask & (a1mods & ~(XGC_M_AGING | XGC_M_DEPARTURE))) {
+    br0 = branch_begin(h, 0);
+    LAUNCHD(h, inj, k_agent1b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
+    branch_end(h, 0, br0);
+  }
   bool native = inj.u == nullptr;
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0, 0);
   if (mask & XGC_M_RESIM_NETS) {
@@ -536,6 +567,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
       prof_end(h); h->launches++;
     }
   }
+  branch_join(h, 0, br0);
   // edge kernels: the three layers as one index space, a few CTAs per replicate striding over it
   int etiles = (int)((g.e_stride + TPB - 1) / TPB);
   dim3 gef((unsigned)std::max(1, std::min(etiles, (148 * 32 + g.R - 1) / g.R)), g.R);
@@ -545,12 +577,15 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
     LAUNCH(h, k_edge2a, gef, TPB, g, mask);
     unsigned qb = qgrid((int)((g.e_stride + TPB - 1) / TPB));
+    bool br1 = branch_begin(h, 1);          // anal acts on the side branch, oral / kissing / rimming on the main stream
     prof_begin(h, "k_edge2b_anal");
     if (inj.u) kl(h, k_edge2b<true, true>, dim3(qb, 1, g.R), TPB, 0, g, inj, mask); else kl(h, k_edge2b<false, true>, dim3(qb, 1, g.R), TPB, 0, g, inj, mask);
     prof_end(h); h->launches++;
+    branch_end(h, 1, br1);
     prof_begin(h, "k_edge2b_oral_kiss_rim");
     if (inj.u) kl(h, k_edge2b<true, false>, dim3(qb, 3, g.R), TPB, 0, g, inj, mask); else kl(h, k_edge2b<false, false>, dim3(qb, 3, g.R), TPB, 0, g, inj, mask);
     prof_end(h); h->launches++;
+    branch_join(h, 1, br1);
   }
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3a, ga, TPB, g, mask, tpc);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCHD(h, inj, k_agent3b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
