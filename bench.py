@@ -193,11 +193,14 @@ def week_stats(h, K, at):
             "edges": float(c[K.K_NEDGES:K.K_NEDGES + 3].sum())}
 
 
-def host_network_pool(R, e_cap, n_lo, rng, torch):
-    """Pinned host edge lists standing for what host-side simnet_msm returns each week: [R][2][e_cap] 1-based positions."""
+def host_network_pool(R, e_cap, n_lo, rng, torch, n_edges=None):
+    """Pinned host edge lists standing for what host-side simnet_msm returns each week: [R][2][ne] 1-based positions.
+    n_edges: edges per layer (default: the layer's design equilibrium); the bench passes the counts the device-resident
+    arm actually holds, so that both arms process the same number of edges."""
     bufs = []
     for l in range(3):
-        ne = int(e_cap[l] / 1.35) - 100                # the layer's equilibrium edge count; buffers hold exactly ne edges
+        ne = int(n_edges[l]) if n_edges is not None else int(e_cap[l] / 1.35) - 100
+        ne = max(1, min(ne, int(e_cap[l])))            # buffers hold exactly ne edges
         a = rng.integers(1, n_lo, size=(R, ne), dtype=np.int32)
         b = rng.integers(1, n_lo - 1, size=(R, ne), dtype=np.int32)
         b = np.where(b >= a, b + 1, b)
@@ -313,7 +316,8 @@ def run_xgc(args, rank, world, local_rank):
         groups.append(hg)
     rng = np.random.default_rng(args.seed + rank)
     nmin = min(int(hg.num_agents_all().min()) for hg in groups)
-    pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch)
+    ne_dev = h.counters_all(t_last)[:, K.K_NEDGES:K.K_NEDGES + 3].astype(np.float64).mean(0)     # edges per layer the resident arm held
+    pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev))
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
     n_host = torch.empty(R, dtype=torch.int32).pin_memory()

@@ -17,7 +17,8 @@ workload.load_sweep(h, spec, rid0=0)
 h.run(2, 60)
 h.set_control(control_msm(network_mode="host").flags)
 rng = np.random.default_rng(1)
-pool = bench.host_network_pool(R, spec.e_cap, int(h.num_agents_all().min() * 0.97), rng, torch)
+pool = bench.host_network_pool(R, spec.e_cap, int(h.num_agents_all().min() * 0.97), rng, torch,
+                               n_edges=np.rint(h.counters_all(60)[:, K.K_NEDGES:K.K_NEDGES + 3].astype(np.float64).mean(0)))
 pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
 post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
 n_host = torch.empty(R, dtype=torch.int32).pin_memory().numpy()
