@@ -104,3 +104,55 @@ def test_screening_scenario_grid():
     assert res["symp"]["sum_num.gc.test"].sum() < res["base"]["sum_num.gc.test"].sum()        # symptomatic-only testing tests least
     for k in ("nia_gc", "pia_rgc", "ntia_pgc", "sum_incid.ugc"):
         assert res["cdc1"][k].shape == (R,)
+
+
+def test_full_size_sweep_properties():
+    """BASELINE configs[1] at full size (1000 replicates x 10k agents, LHS parameters): the oracle cannot follow at this
+    size, so the device path is checked through size-independent properties -- accounting identities of the weekly
+    tallies, run-mode idempotence (CUDA-graph xgc_run == week-by-week xgc_step, bit for bit), and shard invariance
+    (two 500-replicate handles with replicate offsets == the 1000-replicate handle)."""
+    from xgc_msm_b200 import workload as W
+    from xgc_msm_b200.abi import Handle, K
+    R, weeks = 1000, 12
+    spec = W.SweepSpec(n_agents=10000, seed=1971)
+
+    def make(r0, n):
+        h = Handle(n, spec.n_cap, spec.e_cap, weeks + 4, seed=1971, device=0, replicate_offset=r0, compact_every=5)
+        W.load_sweep(h, spec, rid0=r0)
+        return h
+
+    full = make(0, R)
+    full.run(2, 1 + weeks)                                   # graph replay incl. two slot compactions (weeks 5, 10)
+    C = np.stack([full.counters_all(t) for t in range(1, 2 + weeks)]).astype(np.int64)       # [week, R, counter]; row 0 = week 1
+    G = K.NCELL
+    grp = lambda g: C[:, :, g * G:(g + 1) * G].sum(-1)
+    num, inum, gc_any = grp(K.K_NUM), grp(K.K_INUM), grp(K.K_INUM_GC)
+    site = [grp(K.K_INUM_RGC + s) for s in range(3)]
+    incid_site = sum(grp(K.K_INCID_RGC + s) for s in range(3))
+    assert full.status(0) == 0 and int(np.bitwise_or.reduce([full.status(r) for r in range(0, R, 37)])) == 0
+    assert np.array_equal(num[-1], full.num_agents_all())                                   # tallied population == living slots
+    dep_g, dep_a, nnew = C[2:, :, K.K_DEP_GEN], C[2:, :, K.K_DEP_AIDS], C[2:, :, K.K_NNEW]     # week 1 (row 0) holds no tallies
+    dnum = num[2:] - num[1:-1]
+    assert np.all(dnum <= nnew - np.maximum(dep_g, dep_a)) and np.all(dnum >= nnew - dep_g - dep_a)   # an agent may draw both deaths
+    assert np.array_equal(C[1:, :, K.K_PATH:K.K_PATH + K.NPATH].sum(-1), incid_site[1:])    # every new site infection has one pathway
+    assert np.all(gc_any <= site[0] + site[1] + site[2]) and np.all(site[0] + site[1] + site[2] <= 3 * gc_any)
+    assert np.all(inum[2:] <= inum[1:-1] + grp(K.K_INCID_HIV)[2:]) and np.all(grp(K.K_INUM_DX) <= inum) and np.all(grp(K.K_VSUPP) <= grp(K.K_INUM_DX))
+    assert np.all(C[1:, :, K.K_POS:K.K_POS + 3] <= C[1:, :, K.K_TESTED:K.K_TESTED + 3]) and np.all(C[1:, :, K.K_VISITS_SYMPT] <= C[1:, :, K.K_VISITS])
+    assert (C[1:, :, K.K_NACTS] > 0).all() and incid_site[1:].sum() > 0 and grp(K.K_INCID_HIV)[1:].sum() > 0
+    # the parameters differ per replicate (LHS): so do the epidemics
+    assert np.unique(gc_any[-1]).size > 100
+
+    # run-mode idempotence and shard invariance, bit for bit on every tally of every week
+    halves = [make(0, R // 2), make(R // 2, R // 2)]
+    for at in range(2, 2 + weeks):
+        for h in halves:
+            h.step(at)
+            if at % 5 == 0:
+                h.compact()
+    for k, h in enumerate(halves):
+        for t in range(2, 2 + weeks):
+            assert np.array_equal(h.counters_all(t), C[t - 1, k * (R // 2):(k + 1) * (R // 2)].astype(np.uint32)), (k, t)
+        h.close()
+    tg = full.targets(1 + weeks, 5)
+    assert tg.shape == (R, K.NTARGET) and np.isfinite(tg[:, :3]).all()
+    full.close()
