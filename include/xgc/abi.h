@@ -250,6 +250,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_T_NET_DEG) X(XGC_T_NET_DUR) \
   X(XGC_C_transRoute_Kissing) X(XGC_C_transRoute_Rimming) X(XGC_C_gcUntreatedRecovDist) X(XGC_C_stiScreeningProtocol) \
   X(XGC_C_cdcExposureSite_Kissing) X(XGC_C_network_mode) \
+  X(XGC_RECOV_GEOM) X(XGC_RECOV_POIS) X(XGC_SCREEN_BASE) X(XGC_SCREEN_SYMPTOMATIC) X(XGC_SCREEN_CDC) X(XGC_SCREEN_UNIVERSAL) \
   X(XGC_M_AGING) X(XGC_M_DEPARTURE) X(XGC_M_ARRIVAL) X(XGC_M_HIVTEST) X(XGC_M_HIVTX) X(XGC_M_HIVPROGRESS) X(XGC_M_HIVVL) \
   X(XGC_M_RESIM_NETS) X(XGC_M_ACTS) X(XGC_M_CONDOMS) X(XGC_M_POSITION) X(XGC_M_PREP) X(XGC_M_HIVTRANS) X(XGC_M_STIRECOV) \
   X(XGC_M_STITX) X(XGC_M_STITRANS) X(XGC_M_PREV) X(XGC_M_ALL) \

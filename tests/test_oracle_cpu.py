@@ -252,3 +252,46 @@ def test_r_shim_compiles_against_the_r_api_and_binds_only_declared_symbols():
     calls = set(re.findall(r'\.Call\("(xgcR_[a-z_]+)"', mods))
     defined = set(re.findall(r"^SEXP (xgcR_[a-z_]+)\(", src, flags=re.M))
     assert calls and calls <= defined, calls - defined
+
+
+def test_host_mirror_matches_the_reference_driver_scripts():
+    """tests/golden/driver_contract.json is parsed from the reference's own driver scripts (make_driver_contract.py):
+    param_msm argument names and the env var each reads, init_msm literals, the control_msm module slots in the order
+    written, the option flags, and the screening arms.  The host-side mirror must agree with all of it."""
+    from xgc_msm_b200 import scenarios
+    root = os.path.dirname(os.path.abspath(__file__))
+    ref = json.load(open(os.path.join(root, "golden", "driver_contract.json")))
+    # modules: same slots, same order (initialize.FUN is the constructor, not a weekly module)
+    slots = [m["slot"] for m in ref["modules"]]
+    assert slots[0] == "initialize" and slots[1:] == P.MODULE_ORDER
+    assert [m["fun"] for m in ref["modules"]][-2:] == ["stitrans_msm_rand", "prevalence_msm"]
+    assert [P.MODULE_BIT[m] for m in P.MODULE_ORDER] == [1 << k for k in range(17)] and K.M_ALL == (1 << 17) - 1
+    # option flags: the defaults of the mirror are the reference's settings
+    f = ref["control_flags"]
+    ctl = P.control_msm()
+    idx = P.CONTROL_INDEX
+    assert ctl.flags[idx["transRoute_Kissing"]] == int(f["transRoute_Kissing"]) == 1
+    assert ctl.flags[idx["transRoute_Rimming"]] == int(f["transRoute_Rimming"]) == 1
+    assert ctl.flags[idx["cdcExposureSite_Kissing"]] == int(f["cdcExposureSite_Kissing"]) == 0
+    assert f["gcUntreatedRecovDist"] == "geom" and ctl.flags[idx["gcUntreatedRecovDist"]] == K.RECOV_GEOM
+    assert f["stiScreeningProtocol"] == "base" and ctl.flags[idx["stiScreeningProtocol"]] == K.SCREEN_BASE
+    # every epidemic argument of the param_msm() call is a parameter of the ABI (site-specific triplets are one vector)
+    known = set(P.PARAM_INDEX) | set(P._SITE_ALIASES)
+    for a in ref["param_msm"]:
+        if a["name"] in ("netstats", "epistats"):
+            continue                                   # fitted inputs: xgc_set_tables
+        n = a["name"].replace(".", "_")
+        assert n in known, f"param_msm argument {a['name']} (sim1_02_lhs.r:{a['line']}) has no ABI parameter"
+    # the env vars the call reads are exactly the 62 calibration inputs plus the arrival-rate tweak
+    envs = {e for a in ref["param_msm"] for e in a["env"]}
+    assert envs == {p[0] for p in P.PRIORS} | {"ARRIVE_RATE_ADD_PER20K"}
+    assert ref["init_msm"] == {"prev.ugc": 0.05, "prev.rgc": 0.05, "prev.pgc": 0.05}
+    i0 = P.init_msm()
+    assert i0 == ref["init_msm"]
+    # and the R-style call itself goes through the mirror with the reference's own argument names
+    kw = {a["name"].replace(".", "_"): 0.5 for a in ref["param_msm"] if a["name"] not in ("netstats", "epistats")}
+    vec = P.param_msm(**kw)
+    assert vec.shape == (K.NPARAM,) and P.get(vec, "gc_ntx_int").tolist() == [0.5, 0.5, 0.5]
+    # screening arms
+    arms = {a["name"].replace("sti_", ""): (a["scenario"], a["kiss_exposure"]) for a in ref["screening_arms"] if a["runtype"] == "scenario"}
+    assert arms == {k: tuple(v) for k, v in scenarios.ARMS.items()}
