@@ -5,6 +5,7 @@
   burnin/cal/sim1_02_lhs.r:180-184   init_msm(...) initial site prevalences
   burnin/cal/sim1_02_lhs.r:195-230   control_msm(...): module slots in the order written, option flags
   inst/analysis02_screening/01_setup.r:116-159   screening arms (scenario, kiss_exposure)
+  inst/cal/sim3_01_analyze.r:169-176  the variable patterns summed into `mase`; sim1_01_lhs_params.r:118-120 LHS seed / size
 
 Only names, literals and ordering are recorded (no code).  tests/test_oracle_cpu.py checks the host-side mirror
 (params.def, MODULE_ORDER, control_msm defaults, scenarios.ARMS, PRIORS) against it.
@@ -60,7 +61,17 @@ arms_src = open(os.path.join(REF, "inst/analysis02_screening/01_setup.r")).read(
 arms = [{"name": a, "runtype": rt, "scenario": sc, "kiss_exposure": ke == "TRUE"}
         for a, rt, sc, ke in re.findall(r'(sti_[a-z0-9]+) = data\.table\(\s*runtype\s*=\s*"([a-z]+)",\s*scenario\s*=\s*"([a-z]+)",\s*kiss_exposure\s*=\s*"([A-Z]+)"', arms_src)]
 
-out = {"source": "parsed from burnin/cal/sim1_02_lhs.r and inst/analysis02_screening/01_setup.r by tests/golden/make_driver_contract.py",
+an = open(os.path.join(REF, "inst/cal/sim3_01_analyze.r")).read()
+vp = re.search(r"varpats <- paste0\(c\((.*?)\), collapse", an, re.S).group(1)
+varpats = re.findall(r'"([^"]+)"', vp)
+lhs = open(os.path.join(REF, "burnin/cal/sim1_01_lhs_params.r")).read()
+lhs_seed = int(re.search(r"set\.seed\((\d+)\)", lhs).group(1))
+lhs_n = int(re.search(r"randomLHS\((\d+),", lhs).group(1))
+setup = open(os.path.join(REF, "inst/cal/sim0.0_setup.r")).read()
+pop = re.search(r"pop_N\s*<-\s*(\d+)", setup)
+
+out = {"mase_varpats": varpats, "lhs_seed": lhs_seed, "lhs_n": lhs_n, "pop_N": int(pop.group(1)) if pop else None,
+       "source": "parsed from burnin/cal/sim1_02_lhs.r and inst/analysis02_screening/01_setup.r by tests/golden/make_driver_contract.py",
        "param_msm": params, "init_msm": init, "modules": modules, "control_flags": flags, "screening_arms": arms}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "driver_contract.json"), "w"), indent=1)
 print(len(params), "param_msm arguments;", len(modules), "module slots;", flags, ";", [a["name"] for a in arms], init)

@@ -91,3 +91,20 @@ def test_keepvars_are_series_the_library_serves():
     from xgc_msm_b200.export import KEEPVARS
     known = set(abi.names("epi"))
     assert len(KEEPVARS) == 81 and not [k for k in KEEPVARS if k not in known]
+
+
+def test_selection_constants_match_the_reference_scripts():
+    """mase variable patterns, LHS seed / size and the population filter as the reference's scripts state them
+    (tests/golden/driver_contract.json, parsed from sim3_01_analyze.r:169-176, sim1_01_lhs_params.r:118-120,
+    sim0.0_setup.r:317-318)."""
+    import json, os, re
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver_contract.json")))
+    names = [n for n in T.device_target_names() if n in T.TARGET_OF_COLUMN]
+    theirs = re.compile("|".join(ref["mase_varpats"]))
+    ours = re.compile(CAL.MASE_VARPATS)
+    assert [n for n in names if theirs.search(n)] == [n for n in names if ours.search(n)] and len([n for n in names if ours.search(n)]) == 18
+    assert ref["lhs_seed"] == 1971 and ref["lhs_n"] == 5000 and ref["pop_N"] == 20000
+    import inspect
+    assert inspect.signature(P.lhs_envs).parameters["seed"].default == ref["lhs_seed"]
+    assert inspect.signature(T.select_by_popsize).parameters["pop_n"].default == float(ref["pop_N"])
+    assert inspect.signature(T.select_by_popsize).parameters["tol"].default == 0.05
