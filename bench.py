@@ -212,6 +212,29 @@ def host_network_pool(R, e_cap, n_lo, rng, torch, n_edges=None):
     return bufs
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Several ranks share one host: keep this rank's threads, and therefore its page-locked staging buffers (first
+    touch), on the NUMA node its GPU hangs off, so that the weekly uploads of 8 ranks do not cross the socket link.
+    Best effort: returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_xgc(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -221,6 +244,7 @@ def run_xgc(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the xgc arm has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -374,7 +398,7 @@ def run_xgc(args, rank, world, local_rank):
         tt = torch.tensor([dt_e], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt_e = float(tt.item())
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
-           "ms_per_step": dt_e / En * 1e3, "groups": Ge,
+           "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
            "path": f"{Ge} handles x {Rg} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 3x xgc_set_edgelists_all (pinned) -> "
                    "xgc_step(post) -> xgc_get_counters_all"}
     e2e_status = 0
