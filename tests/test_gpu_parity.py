@@ -256,3 +256,33 @@ def test_host_network_weekly_contract_all_replicates():
     bad = np.zeros((R, 2, 4), dtype=np.int32); bad[:, 0, :] = 1; bad[:, 1, :] = 2; bad[1, 1, 2] = int(alive[1]) + 50
     h.set_edgelists_all(0, bad.ctypes.data, np.full(R, 4, np.int32).ctypes.data, 0, stride=4); h.sync()
     assert h.status(1) & K.ST_BAD_EDGE and not (h.status(0) & K.ST_BAD_EDGE)
+
+
+def test_capacity_overflow_is_flagged_and_contained():
+    """A replicate whose arrivals outgrow the slot capacity (and whose formation outgrows a layer's edge capacity) sets
+    its status flags, stays within its capacities and keeps stepping; the replicate next to it in the same handle is
+    untouched -- still bit-exact against the oracle."""
+    n = 600
+    ok = make_case(n, 11, midcourse=True, network_mode="surrogate")
+    hot = make_case(n, 12, midcourse=True, network_mode="surrogate")
+    hot["params"] = P.param_msm(hot["params"], a_rate=0.08)                 # ~48 arrivals a week into ~10 % head-room
+    e_cap = [int(len(ok["els"][0]) * 1.02) + 4, ok["e_cap"][1], ok["e_cap"][2]]   # main layer: almost no head-room
+    for c in (ok, hot):
+        c["e_cap"] = e_cap
+    h = load_handle([ok, hot], SEED, t_cap=40)
+    o = load_oracle(ok, SEED, 0, t_cap=40)
+    cap = ok["cap"]
+    for at in range(2, 30):
+        h.step(at)
+        o.step(at, K.M_ALL)
+        if o.status() == 0:
+            compare_state(h, 0, o, at, f"neighbour of the overflowing replicate, week {at}")
+        assert h.num_agents(1) <= cap
+        for l in range(3):
+            assert h.get_edgelist(1, l)[0].shape[0] <= e_cap[l]
+    assert h.status(1) & K.ST_AGENT_OVERFLOW
+    assert h.num_agents(1) > n                                             # it did grow until the cap stopped it
+    assert not (h.status(0) & K.ST_AGENT_OVERFLOW)
+    c = h.counters(1, 2, 29).astype(np.int64)
+    G = K.NCELL
+    assert (c[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum(1) <= cap).all() and c[-1, K.K_NACTS] > 0      # still a living epidemic
