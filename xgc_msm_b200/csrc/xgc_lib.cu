@@ -534,12 +534,14 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   const Dev& g = h->g;
   // agent kernels: tiles per CTA chosen so the grid stays a few waves of the 148 SMs
   int tiles = (g.n_cap + TPB - 1) / TPB;
-  int tpc = std::max(1, std::min(tiles, (int)(((long long)tiles * g.R) / (148 * 16))));
+  static const int TA = getenv("XGC_TUNE_A") ? atoi(getenv("XGC_TUNE_A")) : 16, TQ = getenv("XGC_TUNE_Q") ? atoi(getenv("XGC_TUNE_Q")) : 16,
+                   TE = getenv("XGC_TUNE_E") ? atoi(getenv("XGC_TUNE_E")) : 32;      // CTAs per SM each kernel family is sized for
+  int tpc = std::max(1, std::min(tiles, (int)(((long long)tiles * g.R) / (148 * TA))));
   dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
   // queue kernels: a few CTAs per replicate striding over its queue, ~2 waves of the GPU in total
-  auto qgrid = [&](int max_tiles) { return (unsigned)std::max(1, std::min(max_tiles, (148 * 16 + g.R - 1) / g.R)); };
+  auto qgrid = [&](int max_tiles) { return (unsigned)std::max(1, std::min(max_tiles, (148 * TQ + g.R - 1) / g.R)); };
   LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
@@ -570,7 +572,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   branch_join(h, 0, br0);
   // edge kernels: the three layers as one index space, a few CTAs per replicate striding over it
   int etiles = (int)((g.e_stride + TPB - 1) / TPB);
-  dim3 gef((unsigned)std::max(1, std::min(etiles, (148 * 32 + g.R - 1) / g.R)), g.R);
+  dim3 gef((unsigned)std::max(1, std::min(etiles, (148 * TE + g.R - 1) / g.R)), g.R);
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, gef, TPB, g, inj, mask);
   if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2a, ga, TPB, g, inj, mask, tpc);
   if (mask & (XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
