@@ -311,6 +311,19 @@ def run_xgc(args, rank, world, local_rank):
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
             "step": {"algorithmic_bytes": roofline.step_bytes(stats), "achieved": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9,
                      "frac": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9 / peak}}
+    # what actually bounds the step: issue slots.  warp instructions per launch come from the committed ncu
+    # capture, the time is this run's; peak = SMs x 4 schedulers x 1 warp instruction per clock at the sampled SM clock
+    wi = os.path.join(ROOT, "profiles", "warp_inst.json")
+    if os.path.exists(wi) and clk.get("sm_mhz"):
+        try:
+            w = json.load(open(wi))
+            per_week = float(sum(w[k] * (prof[k][1] / Pn) for k in per if k in w))
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            peak_i = sms * 4 * clk["sm_mhz"] * 1e6
+            roof["issue_slots"] = {"warp_inst_per_step": per_week, "achieved_ginst_s": per_week / (ms / Kt * 1e-3) / 1e9,
+                                   "peak_ginst_s": peak_i / 1e9, "frac": per_week / (ms / Kt * 1e-3) / peak_i, "source": w.get("_source")}
+        except Exception:
+            pass
     tr = os.path.join(ROOT, "profiles", "traffic.json")          # ncu dram bytes per launch, committed with the profile
     if os.path.exists(tr):
         try:

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/ncu_rNN
 Writes <out>.md (key metrics per kernel, mean over captured launches) and updates profiles/traffic.json
-(dram__bytes_read.sum + dram__bytes_write.sum per launch, consumed by bench.py as roofline.traffic)."""
+(dram__bytes_read.sum + dram__bytes_write.sum per launch, consumed by bench.py as roofline.traffic) and
+profiles/warp_inst.json (smsp__inst_executed.sum per launch, consumed by bench.py as roofline.issue_slots)."""
 import collections, csv, io, json, os, subprocess, sys
 
 rep, out = sys.argv[1], sys.argv[2]
@@ -42,10 +43,11 @@ lines = [f"# ncu --set full summary ({os.path.basename(rep)})", "",
          "Mean over the captured launches of each kernel; `--clock-control none`. DRAM GB/s = (read+write)/duration.", "",
          "| kernel | n | ms | DRAM rd MB | DRAM wr MB | DRAM GB/s | dram % | sm % | occ % | regs | warp-inst M | thr/inst | issue % | L2 hit % | stall long_sb | wait | math | short_sb | branch | lg |",
          "|" + "---|" * 20]
-traffic = {}
+traffic, winst = {}, {}
 for k, a in agg.items():
     ms, rd, wr = mean(a["ms"]), mean(a["rd"]), mean(a["wr"])
     traffic[k] = rd + wr
+    winst[k] = mean(a["winst"])
     lines.append(f"| {k} | {len(a['ms'])} | {ms:.4f} | {rd/1e6:.1f} | {wr/1e6:.1f} | {(rd+wr)/ms/1e6:.0f} | {mean(a['dram_pct']):.1f} | {mean(a['sm_pct']):.1f} | "
                  f"{mean(a['occ_pct']):.1f} | {mean(a['regs']):.0f} | {mean(a['winst'])/1e6:.1f} | {mean(a['thr_per_inst']):.1f} | {mean(a['issue_pct']):.1f} | {mean(a['l2_hit']):.1f} | "
                  f"{mean(a['stall_long_sb']):.2f} | {mean(a['stall_wait']):.2f} | {mean(a['stall_math']):.2f} | {mean(a['stall_short_sb']):.2f} | {mean(a['stall_branch']):.2f} | {mean(a['stall_lg']):.2f} |")
@@ -54,4 +56,6 @@ tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
 old = json.load(open(tp)) if os.path.exists(tp) else {}
 old.update(traffic); old["_source"] = os.path.basename(out) + ".md"
 json.dump(old, open(tp, "w"), indent=1)
+winst["_source"] = os.path.basename(out) + ".md"
+json.dump(winst, open(os.path.join(os.path.dirname(tp), "warp_inst.json"), "w"), indent=1)      # warp instructions per launch (issue-slot accounting)
 print("\n".join(lines))
