@@ -295,3 +295,43 @@ def test_host_mirror_matches_the_reference_driver_scripts():
     # screening arms
     arms = {a["name"].replace("sti_", ""): (a["scenario"], a["kiss_exposure"]) for a in ref["screening_arms"] if a["runtype"] == "scenario"}
     assert arms == {k: tuple(v) for k, v in scenarios.ARMS.items()}
+
+
+def test_rngstreams_mrg32k3a_known_answers_and_jumps():
+    """xgc_msm_b200/rngstreams.py (rlecuyer-compatible uniforms for injected-draw tables): published known answers of
+    MRG32k3a with the default seed, jump-ahead == stepping, stream / substream spacing, and use as an inject table."""
+    from xgc_msm_b200 import abi
+    from xgc_msm_b200 import rngstreams as RS
+    g = RS.RngStream()
+    u = [g.rand_u01() for _ in range(3)]
+    assert 0 <= u[1] - 0.3185275653 < 1e-10 and 0 <= u[2] - 0.3091860155 < 1e-10 and abs(u[0] - 0.12701112) < 1e-8   # published to 10 digits (truncated)
+    assert all(0.0 < v < 1.0 for v in u)
+    a, b = RS.RngStream(), RS.RngStream()
+    ref = [a.rand_u01() for _ in range(1500)]
+    assert np.array_equal(b.uniform(1500), np.array(ref))                      # vector path == scalar path
+    c = RS.RngStream(); c.advance(1000)
+    assert c.rand_u01() == ref[1000]                                           # O(log n) jump == 1000 steps
+    # streams are 2^127 apart, substreams 2^76: jumping in two halves gives the same state
+    s = RS.RngStream.create_streams(3)
+    d = RS.RngStream(); d.advance(1 << 126); d.advance(1 << 126)
+    assert d.cg == s[1].ig and s[0].ig == list(RS.DEFAULT_SEED)
+    e = RS.RngStream(s[1].ig); e.advance(1 << 127)
+    assert e.cg == s[2].ig
+    f = RS.RngStream(); f.reset_next_substream()
+    h = RS.RngStream(); h.advance(1 << 76)
+    assert f.cg == h.cg
+    f.rand_u01(); f.reset_start_stream()
+    assert f.cg == list(RS.DEFAULT_SEED)
+    with pytest.raises(ValueError):
+        RS.RngStream([0, 0, 0, 1, 2, 3])
+    # as an injected-draw table: same stream -> same week, different stream -> different week
+    case = make_case(150, 9, network_mode="surrogate")
+    stride = abi.inject_size(case["cap"], case["e_cap"], 64)
+    res = []
+    for k in (0, 0, 1):
+        o = load_oracle(case, 1, 0)
+        tab = RS.inject_table(RS.RngStream.create_streams(2)[k], 1, stride)
+        assert tab.shape == (1, stride)
+        o.step(2, K.M_ALL, O.make_inject(tab[0], stride, case["cap"], case["e_cap"], 64))
+        res.append(o.counters(2).copy())
+    assert np.array_equal(res[0], res[1]) and not np.array_equal(res[0], res[2])
