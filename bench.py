@@ -359,7 +359,8 @@ def run_xgc(args, rank, world, local_rank):
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
     n_host = torch.empty(R, dtype=torch.int32).pin_memory()
     c_host = torch.empty((R, K.NCOUNTER), dtype=torch.int32).pin_memory()
-    h2d = sum(t_el.numel() * 4 + t_ne.numel() * 4 + t_st.numel() * 4 for t_el, t_ne, t_st, _ in pool)
+    # one-off partnerships carry no start week (the plist of the reference tracks main / casual only; rshim/modules.R passes NULL)
+    h2d = sum(t_el.numel() * 4 + t_ne.numel() * 4 + (t_st.numel() * 4 if l < 2 else 0) for l, (t_el, t_ne, t_st, _) in enumerate(pool))
     d2h = n_host.numel() * 4 + c_host.numel() * 4
     n_np, c_np = n_host.numpy(), c_host.numpy().view(np.uint32)
 
@@ -369,7 +370,7 @@ def run_xgc(args, rank, world, local_rank):
         hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
         for l, (t_el, t_ne, t_st, _ne) in enumerate(pool):
-            hg.set_edgelists_all(l, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), t_st[r0:r0 + Rg].data_ptr(),
+            hg.set_edgelists_all(l, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), t_st[r0:r0 + Rg].data_ptr() if l < 2 else 0,
                                  stride=t_el.shape[2])
         hg.step(t, post)
         hg.counters_all(t, c_np[r0:r0 + Rg])
