@@ -472,6 +472,40 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
   if ((bits >> lane) & 1u) P2S[base + __popc(bits & ((1u << lane) - 1u))] = i0 + tid;
 }
 
+// k_rank for calibration-size replicates (n_cap <= 32k slots): ONE CTA per replicate builds the popcount prefix of the
+// alive bitmap in shared memory and then walks the tiles, instead of 40 CTAs per replicate each re-summing the prefix.
+__global__ void __launch_bounds__(TPB) k_rank_cta(const __grid_constant__ Dev g) {
+  pdl_prologue();
+  extern __shared__ unsigned rk_smem[];            // [words] bitmap, [words + 1] exclusive popcount prefix
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n_slots = g.rep[r].n_slots, words = (n_slots + 31) >> 5;
+  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  unsigned* bits = rk_smem; unsigned* pre = rk_smem + g.n_cap / 32;
+  __shared__ unsigned wtot[TPB / 32];
+  __shared__ unsigned carry;
+  if (tid == 0) carry = 0u;
+  __syncthreads();
+  for (int w0 = 0; w0 < words; w0 += TPB) {        // block-wide exclusive scan of the per-word popcounts, TPB words per round
+    int k = w0 + tid;
+    unsigned b = k < words ? A[k] : 0u, c = (unsigned)__popc(b), inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    unsigned off = carry;
+    for (int q = 0; q < w; ++q) off += wtot[q];
+    if (k < words) { bits[k] = b; pre[k] = off + inc - c; }
+    __syncthreads();
+    if (tid == TPB - 1) carry = off + inc;
+    __syncthreads();
+  }
+  for (int i = tid; i < n_slots; i += TPB) {
+    unsigned b = bits[i >> 5];
+    if ((b >> (i & 31)) & 1u) P2S[pre[i >> 5] + __popc(b & ((1u << (i & 31)) - 1u))] = i;
+  }
+}
+
 // k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order.
 // R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.

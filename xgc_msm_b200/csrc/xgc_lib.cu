@@ -103,7 +103,7 @@ static void preload_kernels() {
   cudaFuncAttributes a;
 #define PRELOAD(k) cudaFuncGetAttributes(&a, k)
   PRELOAD(k_derive); PRELOAD(k_begin<false>); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
-  PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank);
+  PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank); PRELOAD(k_rank_cta);
   PRELOAD((k_form<false, true, TPB>)); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
   PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
   PRELOAD(k_agent3a); PRELOAD(k_agent3b<false>); PRELOAD(k_targets); PRELOAD(k_compact_agents); PRELOAD(k_compact_edges);
@@ -996,7 +996,11 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   CU(h, cudaMemcpyAsync(d_el, el, R * st * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (start) CU(h, cudaMemcpyAsync(d_start, start, R * st * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  if (!h->rank_fresh) { LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g); h->rank_fresh = true; }
+  if (!h->rank_fresh) {
+    if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
+    else LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+    h->rank_fresh = true;
+  }
   LAUNCH(h, k_edges_upload, dim3((unsigned)((st + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr, stride);
   h->acts_valid = false;
   CU(h, cudaGetLastError());
