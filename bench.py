@@ -72,7 +72,8 @@ def run_reference(args, rank):
     from xgc_msm_b200.params import MODULE_BIT
     mask = sum(MODULE_BIT.values())
     cores = os.cpu_count() or 1
-    reps = cores * 2                                  # bounded sample: 2 replicates per core per step
+    reps = cores * 8                                  # bounded sample: 8 replicates per core per step (keeps the per-step
+                                                      # synchronisation of the worker pool below 1 % of a step)
     pool = cpu_bench.PersistentPool(args.agents, reps, args.seed, mask, cores)
     at = 2
     for _ in range(args.warmup):
