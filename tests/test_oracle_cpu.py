@@ -7,6 +7,7 @@ import json
 import math
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -335,3 +336,19 @@ def test_rngstreams_mrg32k3a_known_answers_and_jumps():
         o.step(2, K.M_ALL, O.make_inject(tab[0], stride, case["cap"], case["e_cap"], 64))
         res.append(o.counters(2).copy())
     assert np.array_equal(res[0], res[1]) and not np.array_equal(res[0], res[2])
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device xgc_create returns a non-zero status with a message, the Python Handle
+    raises, and bench.py's CUDA arm exits with an error instead of computing on the host."""
+    import subprocess
+    import torch
+    from xgc_msm_b200 import abi
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the failure path cannot be exercised")
+    with pytest.raises(abi.XgcError) as ei:
+        abi.Handle(1, 256, [64, 64, 64], 8)
+    assert "xgc_create failed" in str(ei.value) and len(str(ei.value)) > 25
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout) and '"value"' not in r.stdout
