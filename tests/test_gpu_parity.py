@@ -286,3 +286,36 @@ def test_capacity_overflow_is_flagged_and_contained():
     c = h.counters(1, 2, 29).astype(np.int64)
     G = K.NCELL
     assert (c[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum(1) <= cap).all() and c[-1, K.K_NACTS] > 0      # still a living epidemic
+
+
+def test_abi_error_behaviour():
+    """The reference-facing error contract: every misuse returns a non-zero status with a message through
+    xgc_last_error, nothing throws across the ABI or kills the process, and the handle keeps working afterwards."""
+    from xgc_msm_b200.abi import XgcError
+    case = make_case(300, 21, network_mode="surrogate")
+    h = load_handle([case], SEED, t_cap=16)
+    o = load_oracle(case, SEED, 0, t_cap=16)
+
+    def fails(f, *words):
+        with pytest.raises(XgcError) as ei:
+            f()
+        msg = str(ei.value)
+        assert all(w in msg for w in words), msg
+
+    fails(lambda: h.step(0), "outside")                                    # at = 0 is not a week
+    fails(lambda: h.step(16), "t_cap")                                     # beyond the counter rows
+    fails(lambda: h.run(5, 99), "week range")
+    fails(lambda: h.download_attr(3, "age"), "replicate")                  # only replicate 0 exists
+    fails(lambda: h.download_attr(0, "no.such.attr"), "no.such.attr")
+    fails(lambda: h.upload_attr(0, "age", np.zeros(7)), "length")          # wrong vector length
+    fails(lambda: h.set_edgelist(0, 5, np.zeros((0, 2), np.int32), np.zeros(0, np.int32)), "layer")
+    fails(lambda: h.set_edgelist(0, 0, np.array([[1, 9999]], np.int32), np.zeros(1, np.int32)))   # endpoint beyond the population
+    fails(lambda: h.epi(0, "not.a.series", 2, 3), "not.a.series")
+    fails(lambda: h.targets(3, 50), "tail")                                # window longer than the history
+    fails(lambda: h.set_edgelists_all(7, 0, 0, 0, stride=4), "layer")
+    # the handle is still usable and still exact
+    for at in (2, 3):
+        h.step(at); o.step(at, K.M_ALL)
+        compare_state(h, 0, o, at, f"after the misuse, week {at}")
+    h.close()
+    h.close()                                                               # closing twice is harmless
