@@ -194,12 +194,12 @@ def week_stats(h, K, at):
             "edges": float(c[K.K_NEDGES:K.K_NEDGES + 3].sum())}
 
 
-def host_network_pool(R, e_cap, n_lo, rng, torch, n_edges=None):
+def host_network_pool(R, e_cap, n_lo, rng, torch, n_edges=None, layers=(0, 1, 2)):
     """Pinned host edge lists standing for what host-side simnet_msm returns each week: [R][2][ne] 1-based positions.
     n_edges: edges per layer (default: the layer's design equilibrium); the bench passes the counts the device-resident
     arm actually holds, so that both arms process the same number of edges."""
     bufs = []
-    for l in range(3):
+    for l in layers:
         ne = int(n_edges[l]) if n_edges is not None else int(e_cap[l] / 1.35) - 100
         ne = max(1, min(ne, int(e_cap[l])))            # buffers hold exactly ne edges
         a = rng.integers(1, n_lo, size=(R, ne), dtype=np.int32)
@@ -356,6 +356,8 @@ def run_xgc(args, rank, world, local_rank):
     nmin = min(int(hg.num_agents_all().min()) for hg in groups)
     ne_dev = h.counters_all(t_last)[:, K.K_NEDGES:K.K_NEDGES + 3].astype(np.float64).mean(0)     # edges per layer the resident arm held
     pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev))
+    # one-off partnerships are new every week: cycle through several one-off layers (main / casual ties persist for years)
+    oneoff = [pool[2]] + [host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev), layers=(2,))[0] for _ in range(7)]
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
     n_host = torch.empty(R, dtype=torch.int32).pin_memory()
@@ -370,7 +372,7 @@ def run_xgc(args, rank, world, local_rank):
         hg, r0 = groups[gi], gi * Rg
         hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
-        for l, (t_el, t_ne, t_st, _ne) in enumerate(pool):
+        for l, (t_el, t_ne, t_st, _ne) in enumerate((pool[0], pool[1], oneoff[t % len(oneoff)])):
             hg.set_edgelists_all(l, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), t_st[r0:r0 + Rg].data_ptr() if l < 2 else 0,
                                  stride=t_el.shape[2])
         hg.step(t, post)
