@@ -174,7 +174,7 @@ _R4 = ("BLACK", "HISP", "OTHER", "WHITE")
 _S3 = ("RECT", "URETH", "PHAR")
 
 
-def params_from_env(env: Dict[str, float], base: Optional[np.ndarray] = None, a_rate_base: float = 0.00049,
+def params_from_env(env: Dict[str, float], base: Optional[np.ndarray] = None, a_rate_base: float = 0.00042,
                     arrive_rate_add_per20k: float = 1.285, n_init: float = 10000.0) -> np.ndarray:
     """The param_msm() call of sim1_02_lhs.r:58-178 with `env` standing for the environment variables."""
     e = lambda k: float(env[k])
