@@ -124,6 +124,32 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   }
 }
 
+// Per-CTA staging of a work queue: the agent passes walk `tpc` tiles per CTA and used to do one RETURNING global atomicAdd
+// per warp and tile to reserve queue slots -- a ~700-cycle round trip in most warps.  Instead the CTA collects its items
+// in shared memory (capacity tpc * TPB, so it cannot overflow), reserves its range with ONE global atomicAdd at the end
+// and writes the range coalesced.
+struct CtaQueue {
+  unsigned* items; unsigned* n;
+  __device__ __forceinline__ void init(unsigned* smem) { items = smem + 2; n = smem; if (threadIdx.x == 0) smem[0] = 0u; }
+  __device__ __forceinline__ void push(bool q, unsigned item, unsigned lane) {        // reached by every lane of the warp
+    unsigned m = __ballot_sync(0xffffffffu, q);
+    if (!m) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(n, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (q) items[base + __popc(m & ((1u << lane) - 1u))] = item;
+  }
+  __device__ __forceinline__ void flush(unsigned* gcount, unsigned* gitems) {           // reached by every thread of the CTA
+    __syncthreads();
+    unsigned cnt = *n;
+    if (cnt == 0) return;
+    if (threadIdx.x == 0) n[1] = atomicAdd(gcount, cnt);
+    __syncthreads();
+    unsigned gbase = n[1];
+    for (unsigned k = threadIdx.x; k < cnt; k += blockDim.x) gitems[gbase + k] = items[k];
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_agent1: aging_msm, departure_msm, hivtest_msm, hivtx_msm, hivprogress_msm, hivvl_msm (sim1_02_lhs.r:202-208)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -145,6 +171,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
+  extern __shared__ unsigned cq_smem[];
+  CtaQueue cq; cq.init(cq_smem);
+  __syncthreads();
   int at = g.at_ptr[r], lane = threadIdx.x & 31;
   int n_pre = rp->n_slots_pre;
   const double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
@@ -211,14 +240,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
     }
     // queue the surviving HIV-positive agents
     bool queue = hivmods && hivpos && !isnew && !dead;
-    unsigned m = __ballot_sync(0xffffffffu, queue);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(g.qh_count + r, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (tested ? 0x80000000u : 0u);
-    }
+    cq.push(queue, (unsigned)i | (tested ? 0x80000000u : 0u), lane);
   }
+  cq.flush(g.qh_count + r, Q);
 }
 
 // k_agent1b: HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued (surviving) HIV-positive agents.
@@ -846,6 +870,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __gri
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
+  extern __shared__ unsigned cq_smem[];
+  CtaQueue cq; cq.init(cq_smem);
+  __syncthreads();
   int at = g.at_ptr[r], lane = threadIdx.x & 31;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
@@ -889,14 +916,9 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __gri
       bool cdc_active = proto == XGC_SCREEN_CDC && ((ex & 7u) || (kissx && (ex & 8u)));
       queue = (mask & (XGC_M_STIRECOV | XGC_M_STITX)) && ((gc & 7u) || ((mask & XGC_M_STITX) && (avd || cdc_active)));
     }
-    unsigned m = __ballot_sync(0xffffffffu, queue);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(g.qa_count + r, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i | (avd ? 0x80000000u : 0u);
-    }
+    cq.push(queue, (unsigned)i | (avd ? 0x80000000u : 0u), lane);
   }
+  cq.flush(g.qa_count + r, Q);
 }
 
 // k_agent2b: stirecov_msm, stitx_msm (sim1_02_lhs.r:215-216) over the queued agents
@@ -1230,6 +1252,9 @@ __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, 
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
+  extern __shared__ unsigned cq_smem[];
+  CtaQueue cq; cq.init(cq_smem);
+  __syncthreads();
   __shared__ unsigned hist[A3_NHIST];
   for (int k = threadIdx.x; k < A3_NHIST; k += TPB) hist[k] = 0u;
   __syncthreads();
@@ -1252,13 +1277,7 @@ __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, 
       if (nm & A3_SITE_MASK(2)) gc |= GC_ST(2);
       if (hnew) hiv |= HV_STATUS;
     }
-    unsigned m = __ballot_sync(0xffffffffu, queue);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(g.q3_count + r, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (queue) Q[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i;
-    }
+    cq.push(queue, (unsigned)i, lane);
     if (mask & XGC_M_PREV) {
       // warp-aggregated tallies: lanes of the same (race, age group) cell vote, one shared-memory add per cell and series
       unsigned grp = __match_any_sync(0xffffffffu, live ? cell : 31u);
@@ -1278,6 +1297,7 @@ __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, 
 #undef A3_TALLY
     }
   }
+  cq.flush(g.q3_count + r, Q);
   if (!(mask & XGC_M_PREV)) return;
   __syncthreads();
   unsigned* row = counter_row(g, r, at);

@@ -48,7 +48,10 @@ struct xgc_handle {
   cudaEvent_t ev_fork[2] = { nullptr, nullptr }, ev_join[2] = { nullptr, nullptr };
   cudaStream_t cur = nullptr;            // stream the next kl() launches on (main stream unless inside a side branch)
   bool overlap = true;                   // XGC_OVERLAP=0 keeps everything on one stream
-  bool pdl = true;            // programmatic dependent launch of the weekly kernels (XGC_PDL=0 turns it off)
+  bool pdl = true;            // programmatic dependent launch for kernels launched on the stream by xgc_step (XGC_PDL=0: off).  Measured: +8 % on the
+                              // step-by-step host-buffer path; inside the captured week graph it is OFF (no gain there, and a 6 % loss once
+                              // neighbouring kernels differ in shared-memory carve-out)
+  bool capturing = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<void*> allocs;
@@ -487,7 +490,7 @@ static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->cur ? h->cur : h->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling && !h->capturing) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
   if (e != cudaSuccess && !h->launch_err) {          // remembered for xgc_last_error; the caller's cudaGetLastError() reports it
     h->launch_err = true;
@@ -536,7 +539,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   int tiles = (g.n_cap + TPB - 1) / TPB;
   static const int TA = getenv("XGC_TUNE_A") ? atoi(getenv("XGC_TUNE_A")) : 16, TQ = getenv("XGC_TUNE_Q") ? atoi(getenv("XGC_TUNE_Q")) : 16,
                    TE = getenv("XGC_TUNE_E") ? atoi(getenv("XGC_TUNE_E")) : 32;      // CTAs per SM each kernel family is sized for
-  int tpc = std::max(1, std::min(tiles, (int)(((long long)tiles * g.R) / (148 * TA))));
+  int tpc = std::max(1, std::min(std::min(tiles, 40), (int)(((long long)tiles * g.R) / (148 * TA))));     // <= 40 tiles: the CTA's queue staging stays under 48 KB
   dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
@@ -545,7 +548,12 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
-  if (zero_row || (mask & a1mods)) LAUNCHD(h, inj, k_agent1a, ga, TPB, g, inj, mask, zero_row, tpc);
+  const size_t cq_smem = ((size_t)tpc * TPB + 2) * sizeof(unsigned);        // per-CTA queue staging of the agent passes
+  if (zero_row || (mask & a1mods)) {
+    prof_begin(h, "k_agent1a");
+    if (inj.u) kl(h, k_agent1a<true>, ga, TPB, cq_smem, g, inj, mask, zero_row, tpc); else kl(h, k_agent1a<false>, ga, TPB, cq_smem, g, inj, mask, zero_row, tpc);
+    prof_end(h); h->launches++;
+  }
   // the HIV-positive queue touches only HIV fields of its agents: side branch, joined before the kernels that read them
   bool br0 = false;
   if (mask & (a1mods & ~(XGC_M_AGING | XGC_M_DEPARTURE))) {
@@ -574,7 +582,11 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   int etiles = (int)((g.e_stride + TPB - 1) / TPB);
   dim3 gef((unsigned)std::max(1, std::min(etiles, (148 * TE + g.R - 1) / g.R)), g.R);
   if (mask & (XGC_M_ACTS | XGC_M_PREP)) LAUNCHD(h, inj, k_edge1, gef, TPB, g, inj, mask);
-  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2a, ga, TPB, g, inj, mask, tpc);
+  if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX)) {
+    prof_begin(h, "k_agent2a");
+    if (inj.u) kl(h, k_agent2a<true>, ga, TPB, cq_smem, g, inj, mask, tpc); else kl(h, k_agent2a<false>, ga, TPB, cq_smem, g, inj, mask, tpc);
+    prof_end(h); h->launches++;
+  }
   if (mask & (XGC_M_STIRECOV | XGC_M_STITX)) LAUNCHD(h, inj, k_agent2b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
     LAUNCH(h, k_edge2a, gef, TPB, g, mask);
@@ -589,7 +601,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     prof_end(h); h->launches++;
     branch_join(h, 1, br1);
   }
-  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) LAUNCH(h, k_agent3a, ga, TPB, g, mask, tpc);
+  if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS | XGC_M_PREV)) { prof_begin(h, "k_agent3a"); kl(h, k_agent3a, ga, TPB, cq_smem, g, mask, tpc); prof_end(h); h->launches++; }
   if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) LAUNCHD(h, inj, k_agent3b, dim3(qgrid(tiles), g.R), TPB, g, inj, mask);
   return 0;
 }
@@ -649,7 +661,9 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
     cudaGraph_t graph;
     uint64_t l0 = h->launches;
     CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
     enqueue_week(h, -1, XGC_M_ALL, j, 1);
+    h->capturing = false;
     CU(h, cudaStreamEndCapture(h->stream, &graph));
     CU(h, cudaGraphInstantiate(&h->week_graph, graph, 0));
     CU(h, cudaGraphDestroy(graph));
