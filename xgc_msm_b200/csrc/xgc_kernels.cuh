@@ -20,8 +20,7 @@ __device__ __forceinline__ void warp_tally(unsigned* row, int idx, bool pred) {
   if (m && (threadIdx.x & 31) == 0) atomicAdd(row + idx, (unsigned)__popc(m));
 }
 __device__ __forceinline__ void warp_tally_n(unsigned* row, int idx, unsigned v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  v = __reduce_add_sync(0xffffffffu, v);            // one REDUX instead of five shuffle + add steps
   if (v && (threadIdx.x & 31) == 0) atomicAdd(row + idx, v);
 }
 __device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
