@@ -167,6 +167,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];      // speculative: always inside the plane
   Aux axn = g.aux[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
   short lntn = g.tck[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x].x;
+  int arrn = g.arr_t[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];      // arrival week: the test clock of the never-tested (loaded with the tile, not on demand)
   int n_slots = rp->n_slots;
   int t0 = blockIdx.x * tpc, t1 = min(t0 + tpc, (n_slots + TPB - 1) / TPB);
   if (t0 >= t1) return;
@@ -183,8 +184,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
   for (int t = t0; t < t1; ++t) {
     int i = t * TPB + threadIdx.x;
     size_t idx = rbase + i;
-    uint4 c = cn; Aux ax = axn; short lnt = lntn;
-    if (t + 1 < t1) { cn = g.core[idx + TPB]; axn = g.aux[idx + TPB]; lntn = g.tck[idx + TPB].x; }
+    uint4 c = cn; Aux ax = axn; short lnt = lntn; int arr = arrn;
+    if (t + 1 < t1) { cn = g.core[idx + TPB]; axn = g.aux[idx + TPB]; lntn = g.tck[idx + TPB].x; arrn = g.arr_t[idx + TPB]; }
     bool live = i < n_slots && (c.y & DM_ACTIVE);
     unsigned uid = c.x, demo = c.y, gc = c.z, hiv = c.w;
     if (snap) {     // start of week: remember the GC / PrEP bits that acts, condoms and hivtrans must see (they run before
@@ -224,7 +225,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
     // hivtest_msm: who gets tested this week (the result of a positive's test is settled in k_agent1b)
     bool tested = false;
     if ((mask & XGC_M_HIVTEST) && live && !dead && !(hiv & HV_DIAG)) {
-      int last = lnt == XGC_NA16 ? g.arr_t[idx] : (int)lnt;
+      int last = lnt == XGC_NA16 ? arr : (int)lnt;
       double tsl = (double)(at - last);
       if (!(hiv & HV_PREP) && !(demo & DM_LATE) && tsl >= 2.0) tested = xgc_bern(d(2), P[XGC_P_hiv_test_rate + race]);
       if (HV_STAGE(hiv) == 4 && tsl >= P[XGC_P_aids_test_int]) tested = true;
