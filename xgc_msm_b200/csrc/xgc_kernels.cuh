@@ -265,13 +265,15 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
     bool tested = item >> 31;
     int i = (int)(item & 0x7FFFFFFFu);
     size_t idx = rbase + i;
+    // every gather of this agent is issued at once (they depend only on the slot): one memory round trip, not a chain
     uint4 c = g.core[idx];
+    short4 ha = g.hck_a[idx], hb = g.hck_b[idx];
+    float vl0 = g.aux[idx].vl;
     unsigned uid = c.x, demo = c.y, hiv = c.w;
     int race = (int)DM_RACE(demo);
     unsigned traj = DM_TTTRAJ(demo);
     DrawT<INJ> d(inj, g, r, at, XGC_S_AGENT1, uid, 0u, uid);
     {
-      short4 ha = g.hck_a[idx], hb = g.hck_b[idx];
       bool ha_dirty = false, hb_dirty = false;
       if ((mask & XGC_M_HIVTEST) && tested) {
         if ((double)(at - (int)ha.x) >= P[XGC_P_test_window_int]) { hiv |= HV_DIAG; ha.y = (short)at; ha_dirty = true; }
@@ -308,7 +310,6 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
       }
       if (mask & XGC_M_HIVVL) {
         unsigned stage = HV_STAGE(hiv);
-        float vl0 = g.aux[idx].vl;
         double v, vl = (double)vl0, peak = P[XGC_P_vl_acute_peak], sp = P[XGC_P_vl_set_point];
         if (!(hiv & HV_TX)) {
           if (stage == 1) { v = peak * (tsi / P[XGC_P_vl_acute_rise_int]); if (v > peak) v = peak; }
@@ -1327,10 +1328,10 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __gri
   for (unsigned qi = blockIdx.x * TPB + threadIdx.x; qi < n; qi += gridDim.x * TPB) {
   size_t idx = rbase + g.qa_items[rbase + qi];
   uint4 c = g.core[idx];
+  short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();       // issued with the core word: one round trip (nearly every queued agent has a GC flag)
   unsigned uid = c.x, gc = c.z, hiv = c.w, cell = DM_CELL(c.y);
   unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
   if (nm && (mask & XGC_M_STITRANS)) {
-    short4 ga = g.gck_a[idx], gb = g.gck_b[idx], gd = na4();
     bool pois = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
     if (pois) gd = g.gck_d[idx];
     DrawT<INJ> d(inj, g, r, at, XGC_S_INFECT, uid, 0u, uid);
