@@ -1162,6 +1162,8 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   const uint4* core = g.core + (size_t)r * g.n_cap;
+  unsigned* const Qr = g.q_items + (size_t)r * 4 * g.e_stride;      // this replicate's four queues; 32-bit offsets below
+  const unsigned estride = (unsigned)g.e_stride;
   for (int fbase = blockIdx.x * TPB; fbase < ne_all; fbase += gridDim.x * TPB) {
   const int fi = fbase + tid;
   const int l = fi >= ne01 ? 2 : fi >= ne0 ? 1 : 0;
@@ -1203,9 +1205,10 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
     s_off[tid >> 3][tid & 7] = base + inc - cnt;
   }
   __syncthreads();
+  const unsigned item = ((unsigned)l << 28) | (unsigned)e, lt = (1u << lane) - 1u;
 #pragma unroll
   for (int t = 0; t < 4; ++t)
-    if (f[t]) g.q_items[((size_t)r * 4 + t) * g.e_stride + s_off[t][w] + __popc(b[t] & ((1u << lane) - 1u))] = ((unsigned)l << 28) | (unsigned)e;
+    if (f[t]) Qr[(unsigned)t * estride + s_off[t][w] + __popc(b[t] & lt)] = item;
   // (no barrier needed before the next tile: s_wc is rewritten only after this tile's second barrier, s_off only after the next tile's first)
   }
 }
