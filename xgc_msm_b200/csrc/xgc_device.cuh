@@ -87,6 +87,7 @@ struct Dev {                 // everything a kernel needs; passed by value
   int* pos2slot;             // [R][n_cap] rank -> slot (built by k_rank)
   int4* edge;                // [R][e_stride]: layer l at e_off[l]
   Rep* rep; const double* params; const int* control; const double* tables;
+  const double* inv_ntx;     // [R][4] 1 / gc.ntx.int[site] (weekly untreated-recovery probability, "geom"): one division per replicate, not per site-week
   const double* pois;        // [R][4][XGC_MAX_ACTS+1] Poisson CDF tables of the constant weekly rates: kiss main/casual, rim main/casual
   unsigned* q_items;         // [R][4][e_stride] work queue of k_edge2: (layer << 28 | edge index) per act type
   unsigned* q_count;         // [R][4]

@@ -29,11 +29,12 @@ __device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
 __device__ __forceinline__ short4 na4() { return make_short4(-1, -1, -1, -1); }
 
 // k_derive: per-replicate tables derived from the parameters (run whenever parameters change)
-__global__ void k_derive(const __grid_constant__ Dev g, double* pois) {
+__global__ void k_derive(const __grid_constant__ Dev g, double* pois, double* inv_ntx) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.R * 4) return;
   int r = t >> 2, w = t & 3;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
+  inv_ntx[t] = w < 3 ? 1.0 / P[XGC_P_gc_ntx_int + w] : 0.0;          // IEEE division, same bits as the oracle's 1.0 / p
   double mu = w == 0 ? P[XGC_P_kiss_rate_main] : w == 1 ? P[XGC_P_kiss_rate_casl] : w == 2 ? P[XGC_P_rim_rate_main] : P[XGC_P_rim_rate_casl];
   double* tab = pois + (size_t)t * (XGC_MAX_ACTS + 1);
   if (!(mu > 0.0)) { for (int k = 0; k <= XGC_MAX_ACTS; ++k) tab[k] = __longlong_as_double(0x7ff0000000000000LL); return; }
@@ -960,7 +961,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __gri
           int k = at - (int)txT;
           if (k >= 1) recov = xgc_bern(d(1 + s), P[txpr[s] + (k >= 3 ? 2 : k - 1)]);
         } else if ((int)infT < at) {
-          if (!pois) recov = xgc_bern(d(1 + s), 1.0 / P[XGC_P_gc_ntx_int + s]);
+          if (!pois) recov = xgc_bern(d(1 + s), g.inv_ntx[(size_t)r * 4 + s]);
           else recov = (at - (int)infT) >= (int)dur;
         }
         if (recov) {

@@ -36,7 +36,7 @@ struct xgc_handle {
   HostRep cache;
   double* d_inj = nullptr; size_t d_inj_cap = 0;
   void* d_cscratch = nullptr;   // 16 B per slot, large-replicate compaction only
-  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr;
+  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr; double* d_inv_ntx = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
   bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
@@ -165,10 +165,10 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
   g.lb_tiles = (std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2])) + 1023) / 1024;
   rc |= dalloc(h, &g.lb_status, (size_t)g.R * 3 * g.lb_tiles); rc |= dalloc(h, &g.lb_ticket, (size_t)g.R * 3);
-  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1));
+  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1)); rc |= dalloc(h, &h->d_inv_ntx, (size_t)g.R * 4);
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
-  g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat; g.pois = h->d_pois;
+  g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat; g.pois = h->d_pois; g.inv_ntx = h->d_inv_ntx;
   // defaults: parameter defaults from params.def, kissing/rimming routes on
   std::vector<double> P(XGC_NPARAM);
 #define XGC_PARAM(name, count, v) for (int k = 0; k < (count); ++k) P[XGC_P_##name + k] = (v);
@@ -204,7 +204,7 @@ extern "C" int xgc_stream_ptr(xgc_handle* h, void** s) { *s = (void*)h->stream; 
 // --------------------------------------------------------------------------------------------------------------------
 static int derive(xgc_handle* h) {       // per-replicate tables that depend on the parameters
   int n = h->g.R * 4;
-  k_derive<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_pois);
+  k_derive<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_pois, h->d_inv_ntx);
   CU(h, cudaGetLastError());
   CU(h, cudaStreamSynchronize(h->stream));
   return 0;
