@@ -80,6 +80,7 @@ struct Inj {                 // injected-draw table (device copy), u == nullptr 
 
 struct Dev {                 // everything a kernel needs; passed by value
   int R, n_cap, t_cap, rep0; int e_cap[3]; size_t e_off[3]; size_t e_stride;
+  int r0;                    // first replicate of THIS launch and R = how many it covers: xgc_run drives the replicates as two concurrent lanes
   unsigned seed;
   double inv_dur[2];         // 1 / mean duration of main, casual ties (surrogate dissolution probability), set with the tables
   uint4* core; Aux* aux; short4 *gck_a, *gck_b, *gck_d, *hck_a, *hck_b, *tck; int* arr_t;

@@ -51,6 +51,7 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
   pdl_prologue();
   int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= g.R) return;
+  r += g.r0;
   Rep* rp = g.rep + r;
   int at = at_host >= 0 ? at_host : g.at_ptr[r] + 1;
   unsigned* row = counter_row(g, r, at);
@@ -162,7 +163,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // treatment, progression, viral load) are appended to the replicate's work queue and finished densely by k_agent1b.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int snap, int tpc) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];      // speculative: always inside the plane
@@ -250,7 +251,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
 // Touches only HIV fields of the queued agents: independent of the network kernels that follow k_agent1a.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   unsigned n = g.qh_count[r];
   if (blockIdx.x * TPB >= n) return;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -344,7 +345,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1b(const __gri
 // configs where one CTA walks a whole layer (4096 edges per iteration keeps the sequential part short).
 template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edges_resim(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve) {
   pdl_prologue();
-  int r = blockIdx.y, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.y + g.r0, l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne = rp->ne[l], at = g.at_ptr[r];
   int surrogate = dissolve && g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] == 1;
@@ -401,7 +402,7 @@ template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edg
 #define LB_TILE 1024
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int dissolve, int kind) {
   pdl_prologue();
-  int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.z + g.r0, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int at = g.at_ptr[r];
   int ne = *(volatile int*)&rp->ne[l];               // read BEFORE taking the ticket (the last tile overwrites both)
@@ -474,7 +475,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(cons
 // tile (<= n_cap/32 words, a block reduction) and ranks its own 256 slots with popcounts.
 __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
   pdl_prologue();
-  int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.y + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int n_slots = g.rep[r].n_slots;
   int i0 = blockIdx.x * TPB;
   if (i0 >= n_slots) return;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
 __global__ void __launch_bounds__(TPB) k_rank_cta(const __grid_constant__ Dev g) {
   pdl_prologue();
   extern __shared__ unsigned rk_smem[];            // [words] bitmap, [words + 1] exclusive popcount prefix
-  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int r = blockIdx.x + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int n_slots = g.rep[r].n_slots, words = (n_slots + 31) >> 5;
   const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
   int* P2S = g.pos2slot + (size_t)r * g.n_cap;
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(TPB) k_rank_cta(const __grid_constant__ Dev g)
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
 template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_form(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   pdl_prologue();
-  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // one CTA per replicate, the three layers in turn
+  int r = blockIdx.x + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;        // one CTA per replicate, the three layers in turn
   if (g.control[(size_t)r * XGC_NCONTROL + XGC_C_network_mode] != 1) return;
   Rep* rp = g.rep + r;
   int at = g.at_ptr[r], n = rp->n_alive;
@@ -623,7 +624,7 @@ template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_f
 // status words / epoch with k_edges_resim_lb; launches are serialised on the stream).  Needs pos2slot (k_rank).
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   pdl_prologue();
-  int r = blockIdx.z, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.z + g.r0, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne0 = *(volatile int*)&rp->ne[l];
   unsigned epoch = *(volatile unsigned*)&rp->lb_epoch[l];
@@ -763,7 +764,7 @@ template <class D> __device__ __forceinline__ void edge_kiss_rim(const double* P
 // k_edge1: acts_msm (sim1_02_lhs.r:210) + exposure history + PrEP risk history.  grid (tiles, 3 layers, R)
 template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   const Rep* rp = g.rep + r;
   // the three layers of the replicate are walked as one index space [0, ne0 + ne1 + ne2): full tiles except the last,
   // a few CTAs per replicate striding over it
@@ -864,7 +865,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __gr
 // are appended to the replicate's work queue; k_agent2b runs stirecov_msm / stitx_msm on the queue with all lanes busy.
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask, int tpc) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
@@ -926,7 +927,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2a(const __gri
 // k_agent2b: stirecov_msm, stitx_msm (sim1_02_lhs.r:215-216) over the queued agents
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   unsigned n = g.qa_count[r];
   if (blockIdx.x * TPB >= n) return;
   const size_t rbase = (size_t)r * g.n_cap;
@@ -1153,7 +1154,7 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
 // work queues (one atomicAdd per CTA and type).  No draws here.
 __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   const Rep* rp = g.rep + r;
   const int ne0 = rp->ne[0], ne01 = ne0 + rp->ne[1], ne_all = ne01 + rp->ne[2];     // one index space over the three layers
   if ((int)(blockIdx.x * TPB) >= ne_all) return;
@@ -1217,7 +1218,7 @@ __global__ void __launch_bounds__(TPB) k_edge2a(const __grid_constant__ Dev g, u
 // k_edge2b: dense processing of the work queues; blockIdx.y = act type, so every warp runs one act type with all lanes busy.
 template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 : 4) k_edge2b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.z, type = ANAL ? 0 : 1 + blockIdx.y;
+  int r = blockIdx.z + g.r0, type = ANAL ? 0 : 1 + blockIdx.y;
   unsigned n = g.q_count[(size_t)r * 4 + type];
   if (blockIdx.x * TPB >= n) return;
   const Rep* rp = g.rep + r;
@@ -1250,7 +1251,7 @@ template <bool INJ, bool ANAL> __global__ void __launch_bounds__(TPB, ANAL ? 3 :
                                   : ((1u << XGC_PATH_U2P) | (1u << XGC_PATH_R2P) | (1u << XGC_PATH_P2P)))
 __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, unsigned mask, int tpc) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   const Rep* rp = g.rep + r;
   const size_t rbase = (size_t)r * g.n_cap;
   uint4 cn = g.core[rbase + (size_t)blockIdx.x * tpc * TPB + threadIdx.x];
@@ -1315,7 +1316,7 @@ __global__ void __launch_bounds__(TPB) k_agent3a(const __grid_constant__ Dev g, 
 
 template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent3b(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, unsigned mask) {
   pdl_prologue();
-  int r = blockIdx.y;
+  int r = blockIdx.y + g.r0;
   unsigned n = g.q3_count[r];
   if (blockIdx.x * TPB >= n) return;
   const Rep* rp = g.rep + r;
@@ -1433,7 +1434,7 @@ __global__ void k_targets(const __grid_constant__ Dev g, int at_last, int tailn,
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ Dev g, int* remap /*[R][n_cap] old slot -> new slot*/) {
   pdl_prologue();
-  int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int r = blockIdx.x + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int n_slots = rp->n_slots;
   size_t o = (size_t)r * g.n_cap;
@@ -1480,28 +1481,28 @@ __global__ void __launch_bounds__(TPB) k_compact_agents(const __grid_constant__ 
 //   k_compact_finish   clears the freed tail, rebuilds the alive bitmap, resets the slot counters
 __global__ void __launch_bounds__(TPB) k_compact_remap(const __grid_constant__ Dev g, int* remap) {
   pdl_prologue();
-  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  int r = blockIdx.y + g.r0, j = blockIdx.x * TPB + threadIdx.x;
   if (j >= g.rep[r].n_alive) return;
   size_t o = (size_t)r * g.n_cap;
   remap[o + g.pos2slot[o + j]] = j;
 }
 template <class T> __global__ void __launch_bounds__(TPB) k_compact_gather(const __grid_constant__ Dev g, const T* plane, T* scratch) {
   pdl_prologue();
-  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  int r = blockIdx.y + g.r0, j = blockIdx.x * TPB + threadIdx.x;
   if (j >= g.rep[r].n_alive) return;
   size_t o = (size_t)r * g.n_cap;
   scratch[o + j] = plane[o + g.pos2slot[o + j]];
 }
 template <class T> __global__ void __launch_bounds__(TPB) k_compact_putback(const __grid_constant__ Dev g, T* plane, const T* scratch) {
   pdl_prologue();
-  int r = blockIdx.y, j = blockIdx.x * TPB + threadIdx.x;
+  int r = blockIdx.y + g.r0, j = blockIdx.x * TPB + threadIdx.x;
   if (j >= g.rep[r].n_alive) return;
   size_t o = (size_t)r * g.n_cap;
   plane[o + j] = scratch[o + j];
 }
 __global__ void __launch_bounds__(TPB) k_compact_finish(const __grid_constant__ Dev g, int stage) {
   pdl_prologue();
-  int r = blockIdx.y, i = blockIdx.x * TPB + threadIdx.x;
+  int r = blockIdx.y + g.r0, i = blockIdx.x * TPB + threadIdx.x;
   Rep* rp = g.rep + r;
   size_t o = (size_t)r * g.n_cap;
   int n = rp->n_alive;
@@ -1515,7 +1516,7 @@ __global__ void __launch_bounds__(TPB) k_compact_finish(const __grid_constant__ 
 }
 __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ Dev g, const int* remap) {
   pdl_prologue();
-  int r = blockIdx.z, l = blockIdx.y;
+  int r = blockIdx.z + g.r0, l = blockIdx.y;
   int ne = g.rep[r].ne[l];
   int e = blockIdx.x * TPB + threadIdx.x;
   if (e >= ne) return;

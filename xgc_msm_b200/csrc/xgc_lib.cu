@@ -39,6 +39,17 @@ struct xgc_handle {
   int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr; double* d_inv_ntx = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
+  // xgc_run drives the replicates as TWO concurrent lanes (halves of the replicate range, each with its own streams and
+  // captured week graph): every kernel of this path is latency-bound, so a second, independent kernel sequence fills the
+  // issue slots and tails the first leaves idle (measured -8 % per week).  Lane 0 lives on the handle's own streams.
+  int n_lanes = 2;                        // XGC_LANES=1: one lane
+  const Dev* gl = nullptr;                // Dev of the lane being enqueued (nullptr: the whole handle)
+  cudaStream_t lane_main = nullptr, lane_side = nullptr;      // streams the enqueue helpers use (lane 0: stream / stream2)
+  cudaEvent_t* lane_fork = nullptr; cudaEvent_t* lane_join = nullptr;
+  cudaStream_t l1_stream = nullptr, l1_stream2 = nullptr;
+  cudaEvent_t l1_fork[2] = { nullptr, nullptr }, l1_join[2] = { nullptr, nullptr }, l1_start = nullptr, l1_done = nullptr;
+  cudaGraphExec_t l1_graph = nullptr; uint64_t l1_graph_launches = 0;
+  int lanes_captured = 0;
   bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
@@ -142,6 +153,19 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
       h->err = "cudaEventCreate failed"; return fail(3);
     }
+  { const char* e = getenv("XGC_LANES"); if (e && e[0] == '1') h->n_lanes = 1; }
+  if (cfg->n_replicates < 16) h->n_lanes = 1;
+  if (cudaStreamCreateWithFlags(&h->l1_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->l1_stream2, cudaStreamNonBlocking) != cudaSuccess) {
+    h->err = "cudaStreamCreate failed"; return fail(3);
+  }
+  for (int k = 0; k < 2; ++k)
+    if (cudaEventCreateWithFlags(&h->l1_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->l1_join[k], cudaEventDisableTiming) != cudaSuccess) {
+      h->err = "cudaEventCreate failed"; return fail(3);
+    }
+  if (cudaEventCreateWithFlags(&h->l1_start, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->l1_done, cudaEventDisableTiming) != cudaSuccess) {
+    h->err = "cudaEventCreate failed"; return fail(3);
+  }
+  h->lane_main = h->stream; h->lane_side = h->stream2; h->lane_fork = h->ev_fork; h->lane_join = h->ev_join;
   h->cur = h->stream;
   Dev& g = h->g; memset(&g, 0, sizeof g);
   g.R = cfg->n_replicates; g.n_cap = cfg->n_cap; g.t_cap = cfg->t_cap; g.rep0 = cfg->replicate_offset; g.seed = (unsigned)cfg->seed;
@@ -185,6 +209,12 @@ extern "C" int xgc_destroy(xgc_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->week_graph) cudaGraphExecDestroy(h->week_graph);
+  if (h->l1_graph) cudaGraphExecDestroy(h->l1_graph);
+  for (int k = 0; k < 2; ++k) { if (h->l1_fork[k]) cudaEventDestroy(h->l1_fork[k]); if (h->l1_join[k]) cudaEventDestroy(h->l1_join[k]); }
+  if (h->l1_start) cudaEventDestroy(h->l1_start);
+  if (h->l1_done) cudaEventDestroy(h->l1_done);
+  if (h->l1_stream) { cudaStreamSynchronize(h->l1_stream); cudaStreamDestroy(h->l1_stream); }
+  if (h->l1_stream2) cudaStreamDestroy(h->l1_stream2);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_inj) cudaFree(h->d_inj);
   if (h->d_el_stage) cudaFree(h->d_el_stage);
@@ -241,6 +271,7 @@ extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
   CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
   for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];       // same IEEE division the oracle performs
   if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }   // kernel arguments changed
+  h->lanes_captured = 0;
   return 0;
 }
 
@@ -487,7 +518,7 @@ static void prof_end(xgc_handle* h) { if (h->profiling) cudaEventRecord(h->prof.
 template <class... KArgs, class... Args>
 static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->cur ? h->cur : h->stream;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->cur ? h->cur : h->lane_main;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling && !h->capturing) ? 1 : 0;
@@ -503,13 +534,13 @@ static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 // Per-kernel profiling keeps everything on one stream (the events would serialise the branches anyway).
 static bool branch_begin(xgc_handle* h, int k) {
   if (!h->overlap || h->profiling) return false;
-  cudaEventRecord(h->ev_fork[k], h->stream);
-  cudaStreamWaitEvent(h->stream2, h->ev_fork[k], 0);
-  h->cur = h->stream2;
+  cudaEventRecord(h->lane_fork[k], h->lane_main);
+  cudaStreamWaitEvent(h->lane_side, h->lane_fork[k], 0);
+  h->cur = h->lane_side;
   return true;
 }
-static void branch_end(xgc_handle* h, int k, bool on) { if (on) { cudaEventRecord(h->ev_join[k], h->stream2); h->cur = h->stream; } }
-static void branch_join(xgc_handle* h, int k, bool on) { if (on) cudaStreamWaitEvent(h->stream, h->ev_join[k], 0); }
+static void branch_end(xgc_handle* h, int k, bool on) { if (on) { cudaEventRecord(h->lane_join[k], h->lane_side); h->cur = h->lane_main; } }
+static void branch_join(xgc_handle* h, int k, bool on) { if (on) cudaStreamWaitEvent(h->lane_main, h->lane_join[k], 0); }
 #define LAUNCH(h, kern, grid, block, ...) do { prof_begin(h, #kern); kl(h, kern, grid, block, 0, __VA_ARGS__); prof_end(h); (h)->launches++; } while (0)
 // kernels that draw: native instantiation unless an injected table is attached
 #define LAUNCHD(h, inj, kern, grid, block, ...) do { prof_begin(h, #kern); \
@@ -518,7 +549,7 @@ static void branch_join(xgc_handle* h, int k, bool on) { if (on) cudaStreamWaitE
 
 // stable in-place edge compaction: small CTAs for calibration-size layers, 1024 x 4 for very long layers
 static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve, int kind) {
-  const Dev& g = h->g;
+  const Dev& g = h->gl ? *h->gl : h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   prof_begin(h, "k_edges_resim");
   if (emax > 16384) {           // very long layers: many CTAs per layer, decoupled look-back
@@ -534,7 +565,7 @@ static void launch_resim(xgc_handle* h, const Inj& inj, int dissolve, int kind) 
 
 // enqueue one week.  at_host < 0: week = previous + 1 (graph replay).
 static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& inj, int zero_row) {
-  const Dev& g = h->g;
+  const Dev& g = h->gl ? *h->gl : h->g;
   // agent kernels: tiles per CTA chosen so the grid stays a few waves of the 148 SMs
   int tiles = (g.n_cap + TPB - 1) / TPB;
   static const int TA = getenv("XGC_TUNE_A") ? atoi(getenv("XGC_TUNE_A")) : 16, TQ = getenv("XGC_TUNE_Q") ? atoi(getenv("XGC_TUNE_Q")) : 16,
@@ -622,17 +653,15 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   return 0;
 }
 
-extern "C" int xgc_compact(xgc_handle* h) {
-  int rc = cache_drop(h); if (rc) return rc;
-  CU(h, cudaSetDevice(h->cfg.device));
-  const Dev& g = h->g;
+// slot compaction of the replicates of the current lane (h->gl) or of the whole handle
+static int compact_impl(xgc_handle* h) {
+  const Dev& g = h->gl ? *h->gl : h->g;
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   launch_resim(h, make_inj(h, nullptr, nullptr), 0, 2);       // no dangling endpoints before re-numbering
   h->rank_fresh = false;
   if (g.n_cap <= 32768) {
     LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);       // one CTA walks the replicate's ~40 tiles
   } else {                                                      // 100k .. 1M-agent replicates: parallel gathers through pos2slot
-    size_t NA = h->n_agent();
     dim3 gp((g.n_cap + TPB - 1) / TPB, g.R);
     LAUNCH(h, k_rank, gp, TPB, g);
     LAUNCH(h, k_compact_remap, gp, TPB, g, h->d_remap);
@@ -651,33 +680,71 @@ extern "C" int xgc_compact(xgc_handle* h) {
   return 0;
 }
 
+extern "C" int xgc_compact(xgc_handle* h) {
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  return compact_impl(h);
+}
+
 extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   if (at0 < 1 || at1 >= h->cfg.t_cap || at1 < at0 - 1) FAIL(h, 2, "bad week range [%d,%d], t_cap = %d", at0, at1, h->cfg.t_cap);
   if (at1 > 32766) FAIL(h, 2, "at exceeds the 16-bit week clocks");
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   Inj j = make_inj(h, nullptr, nullptr);
-  if (!h->week_graph) {                   // capture one week (week = previous + 1) once, replay it for every later week
-    cudaGraph_t graph;
-    uint64_t l0 = h->launches;
-    CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    h->capturing = true;
-    enqueue_week(h, -1, XGC_M_ALL, j, 1);
-    h->capturing = false;
-    CU(h, cudaStreamEndCapture(h->stream, &graph));
-    CU(h, cudaGraphInstantiate(&h->week_graph, graph, 0));
-    CU(h, cudaGraphDestroy(graph));
-    h->graph_launches = h->launches - l0;
-    h->launches = l0;
+  const int L = h->n_lanes, R = h->cfg.n_replicates;
+  Dev gl[2]; gl[0] = h->g; gl[1] = h->g;
+  if (L == 2) { gl[0].r0 = 0; gl[0].R = R / 2; gl[1].r0 = R / 2; gl[1].R = R - R / 2; }
+  auto use_lane = [&](int k) {             // point the enqueue helpers at lane k's Dev, streams and events
+    h->gl = &gl[k];
+    h->lane_main = k ? h->l1_stream : h->stream; h->lane_side = k ? h->l1_stream2 : h->stream2;
+    h->lane_fork = k ? h->l1_fork : h->ev_fork; h->lane_join = k ? h->l1_join : h->ev_join;
+    h->cur = h->lane_main;
+  };
+  auto use_whole = [&]() { h->gl = nullptr; h->lane_main = h->stream; h->lane_side = h->stream2; h->lane_fork = h->ev_fork; h->lane_join = h->ev_join; h->cur = h->stream; };
+  if (h->lanes_captured != L) {            // capture one week (week = previous + 1) per lane once, replay it for every later week
+    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }
+    if (h->l1_graph) { cudaGraphExecDestroy(h->l1_graph); h->l1_graph = nullptr; }
+    for (int k = 0; k < L; ++k) {
+      cudaGraph_t graph;
+      uint64_t l0 = h->launches;
+      use_lane(k);
+      CU(h, cudaStreamBeginCapture(h->lane_main, cudaStreamCaptureModeThreadLocal));
+      h->capturing = true;
+      enqueue_week(h, -1, XGC_M_ALL, j, 1);
+      h->capturing = false;
+      cudaError_t e = cudaStreamEndCapture(h->lane_main, &graph);
+      if (e != cudaSuccess) { use_whole(); CU(h, e); }
+      e = cudaGraphInstantiate(k ? &h->l1_graph : &h->week_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { use_whole(); CU(h, e); }
+      (k ? h->l1_graph_launches : h->graph_launches) = h->launches - l0;
+      h->launches = l0;
+    }
+    h->lanes_captured = L;
+    use_whole();
   }
   // the graph advances the device-side week itself; make sure it continues from at0 - 1
   std::vector<int> atv(h->cfg.n_replicates, at0 - 1);
   CU(h, cudaMemcpyAsync((int*)h->g.at_ptr, atv.data(), sizeof(int) * atv.size(), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  if (L == 2) {                            // lane 1 starts after everything already queued on the handle's stream
+    CU(h, cudaEventRecord(h->l1_start, h->stream));
+    CU(h, cudaStreamWaitEvent(h->l1_stream, h->l1_start, 0));
+  }
   for (int at = at0; at <= at1; ++at) {
     CU(h, cudaGraphLaunch(h->week_graph, h->stream));
     h->launches += h->graph_launches;
-    if (at % h->cfg.compact_every == 0) { rc = xgc_compact(h); if (rc) return rc; }
+    if (L == 2) { CU(h, cudaGraphLaunch(h->l1_graph, h->l1_stream)); h->launches += h->l1_graph_launches; }
+    if (at % h->cfg.compact_every == 0) {
+      for (int k = 0; k < L; ++k) { use_lane(k); rc = compact_impl(h); if (rc) break; }
+      use_whole();
+      if (rc) return rc;
+    }
+  }
+  if (L == 2) {                            // ... and the handle's stream continues after lane 1
+    CU(h, cudaEventRecord(h->l1_done, h->l1_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->l1_done, 0));
   }
   h->last_at = at1; h->rank_fresh = false; h->acts_valid = true; memset(&h->last_inj, 0, sizeof(Inj));
   CU(h, cudaGetLastError());
@@ -953,7 +1020,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   h->last_at = -1; h->acts_valid = false; h->rank_fresh = false;
   { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
-    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; } }
+    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; } h->lanes_captured = 0; }
   return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
@@ -983,7 +1050,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
 // bulk edge-list upload for the weekly host<->device contract (host network resimulation)
 // --------------------------------------------------------------------------------------------------------------------
 __global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el /*[R][2][stride]*/, const int* ne /*[R]*/, const int* start /*[R][stride] or null*/, int stride) {
-  int r = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y + g.r0, e = blockIdx.x * blockDim.x + threadIdx.x;
   int n = ne[r], cap = g.e_cap[l] < stride ? g.e_cap[l] : stride;
   if (e == 0) { g.rep[r].ne[l] = n < cap ? n : cap; if (n > cap) atomicOr(&g.rep[r].status, XGC_ST_EDGE_OVERFLOW); }
   if (e >= n || e >= cap) return;
