@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from xgc_msm_b200 import workload
 from xgc_msm_b200.abi import Handle
-R, weeks = 1000, 60
+R, weeks = 996, 60
 spec = workload.SweepSpec(n_agents=10000, seed=1971)
 for G in [int(a) for a in sys.argv[1:]] or [1, 2, 4]:
     hs = []
