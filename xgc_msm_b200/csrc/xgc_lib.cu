@@ -154,7 +154,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
       h->err = "cudaEventCreate failed"; return fail(3);
     }
   { const char* e = getenv("XGC_LANES"); if (e && e[0] == '1') h->n_lanes = 1; }
-  if (cfg->n_replicates < 16) h->n_lanes = 1;
+  if (cfg->n_replicates < 2) h->n_lanes = 1;
   if (cudaStreamCreateWithFlags(&h->l1_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->l1_stream2, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "cudaStreamCreate failed"; return fail(3);
   }
