@@ -239,7 +239,12 @@ enum xgc_target_index {
 enum xgc_dtype { XGC_F64 = 0, XGC_I32 = 1 };
 
 /* Status bits in xgc_status(). */
-enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_ST_GC_EXTINCT = 4, XGC_ST_BAD_EDGE = 8 };
+enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_ST_GC_EXTINCT = 4, XGC_ST_BAD_EDGE = 8,
+       /* a constant weekly act rate (kiss.rate.main/.casl, rim.rate.main/.casl) is so high that the XGC_MAX_ACTS truncation
+        * of its Poisson draw is no longer negligible: P(X > XGC_MAX_ACTS) > XGC_TRUNC_TOL.  The top of the reference's
+        * prior box (rates up to 10/week, sim1_01_lhs_params.r:66-71) is far below it (P ~ 1e-9). */
+       XGC_ST_RATE_TRUNCATED = 16 };
+#define XGC_TRUNC_TOL 1e-6
 
 /* Named constants of this header, so that bindings (ctypes, .Call) need not re-declare the enums. */
 #define XGC_CONSTANT_LIST(X) \
@@ -263,7 +268,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_K_DEP_GEN) X(XGC_K_DEP_AIDS) X(XGC_K_NNEW) X(XGC_K_HIVTESTS) X(XGC_K_NEDGES) X(XGC_K_NACTS) \
   X(XGC_TG_NUM) X(XGC_TG_I_PREV) X(XGC_TG_IR100_POP) X(XGC_TG_HIVDX_RACE) X(XGC_TG_HIVDX_AGE) X(XGC_TG_VLS_RACE) X(XGC_TG_VLS_AGE) \
   X(XGC_TG_PREPCOV_RACE) X(XGC_TG_PROP_TESTED) X(XGC_TG_PROB_POS) X(XGC_TG_PREV_GC) X(XGC_TG_IR100_GC) \
-  X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_F64) X(XGC_I32)
+  X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_ST_RATE_TRUNCATED) X(XGC_F64) X(XGC_I32)
 int  xgc_constant(const char* name, int64_t* value);          /* 0 if found */
 int  xgc_param_index(const char* name, int* offset, int* count);   /* params.def lookup */
 int  xgc_inject_stream_width(int stream);                       /* = xgc_stream_width() for bindings that cannot include this header */
@@ -295,6 +300,11 @@ int  xgc_get_params (xgc_handle* h, int r, double* params);
 int  xgc_set_params_all(xgc_handle* h, const double* params /*[n_replicates][XGC_NPARAM]*/);
 int  xgc_set_control(xgc_handle* h, int r, const int32_t* control /*[XGC_NCONTROL]*/);
 int  xgc_set_tables (xgc_handle* h, const double* tables /*[XGC_NTABLE]*/);
+/* read back what a handle runs with (a scenario arm forked from a burn-in continues with the burn-in's own netstats /
+ * epistats tables, parameters and flags: 02.00_epi.r:292-296 reuses the burn-in's param / control objects) */
+int  xgc_get_tables (xgc_handle* h, double* tables /*[XGC_NTABLE]*/);
+int  xgc_get_params_all(xgc_handle* h, double* params /*[n_replicates][XGC_NPARAM]*/);
+int  xgc_get_control(xgc_handle* h, int r, int32_t* control /*[XGC_NCONTROL]*/);
 
 /* state exchange: replaces dat$attr / dat$el.  Attribute vectors are in R position order.
  * xgc_set_population sets N for replicate r, marks slots 0..n-1 alive, assigns uid = 0..n-1 and resets all attributes

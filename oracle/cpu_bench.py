@@ -142,3 +142,69 @@ def run_targets(n_agents: int, n_replicates: int, weeks: int, tailn: int, seed: 
             out = np.empty((n_replicates, t.shape[1]))
         out[ids] = t
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-state runs for the BASELINE-size parity tests (tests/test_gpu_fullsize_parity.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def host_edges(seed: int, rid: int, at: int, layer: int, n_alive: int, e_cap):
+    """Deterministic stand-in for what host-side simnet_msm returns for (replicate, week, layer): a ragged list of
+    1-based positions among the living (tail < head) and partnership start weeks.  Pure function of its arguments, so
+    the GPU driver and the oracle workers build identical lists without talking to each other."""
+    rng = np.random.default_rng([seed, rid, at, layer])
+    ne = int(rng.integers(int(e_cap[layer] * 0.55), int(e_cap[layer] * 0.74)))
+    a = rng.integers(1, n_alive + 1, size=ne)
+    b = rng.integers(1, n_alive, size=ne)
+    b = np.where(b >= a, b + 1, b)
+    el = np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1).astype(np.int32)
+    st = (at - rng.integers(0, 300 if layer < 2 else 1, size=ne)).astype(np.int32)
+    return el, st
+
+
+def _state_worker(args):
+    n_agents, ids, seed, weeks, mask, spec_kw, tailn, attr_names, host_net, overrides = args
+    reps = _build_replicates(n_agents, ids, seed, spec_kw)
+    from oracle.oracle import NCOUNTER
+    from xgc_msm_b200.params import MODULE_BIT as MB
+    pre = MB["aging"] | MB["departure"] | MB["arrival"] | MB["hivtest"] | MB["hivtx"] | MB["hivprogress"] | MB["hivvl"]
+    out = {}
+    for rid, o in zip(ids, reps):
+        if overrides and rid in overrides:
+            ov = overrides[rid]
+            if "params" in ov:
+                o.set_params(ov["params"])
+            if "control" in ov:
+                o.set_control(ov["control"])
+        cnt = np.zeros((weeks, NCOUNTER), np.uint32)
+        alive = np.zeros(weeks, np.int64)
+        for at in range(2, 2 + weeks):
+            if host_net:
+                o.step(at, pre)
+                n = o.num_agents()
+                for l in range(3):
+                    el, st = host_edges(seed, rid, at, l, n, o.e_cap)
+                    o.set_edgelist(l, el, st if l < 2 else None)
+                o.step(at, mask & ~pre & ~MB["resim_nets"])
+            else:
+                o.step(at, mask)
+            cnt[at - 2] = o.counters(at)
+            alive[at - 2] = o.num_agents()
+        out[rid] = dict(counters=cnt, alive=alive, attrs={k: o.get_attr(k) for k in attr_names},
+                        els=[o.get_edgelist(l) for l in range(3)], acts=[o.get_actcounts(l) for l in range(3)],
+                        targets=o.targets(1 + weeks, tailn), status=o.status())
+        o.close()
+    return out
+
+
+def run_states(n_agents: int, ids, weeks: int, tailn: int, seed: int, mask: int, attr_names, spec_kw=None, host_net: bool = False,
+               overrides=None, cores: int | None = None) -> dict:
+    """{rid: full final state + weekly tallies} of the oracle for the given global replicate ids of the sweep workload."""
+    ids = list(ids)
+    cores = max(1, min(cores or os.cpu_count() or 1, len(ids)))
+    chunks = [ids[c::cores] for c in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_state_worker, [(n_agents, ch, seed, weeks, mask, spec_kw, tailn, list(attr_names), host_net, overrides) for ch in chunks])
+    out = {}
+    for r in res:
+        out.update(r)
+    return out

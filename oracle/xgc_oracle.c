@@ -176,7 +176,20 @@ void orc_set_params(orc_dat* d, const double* p) { memcpy(d->p, p, sizeof(double
 void orc_set_control(orc_dat* d, const int32_t* c) { memcpy(d->c, c, sizeof(int32_t) * XGC_NCONTROL); }
 void orc_set_tables(orc_dat* d, const double* t) { memcpy(d->tb, t, sizeof(double) * XGC_NTABLE); }
 int orc_num_agents(const orc_dat* d) { return d->n; }
-uint32_t orc_status(const orc_dat* d) { return d->status; }
+/* XGC_ST_RATE_TRUNCATED: the tail mass of a constant-rate Poisson beyond XGC_MAX_ACTS, with the recurrence of orc_pois */
+static uint32_t rate_status(const orc_dat* d) {
+  static const int rate[4] = { XGC_P_kiss_rate_main, XGC_P_kiss_rate_casl, XGC_P_rim_rate_main, XGC_P_rim_rate_casl };
+  uint32_t st = 0;
+  for (int w = 0; w < 4; ++w) {
+    double mu = d->p[rate[w]];
+    if (!(mu > 0.0)) continue;
+    double pr = orc_exp(-mu), cdf = pr;
+    for (int k = 1; k <= XGC_MAX_ACTS; ++k) { pr = pr * mu * (1.0 / (double)k); cdf = cdf + pr; }
+    if (1.0 - cdf > XGC_TRUNC_TOL) st |= XGC_ST_RATE_TRUNCATED;
+  }
+  return st;
+}
+uint32_t orc_status(const orc_dat* d) { return d->status | rate_status(d); }
 
 static void new_agent_defaults(orc_dat* d, int i) {
   for (int k = 0; k < A_NATTR; ++k) d->a[k][i] = 0.0;

@@ -42,6 +42,7 @@ def _load() -> C.CDLL:
         "xgc_create": [C.POINTER(xgc_config), C.POINTER(vp)], "xgc_destroy": [vp], "xgc_abi_version": [],
         "xgc_set_params": [vp, ci, pd], "xgc_get_params": [vp, ci, pd], "xgc_set_params_all": [vp, pd],
         "xgc_set_control": [vp, ci, pi], "xgc_set_tables": [vp, pd],
+        "xgc_get_tables": [vp, pd], "xgc_get_params_all": [vp, pd], "xgc_get_control": [vp, ci, pi],
         "xgc_set_population": [vp, ci, ci, ci], "xgc_num_agents": [vp, ci, pi],
         "xgc_upload_attr": [vp, ci, C.c_char_p, vp, C.c_size_t, ci],
         "xgc_download_attr": [vp, ci, C.c_char_p, vp, C.c_size_t, ci, C.POINTER(C.c_size_t)],
@@ -178,6 +179,21 @@ class Handle:
         p = np.empty(K.NPARAM)
         self._ck(lib.xgc_get_params(self._h, r, _ptr(p, C.c_double)))
         return p
+
+    def get_params_all(self) -> np.ndarray:
+        p = np.empty((self.n_replicates, K.NPARAM))
+        self._ck(lib.xgc_get_params_all(self._h, _ptr(p, C.c_double)))
+        return p
+
+    def get_tables(self) -> np.ndarray:
+        t = np.empty(K.NTABLE)
+        self._ck(lib.xgc_get_tables(self._h, _ptr(t, C.c_double)))
+        return t
+
+    def get_control(self, r: int) -> np.ndarray:
+        c = np.empty(K.NCONTROL, dtype=np.int32)
+        self._ck(lib.xgc_get_control(self._h, r, _ptr(c, C.c_int32)))
+        return c
 
     def set_control(self, c: np.ndarray, r: int = -1):
         c = np.ascontiguousarray(c, dtype=np.int32)

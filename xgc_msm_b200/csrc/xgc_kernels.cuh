@@ -29,10 +29,11 @@ __device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
 __device__ __forceinline__ short4 na4() { return make_short4(-1, -1, -1, -1); }
 
 // k_derive: per-replicate tables derived from the parameters (run whenever parameters change)
-__global__ void k_derive(const __grid_constant__ Dev g, double* pois, double* inv_ntx) {
+__global__ void k_derive(const __grid_constant__ Dev g, double* pois, double* inv_ntx, unsigned* pstat /*[R][4] parameter-derived status bits*/) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.R * 4) return;
   int r = t >> 2, w = t & 3;
+  pstat[t] = 0u;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   inv_ntx[t] = w < 3 ? 1.0 / P[XGC_P_gc_ntx_int + w] : 0.0;          // IEEE division, same bits as the oracle's 1.0 / p
   double mu = w == 0 ? P[XGC_P_kiss_rate_main] : w == 1 ? P[XGC_P_kiss_rate_casl] : w == 2 ? P[XGC_P_rim_rate_main] : P[XGC_P_rim_rate_casl];
@@ -41,6 +42,7 @@ __global__ void k_derive(const __grid_constant__ Dev g, double* pois, double* in
   double pr = xgc_exp(-mu), cdf = pr;
   tab[0] = cdf;
   for (int k = 1; k <= XGC_MAX_ACTS; ++k) { pr = xgc_pois_next(pr, mu, k); cdf = cdf + pr; tab[k] = cdf; }
+  if (1.0 - cdf > XGC_TRUNC_TOL) pstat[t] = XGC_ST_RATE_TRUNCATED;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

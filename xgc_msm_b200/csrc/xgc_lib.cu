@@ -33,10 +33,11 @@ struct xgc_handle {
   std::string err;
   uint64_t launches = 0;
   int last_at = -1;
+  int compacted_at = -1;               // last week after which the slots were compacted
   HostRep cache;
   double* d_inj = nullptr; size_t d_inj_cap = 0;
   void* d_cscratch = nullptr;   // 16 B per slot, large-replicate compaction only
-  int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr; double* d_inv_ntx = nullptr;
+  unsigned* d_pstat = nullptr; int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr; double* d_inv_ntx = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
   // xgc_run drives the replicates as TWO concurrent lanes (halves of the replicate range, each with its own streams and
@@ -44,6 +45,7 @@ struct xgc_handle {
   // issue slots and tails the first leaves idle (measured -8 % per week).  Lane 0 lives on the handle's own streams.
   int n_lanes = 2;                        // XGC_LANES=1: one lane
   const Dev* gl = nullptr;                // Dev of the lane being enqueued (nullptr: the whole handle)
+  Dev lane_dev[2];                        // per-lane views of g (kept on the handle: gl never points at a dead stack frame)
   cudaStream_t lane_main = nullptr, lane_side = nullptr;      // streams the enqueue helpers use (lane 0: stream / stream2)
   cudaEvent_t* lane_fork = nullptr; cudaEvent_t* lane_join = nullptr;
   cudaStream_t l1_stream = nullptr, l1_stream2 = nullptr;
@@ -173,9 +175,12 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   for (int l = 0; l < 3; ++l) { g.e_cap[l] = std::max(cfg->e_cap[l], 1); g.e_off[l] = eo; eo += ((size_t)g.e_cap[l] + 31) & ~(size_t)31; }
   g.e_stride = eo;
   size_t NA = h->n_agent(); int rc = 0;
-  rc |= dalloc(h, &g.core, NA); rc |= dalloc(h, &g.aux, NA);
-  rc |= dalloc(h, &g.gck_a, NA); rc |= dalloc(h, &g.gck_b, NA); rc |= dalloc(h, &g.gck_d, NA);
-  rc |= dalloc(h, &g.hck_a, NA); rc |= dalloc(h, &g.hck_b, NA); rc |= dalloc(h, &g.tck, NA); rc |= dalloc(h, &g.arr_t, NA);
+  // n_cap is a multiple of 128 but the agent passes load whole 256-slot tiles (the first tile of a CTA and the next tile
+  // of the register double buffer are loaded before the bounds check): every agent plane carries one tile of padding
+  const size_t NAP = NA + TPB;
+  rc |= dalloc(h, &g.core, NAP); rc |= dalloc(h, &g.aux, NAP);
+  rc |= dalloc(h, &g.gck_a, NAP); rc |= dalloc(h, &g.gck_b, NAP); rc |= dalloc(h, &g.gck_d, NAP);
+  rc |= dalloc(h, &g.hck_a, NAP); rc |= dalloc(h, &g.hck_b, NAP); rc |= dalloc(h, &g.tck, NAP); rc |= dalloc(h, &g.arr_t, NAP);
   rc |= dalloc(h, &g.alive, NA / 32); rc |= dalloc(h, &g.pos2slot, NA);
   if (g.n_cap > 32768) { uint4* cs = nullptr; rc |= dalloc(h, &cs, NA); h->d_cscratch = cs; }     // parallel slot compaction, 16 B per slot
   rc |= dalloc(h, &g.edge, (size_t)g.R * g.e_stride);
@@ -189,7 +194,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
   g.lb_tiles = (std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2])) + 1023) / 1024;
   rc |= dalloc(h, &g.lb_status, (size_t)g.R * 3 * g.lb_tiles); rc |= dalloc(h, &g.lb_ticket, (size_t)g.R * 3);
-  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1)); rc |= dalloc(h, &h->d_inv_ntx, (size_t)g.R * 4);
+  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1)); rc |= dalloc(h, &h->d_inv_ntx, (size_t)g.R * 4); rc |= dalloc(h, &h->d_pstat, (size_t)g.R * 4);
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
   g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat; g.pois = h->d_pois; g.inv_ntx = h->d_inv_ntx;
@@ -232,9 +237,14 @@ extern "C" int xgc_stream_ptr(xgc_handle* h, void** s) { *s = (void*)h->stream; 
 // --------------------------------------------------------------------------------------------------------------------
 // configuration
 // --------------------------------------------------------------------------------------------------------------------
+static void drop_graphs(xgc_handle* h) {            // kernel arguments baked into the captured week graphs changed
+  if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }
+  if (h->l1_graph) { cudaGraphExecDestroy(h->l1_graph); h->l1_graph = nullptr; }
+  h->lanes_captured = 0;
+}
 static int derive(xgc_handle* h) {       // per-replicate tables that depend on the parameters
   int n = h->g.R * 4;
-  k_derive<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_pois, h->d_inv_ntx);
+  k_derive<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_pois, h->d_inv_ntx, h->d_pstat);
   CU(h, cudaGetLastError());
   CU(h, cudaStreamSynchronize(h->stream));
   return 0;
@@ -243,8 +253,11 @@ extern "C" int xgc_set_params(xgc_handle* h, int r, const double* p) {
   CU(h, cudaSetDevice(h->cfg.device));
   if (r >= h->cfg.n_replicates) FAIL(h, 2, "replicate out of range");
   CU(h, cudaStreamSynchronize(h->stream));
-  for (int k = r < 0 ? 0 : r; k < (r < 0 ? h->cfg.n_replicates : r + 1); ++k)
-    CU(h, cudaMemcpy((double*)h->g.params + (size_t)k * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM, cudaMemcpyHostToDevice));
+  if (r < 0) {                           // every replicate: one host-side replication, one copy
+    std::vector<double> all((size_t)h->cfg.n_replicates * XGC_NPARAM);
+    for (int k = 0; k < h->cfg.n_replicates; ++k) memcpy(all.data() + (size_t)k * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM);
+    CU(h, cudaMemcpy((double*)h->g.params, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
+  } else CU(h, cudaMemcpy((double*)h->g.params + (size_t)r * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM, cudaMemcpyHostToDevice));
   return derive(h);
 }
 extern "C" int xgc_set_params_all(xgc_handle* h, const double* p /*[R][XGC_NPARAM]*/) {
@@ -262,16 +275,33 @@ extern "C" int xgc_set_control(xgc_handle* h, int r, const int32_t* c) {
   CU(h, cudaSetDevice(h->cfg.device));
   if (r >= h->cfg.n_replicates) FAIL(h, 2, "replicate out of range");
   CU(h, cudaStreamSynchronize(h->stream));
-  for (int k = r < 0 ? 0 : r; k < (r < 0 ? h->cfg.n_replicates : r + 1); ++k)
-    CU(h, cudaMemcpy((int*)h->g.control + (size_t)k * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyHostToDevice));
+  if (r < 0) {
+    std::vector<int32_t> all((size_t)h->cfg.n_replicates * XGC_NCONTROL);
+    for (int k = 0; k < h->cfg.n_replicates; ++k) memcpy(all.data() + (size_t)k * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL);
+    CU(h, cudaMemcpy((int*)h->g.control, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  } else CU(h, cudaMemcpy((int*)h->g.control + (size_t)r * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int xgc_get_tables(xgc_handle* h, double* t) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(t, h->g.tables, sizeof(double) * XGC_NTABLE, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int xgc_get_params_all(xgc_handle* h, double* p) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(p, h->g.params, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int xgc_get_control(xgc_handle* h, int r, int32_t* c) {
+  CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(c, h->g.control + (size_t)r * XGC_NCONTROL, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyDeviceToHost));
   return 0;
 }
 extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
   for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];       // same IEEE division the oracle performs
-  if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }   // kernel arguments changed
-  h->lanes_captured = 0;
+  drop_graphs(h);
   return 0;
 }
 
@@ -637,6 +667,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   return 0;
 }
 
+static int compact_impl(xgc_handle* h);
 extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* inj) {
   if (at < 1 || at >= h->cfg.t_cap) FAIL(h, 2, "at = %d outside [1, t_cap = %d)", at, h->cfg.t_cap);
   if (at > 32766) FAIL(h, 2, "at = %d exceeds the 16-bit week clocks", at);
@@ -647,6 +678,13 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   if (at != h->last_at) h->acts_valid = false;          // a new week: last week's act counts are history
   if (mask & XGC_M_ACTS) h->acts_valid = true;
   int zero_row = at != h->last_at; h->last_at = at;
+  // slot compaction on the same schedule as xgc_run (after every week that is a multiple of compact_every), so that the
+  // step-by-step boundary -- module(dat, at) calls, the host-network loop, the R shim -- never runs out of slots on a
+  // reference-length burn-in.  Results do not depend on it: draws are keyed by uid, positions are preserved.
+  if (zero_row && at >= 2 && (at - 1) % h->cfg.compact_every == 0 && h->compacted_at != at - 1) {
+    rc = compact_impl(h); if (rc) return rc;
+    h->compacted_at = at - 1;
+  }
   rc = enqueue_week(h, at, mask, j, zero_row); if (rc) return rc;
   CU(h, cudaGetLastError());
   if (inj && inj->u) CU(h, cudaStreamSynchronize(h->stream));     // caller may free the table after return
@@ -683,7 +721,9 @@ static int compact_impl(xgc_handle* h) {
 extern "C" int xgc_compact(xgc_handle* h) {
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
-  return compact_impl(h);
+  rc = compact_impl(h);
+  if (!rc) h->compacted_at = h->last_at;
+  return rc;
 }
 
 extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
@@ -693,7 +733,7 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   CU(h, cudaSetDevice(h->cfg.device));
   Inj j = make_inj(h, nullptr, nullptr);
   const int L = h->n_lanes, R = h->cfg.n_replicates;
-  Dev gl[2]; gl[0] = h->g; gl[1] = h->g;
+  Dev* gl = h->lane_dev; gl[0] = h->g; gl[1] = h->g;
   if (L == 2) { gl[0].r0 = 0; gl[0].R = R / 2; gl[1].r0 = R / 2; gl[1].R = R - R / 2; }
   auto use_lane = [&](int k) {             // point the enqueue helpers at lane k's Dev, streams and events
     h->gl = &gl[k];
@@ -703,13 +743,12 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   };
   auto use_whole = [&]() { h->gl = nullptr; h->lane_main = h->stream; h->lane_side = h->stream2; h->lane_fork = h->ev_fork; h->lane_join = h->ev_join; h->cur = h->stream; };
   if (h->lanes_captured != L) {            // capture one week (week = previous + 1) per lane once, replay it for every later week
-    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }
-    if (h->l1_graph) { cudaGraphExecDestroy(h->l1_graph); h->l1_graph = nullptr; }
+    drop_graphs(h);
     for (int k = 0; k < L; ++k) {
       cudaGraph_t graph;
       uint64_t l0 = h->launches;
       use_lane(k);
-      CU(h, cudaStreamBeginCapture(h->lane_main, cudaStreamCaptureModeThreadLocal));
+      { cudaError_t eb = cudaStreamBeginCapture(h->lane_main, cudaStreamCaptureModeThreadLocal); if (eb != cudaSuccess) { use_whole(); CU(h, eb); } }
       h->capturing = true;
       enqueue_week(h, -1, XGC_M_ALL, j, 1);
       h->capturing = false;
@@ -740,6 +779,7 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
       for (int k = 0; k < L; ++k) { use_lane(k); rc = compact_impl(h); if (rc) break; }
       use_whole();
       if (rc) return rc;
+      h->compacted_at = at;
     }
   }
   if (L == 2) {                            // ... and the handle's stream continues after lane 1
@@ -779,7 +819,8 @@ extern "C" int xgc_num_agents_all(xgc_handle* h, int32_t* out /*[R]*/) {
 extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   Rep rp; CU(h, cudaMemcpy(&rp, h->g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));
-  *status = rp.status; return 0;
+  unsigned ps[4]; CU(h, cudaMemcpy(ps, h->d_pstat + (size_t)r * 4, sizeof ps, cudaMemcpyDeviceToHost));
+  *status = rp.status | ps[0] | ps[1] | ps[2] | ps[3]; return 0;
 }
 
 static int materialise_actcounts(xgc_handle* h, int r, const Inj& j) {      // kissing / rimming counts are lazy on the hot path
@@ -1017,10 +1058,10 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
-  h->last_at = -1; h->acts_valid = false; h->rank_fresh = false;
+  h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false;
   { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
-    if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; } h->lanes_captured = 0; }
+    drop_graphs(h); }
   return derive(h);
 }
 extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
@@ -1042,7 +1083,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   acc(cp(b.rep + dr, a.rep + sr, sizeof(Rep))); acc(cp((int*)b.at_ptr + dr, a.at_ptr + sr, 4));
   acc(cp(b.counters + (size_t)dr * b.t_cap * XGC_NCOUNTER, a.counters + (size_t)sr * a.t_cap * XGC_NCOUNTER, (size_t)a.t_cap * XGC_NCOUNTER * 4));
   if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
-  dst->last_at = -1;
+  dst->last_at = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
   return 0;
 }
 

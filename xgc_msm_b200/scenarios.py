@@ -27,15 +27,17 @@ SITES = ("gc", "rgc", "ugc", "pgc")
 
 def fork_arms(burnin: Handle, seed: int = 1971, device: int = 0) -> Dict[str, Handle]:
     """One handle per arm, every replicate a device-to-device copy of the burn-in replicate (xgc_fork); arm k draws from
-    its own Philox key (seed + 1 + k), like the reference's separate scenario streams."""
-    base_ctl = np.zeros(K.NCONTROL, dtype=np.int32)
+    its own Philox key (seed + 1 + k), like the reference's separate scenario streams.  Every arm continues with the
+    burn-in's OWN tables (netstats / epistats stand-ins) and per-replicate parameters, read back from the burn-in handle."""
+    tables, params = burnin.get_tables(), burnin.get_params_all()
     arms = {}
     for k, (name, (proto, kiss)) in enumerate(ARMS.items()):
         h = Handle(burnin.n_replicates, burnin.n_cap, burnin.e_cap, burnin.t_cap, seed=seed + 1 + k, device=device,
                    replicate_offset=burnin.cfg.replicate_offset)
+        h.set_tables(tables)
         for r in range(burnin.n_replicates):
             h.fork_from(burnin, r, r)
-            h.set_params(burnin.get_params(r), r)
+        h.set_params(params)
         arms[name] = h
     return arms
 
@@ -43,7 +45,6 @@ def fork_arms(burnin: Handle, seed: int = 1971, device: int = 0) -> Dict[str, Ha
 def run_screening_grid(burnin: Handle, at_burnin_end: int, weeks: int, control_base: P.Control, seed: int = 1971,
                        device: int = 0) -> Dict[str, Dict[str, np.ndarray]]:
     """Continue every arm for `weeks` weeks and return per-arm, per-replicate summaries plus NIA / PIA / NTIA vs base."""
-    from . import synth
     burnin.sync()
     arms = fork_arms(burnin, seed, device)
     t0, t1 = at_burnin_end + 1, at_burnin_end + weeks
@@ -54,7 +55,6 @@ def run_screening_grid(burnin: Handle, at_burnin_end: int, weeks: int, control_b
         flags = control_base.flags.copy()
         flags[P.CONTROL_INDEX["stiScreeningProtocol"]] = {"base": 0, "symptomatic": 1, "cdc": 2, "universal": 3}[proto]
         flags[P.CONTROL_INDEX["cdcExposureSite_Kissing"]] = int(kiss)
-        h.set_tables(synth.make_tables())
         h.set_control(flags)
         h.run(t0, t1)
         h.sync()
