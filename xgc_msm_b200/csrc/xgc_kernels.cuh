@@ -1532,6 +1532,7 @@ __global__ void __launch_bounds__(TPB) k_compact_edges(const __grid_constant__ D
 // k_actcounts: materialise the lazily evaluated kissing / rimming counts of one replicate into the edge records
 // (xgc_get_actcounts / dat$temp$el parity); the hot path never needs them for non-discordant edges.
 template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* out /*[3][emax]: ki | ri << 8*/, int emax) {
+  pdl_prologue();
   int l = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= g.rep[r].ne[l]) return;
   int at = g.at_ptr[r];
@@ -1550,6 +1551,7 @@ template <bool INJ> __global__ void k_actcounts(const __grid_constant__ Dev g, c
 // k_actlist: materialise dat$temp$al for one replicate (debug / parity of condoms_msm + position_msm)
 template <bool INJ> __global__ void k_actlist(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int r, int* al, int cap, int* n_out) {
   // single thread: tiny test-only kernel, rows must come out in (layer, edge, type, k) order
+  pdl_prologue();
   if (blockIdx.x || threadIdx.x) return;
   const Rep* rp = g.rep + r;
   int at = g.at_ptr[r], n = 0;

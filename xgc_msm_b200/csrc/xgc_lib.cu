@@ -1091,6 +1091,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
 // bulk edge-list upload for the weekly host<->device contract (host network resimulation)
 // --------------------------------------------------------------------------------------------------------------------
 __global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el /*[R][2][stride]*/, const int* ne /*[R]*/, const int* start /*[R][stride] or null*/, int stride) {
+  pdl_prologue();         // launched with programmatic stream serialization right after k_rank: must wait for pos2slot
   int r = blockIdx.y + g.r0, e = blockIdx.x * blockDim.x + threadIdx.x;
   int n = ne[r], cap = g.e_cap[l] < stride ? g.e_cap[l] : stride;
   if (e == 0) { g.rep[r].ne[l] = n < cap ? n : cap; if (n > cap) atomicOr(&g.rep[r].status, XGC_ST_EDGE_OVERFLOW); }
