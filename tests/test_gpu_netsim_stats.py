@@ -107,10 +107,11 @@ def test_screening_scenario_grid():
 
 
 def test_full_size_sweep_properties():
-    """BASELINE configs[1] at full size (1000 replicates x 10k agents, LHS parameters): the oracle cannot follow at this
-    size, so the device path is checked through size-independent properties -- accounting identities of the weekly
-    tallies, run-mode idempotence (CUDA-graph xgc_run == week-by-week xgc_step, bit for bit), and shard invariance
-    (two 500-replicate handles with replicate offsets == the 1000-replicate handle)."""
+    """BASELINE configs[1] at full size, ALL 1000 replicates x 10k agents with LHS parameters: size-independent
+    properties -- accounting identities of the weekly tallies, run-mode idempotence (CUDA-graph xgc_run == week-by-week
+    xgc_step, bit for bit), and shard invariance (two 500-replicate handles with replicate offsets == the 1000-replicate
+    handle).  Bit-exact parity against the oracle on sampled replicates of this same sweep (104 weeks, 10k and 20k
+    agents, run-graph and host-network paths) is tests/test_gpu_fullsize_parity.py."""
     from xgc_msm_b200 import workload as W
     from xgc_msm_b200.abi import Handle, K
     R, weeks = 1000, 12
