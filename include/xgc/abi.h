@@ -268,7 +268,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_K_DEP_GEN) X(XGC_K_DEP_AIDS) X(XGC_K_NNEW) X(XGC_K_HIVTESTS) X(XGC_K_NEDGES) X(XGC_K_NACTS) \
   X(XGC_TG_NUM) X(XGC_TG_I_PREV) X(XGC_TG_IR100_POP) X(XGC_TG_HIVDX_RACE) X(XGC_TG_HIVDX_AGE) X(XGC_TG_VLS_RACE) X(XGC_TG_VLS_AGE) \
   X(XGC_TG_PREPCOV_RACE) X(XGC_TG_PROP_TESTED) X(XGC_TG_PROB_POS) X(XGC_TG_PREV_GC) X(XGC_TG_IR100_GC) \
-  X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_ST_RATE_TRUNCATED) X(XGC_F64) X(XGC_I32)
+  X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_ST_RATE_TRUNCATED) X(XGC_MODE_STRICT) X(XGC_MODE_FAST) X(XGC_F64) X(XGC_I32)
 int  xgc_constant(const char* name, int64_t* value);          /* 0 if found */
 int  xgc_param_index(const char* name, int* offset, int* count);   /* params.def lookup */
 int  xgc_inject_stream_width(int stream);                       /* = xgc_stream_width() for bindings that cannot include this header */
@@ -324,6 +324,21 @@ int  xgc_get_actcounts(xgc_handle* h, int r, int layer, int32_t* counts /*[E,4] 
 /* materialise the act list of week `at` (dat$temp$al): rows (layer, edge index, act type 0 ai/1 oi/2 kiss/3 rim,
  * act index, uai (1 = condomless; anal only), p1_active (1 = p1 insertive / rimmer)).  Column-major int32 [A,6]. */
 int  xgc_get_actlist  (xgc_handle* h, int r, int at, int32_t* al, int cap, int* n_acts, const xgc_inject* inj);
+
+/* Arithmetic / sampling contract of NATIVE-draw runs (north_star: bit-exact with injected draws, statistically
+ * indistinguishable targets with native RNG).
+ *   XGC_MODE_STRICT (default): one indexed Philox draw per decision, fp64 in a fixed operation order -- bit-identical to
+ *                              the CPU oracle also with native draws; the only mode injected draws ever use.
+ *   XGC_MODE_FAST            : replicate-resident kernel (one CTA per replicate, agent state staged in shared memory for
+ *                              up to compact_every weeks), gap-sampled rare events, fp32 probabilities.  Same modules,
+ *                              same state machine, same outputs; trajectories differ from STRICT draw by draw and are
+ *                              equal in distribution.  xgc_step uses it for the module groups a host-network loop calls
+ *                              (all modules; aging..hivvl [+ resim_nets]; [resim_nets +] acts..prev) and falls back to
+ *                              the strict kernels for any other module mask and whenever draws are injected.
+ * xgc_set_mode fails (non-zero) when a replicate of this handle does not fit one SM's shared memory. */
+enum { XGC_MODE_STRICT = 0, XGC_MODE_FAST = 1 };
+int  xgc_set_mode(xgc_handle* h, int mode);
+int  xgc_get_mode(xgc_handle* h, int* mode);
 
 /* the step: runs the modules selected by module_mask for week `at` on every replicate, in reference order.
  * inj = NULL -> native Philox; otherwise draws come from the injected table. */

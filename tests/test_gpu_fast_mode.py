@@ -1,0 +1,152 @@
+"""XGC_MODE_FAST: the replicate-resident native-draw path (xgc_fast.cu).
+
+north_star's contract for native RNG is statistical: prevalence / incidence / screening targets across >= 1000 replicates
+must be indistinguishable from the reference arithmetic.  The fast path changes the sampling scheme (gap-sampled rare
+events, fp32 probabilities), so it is gated here (1) structurally -- an independent recount of every prevalence tally from
+the downloaded attribute vectors, accounting identities, state-machine invariants, run == step-group equivalence bit for
+bit -- and (2) statistically against the CPU ORACLE (strict fp64 arithmetic, different seeds): two-sample KS at
+alpha = 0.001 per target and |difference of means| <= 5 standard errors, on every target that is defined.
+"""
+import numpy as np
+import pytest
+
+from common import K, P, load_handle, make_case
+
+pytestmark = pytest.mark.gpu
+SEED = 1971
+
+
+def _recount(h, r):
+    """Prevalence tallies recomputed on the host from the attribute vectors (what prevalence_msm counts)."""
+    a = {k: h.download_attr(r, k) for k in ("race", "age.grp", "age", "status", "diag.status", "vl", "prepElig", "prepStat", "rGC", "uGC", "pGC")}
+    cell = ((a["race"] - 1) * 5 + (a["age.grp"] - 1)).astype(int)
+    G = K.NCELL
+    out = np.zeros(K.NCOUNTER, np.int64)
+
+    def put(group, pred):
+        out[group * G:(group + 1) * G] = np.bincount(cell[pred], minlength=G)
+
+    one = np.ones(cell.size, bool)
+    put(K.K_NUM, one); put(K.K_INUM, a["status"] == 1); put(K.K_INUM_DX, a["diag.status"] == 1)
+    put(K.K_VSUPP, (a["diag.status"] == 1) & (a["vl"] <= 2.301029995663981))
+    put(K.K_PREPELIG, a["prepElig"] == 1); put(K.K_PREPCURR, a["prepStat"] == 1)
+    put(K.K_INUM_GC, (a["rGC"] == 1) | (a["uGC"] == 1) | (a["pGC"] == 1))
+    put(K.K_INUM_RGC, a["rGC"] == 1); put(K.K_INUM_UGC, a["uGC"] == 1); put(K.K_INUM_PGC, a["pGC"] == 1)
+    return out, a
+
+
+@pytest.mark.parametrize("recov,protocol", [("geom", "base"), ("pois", "cdc"), ("geom", "universal")])
+def test_fast_mode_structure_and_recount(recov, protocol):
+    n, T, R = 3000, 40, 4
+    cases = [make_case(n, 700 + r, midcourse=True, gcUntreatedRecovDist=recov, stiScreeningProtocol=protocol, network_mode="surrogate") for r in range(R)]
+    h = load_handle(cases, SEED, t_cap=T + 4, compact_every=16)
+    h.set_mode("fast")
+    assert h.get_mode() == "fast"
+    h.run(2, T)
+    G = K.NCELL
+    prev_groups = [K.K_NUM, K.K_INUM, K.K_INUM_DX, K.K_VSUPP, K.K_PREPELIG, K.K_PREPCURR, K.K_INUM_GC, K.K_INUM_RGC, K.K_INUM_UGC, K.K_INUM_PGC]
+    for r in range(R):
+        assert h.status(r) == 0
+        c = h.counters(r, 2, T).astype(np.int64)
+        rec, a = _recount(h, r)
+        for gidx in prev_groups:
+            assert np.array_equal(c[-1, gidx * G:(gidx + 1) * G], rec[gidx * G:(gidx + 1) * G]), f"replicate {r}: tally group {gidx} != recount of the attributes"
+        # attribute consistency of the state machine
+        age = a["age"]
+        # the fast path ages on a birth week quantised to 1/8 week: the group may switch one week off the exact birthday
+        grp = 1 + (age >= 25) + (age >= 35) + (age >= 45) + (age >= 55)
+        near = np.min(np.abs(age[:, None] - np.array([25.0, 35.0, 45.0, 55.0])[None, :]), axis=1) < 0.02
+        assert np.array_equal(a["age.grp"][~near], grp[~near]) and near.mean() < 0.01
+        for site in ("rGC", "uGC", "pGC"):
+            st, it, tx, tt, sy = (h.download_attr(r, site + s) for s in ("", ".infTime", ".tx", ".txTime", ".sympt"))
+            assert np.all((st == 1) == (it != -1)) and np.all(tx <= st) and np.all(sy <= st) and np.all((tx == 1) == (tt != -1))
+            assert np.all(it[st == 1] <= T)
+        stt, inf, diag, dt, stage, txs = (h.download_attr(r, k) for k in ("status", "inf.time", "diag.status", "diag.time", "stage", "tx.status"))
+        assert np.all((stt == 1) == (inf != -1)) and np.all(diag <= stt) and np.all(txs <= diag) and np.all((stage > 0) == (stt == 1))
+        assert np.all(h.download_attr(r, "prepStat") <= 1 - diag)
+        # edges: living endpoints (positions), tail < head, act counts present
+        nliv = h.num_agents(r)
+        for l in range(3):
+            el, st0 = h.get_edgelist(r, l)
+            assert el.shape[0] == c[-1, K.K_NEDGES + l] and np.all(el[:, 0] < el[:, 1]) and el.min() >= 1 and el.max() <= nliv
+            assert np.all(st0 <= T)
+        # accounting identities over the weeks
+        num = c[:, K.K_NUM * G:(K.K_NUM + 1) * G].sum(1)
+        dn = num[1:] - num[:-1]
+        assert np.array_equal(dn, c[1:, K.K_NNEW] - c[1:, K.K_DEP_GEN] - c[1:, K.K_DEP_AIDS])
+        incid_site = sum(c[:, (K.K_INCID_RGC + s) * G:(K.K_INCID_RGC + s + 1) * G].sum(1) for s in range(3))
+        assert np.array_equal(c[:, K.K_PATH:K.K_PATH + K.NPATH].sum(1), incid_site)
+        assert np.all(c[:, K.K_POS:K.K_POS + 3] <= c[:, K.K_TESTED:K.K_TESTED + 3]) and np.all(c[:, K.K_VISITS_SYMPT] <= c[:, K.K_VISITS])
+        tot = c.sum(0)
+        fired = [tot[K.K_DEP_GEN], tot[K.K_NNEW], tot[K.K_HIVTESTS], tot[K.K_VISITS], tot[K.K_NACTS], tot[K.K_NACTS + 1],
+                 tot[K.K_INCID_HIV * G:(K.K_INCID_HIV + 1) * G].sum(), tot[K.K_TXSTART:K.K_TXSTART + 3].min(), tot[K.K_PATH:K.K_PATH + K.NPATH].min()]
+        assert all(v > 0 for v in fired), fired
+    h.close()
+
+
+def test_fast_mode_step_groups_equal_run():
+    """The weekly host-network call pattern (aging..hivvl, then resim_nets + acts..prev as a second call, state written
+    back to HBM and re-staged in between) gives bit for bit the trajectory of the multi-week resident run."""
+    n, T, R = 2500, 24, 3
+    cases = [make_case(n, 40 + r, midcourse=True, network_mode="surrogate", stiScreeningProtocol="cdc") for r in range(R)]
+    pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
+    ha = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); ha.set_mode("fast")
+    hb = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hb.set_mode("fast")
+    hc = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hc.set_mode("fast")
+    ha.run(2, T)
+    for at in range(2, T + 1):
+        hb.step(at, pre)
+        hb.step(at, K.M_ALL & ~pre)
+        hc.step(at)
+    for r in range(R):
+        ca = ha.counters(r, 2, T)
+        assert np.array_equal(ca, hb.counters(r, 2, T)), "step groups != resident run"
+        assert np.array_equal(ca, hc.counters(r, 2, T)), "weekly full steps != resident run"
+        for name in ("age", "rGC", "uGC.infTime", "status", "vl", "prepStat", "last.screen", "prep.ind.last", "sti.expo"):
+            assert np.array_equal(ha.download_attr(r, name), hb.download_attr(r, name)), name
+    # and the fast path is a different sampler than the strict one, not a copy of it
+    hs = load_handle(cases, SEED, t_cap=T + 4, compact_every=8)
+    hs.run(2, T)
+    assert not np.array_equal(hs.counters(0, 2, T), ha.counters(0, 2, T))
+    for x in (ha, hb, hc, hs):
+        x.close()
+
+
+def _ks_report(g, c, names, keys, R):
+    from scipy.stats import ks_2samp
+    report = {}
+    for k in keys:
+        j = names.index(k)
+        gv, cv = g[:, j], c[:, j]
+        if not (np.isfinite(gv).all() and np.isfinite(cv).all()) or (gv.std() == 0 and cv.std() == 0):
+            continue
+        p = ks_2samp(gv, cv).pvalue
+        se = np.sqrt(gv.var(ddof=1) / R + cv.var(ddof=1) / R)
+        z = abs(gv.mean() - cv.mean()) / max(se, 1e-300)
+        report[k] = (round(float(p), 4), round(float(z), 2), round(float(gv.mean()), 5), round(float(cv.mean()), 5))
+    return report
+
+
+@pytest.mark.parametrize("R,N,WEEKS,TAIL", [(1000, 1200, 60, 26), (256, 10000, 156, 52)])
+def test_fast_mode_statistically_equivalent_to_oracle(R, N, WEEKS, TAIL):
+    """north_star test 2 for the fast path: R fast-mode GPU replicates vs R oracle replicates (strict fp64 arithmetic,
+    another Philox seed), same parameters and starting population: KS p > 0.001 and |z| < 5 on every defined target."""
+    from oracle import cpu_bench
+    from xgc_msm_b200 import targets as T, workload
+    from xgc_msm_b200.abi import Handle
+    kw = dict(lhs=False, n_distinct=1)
+    spec = workload.SweepSpec(n_agents=N, seed=SEED, **kw)
+    h = Handle(R, spec.n_cap, spec.e_cap, WEEKS + 3, seed=SEED)
+    workload.load_sweep(h, spec)
+    h.set_mode("fast")
+    h.run(2, WEEKS + 1)
+    g = h.targets(WEEKS + 1, TAIL)
+    assert int(np.bitwise_or.reduce([h.status(r) for r in range(0, R, max(R // 32, 1))])) == 0
+    c = cpu_bench.run_targets(N, R, WEEKS, TAIL, SEED, K.M_ALL, kw, philox_seed=424242)
+    names = T.device_target_names()
+    rep = _ks_report(g, c, names, names, R)
+    print("target: (KS p, |z|, fast mean, oracle mean)", rep)
+    assert len(rep) >= 30, sorted(rep)
+    bad = {k: v for k, v in rep.items() if not (v[0] > 1e-3 and v[1] < 5.0)}
+    assert not bad, bad
+    h.close()

@@ -42,6 +42,7 @@ def _load() -> C.CDLL:
         "xgc_create": [C.POINTER(xgc_config), C.POINTER(vp)], "xgc_destroy": [vp], "xgc_abi_version": [],
         "xgc_set_params": [vp, ci, pd], "xgc_get_params": [vp, ci, pd], "xgc_set_params_all": [vp, pd],
         "xgc_set_control": [vp, ci, pi], "xgc_set_tables": [vp, pd],
+        "xgc_set_mode": [vp, ci], "xgc_get_mode": [vp, pi],
         "xgc_get_tables": [vp, pd], "xgc_get_params_all": [vp, pd], "xgc_get_control": [vp, ci, pi],
         "xgc_set_population": [vp, ci, ci, ci], "xgc_num_agents": [vp, ci, pi],
         "xgc_upload_attr": [vp, ci, C.c_char_p, vp, C.c_size_t, ci],
@@ -179,6 +180,16 @@ class Handle:
         p = np.empty(K.NPARAM)
         self._ck(lib.xgc_get_params(self._h, r, _ptr(p, C.c_double)))
         return p
+
+    def set_mode(self, mode):
+        """'strict' (default; bit-exact contract) or 'fast' (replicate-resident kernel, native draws only)."""
+        m = {"strict": K.MODE_STRICT, "fast": K.MODE_FAST}.get(mode, mode)
+        self._ck(lib.xgc_set_mode(self._h, int(m)))
+
+    def get_mode(self) -> str:
+        m = C.c_int32()
+        self._ck(lib.xgc_get_mode(self._h, C.byref(m)))
+        return "fast" if m.value == K.MODE_FAST else "strict"
 
     def get_params_all(self) -> np.ndarray:
         p = np.empty((self.n_replicates, K.NPARAM))

@@ -13,6 +13,7 @@
 #include <vector>
 #include "xgc/abi.h"
 #include "xgc_kernels.cuh"
+#include "xgc_fast.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -34,6 +35,9 @@ struct xgc_handle {
   uint64_t launches = 0;
   int last_at = -1;
   int compacted_at = -1;               // last week after which the slots were compacted
+  int mode = XGC_MODE_STRICT;          // arithmetic / sampling contract of native-draw runs (abi.h)
+  size_t fast_smem = 0;                // dynamic shared memory of k_week_fast for this geometry (0: does not fit)
+  bool fast_dirty = true;              // the spare core bits the fast path reads (birth week, ins.quot) need recomputing
   HostRep cache;
   double* d_inj = nullptr; size_t d_inj_cap = 0;
   void* d_cscratch = nullptr;   // 16 B per slot, large-replicate compaction only
@@ -174,6 +178,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   size_t eo = 0;
   for (int l = 0; l < 3; ++l) { g.e_cap[l] = std::max(cfg->e_cap[l], 1); g.e_off[l] = eo; eo += ((size_t)g.e_cap[l] + 31) & ~(size_t)31; }
   g.e_stride = eo;
+  h->fast_smem = xgc_fast_smem_bytes(g.n_cap, g.e_stride);
   size_t NA = h->n_agent(); int rc = 0;
   // n_cap is a multiple of 128 but the agent passes load whole 256-slot tiles (the first tile of a CTA and the next tile
   // of the register double buffer are loaded before the bounds check): every agent plane carries one tile of padding
@@ -446,7 +451,7 @@ extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemset(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap));
   CU(h, cudaMemcpy((int*)g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice));
-  h->last_at = -1; h->acts_valid = false;
+  h->last_at = -1; h->acts_valid = false; h->fast_dirty = true;
   return cache_flush(h);
 }
 extern "C" int xgc_num_agents(xgc_handle* h, int r, int* n) {
@@ -467,6 +472,7 @@ extern "C" int xgc_upload_attr(xgc_handle* h, int r, const char* name, const voi
     a->set(c, c.pos2slot[p], v);
   }
   if (!strcmp(name, "age")) c.rep.t_ref = c.rep.t_age;      // re-base the closed-form age clock
+  h->fast_dirty = true;
   if (!strcmp(name, "uid")) { unsigned mx = 0; for (size_t p = 0; p < n; ++p) mx = std::max(mx, c.core[c.pos2slot[p]].x + 1u); c.rep.next_uid = (int)mx; }
   c.dirty = true;
   return 0;
@@ -667,7 +673,36 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   return 0;
 }
 
+extern "C" int xgc_set_mode(xgc_handle* h, int mode) {
+  if (mode != XGC_MODE_STRICT && mode != XGC_MODE_FAST) FAIL(h, 2, "unknown mode %d", mode);
+  if (mode == XGC_MODE_FAST && h->fast_smem == 0)
+    FAIL(h, 10, "XGC_MODE_FAST needs a replicate (n_cap = %d slots, %zu edge records) to fit one SM's shared memory", h->cfg.n_cap, h->g.e_stride);
+  h->mode = mode;
+  return 0;
+}
+extern "C" int xgc_get_mode(xgc_handle* h, int* mode) { *mode = h->mode; return 0; }
+
 static int compact_impl(xgc_handle* h);
+// module mask -> phase groups of the replicate-resident kernel (0: not a group the fast path runs)
+static unsigned fast_phases(uint32_t mask) {
+  const uint32_t PREG = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_ARRIVAL | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
+  const uint32_t POSTG = XGC_M_ACTS | XGC_M_CONDOMS | XGC_M_POSITION | XGC_M_PREP | XGC_M_HIVTRANS | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_STITRANS | XGC_M_PREV;
+  if (mask == XGC_M_ALL) return XF_ALL;
+  if (mask == PREG) return XF_PRE | XF_PRUNE;
+  if (mask == (PREG | XGC_M_RESIM_NETS)) return XF_PRE | XF_PRUNE | XF_FORM;
+  if (mask == POSTG) return XF_POST;
+  if (mask == (POSTG | XGC_M_RESIM_NETS)) return XF_PRUNE | XF_FORM | XF_POST;
+  return 0;
+}
+static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32_t mask, int write_acts) {
+  if (h->fast_dirty) { CU(h, xgc_fast_prepare(h->g, h->stream)); h->fast_dirty = false; h->launches++; }
+  FastArgs a; a.at0 = at0; a.at1 = at1; a.phases = phases; a.mask = mask; a.write_acts = write_acts;
+  prof_begin(h, "k_week_fast");
+  cudaError_t e = xgc_fast_launch(h->g, a, h->fast_smem, h->stream);
+  prof_end(h); h->launches++;
+  CU(h, e);
+  return 0;
+}
 extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* inj) {
   if (at < 1 || at >= h->cfg.t_cap) FAIL(h, 2, "at = %d outside [1, t_cap = %d)", at, h->cfg.t_cap);
   if (at > 32766) FAIL(h, 2, "at = %d exceeds the 16-bit week clocks", at);
@@ -678,12 +713,19 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   if (at != h->last_at) h->acts_valid = false;          // a new week: last week's act counts are history
   if (mask & XGC_M_ACTS) h->acts_valid = true;
   int zero_row = at != h->last_at; h->last_at = at;
+  const unsigned fph = (h->mode == XGC_MODE_FAST && !(inj && inj->u)) ? fast_phases(mask) : 0u;
+  if (!fph && (mask & XGC_M_ARRIVAL)) h->fast_dirty = true;       // arrivals of the strict kernels carry no fast-path bits
   // slot compaction on the same schedule as xgc_run (after every week that is a multiple of compact_every), so that the
   // step-by-step boundary -- module(dat, at) calls, the host-network loop, the R shim -- never runs out of slots on a
   // reference-length burn-in.  Results do not depend on it: draws are keyed by uid, positions are preserved.
   if (zero_row && at >= 2 && (at - 1) % h->cfg.compact_every == 0 && h->compacted_at != at - 1) {
     rc = compact_impl(h); if (rc) return rc;
     h->compacted_at = at - 1;
+  }
+  if (fph) {
+    if (!(fph & XF_PRE) && zero_row) FAIL(h, 11, "fast mode: week %d must start with the aging..hivvl module group", at);
+    h->acts_valid = false;                                        // kissing / rimming counts are not materialised in fast mode
+    return fast_enqueue(h, at, at, fph, mask, 1);
   }
   rc = enqueue_week(h, at, mask, j, zero_row); if (rc) return rc;
   CU(h, cudaGetLastError());
@@ -731,6 +773,19 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   if (at1 > 32766) FAIL(h, 2, "at exceeds the 16-bit week clocks");
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
+  if (h->mode == XGC_MODE_FAST) {       // replicate-resident kernel: one launch per stretch of weeks between slot compactions
+    const int ce = h->cfg.compact_every;
+    for (int at = at0; at <= at1;) {
+      int seg = std::min(at1, ((at + ce - 1) / ce) * ce);
+      rc = fast_enqueue(h, at, seg, XF_ALL, XGC_M_ALL, seg == at1); if (rc) return rc;
+      if (seg % ce == 0) { rc = compact_impl(h); if (rc) return rc; h->compacted_at = seg; }
+      at = seg + 1;
+    }
+    h->last_at = at1; h->rank_fresh = false; h->acts_valid = false; memset(&h->last_inj, 0, sizeof(Inj));
+    CU(h, cudaGetLastError());
+    return 0;
+  }
+  h->fast_dirty = true;
   Inj j = make_inj(h, nullptr, nullptr);
   const int L = h->n_lanes, R = h->cfg.n_replicates;
   Dev* gl = h->lane_dev; gl[0] = h->g; gl[1] = h->g;
@@ -1058,7 +1113,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
-  h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false;
+  h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false; h->fast_dirty = true;
   { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
     drop_graphs(h); }
@@ -1084,6 +1139,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   acc(cp(b.counters + (size_t)dr * b.t_cap * XGC_NCOUNTER, a.counters + (size_t)sr * a.t_cap * XGC_NCOUNTER, (size_t)a.t_cap * XGC_NCOUNTER * 4));
   if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
   dst->last_at = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
+  if (src->fast_dirty) dst->fast_dirty = true;
   return 0;
 }
 
