@@ -150,6 +150,11 @@ __device__ __forceinline__ void gap_sample(uint2 key, unsigned at, unsigned stre
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
+// phase clocks (SM cycles summed over CTAs; thread 0 of each CTA): tools/time_modes.py --phases
+enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE_SAMPLE, PH_PRE_SCAN, PH_PRE_TEST, PH_PRE_HIV, PH_NET, PH_ACTS, PH_B_SCAN, PH_B_PREP, PH_B_GC, PH_TRANS_CLASSIFY,
+       PH_TRANS, PH_APPLY, PH_TALLY, PH_WRITEBACK, PH_N };
+__device__ unsigned long long g_fast_prof[PH_N];
+#define TICK(k) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fast_prof[k], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev g, const __grid_constant__ FastArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem S;
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = S.P;
+  long long t_last = clock64();
   for (int rr = blockIdx.x; rr < g.R; rr += gridDim.x) {
     const int r = rr + g.r0;
     Rep* rp = g.rep + r;
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     const float pmax_test = fmaxf(fmaxf(P[XGC_P_hiv_test_rate], P[XGC_P_hiv_test_rate + 1]), fmaxf(P[XGC_P_hiv_test_rate + 2], P[XGC_P_hiv_test_rate + 3]));
     const float arr_age = P[XGC_P_arrival_age];
 
+    TICK(PH_STAGE);
     for (int at = A.at0; at <= A.at1; ++at) {
       const unsigned mask = A.mask;
       unsigned* const grow = g.counters + ((size_t)r * g.t_cap + (size_t)at) * XGC_NCOUNTER;
@@ -218,14 +225,6 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         if (tid == 0) {
           S.sc[SC_NPRE] = S.sc[SC_NSLOTS];
           if (mask & XGC_M_AGING) S.sc[SC_TAGE] = at;
-          if (mask & XGC_M_STITRANS) {                          // weekly random pathway order (stitrans_msm_rand)
-            uint4 x0 = frand(key, at, FS_PATH, 0, 0), x1 = frand(key, at, FS_PATH, 1, 0);
-            unsigned dr[6] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y };
-            int perm[XGC_NPATH];
-            for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
-            for (int i = XGC_NPATH - 1; i >= 1; --i) { int j = (int)__umulhi(dr[XGC_NPATH - 1 - i], (unsigned)(i + 1)); int t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
-            for (int k = 0; k < XGC_NPATH; ++k) S.sc[SC_PATH + perm[k]] = k;
-          }
         }
         __syncthreads();
         // ---- arrival_msm: one warp
@@ -265,6 +264,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           if (lane == 0) { S.sc[SC_NSLOTS] = n_slots + nnew; S.sc[SC_NEXTUID] = uid0 + nnew; S.sc[SC_NALIVE] += nnew; S.row[XGC_K_NNEW] = (unsigned)nnew; }
         }
         __syncthreads();
+        TICK(PH_ARRIVE);
         const int n_slots = S.sc[SC_NSLOTS], n_pre = S.sc[SC_NPRE];
         const bool hivmods = mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL);
         for (int base = 0; base < n_slots; base += FAC) {
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               }
             });
           __syncthreads();
+          TICK(PH_PRE_SAMPLE);
           // ---- scan of the chunk: aging, high-rate mortality (ageing out), HIV-positive queue, rule-based test candidates
           for (int i0 = base; i0 < hi; i0 += FT) {
             int i = i0 + tid;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             }
           }
           __syncthreads();
+          TICK(PH_PRE_SCAN);
           // ---- HIV-test candidates: time since the last negative test / arrival decides
           {
             const unsigned nt = min(S.qn[1], 2u * FQ_REGION);
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             }
           }
           __syncthreads();
+          TICK(PH_PRE_TEST);
           // ---- HIV-positive agents: AIDS mortality, test result, hivtx_msm, hivprogress_msm, hivvl_msm
           {
             const unsigned nh = min(S.qn[0], (unsigned)FQ_REGION);
@@ -407,6 +410,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             }
           }
           __syncthreads();
+          TICK(PH_PRE_HIV);
         }
       } else {
         for (int k = tid; k < XGC_NCOUNTER; k += FT) S.row[k] = grow[k];      // continuing a week started by an earlier call
@@ -521,11 +525,20 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           __syncthreads();
         }
       }
+      TICK(PH_NET);
       // =================================================================================================== POST
       if (A.phases & XF_POST) {
         const int n_slots = S.sc[SC_NSLOTS];
         const int ne0 = S.sc[SC_NE0], ne01 = ne0 + S.sc[SC_NE1], ne_all = ne01 + S.sc[SC_NE2];
         const bool last_week = at == A.at1;
+        if (tid == 0 && (mask & XGC_M_STITRANS)) {              // weekly random pathway order (stitrans_msm_rand)
+          uint4 x0 = frand(key, at, FS_PATH, 0, 0), x1 = frand(key, at, FS_PATH, 1, 0);
+          unsigned dr[6] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y };
+          int perm[XGC_NPATH];
+          for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
+          for (int i = XGC_NPATH - 1; i >= 1; --i) { int j = (int)__umulhi(dr[XGC_NPATH - 1 - i], (unsigned)(i + 1)); int t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
+          for (int k = 0; k < XGC_NPATH; ++k) S.sc[SC_PATH + perm[k]] = k;
+        }
         // ---------------------------------------------------------------- acts_msm + exposure history + PrEP risk history
         if (mask & (XGC_M_ACTS | XGC_M_PREP)) {
           const float sc_ai = P[XGC_P_ai_acts_scale_mc] * (1.f / 52.f), sc_oi = P[XGC_P_oi_acts_scale_mc] * (1.f / 52.f);
@@ -603,6 +616,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
         }
         __syncthreads();
+        TICK(PH_ACTS);
         // ---------------------------------------------------------------- prep_msm, stirecov_msm, stitx_msm
         if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS)) {
           const float pavd = P[XGC_P_gc_asympt_visit_prob];
@@ -639,6 +653,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               qpush(qP, (unsigned)(i - base), qp, &S.qn[1], lane);
             }
             __syncthreads();
+            TICK(PH_B_SCAN);
             {                                                   // prep_msm on the few it concerns
               const unsigned np = min(S.qn[1], (unsigned)FQ_REGION);
               for (unsigned q = tid; q < np; q += FT) {
@@ -664,6 +679,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               }
             }
             __syncthreads();
+            TICK(PH_B_PREP);
             {                                                   // stirecov_msm + stitx_msm on infected or visiting agents
               const unsigned na = min(S.qn[0], (unsigned)FQ_REGION);
               for (unsigned q0 = 0; q0 < na; q0 += FT) {
@@ -757,6 +773,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             __syncthreads();
           }
         }
+        TICK(PH_B_GC);
         // ---------------------------------------------------------------- hivtrans_msm + stitrans_msm_rand over discordant ties
         if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
           const bool gct = mask & XGC_M_STITRANS, hvt = mask & XGC_M_HIVTRANS;
@@ -783,6 +800,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               for (int t = 0; t < 4; ++t) qpush(q[t], (unsigned)(f - fb), S.Q + t * FQ_REGION, &S.qn[t], lane);
             }
             __syncthreads();
+            TICK(PH_TRANS_CLASSIFY);
             const unsigned n0 = min(S.qn[0], (unsigned)FQ_REGION), n1 = n0 + min(S.qn[1], (unsigned)FQ_REGION),
                            n2 = n1 + min(S.qn[2], (unsigned)FQ_REGION), n3 = n2 + min(S.qn[3], (unsigned)FQ_REGION);
             for (unsigned j = tid; j < n3; j += FT) {           // the four queues as one index space: warps run one act type
@@ -878,6 +896,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             __syncthreads();
           }
         }
+        TICK(PH_TRANS);
         // ---------------------------------------------------------------- apply new infections, prevalence_msm
         for (int base = 0; base < n_slots; base += FAC) {
           const int hi = min(base + FAC, n_slots);
@@ -931,6 +950,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
           __syncthreads();
         }
+        TICK(PH_APPLY);
         // prevalence_msm: recount over the staged state; transient week flags are cleared on the way
         for (int i0 = 0; i0 < n_slots; i0 += FT) {
           int i = i0 + tid;
@@ -952,6 +972,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         }
         __syncthreads();
       }
+      TICK(PH_TALLY);
       for (int k = tid; k < XGC_NCOUNTER; k += FT) grow[k] = S.row[k];
       __syncthreads();
     }
@@ -976,6 +997,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         ((int*)g.at_ptr)[r] = A.at1;
       }
     }
+    TICK(PH_WRITEBACK);
   }
 }
 
@@ -995,6 +1017,14 @@ cudaError_t xgc_fast_prepare(const Dev& g, cudaStream_t s) {
   return cudaGetLastError();
 }
 const void* xgc_fast_kernel_ptr() { return (const void*)k_week_fast; }
+// phase clocks of k_week_fast (SM cycles summed over CTAs) since the last reset; instrumentation for tools/time_modes.py
+extern "C" int xgc_debug_fast_profile(unsigned long long* out, int cap, int reset) {
+  unsigned long long h[PH_N];
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(h, g_fast_prof, sizeof h) != cudaSuccess) return -1;
+  for (int k = 0; k < PH_N && k < cap; ++k) out[k] = h[k];
+  if (reset) { unsigned long long z[PH_N] = { 0 }; cudaMemcpyToSymbol(g_fast_prof, z, sizeof z); }
+  return PH_N;
+}
 cudaError_t xgc_fast_launch(const Dev& g, const FastArgs& a, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
