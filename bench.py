@@ -35,7 +35,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=260)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="xgc", choices=["xgc", "reference"])
-    ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU")
+    ap.add_argument("--replicates", type=int, default=1000, help="replicates per GPU (weak scaling)")
+    ap.add_argument("--total-replicates", type=int, default=0,
+                    help="strong scaling: this many replicates in total, sharded over the GPUs (north_star: the 1000-replicate sweep on 8 GPUs = 125 per GPU)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"],
+                    help="native-draw contract of the CUDA arm: fast = replicate-resident kernel (statistical equivalence), strict = bit-exact kernels")
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
@@ -54,12 +58,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def workload_config(args, parallelism):
-    return {"workload": f"calibration sweep (BASELINE configs[1]): {args.replicates} replicates x {args.agents} agents per GPU, "
-                        "per-replicate LHS parameters over the reference prior box, all 17 weekly modules, one step = one week",
-            "replicates_per_gpu": args.replicates, "agents_per_replicate": args.agents, "network": "on-device surrogate for simnet_msm",
-            "parallelism": parallelism,
-            "l2": "no flush needed: per-step working set (~1 GB of agent planes for 1000x10k) is >> 126 MB L2"}
+def workload_config(args, parallelism, mode=None):
+    c = {"workload": f"calibration sweep (BASELINE configs[1]): {args.replicates} replicates x {args.agents} agents per GPU, "
+                     "per-replicate LHS parameters over the reference prior box, all 17 weekly modules, one step = one week",
+         "replicates_per_gpu": args.replicates, "agents_per_replicate": args.agents, "network": "on-device surrogate for simnet_msm",
+         "parallelism": parallelism,
+         "l2": "no flush needed: the timed region sweeps ~1 GB of agent planes (1000 x 10k), >> 126 MB L2; the resident (fast) kernel "
+               "stages each replicate in shared memory for up to 64 weeks by design, so its HBM traffic is far below the per-week model"}
+    if args.total_replicates:
+        c["total_replicates"] = args.total_replicates
+    if mode:
+        c["mode"] = mode
+    return c
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -254,13 +264,23 @@ def run_xgc(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rid_base = rank * args.replicates
+    if args.total_replicates:                          # strong scaling: the sweep is split over the ranks (shard.shard_range)
+        from xgc_msm_b200.shard import shard_range
+        rid_base, args.replicates = shard_range(args.total_replicates, rank, world)
     R = args.replicates
     spec = workload.SweepSpec(n_agents=args.agents, seed=args.seed)
     W, Kt, Pn, En = max(args.warmup, 3), args.steps, args.profile_steps, args.e2e_steps
     t_cap = 2 + W + Kt + Pn + En + 8
-    h = Handle(R, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rank * R,
+    h = Handle(R, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rid_base,
                compact_every=spec.weeks_between_compactions)
-    workload.load_sweep(h, spec, rid0=rank * R)
+    workload.load_sweep(h, spec, rid0=rid_base)
+    mode = args.mode
+    if mode == "fast":
+        try:
+            h.set_mode("fast")
+        except Exception as ex:                         # a replicate that does not fit one SM's shared memory runs on the strict kernels
+            mode = f"strict (fast unavailable: {ex})"
     stream = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local_rank))
 
     # ---- kernel-resident throughput: W warm-up weeks, then exactly K timed weeks (CUDA-graph replay, no host sync)
@@ -295,20 +315,35 @@ def run_xgc(args, rank, world, local_rank):
 
     # ---- per-kernel device times (CUDA events around every launch on the launching stream) -> roofline of the top kernel
     h.profile(True)
-    for _ in range(Pn):
-        h.step(at); at += 1
+    if mode == "fast":
+        # one resident launch over Pn weeks (no compaction boundary inside: at .. at + Pn - 1 lies between multiples of 64)
+        while at % spec.weeks_between_compactions > spec.weeks_between_compactions - Pn or at % spec.weeks_between_compactions == 0:
+            h.profile(False); h.run(at, at); at += 1; h.profile(True)
+        h.run(at, at + Pn - 1); at += Pn
+    else:
+        for _ in range(Pn):
+            h.step(at); at += 1
     prof = h.profile_read()
     h.profile(False)
     stats = week_stats(h, K, at - 1)
     kb = roofline.kernel_bytes(stats)
     per = {k: v[0] / max(v[1], 1) * (v[1] / Pn) for k, v in prof.items()}          # ms per week per kernel
     step_ms_prof = sum(per.values())
-    top = max((k for k in per if k in kb), key=lambda k: per[k])
     peak, peak_src = measured_peak()
+    if mode == "fast":
+        # the dominant (only) kernel of the step is k_week_fast: one launch = Pn weeks of every replicate.  Algorithmic bytes per
+        # launch = Pn x the per-week bytes of the packed layout (what a week-at-a-time implementation must
+        # stream; SURVEY 8(d) x agent-weeks) -- the resident kernel keeps most of them on chip, see `traffic`
+        top = "k_week_fast"
+        kb = dict(kb); kb[top] = roofline.step_bytes(stats) * Pn
+    else:
+        top = max((k for k in per if k in kb), key=lambda k: per[k])
     top_ms = prof[top][0] / prof[top][1]
     achieved = kb[top] / (top_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": kb[top], "launch_ms": top_ms, "share_of_step": per[top] / step_ms_prof,
+            "bytes_model": "per-week HBM bytes of the packed SoA layout (xgc_msm_b200/roofline.py), per agent-week: "
+                           f"{roofline.step_bytes(stats) / max(stats['n'], 1):.0f} B (SURVEY 8(d) first cut: 128 B)",
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
             "step": {"algorithmic_bytes": roofline.step_bytes(stats), "achieved": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9,
                      "frac": roofline.step_bytes(stats) / (ms / Kt * 1e-3) / 1e9 / peak}}
@@ -346,9 +381,11 @@ def run_xgc(args, rank, world, local_rank):
     Rg = R // Ge
     groups = []
     for gi in range(Ge):
-        hg = Handle(Rg, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rank * R + gi * Rg,
+        hg = Handle(Rg, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rid_base + gi * Rg,
                     compact_every=spec.weeks_between_compactions)
-        workload.load_sweep(hg, spec, rid0=rank * R + gi * Rg)
+        workload.load_sweep(hg, spec, rid0=rid_base + gi * Rg)
+        if mode == "fast":
+            hg.set_mode("fast")
         hg.run(2, at - 1)                                   # same point of the epidemic as the kernel-resident arm
         hg.set_control(control_msm(network_mode="host").flags)
         groups.append(hg)
@@ -447,8 +484,9 @@ def run_xgc(args, rank, world, local_rank):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kt, "warmup": W, "ms_per_step": ms / Kt,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int", "data": "synthetic",
-            "config": workload_config(args, f"replicates sharded over {world} GPU(s), no data-path collective; final all_gather of targets"),
+            "higher_is_better": True, "scaling": "strong" if args.total_replicates else "weak", "vs_baseline": None,
+            "dtype": "f32+int (fast native-draw path; injected draws: f64+int)" if mode == "fast" else "f64+int", "data": "synthetic",
+            "config": workload_config(args, f"replicates sharded over {world} GPU(s), no data-path collective; final all_gather of targets", mode),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "targets_shape": list(tg.shape), "status_sample_or": int(np.bitwise_or.reduce(status)),
             "agent_weeks_timed": aw}), flush=True)

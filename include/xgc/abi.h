@@ -232,8 +232,13 @@ enum xgc_target_index {
   XGC_TG_PROB_POS  = XGC_TG_PROP_TESTED + 3,  /* [3] prob.{rGC,uGC,pGC}.tested      */
   XGC_TG_PREV_GC   = XGC_TG_PROB_POS + 3,     /* [4] prev.gc, prev.rgc, prev.ugc, prev.pgc */
   XGC_TG_IR100_GC  = XGC_TG_PREV_GC + 4,      /* [4] ir100.gc, .rgc, .ugc, .pgc     */
-  XGC_NTARGET      = XGC_TG_IR100_GC + 4
+  /* [8] prob.agedx.hiv.<race>.age<k>: age distribution among the HIV-diagnosed by race, the validation target
+   * vt_age_among_hivdx (R/calculate_targets.r:70-105: B.age1, B.age2, H.age1, H.age5, O.age1, W.age1, W.age4, W.age5) */
+  XGC_TG_AGEDX     = XGC_TG_IR100_GC + 4,
+  XGC_NTARGET      = XGC_TG_AGEDX + 8
 };
+/* (race - 1) * 5 + (age group - 1) of the eight XGC_TG_AGEDX columns */
+#define XGC_TG_AGEDX_CELLS { 0, 1, 5, 9, 10, 15, 18, 19 }
 
 /* Attribute dtypes for upload/download. */
 enum xgc_dtype { XGC_F64 = 0, XGC_I32 = 1 };
@@ -267,7 +272,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_K_NGROUP) X(XGC_K_PATH) X(XGC_K_VISITS) X(XGC_K_VISITS_SYMPT) X(XGC_K_TESTED) X(XGC_K_POS) X(XGC_K_TXSTART) \
   X(XGC_K_DEP_GEN) X(XGC_K_DEP_AIDS) X(XGC_K_NNEW) X(XGC_K_HIVTESTS) X(XGC_K_NEDGES) X(XGC_K_NACTS) \
   X(XGC_TG_NUM) X(XGC_TG_I_PREV) X(XGC_TG_IR100_POP) X(XGC_TG_HIVDX_RACE) X(XGC_TG_HIVDX_AGE) X(XGC_TG_VLS_RACE) X(XGC_TG_VLS_AGE) \
-  X(XGC_TG_PREPCOV_RACE) X(XGC_TG_PROP_TESTED) X(XGC_TG_PROB_POS) X(XGC_TG_PREV_GC) X(XGC_TG_IR100_GC) \
+  X(XGC_TG_PREPCOV_RACE) X(XGC_TG_PROP_TESTED) X(XGC_TG_PROB_POS) X(XGC_TG_PREV_GC) X(XGC_TG_IR100_GC) X(XGC_TG_AGEDX) \
   X(XGC_ST_AGENT_OVERFLOW) X(XGC_ST_EDGE_OVERFLOW) X(XGC_ST_GC_EXTINCT) X(XGC_ST_BAD_EDGE) X(XGC_ST_RATE_TRUNCATED) X(XGC_MODE_STRICT) X(XGC_MODE_FAST) X(XGC_F64) X(XGC_I32)
 int  xgc_constant(const char* name, int64_t* value);          /* 0 if found */
 int  xgc_param_index(const char* name, int* offset, int* count);   /* params.def lookup */

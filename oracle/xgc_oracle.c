@@ -230,6 +230,14 @@ int orc_set_attr(orc_dat* d, const char* name, const double* v, int n) {
   return 0;
 }
 int orc_get_attr(const orc_dat* d, const char* name, double* v, int cap) {
+  static const char* const degn[3] = { "deg.main", "deg.casl", "deg.inst" };     /* derived: current degree per layer */
+  for (int l = 0; l < 3; ++l)
+    if (strcmp(name, degn[l]) == 0) {
+      if (cap < d->n) return -1;
+      for (int i = 0; i < d->n; ++i) v[i] = 0.0;
+      for (int e = 0; e < d->ne[l]; ++e) { v[d->el[l][e].p1] += 1.0; v[d->el[l][e].p2] += 1.0; }
+      return d->n;
+    }
   int k = attr_index(name);
   if (k < 0 || cap < d->n) return -1;
   memcpy(v, d->a[k], sizeof(double) * (size_t)d->n);
@@ -1042,6 +1050,11 @@ void orc_targets(const orc_dat* d, int at_last, int tailn, double* out) {
     double any = gsum(c, XGC_K_INUM_GC, 0xFFFFFu);
     w[XGC_TG_PREV_GC] = any / num;
     w[XGC_TG_IR100_GC] = inc_all / (num - any) * 5200.0;
+    {                                  /* target_prob_agedx_byrace (R/calculate_targets.r:70-105) */
+      static const int cells[8] = XGC_TG_AGEDX_CELLS;
+      for (int j = 0; j < 8; ++j)
+        w[XGC_TG_AGEDX + j] = (double)c[XGC_K_INUM_DX * XGC_NCELL + cells[j]] / gsum(c, XGC_K_INUM_DX, 0x1Fu << ((cells[j] / 5) * 5));
+    }
     for (int k = 0; k < XGC_NTARGET; ++k) out[k] += nz(w[k]);
   }
   for (int k = 0; k < XGC_NTARGET; ++k) out[k] = out[k] / (double)tailn;

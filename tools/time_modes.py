@@ -29,12 +29,11 @@ for mode in a.modes.split(","):
     if mode == "fast":
         import ctypes as C
         from xgc_msm_b200 import abi
-        names = ["stage", "arrive", "pre_sample", "pre_scan", "pre_test", "pre_hiv", "net", "acts", "b_scan", "b_prep", "b_gc", "trans_classify",
-                 "trans", "apply", "tally", "writeback"]
+        names = ["stage", "arrive", "pre", "net", "acts", "b", "trans", "apply_tally", "row", "writeback"] + ["-"] * 6
         buf = (C.c_ulonglong * 16)()
         abi.lib.xgc_debug_fast_profile.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
         n = abi.lib.xgc_debug_fast_profile(buf, 16, 1)
         tot = sum(buf[:n]) or 1
-        print(json.dumps({"phase_share": {names[k]: round(buf[k] / tot, 4) for k in range(n)},
+        print(json.dumps({"phase_share": {names[k]: round(buf[k] / tot, 4) for k in range(n) if buf[k]},
                           "cycles_per_replicate_week": tot / (a.replicates * (a.weeks + 8))}), flush=True)
     h.close()

@@ -2,7 +2,7 @@
 
 One calibration round of the reference is ~5000 SLURM array tasks plus three R scripts; here it is one device sweep:
 
-  priors --LHS--> [n x 62] inputs --params_from_env--> R replicates on the device --xgc_run--> xgc_targets [n x 39]
+  priors --LHS--> [n x 62] inputs --params_from_env--> R replicates on the device --xgc_run--> xgc_targets [n x NTARGET]
          --population-size filter--> out_vs_targ (get_absdiff per target) --> selections --> narrowed priors
 
 Reference (behaviour only; none of its code is reused):

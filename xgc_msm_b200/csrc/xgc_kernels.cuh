@@ -1418,6 +1418,10 @@ __device__ double target_week(const unsigned* c, int k) {
     for (int s = 0; s < 3; ++s) inc += gsum(c, XGC_K_INCID_RGC + s, ALL);
     return inc / (num - gsum(c, XGC_K_INUM_GC, ALL)) * 5200.0;
   }
+  if (k >= XGC_TG_AGEDX) {
+    const int cells[8] = XGC_TG_AGEDX_CELLS; int cell = cells[k - XGC_TG_AGEDX];
+    return (double)c[XGC_K_INUM_DX * XGC_NCELL + cell] / gsum(c, XGC_K_INUM_DX, 0x1Fu << ((cell / 5) * 5));
+  }
   int s = k - XGC_TG_IR100_GC - 1;
   return gsum(c, XGC_K_INCID_RGC + s, ALL) / (num - gsum(c, XGC_K_INUM_RGC + s, ALL)) * 5200.0;
 }

@@ -25,6 +25,7 @@ struct HostRep {                      // host mirror of one replicate (cache for
   std::vector<int4> edge[3];
   std::vector<int> lazy[3];            // materialised kissing | rimming << 8 counts (xgc_get_actcounts)
   std::vector<int> pos2slot, slot2pos;
+  std::vector<int> deg[3];             // per slot, filled on demand by the derived degree attributes
 };
 
 struct xgc_handle {
@@ -418,6 +419,11 @@ static std::vector<AttrDef> build_attrs() {
   A.push_back({"prepStartTime", [](const HostRep& c, int i) { return (double)c.tck[i].w; }, [](HostRep& c, int i, double v) { c.tck[i].w = S16(v); }});
   A.push_back({"prepLastRisk", [](const HostRep& c, int i) { return (double)c.tck[i].z; }, [](HostRep& c, int i, double v) { c.tck[i].z = S16(v); }});
   A.push_back({"prep.ind.last", [](const HostRep& c, int i) { return (double)c.tck[i].y; }, [](HostRep& c, int i, double v) { c.tck[i].y = S16(v); }});
+  // derived, read-only: current degree in the main / casual / one-off edge list -- what the reference's simnet_msm
+  // (resim_nets.FUN with tergmLite, sim1_02_lhs.r:209,226) conditions on as dat$attr$deg.main / deg.casl
+  static const char* const degn[3] = { "deg.main", "deg.casl", "deg.inst" };
+  for (int l = 0; l < 3; ++l)
+    A.push_back({degn[l], [l](const HostRep& c, int i) { return (double)c.deg[l][i]; }, nullptr});
   return A;
 }
 static const std::vector<AttrDef>& attrs() { static std::vector<AttrDef> A = build_attrs(); return A; }
@@ -464,6 +470,7 @@ extern "C" int xgc_upload_attr(xgc_handle* h, int r, const char* name, const voi
   CHECK_R(h, r);
   const AttrDef* a = find_attr(name);
   if (!a) FAIL(h, 5, "unknown attribute '%s'", name);
+  if (!a->set) FAIL(h, 5, "attribute '%s' is derived from the edge lists and cannot be uploaded", name);
   int rc = cache_load(h, r); if (rc) return rc;
   HostRep& c = h->cache;
   if (n != c.pos2slot.size()) FAIL(h, 6, "attribute '%s': length %zu != number of agents %zu", name, n, c.pos2slot.size());
@@ -482,7 +489,12 @@ extern "C" int xgc_download_attr(xgc_handle* h, int r, const char* name, void* d
   const AttrDef* a = find_attr(name);
   if (!a) FAIL(h, 5, "unknown attribute '%s'", name);
   int rc = cache_load(h, r); if (rc) return rc;
-  const HostRep& c = h->cache;
+  HostRep& c = h->cache;
+  if (!a->set)                                             // derived degree attributes: count the current edge lists
+    for (int l = 0; l < 3; ++l) {
+      c.deg[l].assign(c.core.size(), 0);
+      for (const int4& ed : c.edge[l]) { c.deg[l][ed.x]++; c.deg[l][ed.y]++; }
+    }
   size_t n = c.pos2slot.size();
   if (n_out) *n_out = n;
   if (cap < n) FAIL(h, 6, "attribute '%s': buffer of %zu too small for %zu agents", name, cap, n);

@@ -113,9 +113,12 @@ def target_prob_hivdx(epi, tailn: int, strat: str) -> Dict[str, float]:
     return {k: float(_nan0(v)) for k, v in out.items()}
 
 
+AGEDX_CELLS = {"B": (1, 2), "H": (1, 5), "O": (1,), "W": (1, 4, 5)}        # R/calculate_targets.r:72-77
+
+
 def target_prob_agedx_byrace(epi, tailn: int) -> Dict[str, float]:
     """R/calculate_targets.r:67-103"""
-    dl = {"B": (1, 2), "H": (1, 5), "O": (1,), "W": (1, 4, 5)}
+    dl = AGEDX_CELLS
     return {f"prob.agedx.hiv.{r}.age{a}": float(np.mean(_tail(epi[f"i.num.dx.{r}.age{a}"], tailn) / _tail(epi[f"i.num.dx.{r}"], tailn)))
             for r, ages in dl.items() for a in ages}
 
@@ -211,6 +214,7 @@ def device_target_names() -> list:
     n += [f"prepCov.{r}" for r in RACES]
     n += [f"prop.{s}.tested" for s in ANAT] + [f"prob.{g}.tested" for g in GCLABS]
     n += ["prev.gc", "prev.rgc", "prev.ugc", "prev.pgc", "ir100.gc", "ir100.rgc", "ir100.ugc", "ir100.pgc"]
+    n += [f"prob.agedx.hiv.{r}.age{a}" for r, ages in AGEDX_CELLS.items() for a in ages]       # XGC_TG_AGEDX
     return n
 
 
