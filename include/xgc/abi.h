@@ -379,6 +379,15 @@ int  xgc_fork    (xgc_handle* src, int src_r, xgc_handle* dst, int dst_r);   /* 
  * capacity are truncated and set XGC_ST_EDGE_OVERFLOW. */
 int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][stride] 1-based positions*/,
                            const int32_t* n_edges /*[R]*/, const int32_t* start_time /*[R][stride] or NULL*/, int stride);
+/* Weekly DELTA of a persistent layer (main / casual ties live for years; tergmLite's simnet_msm toggles a few dozen of them a
+ * week), instead of re-sending the whole list: one packed int32 row per replicate,
+ *   row = { n_removed, n_added, removed[n_removed], tail[n_added], head[n_added] (, start[n_added] if has_start) }
+ * removed[] are ascending 0-based indices into the layer's CURRENT edge list -- the list xgc_get_edgelist would return now,
+ * i.e. after this week's departures were pruned, in the stable order both sides keep; tail/head are 1-based positions among
+ * the living.  The surviving ties keep their order, the added ones are appended in the order given (start = has_start ? the
+ * given week : the current week).  Same asynchrony and error flags as xgc_set_edgelists_all (a removed index outside the
+ * list sets XGC_ST_BAD_EDGE). */
+int  xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t* delta /*[R][stride]*/, int stride, int has_start);
 int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);
 int  xgc_num_agents_all   (xgc_handle* h, int32_t* out /*[R]*/);   /* living agents per replicate (what simnet_msm needs) */
 

@@ -201,3 +201,81 @@ def test_prior_box_corners():
     assert h.status(1) == o.status() == K.ST_RATE_TRUNCATED
     assert h.status(0) == 0
     h.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_host_network_weekly_deltas(mode):
+    """xgc_update_edgelists_all: the persistent layers (main, casual) are kept on the device and only the week's toggles
+    cross the boundary -- removed ties as indices into the current list, formed ties as position pairs -- while the
+    one-off layer is replaced.  Strict mode: bit-exact against the oracle driven with the full lists.  Fast mode: the
+    device lists equal the host's lists every week (the update path does not depend on the arithmetic mode)."""
+    from xgc_msm_b200 import workload as W
+    from xgc_msm_b200.abi import Handle
+    n_agents, weeks, R, s0 = 10000, 40, 4, 321
+    spec = W.SweepSpec(n_agents=n_agents, seed=SEED, network_mode="host", weeks_between_compactions=16)
+    cases = [W.replicate_case(spec, s0 + r) for r in range(R)]
+    h = Handle(R, spec.n_cap, spec.e_cap, weeks + 4, seed=SEED, replicate_offset=s0, compact_every=16)
+    W.load_sweep(h, spec, rid0=s0)
+    h.set_mode(mode)
+    orcs = [load_oracle(c, SEED, s0 + r, t_cap=weeks + 4) for r, c in enumerate(cases)]
+    pre = _pre_mask()
+    post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
+    rng = np.random.default_rng(7)
+    dur = [250.0, 90.0]
+    for at in range(2, 2 + weeks):
+        h.step(at, pre)
+        for o in orcs:
+            o.step(at, pre)
+        alive = h.num_agents_all()
+        if mode == "strict":
+            assert alive.tolist() == [o.num_agents() for o in orcs]
+        lists = []
+        for l in range(2):
+            rows = []
+            for r in range(R):
+                # the host's view of the layer after this week's departures: in strict mode the oracle's own list; in fast mode
+                # the device's (the two trajectories differ), which the delta then edits
+                el, st = orcs[r].get_edgelist(l) if mode == "strict" else h.get_edgelist(r, l)
+                rem = np.flatnonzero(rng.random(el.shape[0]) < 1.0 / dur[l]).astype(np.int32)
+                if at == 5 and r == 1:
+                    rem = np.arange(el.shape[0], dtype=np.int32)[:: 2]          # a big delta: every second tie dissolves
+                nadd = int(rem.size) + int(rng.integers(0, 4))
+                a = rng.integers(1, alive[r] + 1, size=nadd); b = rng.integers(1, alive[r], size=nadd); b = np.where(b >= a, b + 1, b)
+                add = np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1).astype(np.int32)
+                keep = np.ones(el.shape[0], bool); keep[rem] = False
+                full = np.vstack([el[keep], add]); fst = np.concatenate([st[keep], np.full(nadd, at, np.int32)])
+                orcs[r].set_edgelist(l, full, fst)
+                rows.append(np.concatenate([[rem.size, nadd], rem, add[:, 0], add[:, 1], np.full(nadd, at)]).astype(np.int32))
+                lists.append((r, l, full, fst))
+            stride = max(x.size for x in rows) + 5
+            delta = np.zeros((R, stride), np.int32)
+            for r, x in enumerate(rows):
+                delta[r, :x.size] = x
+            h.update_edgelists_all(l, delta.ctypes.data, stride, has_start=True)
+            h.sync()
+        ne2 = rng.integers(300, 500, size=R).astype(np.int32); stride2 = int(ne2.max())
+        el2 = np.zeros((R, 2, stride2), np.int32)
+        for r in range(R):
+            a = rng.integers(1, alive[r] + 1, size=ne2[r]); b = rng.integers(1, alive[r], size=ne2[r]); b = np.where(b >= a, b + 1, b)
+            el2[r, 0, :ne2[r]] = np.minimum(a, b); el2[r, 1, :ne2[r]] = np.maximum(a, b)
+            orcs[r].set_edgelist(2, el2[r, :, :ne2[r]].T, None)
+        h.set_edgelists_all(2, el2.ctypes.data, ne2.ctypes.data, 0, stride=stride2)
+        h.sync()
+        if mode == "fast" or at % 7 == 0:
+            for r, l, full, fst in lists:
+                ge, gs = h.get_edgelist(r, l)
+                assert np.array_equal(ge, full) and np.array_equal(gs, fst), f"week {at} replicate {r} layer {l}: device list != host list"
+        h.step(at, post)
+        for r, o in enumerate(orcs):
+            o.step(at, post)
+            if mode == "strict":
+                assert np.array_equal(h.counters(r, at, at)[0], o.counters(at)), f"week {at} replicate {r}: tallies differ"
+    for r, o in enumerate(orcs):
+        assert h.status(r) == 0
+        if mode == "strict":
+            compare_state(h, r, o, 1 + weeks, f"delta path, replicate {s0 + r}")
+    # a removed index beyond the list is reported, not dereferenced
+    bad = np.zeros((R, 8), np.int32); bad[2, 0] = 1; bad[2, 2] = 10 ** 6
+    h.update_edgelists_all(0, bad.ctypes.data, 8, has_start=False); h.sync()
+    assert h.status(2) & K.ST_BAD_EDGE and not (h.status(0) & K.ST_BAD_EDGE)
+    h.close()

@@ -58,7 +58,7 @@ def _load() -> C.CDLL:
         "xgc_targets": [vp, ci, ci, pd],
         "xgc_snapshot_size": [vp, C.POINTER(C.c_size_t)], "xgc_snapshot": [vp, vp, C.c_size_t],
         "xgc_restore": [vp, vp, C.c_size_t], "xgc_fork": [vp, ci, vp, ci],
-        "xgc_set_edgelists_all": [vp, ci, vp, vp, vp, ci], "xgc_get_counters_all": [vp, ci, vp],
+        "xgc_set_edgelists_all": [vp, ci, vp, vp, vp, ci], "xgc_update_edgelists_all": [vp, ci, vp, ci, ci], "xgc_get_counters_all": [vp, ci, vp],
         "xgc_kernel_launches": [vp, C.POINTER(C.c_uint64)], "xgc_profile": [vp, ci],
         "xgc_profile_read": [vp, C.POINTER(C.c_char_p), pd, C.POINTER(C.c_uint64), ci], "xgc_num_agents_all": [vp, vp], "xgc_stream_ptr": [vp, C.POINTER(vp)],
         "xgc_debug_exp": [pd, pd, ci, ci], "xgc_debug_philox": [cu, cu, pu, pu, ci, ci],
@@ -331,6 +331,11 @@ class Handle:
     def set_edgelists_all(self, layer: int, el_ptr: int, ne_ptr: int, start_ptr: int = 0, stride: int = 0):
         """Raw-pointer variant for pinned host buffers: el [R][2][stride] int32 1-based positions, n_edges [R]."""
         self._ck(lib.xgc_set_edgelists_all(self._h, layer, el_ptr, ne_ptr, start_ptr or None, stride or self.e_cap[layer]))
+
+    def update_edgelists_all(self, layer: int, delta_ptr: int, stride: int, has_start: bool = True):
+        """Weekly delta of a persistent layer: packed int32 rows [R][stride] = {n_removed, n_added, removed idx (0-based, ascending),
+        tails, heads (1-based positions)(, start weeks)}; raw pointer to (ideally pinned) host memory."""
+        self._ck(lib.xgc_update_edgelists_all(self._h, layer, delta_ptr, stride, int(has_start)))
 
     def num_agents_all(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

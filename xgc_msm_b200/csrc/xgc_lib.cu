@@ -44,6 +44,7 @@ struct xgc_handle {
   void* d_cscratch = nullptr;   // 16 B per slot, large-replicate compaction only
   unsigned* d_pstat = nullptr; int* d_remap = nullptr; double* d_targets = nullptr; int* d_scratch = nullptr; double* d_pois = nullptr; double* d_inv_ntx = nullptr;
   int* d_el_stage = nullptr; size_t el_stage_cap = 0;
+  int* d_upd_stage[3] = { nullptr, nullptr, nullptr }; size_t upd_stage_cap[3] = { 0, 0, 0 };    // per layer: the copies of one week overlap
   cudaGraphExec_t week_graph = nullptr; uint64_t graph_launches = 0;
   // xgc_run drives the replicates as TWO concurrent lanes (halves of the replicate range, each with its own streams and
   // captured week graph): every kernel of this path is latency-bound, so a second, independent kernel sequence fills the
@@ -117,6 +118,7 @@ extern "C" const char* xgc_last_error(const xgc_handle* h) { return h ? h->err.c
 // CUDA loads kernels lazily, on their first launch (tens of ms for a large image): touch every native-draw kernel once per
 // process at create time so that no week of a run pays for it (the compaction kernels first run at week 64).
 __global__ void k_edges_upload(const __grid_constant__ Dev g, int l, const int* el, const int* ne, const int* start, int stride);
+__global__ void k_edges_update(const __grid_constant__ Dev g, int l, const int* delta, int stride, int has_start);
 static void preload_kernels() {
   static bool done = false;
   if (done) return;
@@ -128,7 +130,7 @@ static void preload_kernels() {
   PRELOAD((k_form<false, true, TPB>)); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
   PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
   PRELOAD(k_agent3a); PRELOAD(k_agent3b<false>); PRELOAD(k_targets); PRELOAD(k_compact_agents); PRELOAD(k_compact_edges);
-  PRELOAD(k_compact_remap); PRELOAD(k_compact_finish); PRELOAD(k_edges_upload);
+  PRELOAD(k_compact_remap); PRELOAD(k_compact_finish); PRELOAD(k_edges_upload); PRELOAD(k_edges_update);
   PRELOAD(k_compact_gather<uint4>); PRELOAD(k_compact_gather<uint2>); PRELOAD(k_compact_gather<int>);
   PRELOAD(k_compact_putback<uint4>); PRELOAD(k_compact_putback<uint2>); PRELOAD(k_compact_putback<int>);
 #undef PRELOAD
@@ -229,6 +231,7 @@ extern "C" int xgc_destroy(xgc_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_inj) cudaFree(h->d_inj);
   if (h->d_el_stage) cudaFree(h->d_el_stage);
+  for (int l = 0; l < 3; ++l) if (h->d_upd_stage[l]) cudaFree(h->d_upd_stage[l]);
   for (int k = 0; k < 2; ++k) { if (h->ev_fork[k]) cudaEventDestroy(h->ev_fork[k]); if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]); }
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1193,6 +1196,79 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
     h->rank_fresh = true;
   }
   LAUNCH(h, k_edges_upload, dim3((unsigned)((st + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr, stride);
+  h->acts_valid = false;
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+// weekly delta of a persistent layer: one CTA per replicate marks the removed ties in a shared-memory bitmap, compacts the layer
+// in place (stable) and appends the added ties (R positions -> slots through pos2slot)
+__global__ void __launch_bounds__(TPB) k_edges_update(const __grid_constant__ Dev g, int l, const int* delta /*[R][stride]*/, int stride, int has_start) {
+  pdl_prologue();
+  extern __shared__ unsigned upd_kill[];
+  const int r = blockIdx.x + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  Rep* rp = g.rep + r;
+  const int* row = delta + (size_t)r * stride;
+  const int ne = rp->ne[l], nrem = max(0, min(row[0], stride - 2)), nadd = max(0, min(row[1], (stride - 2 - nrem) / (has_start ? 3 : 2)));
+  int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+  __shared__ int wsum[TPB / 32];
+  __shared__ int base;
+  for (int k = tid; k < (ne + 31) / 32; k += TPB) upd_kill[k] = 0u;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  bool bad = row[0] != nrem || row[1] != nadd;
+  for (int k = tid; k < nrem; k += TPB) { int e = row[2 + k]; if (e >= 0 && e < ne) atomicOr(&upd_kill[e >> 5], 1u << (e & 31)); else bad = true; }
+  __syncthreads();
+  for (int e0 = 0; e0 < ne; e0 += TPB) {
+    int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
+    if (e < ne) { ed = E[e]; keep = !((upd_kill[e >> 5] >> (e & 31)) & 1u); }
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (keep && off != e) E[off] = ed;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    __syncthreads();
+  }
+  const int nk = base, na = rp->n_alive, at = g.at_ptr[r];
+  const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
+  const int* tail = row + 2 + nrem; const int* head = tail + nadd; const int* st = head + nadd;
+  for (int k = tid; k < nadd; k += TPB) {
+    int a = tail[k], b = head[k];
+    if (a < 1 || a > na || b < 1 || b > na) { bad = true; a = b = 1; }
+    if (nk + k < g.e_cap[l]) E[nk + k] = make_int4(P2S[a - 1], P2S[b - 1], has_start ? st[k] : at, 0);
+  }
+  if (bad) atomicOr(&rp->status, XGC_ST_BAD_EDGE);
+  if (tid == 0) {
+    int nn = nk + nadd;
+    if (nn > g.e_cap[l]) { nn = g.e_cap[l]; atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW); }
+    rp->ne[l] = nn;
+  }
+}
+extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t* delta, int stride, int has_start) {
+  if (layer < 0 || layer > 2) FAIL(h, 2, "layer out of range");
+  if (stride < 2) FAIL(h, 2, "stride must be >= 2");
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  const Dev& g = h->g; size_t need = (size_t)g.R * (size_t)stride;
+  if (need > h->upd_stage_cap[layer]) {
+    if (h->d_upd_stage[layer]) cudaFree(h->d_upd_stage[layer]);
+    h->d_upd_stage[layer] = nullptr; h->upd_stage_cap[layer] = 0;
+    CU(h, cudaMalloc((void**)&h->d_upd_stage[layer], need * sizeof(int)));
+    h->upd_stage_cap[layer] = need;
+  }
+  CU(h, cudaMemcpyAsync(h->d_upd_stage[layer], delta, need * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (!h->rank_fresh) {
+    if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
+    else LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+    h->rank_fresh = true;
+  }
+  prof_begin(h, "k_edges_update");
+  kl(h, k_edges_update, dim3(g.R), TPB, (size_t)((g.e_cap[layer] + 31) / 32 + 1) * 4, g, layer, (const int*)h->d_upd_stage[layer], stride, has_start);
+  prof_end(h); h->launches++;
   h->acts_valid = false;
   CU(h, cudaGetLastError());
   return 0;
