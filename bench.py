@@ -223,6 +223,29 @@ def host_network_pool(R, e_cap, n_lo, rng, torch, n_edges=None, layers=(0, 1, 2)
     return bufs
 
 
+def host_delta_pool(R, n_lo, ne, dur, rng, torch, weeks=8):
+    """Pinned weekly deltas of ONE persistent layer for `weeks` weeks (cycled): packed int32 rows [R][stride] =
+    {n_removed, n_added, removed indices (ascending, 0-based), tails, heads, start weeks} -- what a host-side simnet_msm has to
+    send when the device keeps the layer: ~ne/dur dissolved ties and as many (+2: ties lost to departures) formed ones."""
+    out = []
+    lam = ne / dur
+    for _ in range(weeks):
+        nrem = rng.poisson(lam, size=R).astype(np.int64)
+        nadd = nrem + 2
+        stride = int(2 + nrem.max() + 3 * nadd.max())
+        d = np.zeros((R, stride), np.int32)
+        for r in range(R):
+            k, m = int(nrem[r]), int(nadd[r])
+            rem = np.sort(rng.choice(int(ne * 0.9), size=k, replace=False)).astype(np.int32)
+            a = rng.integers(1, n_lo, size=m); b = rng.integers(1, n_lo - 1, size=m); b = np.where(b >= a, b + 1, b)
+            d[r, 0], d[r, 1] = k, m
+            d[r, 2:2 + k] = rem
+            d[r, 2 + k:2 + k + m] = np.minimum(a, b); d[r, 2 + k + m:2 + k + 2 * m] = np.maximum(a, b)
+            d[r, 2 + k + 2 * m:2 + k + 3 * m] = 0            # start week: filled by the device (has_start = 0 would do; kept in the row for the byte count)
+        out.append(torch.from_numpy(d).pin_memory())
+    return out
+
+
 def bind_to_gpu_numa_node(torch, local_rank):
     """Several ranks share one host: keep this rank's threads, and therefore its page-locked staging buffers (first
     touch), on the NUMA node its GPU hangs off, so that the weekly uploads of 8 ranks do not cross the socket link.
@@ -392,15 +415,16 @@ def run_xgc(args, rank, world, local_rank):
     rng = np.random.default_rng(args.seed + rank)
     nmin = min(int(hg.num_agents_all().min()) for hg in groups)
     ne_dev = h.counters_all(t_last)[:, K.K_NEDGES:K.K_NEDGES + 3].astype(np.float64).mean(0)     # edges per layer the resident arm held
-    pool = host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev))
-    # one-off partnerships are new every week: cycle through several one-off layers (main / casual ties persist for years)
-    oneoff = [pool[2]] + [host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev), layers=(2,))[0] for _ in range(7)]
+    # one-off partnerships are new every week: cycle through several one-off layers
+    oneoff = [host_network_pool(R, spec.e_cap, max(int(nmin * 0.97), 16), rng, torch, n_edges=np.rint(ne_dev), layers=(2,))[0] for _ in range(8)]
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
     n_host = torch.empty(R, dtype=torch.int32).pin_memory()
     c_host = torch.empty((R, K.NCOUNTER), dtype=torch.int32).pin_memory()
-    # one-off partnerships carry no start week (the plist of the reference tracks main / casual only; rshim/modules.R passes NULL)
-    h2d = sum(t_el.numel() * 4 + t_ne.numel() * 4 + (t_st.numel() * 4 if l < 2 else 0) for l, (t_el, t_ne, t_st, _) in enumerate(pool))
+    # main / casual ties persist for years: the device keeps those layers and the host sends the week's toggles only
+    # (xgc_update_edgelists_all); the one-off layer is replaced every week (xgc_set_edgelists_all, no start weeks)
+    deltas = [host_delta_pool(R, max(int(nmin * 0.97), 16), float(ne_dev[l]), (250.0, 90.0)[l], rng, torch) for l in range(2)]
+    h2d = int(np.mean([sum(deltas[l][w].numel() * 4 for l in range(2)) for w in range(len(deltas[0]))])) + oneoff[0][0].numel() * 4 + oneoff[0][1].numel() * 4
     d2h = n_host.numel() * 4 + c_host.numel() * 4
     n_np, c_np = n_host.numpy(), c_host.numpy().view(np.uint32)
 
@@ -409,9 +433,11 @@ def run_xgc(args, rank, world, local_rank):
         hg, r0 = groups[gi], gi * Rg
         hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
-        for l, (t_el, t_ne, t_st, _ne) in enumerate((pool[0], pool[1], oneoff[t % len(oneoff)])):
-            hg.set_edgelists_all(l, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), t_st[r0:r0 + Rg].data_ptr() if l < 2 else 0,
-                                 stride=t_el.shape[2])
+        for l in range(2):
+            d = deltas[l][t % len(deltas[l])]
+            hg.update_edgelists_all(l, d[r0:r0 + Rg].data_ptr(), d.shape[1], has_start=False)
+        t_el, t_ne, _t_st, _ne = oneoff[t % len(oneoff)]
+        hg.set_edgelists_all(2, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), 0, stride=t_el.shape[2])
         hg.step(t, post)
         hg.counters_all(t, c_np[r0:r0 + Rg])
         return float(c_np[r0:r0 + Rg, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
@@ -453,8 +479,8 @@ def run_xgc(args, rank, world, local_rank):
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
            "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
-           "path": f"{Ge} handles x {Rg} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 3x xgc_set_edgelists_all (pinned) -> "
-                   "xgc_step(post) -> xgc_get_counters_all"}
+           "path": f"{Ge} handles x {Rg} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 2x xgc_update_edgelists_all "
+                   "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> xgc_step(post) -> xgc_get_counters_all"}
     e2e_status = 0
     for hg in groups:
         e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, Rg, max(Rg // 8, 1))]))
