@@ -5,6 +5,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <string.h>
+#include <stdint.h>
 #include "xgc/abi.h"
 
 static void fin(SEXP p) { xgc_handle* h = (xgc_handle*)R_ExternalPtrAddr(p); if (h) { xgc_destroy(h); R_ClearExternalPtr(p); } }
@@ -27,6 +28,8 @@ SEXP xgcR_create(SEXP nrep, SEXP ncap, SEXP ecap, SEXP tcap, SEXP seed, SEXP dev
 }
 SEXP xgcR_set_params(SEXP p, SEXP r, SEXP v) { if (XLENGTH(v) != XGC_NPARAM) Rf_error("params must have %d entries", XGC_NPARAM);
   CK(H(p), xgc_set_params(H(p), Rf_asInteger(r), REAL(v))); return R_NilValue; }
+SEXP xgcR_get_params(SEXP p, SEXP r) { SEXP out = PROTECT(Rf_allocVector(REALSXP, XGC_NPARAM)); int rc = xgc_get_params(H(p), Rf_asInteger(r), REAL(out));
+  UNPROTECT(1); if (rc) Rf_error("xgc error %d: %s", rc, xgc_last_error(H(p))); return out; }
 SEXP xgcR_set_control(SEXP p, SEXP r, SEXP v) { CK(H(p), xgc_set_control(H(p), Rf_asInteger(r), INTEGER(v))); return R_NilValue; }
 SEXP xgcR_set_tables(SEXP p, SEXP v) { CK(H(p), xgc_set_tables(H(p), REAL(v))); return R_NilValue; }
 SEXP xgcR_set_population(SEXP p, SEXP r, SEXP n, SEXP at) { CK(H(p), xgc_set_population(H(p), Rf_asInteger(r), Rf_asInteger(n), Rf_asInteger(at))); return R_NilValue; }
@@ -96,3 +99,36 @@ SEXP xgcR_targets(SEXP p, SEXP nrep, SEXP at_last, SEXP tailn) {      /* [nsims 
   UNPROTECT(1);
   return out;
 }
+SEXP xgcR_attr_names(void) {                                          /* names xgc_upload_attr / xgc_download_attr know */
+  const char* nm[256]; int n = xgc_attr_names(nm, 256);
+  SEXP out = PROTECT(Rf_allocVector(STRSXP, n));
+  for (int k = 0; k < n; ++k) SET_STRING_ELT(out, k, Rf_mkChar(nm[k]));
+  UNPROTECT(1);
+  return out;
+}
+SEXP xgcR_param_index(SEXP name) {                                    /* c(offset, count) of a params.def entry, 0-based offset; NULL if unknown */
+  int off = 0, cnt = 0;
+  if (xgc_param_index(CHAR(STRING_ELT(name, 0)), &off, &cnt)) return R_NilValue;
+  SEXP out = PROTECT(Rf_allocVector(INTSXP, 2)); INTEGER(out)[0] = off; INTEGER(out)[1] = cnt; UNPROTECT(1);
+  return out;
+}
+SEXP xgcR_constant(SEXP name) {                                       /* named constant of abi.h (XGC_NPARAM, XGC_C_..., XGC_SCREEN_...) */
+  int64_t v = 0;
+  if (xgc_constant(CHAR(STRING_ELT(name, 0)), &v)) Rf_error("xgc: unknown constant %s", CHAR(STRING_ELT(name, 0)));
+  return Rf_ScalarInteger((int)v);
+}
+SEXP xgcR_num_agents(SEXP p, SEXP r) { int n = 0; CK(H(p), xgc_num_agents(H(p), Rf_asInteger(r), &n)); return Rf_ScalarInteger(n); }
+SEXP xgcR_status(SEXP p, SEXP r) { uint32_t s = 0; CK(H(p), xgc_status(H(p), Rf_asInteger(r), &s)); return Rf_ScalarInteger((int)s); }
+SEXP xgcR_set_mode(SEXP p, SEXP mode) { CK(H(p), xgc_set_mode(H(p), Rf_asInteger(mode))); return R_NilValue; }
+SEXP xgcR_compact(SEXP p) { CK(H(p), xgc_compact(H(p))); return R_NilValue; }
+SEXP xgcR_snapshot(SEXP p) {                                          /* the whole device state as a raw vector (saveRDS-able: the burn-in file) */
+  size_t nb = 0; CK(H(p), xgc_snapshot_size(H(p), &nb));
+  SEXP out = PROTECT(Rf_allocVector(RAWSXP, (R_xlen_t)nb));
+  int rc = xgc_snapshot(H(p), RAW(out), nb);
+  UNPROTECT(1);
+  if (rc) Rf_error("xgc error %d: %s", rc, xgc_last_error(H(p)));
+  return out;
+}
+SEXP xgcR_restore(SEXP p, SEXP raw) { CK(H(p), xgc_restore(H(p), RAW(raw), (size_t)XLENGTH(raw))); return R_NilValue; }
+SEXP xgcR_fork(SEXP src, SEXP src_r, SEXP dst, SEXP dst_r) {          /* device-to-device copy of one replicate (nsims > 1, scenario arms) */
+  CK(H(src), xgc_fork(H(src), Rf_asInteger(src_r), H(dst), Rf_asInteger(dst_r))); return R_NilValue; }

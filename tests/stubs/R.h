@@ -10,9 +10,10 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
+#define RAWSXP 24
 extern SEXP R_NilValue;
 int Rf_asInteger(SEXP); double Rf_asReal(SEXP); Rboolean Rf_isNull(SEXP);
-double* REAL(SEXP); int* INTEGER(SEXP); int LENGTH(SEXP); R_xlen_t XLENGTH(SEXP);
+double* REAL(SEXP); int* INTEGER(SEXP); unsigned char* RAW(SEXP); int LENGTH(SEXP); R_xlen_t XLENGTH(SEXP);
 SEXP STRING_ELT(SEXP, R_xlen_t); SEXP VECTOR_ELT(SEXP, R_xlen_t); const char* CHAR(SEXP);
 SEXP Rf_allocVector(unsigned, R_xlen_t); SEXP Rf_allocMatrix(unsigned, int, int);
 SEXP Rf_protect(SEXP); void Rf_unprotect(int);
