@@ -105,9 +105,9 @@ struct Dev {                 // everything a kernel needs; passed by value
 };
 
 // ---- Philox4x32-10 (Salmon et al. SC'11), counter-based: draw = pure function of (replicate, week, stream, entity, k)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+template <int ROUNDS> __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -115,6 +115,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<10>(c, k); }
 
 // One stream of one entity; caches the Philox block of 4.  INJ = true reads the injected table instead (parity mode);
 // the native kernels are compiled without that path.

@@ -15,9 +15,15 @@
 //     it to completion on its own: it classifies 32 items at a time, collects the minority that needs work in a 64-entry
 //     shared-memory mini-queue and processes the queue 32 at a time with all lanes busy.  CTA-wide barriers separate only
 //     the phases whose data dependences cross agents (PRE | network | acts | prep/stirecov/stitx | transmission | prev).
-//   * rare per-agent events (natural mortality, HIV interval tests, background clinic visits, tie dissolution) are drawn
-//     as geometric waiting gaps over the slot / edge index (exact for an iid Bernoulli sequence; heterogeneous
-//     probabilities by thinning), so agents nothing happens to cost an integer scan, not a Philox block;
+//   * rare per-agent events (natural mortality, HIV interval tests, background clinic visits) are drawn as geometric
+//     waiting gaps over the slot index (exact for an iid Bernoulli sequence; heterogeneous probabilities by thinning),
+//     so agents nothing happens to cost an integer scan, not a Philox block;
+//   * ties are deleted LAZILY: a tie whose endpoint departed, or that dissolves this week, gets a tombstone bit in the
+//     shared-memory act word when the acts pass meets it (no separate network pass over the ties); new ties are appended
+//     at the tail with endpoints drawn by rejection over the slots (no rank -> slot search); a stable in-place squeeze
+//     runs every 16 weeks, under capacity pressure, and before the write-back, so HBM always holds compact lists.  Every
+//     per-tie draw is keyed by (layer, endpoint slots), never by the tie's index: results do not depend on when the
+//     squeeze happens (weekly step-group calls == one resident run, bit for bit);
 //   * probabilities are fp32 with FMA, exp via ex2.approx, Bernoulli trials are integer compares on raw Philox words.
 //
 // Module semantics are those of xgc_kernels.cuh / oracle (same order, same state machine); tests/test_gpu_fast_mode.py
@@ -38,9 +44,11 @@
 
 enum { FS_PATH = 1, FS_ARRN, FS_ARRA, FS_MORT, FS_MORTHI, FS_TEST, FS_AG1, FS_DISS, FS_NETN = FS_DISS + 2, FS_FORM,
        FS_ACTS = FS_FORM + 3, FS_COND, FS_ANAL, FS_ORAL, FS_RIM, FS_KISS, FS_AVD, FS_PREP, FS_AG2, FS_INF };
+#define EA_DEAD 0x8000u            /* act word of a tie: tombstone (endpoint departed / dissolved), squeezed out later */
 
 // scalar slots
-enum { SC_NSLOTS = 0, SC_NPRE, SC_NALIVE, SC_NEXTUID, SC_TREF, SC_TAGE, SC_NE0, SC_NE1, SC_NE2, SC_STATUS, SC_PATH /*7*/, SC_PMAX = SC_PATH + 8, SC_N = 24 };
+enum { SC_NSLOTS = 0, SC_NPRE, SC_NALIVE, SC_NEXTUID, SC_TREF, SC_TAGE, SC_NE0, SC_NE1, SC_NE2, SC_STATUS, SC_PATH /*7*/, SC_PMAX = SC_PATH + 8,
+       SC_DEAD0, SC_DEAD1, SC_DEAD2, SC_NFORM0, SC_NFORM1, SC_NFORM2, SC_SQUEEZE, SC_N = 32 };
 
 struct Fixed {                     // fixed part of the CTA's shared memory (compile-time offsets)
   unsigned row[XGC_NCOUNTER];
@@ -50,32 +58,29 @@ struct Fixed {                     // fixed part of the CTA's shared memory (com
   float pk[4 * (XGC_MAX_ACTS + 1)];
   unsigned hib[16];
   int sc[SC_N];
-  int wsum[NW], wsum2[NW];
+  int wsum[NW], wsum2[NW], wsum3[NW];
   unsigned short mq[NW][2][MQ_CAP];
 };
 static __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-struct VarOff { size_t ea, bm, pre, kill, V, total; int kw; };
+struct VarOff { size_t ea, V, total; };
 static __host__ __device__ VarOff fast_layout(int n_cap, size_t e_stride) {
   VarOff o; size_t p = al16(sizeof(Fixed));
-  o.kw = (int)(e_stride / 32 + 2);
   o.ea = p; p += al16(e_stride * 2);
-  o.bm = p; p += al16((size_t)(n_cap / 32 + NW) * 4);
-  o.pre = p; p += al16((size_t)(n_cap / 32 + NW) * 4);
-  o.kill = p; p += al16((size_t)2 * o.kw * 4);
   o.V = p; p += al16((size_t)n_cap * 14);
   o.total = p;
   return o;
 }
 size_t xgc_fast_smem_bytes(int n_cap, size_t e_stride) {
   VarOff o = fast_layout(n_cap, e_stride);
-  return (o.total <= 232448 && n_cap <= 32768 && e_stride <= 65535) ? o.total : 0;      // u16 queue items / edge indices
+  return (o.total <= 232448 && n_cap <= 32768 && e_stride <= 16383) ? o.total : 0;      // 14-bit tie indices + 2 type bits in the queue items, 15-bit slots
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 frand(uint2 key, unsigned at, unsigned stream, unsigned a, unsigned b) {
-  return philox4x32_10(make_uint4(at, stream, a, b), key);
+  // 7 rounds: the smallest Philox4x32 variant that passes BigCrush (Salmon et al. SC'11, table 2); the strict path keeps 10
+  return philox4x32<7>(make_uint4(at, stream, a, b), key);
 }
 __device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }     // (0,1), 24 bits
 __device__ __forceinline__ float u01_16(unsigned x16) { return ((float)x16 + 0.5f) * (1.0f / 65536.0f); }
@@ -104,6 +109,7 @@ __device__ __forceinline__ float glm_f(const float* b, float dur, bool casual, f
   if (prep) eta += b[XGC_G_PREP];
   return eta;
 }
+__device__ __forceinline__ unsigned pairkey(const int4& ed) { return (unsigned)ed.x | ((unsigned)ed.y << 16); }      // slots < 32768
 __device__ __forceinline__ int birth8(unsigned h) { return (int)((h >> XF_BIRTH_SHIFT) & XF_BIRTH_MASK); }
 // exclusive prefix of the 32 per-warp counts in cnt[] for this warp, and their total (every warp computes it redundantly)
 __device__ __forceinline__ int warp_base(const int* cnt, int warp, int lane, int* total) {
@@ -160,9 +166,6 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   Fixed& F = *reinterpret_cast<Fixed*>(smem_raw);
   const VarOff vo = fast_layout(g.n_cap, g.e_stride);
   unsigned short* const ea = (unsigned short*)(smem_raw + vo.ea);
-  unsigned* const bm = (unsigned*)(smem_raw + vo.bm);
-  int* const pre = (int*)(smem_raw + vo.pre);
-  unsigned* const kill = (unsigned*)(smem_raw + vo.kill);
   unsigned* const vd = (unsigned*)(smem_raw + vo.V);
   unsigned* const vg = vd + g.n_cap;
   unsigned* const vh = vd + 2 * g.n_cap;
@@ -172,8 +175,16 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   unsigned short* const q0 = F.mq[warp][0];
   unsigned short* const q1 = F.mq[warp][1];
   long long t_last = clock64();
-  for (int rr = blockIdx.x; rr < g.R; rr += gridDim.x) {
+  // Schedule: the launch's replicate-weeks, replicate-major, are cut into gridDim.x equal stretches (148 CTAs x 1000 replicates
+  // would otherwise run 7 waves for 6.76 waves of work).  A CTA walks its stretch from the LAST replicate to the first: the
+  // replicate it shares with the next CTA comes first (its early weeks, no dependence), the one it shares with the previous
+  // CTA last (its late weeks; the previous CTA ran the early ones first and published at_ptr[r]).  A CTA touches a replicate
+  // once per launch, so nothing it reads can be stale in its L1 except the shared Rep / at_ptr lines, read with ld.cg.
+  const long long W = A.at1 - A.at0 + 1, T = (long long)g.R * W;
+  const long long i0 = T * blockIdx.x / gridDim.x, i1 = T * (blockIdx.x + 1) / gridDim.x;
+  for (int rr = i1 > i0 ? (int)((i1 - 1) / W) : -1; rr >= 0 && rr >= (int)(i0 / W); --rr) {
     const int r = rr + g.r0;
+    const int w_first = A.at0 + (int)max(i0 - (long long)rr * W, 0LL), w_last = A.at0 + (int)min(i1 - (long long)rr * W, W) - 1;
     Rep* rp = g.rep + r;
     const size_t rbase = (size_t)r * g.n_cap;
     const uint2 key = make_uint2(g.seed, (unsigned)(g.rep0 + r));
@@ -181,19 +192,25 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     const int proto = C[XGC_C_stiScreeningProtocol], kissx = C[XGC_C_cdcExposureSite_Kissing], surrogate = C[XGC_C_network_mode] == 1;
     const bool pois_mode = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
     const bool route_kiss = C[XGC_C_transRoute_Kissing], route_rim = C[XGC_C_transRoute_Rimming];
+    if (w_first > A.at0) {                                      // the earlier weeks of this replicate run on the previous CTA
+      if (tid == 0) while (__ldcg(&g.at_ptr[r]) != w_first - 1) __nanosleep(500);
+      __syncthreads();
+      __threadfence();
+    }
     __syncthreads();                                            // previous replicate's write-back done with the staging buffers
     // ------------------------------------------------------------------------------------------ stage the replicate
     if (tid == 0) {
-      F.sc[SC_NSLOTS] = rp->n_slots; F.sc[SC_NPRE] = rp->n_slots_pre; F.sc[SC_NALIVE] = rp->n_alive; F.sc[SC_NEXTUID] = rp->next_uid;
-      F.sc[SC_TREF] = rp->t_ref; F.sc[SC_TAGE] = rp->t_age; F.sc[SC_NE0] = rp->ne[0]; F.sc[SC_NE1] = rp->ne[1]; F.sc[SC_NE2] = rp->ne[2];
-      F.sc[SC_STATUS] = 0;
-      for (int k = 0; k < XGC_NPATH; ++k) F.sc[SC_PATH + k] = rp->path_rank[k];
+      F.sc[SC_NSLOTS] = __ldcg(&rp->n_slots); F.sc[SC_NPRE] = __ldcg(&rp->n_slots_pre); F.sc[SC_NALIVE] = __ldcg(&rp->n_alive); F.sc[SC_NEXTUID] = __ldcg(&rp->next_uid);
+      F.sc[SC_TREF] = __ldcg(&rp->t_ref); F.sc[SC_TAGE] = __ldcg(&rp->t_age); F.sc[SC_NE0] = __ldcg(&rp->ne[0]); F.sc[SC_NE1] = __ldcg(&rp->ne[1]); F.sc[SC_NE2] = __ldcg(&rp->ne[2]);
+      F.sc[SC_STATUS] = 0; F.sc[SC_DEAD0] = F.sc[SC_DEAD1] = F.sc[SC_DEAD2] = 0;
+      for (int k = 0; k < XGC_NPATH; ++k) F.sc[SC_PATH + k] = __ldcg(&rp->path_rank[k]);
     }
     for (int k = tid; k < XGC_NPARAM; k += FT) F.P[k] = (float)g.params[(size_t)r * XGC_NPARAM + k];
     for (int k = tid; k < 4 * XGC_GLM_NCOEF; k += FT) F.G[k] = (float)g.tables[XGC_T_GLM_AI + k];
     for (int k = tid; k < 4 * XGC_ASMR_AGES; k += FT) F.asmr[k] = (float)g.tables[XGC_T_ASMR + k];
     for (int k = tid; k < 4 * (XGC_MAX_ACTS + 1); k += FT) F.pk[k] = (float)g.pois[(size_t)r * 4 * (XGC_MAX_ACTS + 1) + k];
     if (tid < 16) F.hib[tid] = 0u;
+    for (int k = tid; k < (int)g.e_stride; k += FT) ea[k] = 0;   // HBM holds compact lists: no tombstones
     __syncthreads();
     if (tid < 4 * XGC_ASMR_AGES && F.asmr[tid] >= HI_MORT) atomicOr(&F.hib[(tid / XGC_ASMR_AGES) * 4 + ((tid % XGC_ASMR_AGES) >> 5)], 1u << ((tid % XGC_ASMR_AGES) & 31));
     {
@@ -213,9 +230,53 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     __syncthreads();
     const float pmax_mort = __int_as_float(F.sc[SC_PMAX]);
     const float pmax_test = fmaxf(fmaxf(P[XGC_P_hiv_test_rate], P[XGC_P_hiv_test_rate + 1]), fmaxf(P[XGC_P_hiv_test_rate + 2], P[XGC_P_hiv_test_rate + 3]));
+    // tie dissolution, Bernoulli(1 / duration) per tie-week: a 16-bit pre-test on spare bits of the tie's acts block, refined
+    // by one more draw in the rare case it passes (exactly p overall)
+    const float pd0 = (float)g.inv_dur[0], pd1 = (float)g.inv_dur[1];
+    const unsigned dthr0 = min(65536u, (unsigned)ceilf(pd0 * 65536.f)), dthr1 = min(65536u, (unsigned)ceilf(pd1 * 65536.f));
+    const unsigned dref0 = dthr0 ? thr32(pd0 * 65536.f / (float)dthr0) : 0u, dref1 = dthr1 ? thr32(pd1 * 65536.f / (float)dthr1) : 0u;
+    auto dissolves = [&](const uint4& x, const int4& ed, int l, int at) -> bool {
+      const unsigned c16 = (x.x & 0xFFu) | ((x.y & 0xFFu) << 8);
+      if (c16 >= (l ? dthr1 : dthr0)) return false;
+      return frand(key, at, FS_DISS + l, pairkey(ed), 0).x <= (l ? dref1 : dref0);
+    };
+    // stable in-place squeeze of the tombstoned ties out of the three lists (CTA-wide; 4096 ties at a time, 128 consecutive ties
+    // per warp held in registers)
+    auto squeeze = [&]() {
+      for (int l = 0; l < 3; ++l) {
+        const int ne = F.sc[SC_NE0 + l];
+        if (F.sc[SC_DEAD0 + l] == 0) continue;
+        int4* const E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+        unsigned short* const eal = ea + g.e_off[l];
+        int run = 0;
+        for (int s0 = 0; s0 < ne; s0 += 4 * FT) {
+          int4 ed[4]; unsigned mk[4]; int cnt = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = s0 + (warp * 4 + k) * 32 + lane; bool keep = false; ed[k] = make_int4(0, 0, 0, 0);
+            if (e < ne && !(eal[e] & EA_DEAD)) { keep = true; ed[k] = E[e]; }
+            mk[k] = __ballot_sync(FULL, keep); cnt += __popc(mk[k]);
+          }
+          if (lane == 0) F.wsum[warp] = cnt;
+          __syncthreads();
+          int tot, dst0 = run + warp_base(F.wsum, warp, lane, &tot);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = s0 + (warp * 4 + k) * 32 + lane, dst = dst0 + __popc(mk[k] & ((1u << lane) - 1u));
+            if (((mk[k] >> lane) & 1u) && dst != e) E[dst] = ed[k];
+            dst0 += __popc(mk[k]);
+          }
+          run += tot;
+          __syncthreads();
+        }
+        for (int e = tid; e < ne; e += FT) eal[e] = 0;           // (act counts are per week: the acts pass rewrites them)
+        if (tid == 0) { F.sc[SC_NE0 + l] = run; F.sc[SC_DEAD0 + l] = 0; }
+        __syncthreads();
+      }
+    };
     TICK(PH_STAGE);
 
-    for (int at = A.at0; at <= A.at1; ++at) {
+    for (int at = w_first; at <= w_last; ++at) {
       const unsigned mask = A.mask;
       unsigned* const grow = g.counters + ((size_t)r * g.t_cap + (size_t)at) * XGC_NCOUNTER;
       const int at8 = (at + XF_BIRTH_OFF) * 8;
@@ -397,124 +458,81 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         __syncthreads();
       }
       // =================================================================================================== NETWORK
+      // (tergmLite::delete_vertices for the departed + surrogate simnet_msm).  Nothing here walks the ties: deletions are
+      // tombstones set by the tie sweep (fused into the acts pass when this call also runs the POST group), new ties are
+      // appended at the tails.
       if (A.phases & (XF_PRUNE | XF_FORM)) {
         const bool form = (A.phases & XF_FORM) && surrogate;
-        const int n_slots = F.sc[SC_NSLOTS];
-        const int AW = ((n_slots + FT - 1) / FT) * 32, a0 = warp * AW, a1 = min(a0 + AW, n_slots), wb = warp * (AW / 32);
-        // alive bitmap + exclusive popcount prefix (rank -> slot selection of the formation step)
-        {
-          int cnt = 0;
-          for (int k = 0; k * 32 < AW; ++k) {
-            int i = a0 + k * 32 + lane;
-            unsigned m = __ballot_sync(FULL, i < a1 && (vd[i] & DM_ACTIVE));
-            if (lane == 0) bm[wb + k] = m;
-            cnt += __popc(m);
-          }
-          if (lane == 0) F.wsum[warp] = cnt;
-          for (int k = tid; k < 2 * vo.kw; k += FT) kill[k] = 0u;
-        }
-        __syncthreads();
-        int n_alive;
-        {
-          int base = warp_base(F.wsum, warp, lane, &n_alive);
-          int c = lane * 32 < AW ? __popc(bm[wb + lane]) : 0, inc = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-          if (lane * 32 < AW) pre[wb + lane] = base + inc - c;
-          if (tid == 0) F.sc[SC_NALIVE] = n_alive;
-        }
-        const int nwords = NW * (AW / 32);
-        // dissolution is drawn over the RANK of a tie among the ties whose endpoints are both alive (segments of 256 ranks, 16
-        // warps per layer), so that pruning the ties of departed agents in an earlier call or in this pass gives the same ties
-        if (form) {
-          const int l = warp >> 4, ne = F.sc[SC_NE0 + l];
-          for (int s = warp & 15; s * 256 < ne; s += 16)
-            gap_warp(key, at, FS_DISS + l, (unsigned)s, s * 256, min(s * 256 + 256, ne), (float)g.inv_dur[l], lane, [&](bool ok, int e, const uint4&) {
-              if (ok) atomicOr(&kill[l * vo.kw + (e >> 5)], 1u << (e & 31)); });
-        }
-        __syncthreads();
-        for (int l = 0; l < 3; ++l) {
-          int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
-          const int ne = F.sc[SC_NE0 + l];
-          const bool diss = form && l < 2;
-          int run = 0, runA = 0;
-          if (!(form && l == 2)) {                              // (one-off contacts last one week: the layer is simply emptied)
-            // stable in-place compaction, 4096 ties at a time (128 consecutive ties per warp, held in registers)
-            for (int s0 = 0; s0 < ne; s0 += 4 * FT) {
-              int4 ed[4]; unsigned mk[4]; int cntA = 0;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                int e = s0 + (warp * 4 + k) * 32 + lane; bool alive = false; ed[k] = make_int4(0, 0, 0, 0);
-                if (e < ne) { ed[k] = E[e]; alive = (vd[ed[k].x] & DM_ACTIVE) && (vd[ed[k].y] & DM_ACTIVE); }
-                mk[k] = __ballot_sync(FULL, alive); cntA += __popc(mk[k]);
-              }
-              if (lane == 0) F.wsum[warp] = cntA;
-              __syncthreads();
-              int totA, baseA = warp_base(F.wsum, warp, lane, &totA);
-              int tot2 = totA, base2 = baseA;
-              if (diss) {
-                int cnt2 = 0, ra = runA + baseA;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  int rank = ra + __popc(mk[k] & ((1u << lane) - 1u));
-                  bool keep = ((mk[k] >> lane) & 1u) && !((kill[l * vo.kw + (rank >> 5)] >> (rank & 31)) & 1u);
-                  ra += __popc(mk[k]);
-                  mk[k] = __ballot_sync(FULL, keep); cnt2 += __popc(mk[k]);
-                }
-                if (lane == 0) F.wsum2[warp] = cnt2;
-                __syncthreads();
-                base2 = warp_base(F.wsum2, warp, lane, &tot2);
-              }
-              int dst0 = run + base2;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                int e = s0 + (warp * 4 + k) * 32 + lane, dst = dst0 + __popc(mk[k] & ((1u << lane) - 1u));
-                if (((mk[k] >> lane) & 1u) && dst != e) E[dst] = ed[k];
-                dst0 += __popc(mk[k]);
-              }
-              run += tot2; runA += totA;
-              __syncthreads();
+        if (tid == 0) {
+          const int n_alive = F.sc[SC_NALIVE];
+          int need = 0, anydead = 0;
+          for (int l = 0; l < 3; ++l) {
+            int nf = 0;
+            if (form) {
+              float target = (float)g.tables[XGC_T_NET_DEG + l] * (float)n_alive * 0.5f;
+              float mu = l == 2 ? target : target / (float)g.tables[XGC_T_NET_DUR + l];
+              float fl = floorf(mu);
+              nf = n_alive < 2 ? 0 : (int)fl + (u01(frand(key, at, FS_NETN, l, 0).x) < mu - fl);
+              if (l == 2) { F.sc[SC_NE2] = 0; F.sc[SC_DEAD2] = 0; }      // one-off contacts last one week: the layer starts empty
             }
+            F.sc[SC_NFORM0 + l] = nf;
+            anydead |= F.sc[SC_DEAD0 + l];
+            if (F.sc[SC_NE0 + l] + nf > g.e_cap[l] && F.sc[SC_DEAD0 + l] > 0) need = 1;
           }
-          int ne_new = run;
-          if (form) {                                            // uniform role-compatible pairs holding the mean degree
-            float target = (float)g.tables[XGC_T_NET_DEG + l] * (float)n_alive * 0.5f;
-            float mu = l == 2 ? target : target / (float)g.tables[XGC_T_NET_DUR + l];
-            float fl = floorf(mu);
-            int nform = (int)fl + (u01(frand(key, at, FS_NETN, l, 0).x) < mu - fl);
-            if (n_alive < 2) nform = 0;
-            auto slot_of = [&](int pos) -> int {
-              int lo = 0, hi = nwords - 1;
-              while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (pre[mid] <= pos) lo = mid; else hi = mid - 1; }
-              return (lo << 5) + (int)__fns(bm[lo], 0, pos - pre[lo] + 1);
-            };
-            for (int j0 = 0; j0 < nform; j0 += FT) {
-              int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
-              if (j < nform) {
-                for (int t = 0; t < XGC_FORM_TRIES && !ok; t += 2) {
-                  uint4 x = frand(key, at, FS_FORM + l, (unsigned)j, (unsigned)(t >> 1));
+          if ((at & 15) == 0 && anydead) need = 1;
+          F.sc[SC_SQUEEZE] = need;
+        }
+        __syncthreads();
+        if (F.sc[SC_SQUEEZE]) squeeze();
+        if (form) {                                              // uniform role-compatible pairs holding the mean degree
+          const int nf0 = F.sc[SC_NFORM0], nf01 = nf0 + F.sc[SC_NFORM1], nf_all = nf01 + F.sc[SC_NFORM2];
+          const int n_slots = F.sc[SC_NSLOTS];
+          int tail0 = F.sc[SC_NE0], tail1 = F.sc[SC_NE1], tail2 = F.sc[SC_NE2];
+          for (int j0 = 0; j0 < nf_all; j0 += FT) {
+            const int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
+            const int l = j >= nf01 ? 2 : j >= nf0 ? 1 : 0, jj = j - (l == 2 ? nf01 : l == 1 ? nf0 : 0);
+            if (j < nf_all) {
+              for (int t = 0; t < 2 * XGC_FORM_TRIES && !ok; t += 2) {      // endpoints by rejection over the slots: uniform over the living
+                uint4 x = frand(key, at, FS_FORM + l, (unsigned)jj, (unsigned)(t >> 1));
 #pragma unroll
-                  for (int q = 0; q < 2 && !ok; ++q) {
-                    int a = (int)__umulhi(q ? x.z : x.x, (unsigned)n_alive), b = (int)__umulhi(q ? x.w : x.y, (unsigned)(n_alive - 1));
-                    if (b >= a) b++;
-                    int sa = slot_of(min(a, b)), sb = slot_of(max(a, b));
-                    if (roles_compatible(vd[sa], vd[sb])) { ok = true; ed.x = sa; ed.y = sb; }
-                  }
+                for (int q = 0; q < 2 && !ok; ++q) {
+                  int sa = (int)__umulhi(q ? x.z : x.x, (unsigned)n_slots), sb = (int)__umulhi(q ? x.w : x.y, (unsigned)(n_slots - 1));
+                  if (sb >= sa) sb++;
+                  const unsigned da = vd[sa], db = vd[sb];
+                  if ((da & db & DM_ACTIVE) && roles_compatible(da, db)) { ok = true; ed.x = min(sa, sb); ed.y = max(sa, sb); }
                 }
               }
-              unsigned m = __ballot_sync(FULL, ok);
-              if (lane == 0) F.wsum[warp] = __popc(m);
-              __syncthreads();
-              int tot, base = warp_base(F.wsum, warp, lane, &tot);
-              int dst = ne_new + base + __popc(m & ((1u << lane) - 1u));
-              if (ok) { if (dst < g.e_cap[l]) E[dst] = ed; else atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_EDGE_OVERFLOW); }
-              ne_new = min(ne_new + tot, g.e_cap[l]);
-              __syncthreads();
             }
+            const unsigned m0 = __ballot_sync(FULL, ok && l == 0), m1 = __ballot_sync(FULL, ok && l == 1), m2 = __ballot_sync(FULL, ok && l == 2);
+            if (lane == 0) { F.wsum[warp] = __popc(m0); F.wsum2[warp] = __popc(m1); F.wsum3[warp] = __popc(m2); }
+            __syncthreads();
+            int tot0, tot1, tot2;
+            const int base0 = warp_base(F.wsum, warp, lane, &tot0), base1 = warp_base(F.wsum2, warp, lane, &tot1), base2 = warp_base(F.wsum3, warp, lane, &tot2);
+            if (ok) {
+              const unsigned m = l == 0 ? m0 : l == 1 ? m1 : m2;
+              const int dst = (l == 0 ? tail0 + base0 : l == 1 ? tail1 + base1 : tail2 + base2) + __popc(m & ((1u << lane) - 1u));
+              if (dst < g.e_cap[l]) { g.edge[(size_t)r * g.e_stride + g.e_off[l] + dst] = ed; ea[g.e_off[l] + dst] = 0; }
+              else atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_EDGE_OVERFLOW);
+            }
+            tail0 = min(tail0 + tot0, g.e_cap[0]); tail1 = min(tail1 + tot1, g.e_cap[1]); tail2 = min(tail2 + tot2, g.e_cap[2]);
+            __syncthreads();
           }
-          if (tid == 0) { F.sc[SC_NE0 + l] = ne_new; if (form) F.row[XGC_K_NEDGES + l] = (unsigned)ne_new; }
+          if (tid == 0) { F.sc[SC_NE0] = tail0; F.sc[SC_NE1] = tail1; F.sc[SC_NE2] = tail2; }
+          __syncthreads();
         }
-        __syncthreads();
+        if (!(A.phases & XF_POST)) {                             // no acts pass in this call: the tie sweep on its own
+          const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
+          for (int f = tid; f < ne_all; f += FT) {
+            const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+            if (ea[sidx] & EA_DEAD) continue;
+            const int4 ed = g.edge[(size_t)r * g.e_stride + sidx];
+            bool dead = !(vd[ed.x] & vd[ed.y] & DM_ACTIVE);
+            if (!dead && form && l < 2 && ed.z < at) dead = dissolves(frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l), ed, l, at);
+            if (dead) { ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); }
+          }
+          __syncthreads();
+          if (tid < 3 && form) F.row[XGC_K_NEDGES + tid] = (unsigned)(F.sc[SC_NE0 + tid] - F.sc[SC_DEAD0 + tid]);
+        }
         TICK(PH_NET);
       }
       // =================================================================================================== POST
@@ -537,12 +555,18 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         if (mask & (XGC_M_ACTS | XGC_M_PREP)) {
           const float sc_ai = P[XGC_P_ai_acts_scale_mc] * (1.f / 52.f), sc_oi = P[XGC_P_oi_acts_scale_mc] * (1.f / 52.f);
           unsigned tot_ai = 0, tot_oi = 0;
+          const bool diss_on = (A.phases & XF_FORM) && surrogate;
           for (int f = tid; f < ne_all; f += FT) {
-            const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, e = f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
-            int4* Ep = g.edge + (size_t)r * g.e_stride + g.e_off[l] + e;
+            const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+            if (ea[sidx] & EA_DEAD) continue;
+            int4* Ep = g.edge + (size_t)r * g.e_stride + sidx;
             const int4 ed = *Ep;
             const unsigned da = vd[ed.x], db = vd[ed.y], ga = vg[ed.x], gb = vg[ed.y], ha = vh[ed.x], hb = vh[ed.y];
-            const uint4 x = frand(key, at, FS_ACTS, (unsigned)f, 0);
+            const uint4 x = frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l);
+            // the tie sweep: ties of departed agents (tergmLite::delete_vertices) and this week's dissolutions become tombstones
+            if (!(da & db & DM_ACTIVE) || (diss_on && l < 2 && ed.z < at && dissolves(x, ed, l, at))) {
+              ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); continue;
+            }
             const float ca = (float)(2 * at8 - birth8(ha) - birth8(hb)) * (float)XF_W8;
             int ai = 0, oi = 0, ki = 0, ri = 0;
             if (mask & XGC_M_ACTS) {
@@ -564,7 +588,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                   oi = bern(x.y, P[XGC_P_oi_prob_oo]); ki = u01_16(x.z & 0xFFFFu) < P[XGC_P_kiss_prob_oo]; ri = u01_16(x.z >> 16) < P[XGC_P_rim_prob_oo];
                 }
               }
-              ea[f] = (unsigned short)(ai | (oi << 6) | (ki << 12) | (ri << 13));
+              ea[sidx] = (unsigned short)(ai | (oi << 6) | (ki << 12) | (ri << 13));
               if (last_week && A.write_acts) Ep->w = (int)((unsigned)ai | ((unsigned)oi << 8) | (0x7FFFu << 16));
               tot_ai += ai; tot_oi += oi;
 #pragma unroll
@@ -577,7 +601,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                 if (l != 0 && (ai | oi | ki | ri)) ex |= 16;
                 if ((ex << GC_EXPO_SHIFT) & ~(side ? gb : ga)) atomicOr(&vg[side ? ed.y : ed.x], ex << GC_EXPO_SHIFT);
               }
-            } else ai = ea[f] & 63;
+            } else ai = ea[sidx] & 63;
             if (mask & XGC_M_PREP) {                            // risk history: condomless anal sex, or anal sex with a diagnosed partner
               const bool ua = !(ha & HV_DIAG), ub = !(hb & HV_DIAG);
               if (ai > 0 && (ua || ub)) {
@@ -590,7 +614,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                   unsigned thr = (unsigned)((1.f - pc) * 65536.f);
                   uai = (x.w & 0xFFFFu) < thr || (ai > 1 && (x.w >> 16) < thr);
                   for (int k0 = 2; k0 < ai && !uai; k0 += 8) {
-                    uint4 c = frand(key, at, FS_COND, (unsigned)f, (unsigned)((k0 - 2) >> 3));
+                    uint4 c = frand(key, at, FS_COND, pairkey(ed), (unsigned)l | ((unsigned)((k0 - 2) >> 3) << 2));
                     unsigned w[4] = { c.x, c.y, c.z, c.w };
 #pragma unroll
                     for (int k = 0; k < 8; ++k) if (k0 + k < ai && ((w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu) < thr) uai = true;
@@ -607,6 +631,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
         }
         __syncthreads();
+        if (tid < 3 && (A.phases & XF_FORM) && surrogate) F.row[XGC_K_NEDGES + tid] = (unsigned)(F.sc[SC_NE0 + tid] - F.sc[SC_DEAD0 + tid]);
         TICK(PH_ACTS);
         // ---------------------------------------------------------------- prep_msm, stirecov_msm, stitx_msm (per-warp agent ranges)
         if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS)) {
@@ -746,47 +771,48 @@ _Pragma("unroll")
         TICK(PH_B);
         // ---------------------------------------------------------------- hivtrans_msm + stitrans_msm_rand over discordant ties
         // every warp classifies its ties 32 at a time and processes the (tie, act type) pairs that can transmit from two
-        // mini-queues; two sweeps: anal + oral, then kissing + rimming
+        // mini-queues: anal pairs, and the light pairs -- oral, rimming, kissing (item bits 14..15), one branch-free body
         if (mask & (XGC_M_HIVTRANS | XGC_M_STITRANS)) {
           const bool gct = mask & XGC_M_STITRANS, hvt = mask & XGC_M_HIVTRANS;
+          const bool kiss_on = gct && route_kiss, rim_on = gct && route_rim;
           const int ngroups = (ne_all + 31) >> 5;
           const int niter = (ngroups + NW - 1) / NW;
-          for (int sweep = 0; sweep < 2; ++sweep) {
-            if (sweep == 1 && !(gct && (route_kiss || route_rim))) break;
-            int c0 = 0, c1 = 0;
-            for (int it = 0; it < niter; ++it) {
-              const bool lastit = it == niter - 1;
-              const int f = (it * NW + warp) * 32 + lane; bool qa = false, qb = false;
-              if (f < ne_all) {
-                const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, e = f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
-                const int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
-                const unsigned eaf = ea[f]; const int ai = eaf & 63, oi = (eaf >> 6) & 63;
+          const int4* const Er = g.edge + (size_t)r * g.e_stride;
+          int c0 = 0, c1 = 0;
+          for (int it = 0; it < niter; ++it) {
+            const bool lastit = it == niter - 1;
+            const int f = (it * NW + warp) * 32 + lane; bool qa = false, qo = false, qk = false, qr = false;
+            if (f < ne_all) {
+              const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+              const unsigned eaf = ea[sidx];
+              if (eaf & 0x3FFFu) {                                // a living tie with any act this week
+                const int4 ed = Er[sidx];
+                const int ai = eaf & 63, oi = (eaf >> 6) & 63;
                 const unsigned x = vg[ed.x] & 7u, y = vg[ed.y] & 7u;
-                if (sweep == 0) {
-                  bool hivdisc = hvt && ai > 0 && ((vh[ed.x] ^ vh[ed.y]) & HV_STATUS);
-                  bool d_ai = (((x >> 1) ^ y) | ((y >> 1) ^ x)) & 1u, d_oi = (((x >> 1) ^ (y >> 2)) | ((y >> 1) ^ (x >> 2))) & 1u;
-                  qa = hivdisc || (gct && ai > 0 && d_ai);
-                  qb = gct && oi > 0 && d_oi;
-                } else {
-                  bool d_ri = (((x >> 2) ^ y) | ((y >> 2) ^ x)) & 1u, d_ki = ((x ^ y) >> 2) & 1u;
-                  qa = ((eaf >> 12) & 1u) && route_kiss && d_ki;
-                  qb = ((eaf >> 13) & 1u) && route_rim && d_ri;
-                }
+                const bool hivdisc = hvt && ai > 0 && ((vh[ed.x] ^ vh[ed.y]) & HV_STATUS);
+                const bool d_ai = (((x >> 1) ^ y) | ((y >> 1) ^ x)) & 1u, d_oi = (((x >> 1) ^ (y >> 2)) | ((y >> 1) ^ (x >> 2))) & 1u;
+                const bool d_ri = (((x >> 2) ^ y) | ((y >> 2) ^ x)) & 1u, d_ki = ((x ^ y) >> 2) & 1u;
+                qa = hivdisc || (gct && ai > 0 && d_ai);
+                qo = gct && oi > 0 && d_oi;
+                qk = ((eaf >> 12) & 1u) && kiss_on && d_ki;
+                qr = ((eaf >> 13) & 1u) && rim_on && d_ri;
               }
+            }
+            {
               WQ_PUSH(q0, c0, qa, f);
-              WQ_PUSH(q1, c1, qb, f);
-              // ---- queue 0: anal acts (sweep 0) or kissing (sweep 1)
+              // ---- queue 0: anal acts
               WQ_DRAIN(q0, c0, lastit, item,
                 const int f = (int)item;
-                const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0; const int e = f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
-                const int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
+                const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0; const int sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+                const int4 ed = Er[sidx];
                 const unsigned gca = vg[ed.x]; const unsigned gcb = vg[ed.y];
                 const unsigned ga = gca & 7u; const unsigned gb = gcb & 7u;
                 unsigned new_a = 0; unsigned new_b = 0; bool hiv_a = false; bool hiv_b = false;
-                const uint4 xa = frand(key, at, FS_ACTS, (unsigned)f, 0);
-                if (sweep == 0) {
+                const unsigned pk2 = pairkey(ed);
+                const uint4 xa = frand(key, at, FS_ACTS, pk2, (unsigned)l);
+                {
                   const unsigned da = vd[ed.x]; const unsigned db = vd[ed.y]; const unsigned ha = vh[ed.x]; const unsigned hb = vh[ed.y];
-                  const int ai = ea[f] & 63;
+                  const int ai = ea[sidx] & 63;
                   const bool hivdisc = hvt && ((ha ^ hb) & HV_STATUS);
                   const bool d_ai = gct && ((((ga >> 1) ^ gb) | ((gb >> 1) ^ ga)) & 1u);
                   // condom use: probabilities as condoms_msm saw them (PrEP status before this week's prep_msm)
@@ -810,11 +836,11 @@ _Pragma("unroll")
                     unsigned c16;
                     if (k < 2) c16 = k ? xa.w >> 16 : xa.w & 0xFFFFu;
                     else { const int kk = k - 2;
-                      if ((kk & 7) == 0) c = frand(key, at, FS_COND, (unsigned)f, (unsigned)(kk >> 3));
+                      if ((kk & 7) == 0) c = frand(key, at, FS_COND, pk2, (unsigned)l | ((unsigned)(kk >> 3) << 2));
                       const unsigned cw = (kk & 7) < 2 ? c.x : (kk & 7) < 4 ? c.y : (kk & 7) < 6 ? c.z : c.w;
                       c16 = (cw >> ((kk & 1) * 16)) & 0xFFFFu; }
                     const bool uai = c16 < cthr;
-                    const uint4 x = frand(key, at, FS_ANAL, (unsigned)f, (unsigned)k);
+                    const uint4 x = frand(key, at, FS_ANAL, pk2, (unsigned)l | ((unsigned)k << 2));
                     const bool p1ins = fixed >= 0 ? fixed != 0 : bern(x.x, pins);
                     if (hivdisc) {
                       const bool pos_ins = p1ins == a_pos;
@@ -842,29 +868,33 @@ _Pragma("unroll")
                       }
                     }
                   }
-                } else {                                         // kissing: pharynx <-> pharynx over all of the week's acts
-                  int n = l < 2 ? pois_tab_f(u01_16(xa.z & 0xFFFFu), F.pk + l * (XGC_MAX_ACTS + 1)) : 1;
-                  const uint4 x = frand(key, at, FS_KISS, (unsigned)f, 0);
-                  if (n > 0 && bern(x.x, any_of_n_f(P[XGC_P_p2pgc_tprob], n))) { if ((ga >> 2) & 1u) new_b |= 1u << XGC_PATH_P2P; else new_a |= 1u << XGC_PATH_P2P; }
                 }
                 if (new_a) atomicOr(&vg[ed.x], new_a << GC_NEW_SHIFT);
                 if (new_b) atomicOr(&vg[ed.y], new_b << GC_NEW_SHIFT);
                 if (hiv_a) atomicOr(&vh[ed.x], HV_NEW);
                 if (hiv_b) atomicOr(&vh[ed.y], HV_NEW);
               );
-              // ---- queue 1: oral acts (urethra <-> pharynx; sweep 0) or rimming (pharynx <-> rectum; sweep 1)
-              WQ_DRAIN(q1, c1, lastit, item,
-                const int f = (int)item;
-                const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0; const int e = f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
-                const int4 ed = g.edge[(size_t)r * g.e_stride + g.e_off[l] + e];
+            }
+#pragma unroll 1
+            for (int ph = 0; ph < 3; ++ph) {
+              WQ_PUSH(q1, c1, ph == 0 ? qo : ph == 1 ? qr : qk, f | (ph << 14));
+              // ---- queue 1: oral acts (urethra <-> pharynx), rimming (pharynx <-> rectum), kissing (pharynx <-> pharynx): the m acts
+              //      of one direction are ONE Bernoulli(1 - (1 - t)^m) trial
+              WQ_DRAIN(q1, c1, lastit && ph == 2, item,
+                const int f = (int)(item & 0x3FFFu); const unsigned ty = item >> 14;
+                const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0; const int sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+                const int4 ed = Er[sidx];
                 const unsigned ga = vg[ed.x] & 7u; const unsigned gb = vg[ed.y] & 7u;
-                const bool oral = sweep == 0;
-                int n = (ea[f] >> 6) & 63;
-                if (!oral) { const uint4 xa = frand(key, at, FS_ACTS, (unsigned)f, 0); n = l < 2 ? pois_tab_f(u01_16(xa.z >> 16), F.pk + (2 + l) * (XGC_MAX_ACTS + 1)) : 1; }
-                const int sx = oral ? 1 : 2; const int sy = oral ? 2 : 0;
-                const float tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob]; const float tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
-                const unsigned pA = oral ? XGC_PATH_U2P : XGC_PATH_P2R; const unsigned pB = oral ? XGC_PATH_P2U : XGC_PATH_R2P;
-                const uint4 x = frand(key, at, oral ? FS_ORAL : FS_RIM, (unsigned)f, 0);
+                const unsigned pk2 = pairkey(ed);
+                int n = (ea[sidx] >> 6) & 63;
+                if (ty) { n = 1;                                  // rimming / kissing counts: drawn here from the bits acts_msm tested for "any"
+                  if (l < 2) { const uint4 xa = frand(key, at, FS_ACTS, pk2, (unsigned)l);
+                    n = pois_tab_f(u01_16(ty == 1 ? xa.z >> 16 : xa.z & 0xFFFFu), F.pk + ((ty == 1 ? 2 : 0) + l) * (XGC_MAX_ACTS + 1)); } }
+                const int sx = ty == 0 ? 1 : 2; const int sy = ty == 0 ? 2 : ty == 1 ? 0 : 2;
+                const float tA = P[ty == 0 ? XGC_P_u2pgc_tprob : ty == 1 ? XGC_P_p2rgc_tprob : XGC_P_p2pgc_tprob];
+                const float tB = P[ty == 0 ? XGC_P_p2ugc_tprob : ty == 1 ? XGC_P_r2pgc_tprob : XGC_P_p2pgc_tprob];
+                const unsigned pA = ty == 0 ? XGC_PATH_U2P : ty == 1 ? XGC_PATH_P2R : XGC_PATH_P2P; const unsigned pB = ty == 0 ? XGC_PATH_P2U : ty == 1 ? XGC_PATH_R2P : XGC_PATH_P2P;
+                const uint4 x = frand(key, at, FS_ORAL + ty, pk2, (unsigned)l);
                 unsigned new_a = 0; unsigned new_b = 0;
                 if (n > 0) {
                   const int m1 = __popc(x.x >> (32 - n)); const int m0 = n - m1;       // acts with p1 / p2 the active partner
@@ -957,6 +987,7 @@ _Pragma("unroll")
       TICK(PH_ROW);
     }
     // ------------------------------------------------------------------------------------------ write the replicate back
+    if (F.sc[SC_DEAD0] | F.sc[SC_DEAD1] | F.sc[SC_DEAD2]) squeeze();     // HBM always holds compact tie lists
     {
       const int n_slots = F.sc[SC_NSLOTS];
       unsigned* Abm = g.alive + (size_t)r * (g.n_cap / 32);
@@ -972,10 +1003,12 @@ _Pragma("unroll")
         rp->n_slots = n_slots; rp->n_slots_pre = F.sc[SC_NPRE]; rp->next_uid = F.sc[SC_NEXTUID]; rp->t_age = F.sc[SC_TAGE];
         rp->ne[0] = F.sc[SC_NE0]; rp->ne[1] = F.sc[SC_NE1]; rp->ne[2] = F.sc[SC_NE2];
         rp->n_alive = F.sc[SC_NALIVE];
-        if (F.sc[SC_STATUS]) rp->status |= (unsigned)F.sc[SC_STATUS];
+        if (F.sc[SC_STATUS]) rp->status = __ldcg(&rp->status) | (unsigned)F.sc[SC_STATUS];
         for (int k = 0; k < XGC_NPATH; ++k) rp->path_rank[k] = F.sc[SC_PATH + k];
-        ((int*)g.at_ptr)[r] = A.at1;
       }
+      __threadfence();                                          // the replicate's state before the week it reached is published
+      __syncthreads();
+      if (tid == 0) __stcg((int*)g.at_ptr + r, w_last);
     }
     TICK(PH_WRITEBACK);
   }
@@ -1005,6 +1038,10 @@ extern "C" int xgc_debug_fast_profile(unsigned long long* out, int cap, int rese
   if (reset) { unsigned long long z[PH_N] = { 0 }; cudaMemcpyToSymbol(g_fast_prof, z, sizeof z); }
   return PH_N;
 }
+__global__ void k_fast_set_at(const __grid_constant__ Dev g, int at) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < g.R) ((int*)g.at_ptr)[g.r0 + r] = at;
+}
 cudaError_t xgc_fast_launch(const Dev& g, const FastArgs& a, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1015,6 +1052,8 @@ cudaError_t xgc_fast_launch(const Dev& g, const FastArgs& a, size_t smem, cudaSt
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = g.R < sms ? g.R : sms;
+  // a replicate whose weeks are split between two CTAs hands over through at_ptr[r]: make sure it cannot match by accident
+  if (a.at1 > a.at0 && g.R % grid) k_fast_set_at<<<(g.R + 255) / 256, 256, 0, s>>>(g, a.at0 - 1);
   k_week_fast<<<grid, FT, smem, s>>>(g, a);
   return cudaGetLastError();
 }
