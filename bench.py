@@ -398,15 +398,18 @@ def run_xgc(args, rank, world, local_rank):
     from xgc_msm_b200.params import control_msm
     # default: 8 host threads per GPU, fewer when the ranks of this node would oversubscribe its cores
     Ge = args.e2e_groups if args.e2e_groups > 0 else min(8, max(2, (os.cpu_count() or 8) // max(world, 1)))
+    if args.e2e_groups <= 0 and mode == "fast":
+        # the resident kernel runs one CTA per replicate: groups of just under one CTA per SM make every call one full wave
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        Ge = min(Ge, max(2, -(-R // sms)))
     Ge = max(1, min(Ge, R))
-    while R % Ge:
-        Ge -= 1
-    Rg = R // Ge
+    g_size = [R // Ge + (1 if gi < R % Ge else 0) for gi in range(Ge)]
+    g_off = [sum(g_size[:gi]) for gi in range(Ge)]
     groups = []
     for gi in range(Ge):
-        hg = Handle(Rg, spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rid_base + gi * Rg,
+        hg = Handle(g_size[gi], spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rid_base + g_off[gi],
                     compact_every=spec.weeks_between_compactions)
-        workload.load_sweep(hg, spec, rid0=rid_base + gi * Rg)
+        workload.load_sweep(hg, spec, rid0=rid_base + g_off[gi])
         if mode == "fast":
             hg.set_mode("fast")
         hg.run(2, at - 1)                                   # same point of the epidemic as the kernel-resident arm
@@ -430,7 +433,7 @@ def run_xgc(args, rank, world, local_rank):
 
     def e2e_week(gi, t):
         """One week of the contract for group gi (what one host-side simnet_msm loop does); returns living agents."""
-        hg, r0 = groups[gi], gi * Rg
+        hg, r0, Rg = groups[gi], g_off[gi], g_size[gi]
         hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
         for l in range(2):
@@ -479,11 +482,11 @@ def run_xgc(args, rank, world, local_rank):
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
            "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
-           "path": f"{Ge} handles x {Rg} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 2x xgc_update_edgelists_all "
+           "path": f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 2x xgc_update_edgelists_all "
                    "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> xgc_step(post) -> xgc_get_counters_all"}
     e2e_status = 0
     for hg in groups:
-        e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, Rg, max(Rg // 8, 1))]))
+        e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, hg.n_replicates, max(hg.n_replicates // 8, 1))]))
         hg.close()
     e2e["status_sample_or"] = e2e_status
 

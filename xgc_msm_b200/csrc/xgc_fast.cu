@@ -148,7 +148,7 @@ __device__ __forceinline__ void gap_warp(uint2 key, unsigned at, unsigned stream
 }
 
 // phase clocks (SM cycles summed over CTAs; thread 0 of each CTA): tools/time_modes.py
-enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE, PH_NET, PH_ACTS, PH_B, PH_TRANS, PH_APPLY_TALLY, PH_ROW, PH_WRITEBACK, PH_N = 16 };
+enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE, PH_NET, PH_ACTS, PH_B, PH_TRANS, PH_APPLY_TALLY, PH_ROW, PH_WRITEBACK, PH_SQUEEZE_WB, PH_STAGE_TABLES, PH_N = 16 };
 __device__ unsigned long long g_fast_prof[PH_N];
 #define TICK(k) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fast_prof[k], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 
@@ -156,7 +156,8 @@ __device__ unsigned long long g_fast_prof[PH_N];
 #define TEST_BODY { const int i = a0 + (int)(item & 0x7FFFu); const bool rule = item & 0x8000u; const unsigned d = vd[i], h = vh[i]; \
   if (d & DM_ACTIVE) { short lnt = g.tck[rbase + i].x; int last = lnt == XGC_NA16 ? g.arr_t[rbase + i] : (int)lnt; float tsl = (float)(at - last); \
     bool tested = rule ? ((HV_STAGE(h) == 4 && tsl >= P[XGC_P_aids_test_int]) || ((h & HV_PREP) && tsl >= P[XGC_P_prep_tst_int])) : tsl >= 2.f; \
-    if (tested && !(atomicOr(&vg[i], FG_TESTED) & FG_TESTED)) { atomicAdd(&F.row[XGC_K_HIVTESTS], 1u); if (!(h & HV_STATUS)) g.tck[rbase + i].x = (short)at; } } }
+    if (tested) { const unsigned g0_ = atomicOr(&vg[i], FG_TESTED); \
+      if (!(g0_ & FG_TESTED)) { if (wt) core_w[4 * (rbase + i) + 2] = g0_ | FG_TESTED; atomicAdd(&F.row[XGC_K_HIVTESTS], 1u); if (!(h & HV_STATUS)) g.tck[rbase + i].x = (short)at; } } } }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
@@ -175,6 +176,10 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   unsigned short* const q0 = F.mq[warp][0];
   unsigned short* const q1 = F.mq[warp][1];
   long long t_last = clock64();
+  // a call that ends before the POST group (the aging..hivvl call of the weekly host-network pattern) changes few agents: it
+  // writes every change of a core word through to HBM and skips the write-back of the plane
+  const bool wt = !(A.phases & XF_POST);
+  unsigned* const core_w = (unsigned*)g.core;
   // Schedule: the launch's replicate-weeks, replicate-major, are cut into gridDim.x equal stretches (148 CTAs x 1000 replicates
   // would otherwise run 7 waves for 6.76 waves of work).  A CTA walks its stretch from the LAST replicate to the first: the
   // replicate it shares with the next CTA comes first (its early weeks, no dependence), the one it shares with the previous
@@ -213,11 +218,17 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     for (int k = tid; k < (int)g.e_stride; k += FT) ea[k] = 0;   // HBM holds compact lists: no tombstones
     __syncthreads();
     if (tid < 4 * XGC_ASMR_AGES && F.asmr[tid] >= HI_MORT) atomicOr(&F.hib[(tid / XGC_ASMR_AGES) * 4 + ((tid % XGC_ASMR_AGES) >> 5)], 1u << ((tid % XGC_ASMR_AGES) & 31));
+    TICK(PH_STAGE_TABLES);
     {
       const int n0 = F.sc[SC_NSLOTS];
-      for (int i = tid; i < n0; i += FT) {
-        uint4 c = g.core[rbase + i];
-        vd[i] = c.y; vg[i] = c.z; vh[i] = c.w; ind[i] = g.tck[rbase + i].y;
+      // four independent 16-byte loads per thread in flight (one per thread leaves the SM latency-bound at ~1/4 of its share
+      // of the HBM bandwidth); the PrEP-indication clock is only needed by the POST group
+      for (int i0 = tid; i0 < n0; i0 += 4 * FT) {
+        uint4 c[4]; short t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = min(i0 + k * FT, n0 - 1); c[k] = g.core[rbase + i]; t[k] = wt ? (short)-1 : g.tck[rbase + i].y; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * FT; if (i < n0) { vd[i] = c[k].y; vg[i] = c[k].z; vh[i] = c[k].w; if (!wt) ind[i] = t[k]; } }
       }
     }
     if (warp == 0) {                                            // largest gap-sampled weekly death probability
@@ -342,7 +353,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (!(d & DM_ACTIVE)) return;
             int ai = min(XGC_ASMR_AGES - 1, max(0, (int)((float)(at8 - birth8(vh[i])) * (float)XF_W8)));
             float pm = F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai];
-            if (pm < HI_MORT && u01(x.y) * pmax_mort < pm) { vd[i] = d & ~DM_ACTIVE; atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); }
+            if (pm < HI_MORT && u01(x.y) * pmax_mort < pm) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+              atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); }
           });
         __syncwarp();
         // hivtest_msm, interval testing: gaps at the largest race rate, thinned by race
@@ -365,12 +377,13 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (live) {
               float age = (float)(at8 - birth8(h)) * (float)XF_W8;
               bool isnew = i >= n_pre;
-              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; } }
+              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; if (wt) core_w[4 * (rbase + i) + 1] = d; } }
               if ((mask & XGC_M_DEPARTURE) && !isnew) {
                 int ai = min(XGC_ASMR_AGES - 1, max(0, (int)age));
                 if ((F.hib[DM_RACE(d) * 4 + (ai >> 5)] >> (ai & 31)) & 1u) {
                   uint4 x = frand(key, at, FS_MORTHI, (unsigned)i, 0);
-                  if (bern(x.x, F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai])) { vd[i] = d & ~DM_ACTIVE; atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); live = false; }
+                  if (bern(x.x, F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai])) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+                    atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); live = false; }
                 }
               }
               qpos = live && hivmods && (h & HV_STATUS) && !isnew;
@@ -392,7 +405,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (d & DM_ACTIVE) {                                // (not) died of natural causes this week
               uint4 x = frand(key, at, FS_AG1, (unsigned)i, 0);
               if ((mask & XGC_M_DEPARTURE) && HV_STAGE(h) == 4 && bern(x.x, P[XGC_P_aids_mr])) {
-                vd[i] = d & ~DM_ACTIVE; atomicAdd(&F.row[XGC_K_DEP_AIDS], 1u); atomicSub(&F.sc[SC_NALIVE], 1);
+                vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * idx + 1] = d & ~DM_ACTIVE;
+                atomicAdd(&F.row[XGC_K_DEP_AIDS], 1u); atomicSub(&F.sc[SC_NALIVE], 1);
               } else {
                 short4 ha = g.hck_a[idx]; short4 hb = g.hck_b[idx]; float vl0 = g.aux[idx].vl;
                 const unsigned h0 = h; bool ha_dirty = false; bool hb_dirty = false;
@@ -446,7 +460,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                 }
                 if (ha_dirty) g.hck_a[idx] = ha;
                 if (hb_dirty) g.hck_b[idx] = hb;
-                if (h != h0) vh[i] = h;
+                if (h != h0) { vh[i] = h; if (wt) core_w[4 * idx + 3] = h; }
               }
             }
           );
@@ -522,13 +536,23 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         }
         if (!(A.phases & XF_POST)) {                             // no acts pass in this call: the tie sweep on its own
           const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
-          for (int f = tid; f < ne_all; f += FT) {
-            const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
-            if (ea[sidx] & EA_DEAD) continue;
-            const int4 ed = g.edge[(size_t)r * g.e_stride + sidx];
-            bool dead = !(vd[ed.x] & vd[ed.y] & DM_ACTIVE);
-            if (!dead && form && l < 2 && ed.z < at) dead = dissolves(frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l), ed, l, at);
-            if (dead) { ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); }
+          for (int f0 = tid; f0 < ne_all; f0 += 4 * FT) {        // four ties per thread in flight
+            int4 ed4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int f = min(f0 + k * FT, ne_all - 1);
+              const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+              ed4[k] = g.edge[(size_t)r * g.e_stride + sidx];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int4 ed = ed4[k]; const int f = f0 + k * FT, l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
+              if (f < ne_all && !(ea[sidx] & EA_DEAD)) {
+                bool dead = !(vd[ed.x] & vd[ed.y] & DM_ACTIVE);
+                if (!dead && form && l < 2 && ed.z < at) dead = dissolves(frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l), ed, l, at);
+                if (dead) { ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); }
+              }
+            }
           }
           __syncthreads();
           if (tid < 3 && form) F.row[XGC_K_NEDGES + tid] = (unsigned)(F.sc[SC_NE0 + tid] - F.sc[SC_DEAD0 + tid]);
@@ -988,6 +1012,7 @@ _Pragma("unroll")
     }
     // ------------------------------------------------------------------------------------------ write the replicate back
     if (F.sc[SC_DEAD0] | F.sc[SC_DEAD1] | F.sc[SC_DEAD2]) squeeze();     // HBM always holds compact tie lists
+    TICK(PH_SQUEEZE_WB);
     {
       const int n_slots = F.sc[SC_NSLOTS];
       unsigned* Abm = g.alive + (size_t)r * (g.n_cap / 32);
@@ -995,7 +1020,10 @@ _Pragma("unroll")
         int i = i0 + tid;
         bool in = i < n_slots;
         unsigned d = in ? vd[i] : 0u;
-        if (in) { uint4 c = g.core[rbase + i]; c.y = d; c.z = vg[i]; c.w = vh[i]; g.core[rbase + i] = c; }
+        if (in && !wt) {                                        // (the uid word never changes: 4 + 8 byte stores, no read-modify-write)
+          core_w[4 * (rbase + i) + 1] = d;
+          *reinterpret_cast<uint2*>(core_w + 4 * (rbase + i) + 2) = make_uint2(vg[i], vh[i]);
+        }
         unsigned m = __ballot_sync(FULL, in && (d & DM_ACTIVE));
         if (lane == 0 && i < g.n_cap) Abm[i >> 5] = m;
       }
