@@ -205,6 +205,24 @@ def test_large_population_100k_plus():
                 compare_state(h, r, o, at, f"170k agents after compaction r={r}", acts=False)
 
 
+def test_config5_one_million_agents():
+    """BASELINE configs[4]: ONE replicate of 1,000,000 agents (~0.5M ties), the shape bench.py --replicates 1 --agents 1000000
+    times: every per-replicate step is multi-CTA (look-back edge compaction and formation, rank plane, parallel slot
+    compaction).  Three weeks + a slot compaction, bit-exact vs the oracle: all attributes, edge lists, act counts, tallies."""
+    case = make_case(1000000, 5, network_mode="surrogate")
+    h = load_handle([case], SEED, t_cap=8, replicate_offset=2)
+    o = load_oracle(case, SEED, 2, t_cap=8)
+    for at in (2, 3, 4):
+        h.step(at)
+        o.step(at, K.M_ALL)
+        compare_state(h, 0, o, at, f"1M agents week {at}")
+        if at == 3:
+            h.compact()
+            compare_state(h, 0, o, at, "1M agents after compaction", acts=False)
+    assert h.status(0) == 0 and h.num_agents(0) > 990000
+    h.close()
+
+
 def test_host_network_weekly_contract_all_replicates():
     """The end-to-end contract bench.py's e2e arm times (INTEGRATION.md "weekly host <-> device traffic"): pre-network
     modules -> living counts to the host -> three ragged edge lists for EVERY replicate in one call each (1-based

@@ -109,6 +109,23 @@ __device__ __forceinline__ float glm_f(const float* b, float dur, bool casual, f
   if (prep) eta += b[XGC_G_PREP];
   return eta;
 }
+// prevalence_msm's state tallies (series = counter group, by race x age cell) are kept INCREMENTALLY: counted once when the
+// replicate is staged, then every change of an agent's tallied state moves its counts.  tally_bits: bit b = agent counts in group b.
+#define STATE_GROUPS ((1u << XGC_K_NUM) | (1u << XGC_K_INUM) | (1u << XGC_K_INUM_DX) | (1u << XGC_K_VSUPP) | (1u << XGC_K_PREPELIG) | (1u << XGC_K_PREPCURR) | \
+                      (1u << XGC_K_INUM_GC) | (1u << XGC_K_INUM_RGC) | (1u << XGC_K_INUM_UGC) | (1u << XGC_K_INUM_PGC))
+__device__ __forceinline__ unsigned tally_bits(unsigned d, unsigned gc, unsigned h) {
+  if (!(d & DM_ACTIVE)) return 0u;
+  return (1u << XGC_K_NUM) | ((h & HV_STATUS) ? 1u << XGC_K_INUM : 0u) | ((h & HV_DIAG) ? 1u << XGC_K_INUM_DX : 0u) | (((h & HV_DIAG) && (h & HV_VSUPP)) ? 1u << XGC_K_VSUPP : 0u) |
+         ((h & HV_PREPELIG) ? 1u << XGC_K_PREPELIG : 0u) | ((h & HV_PREP) ? 1u << XGC_K_PREPCURR : 0u) | ((gc & 7u) ? 1u << XGC_K_INUM_GC : 0u) |
+         ((gc & 1u) ? 1u << XGC_K_INUM_RGC : 0u) | ((gc & 2u) ? 1u << XGC_K_INUM_UGC : 0u) | ((gc & 4u) ? 1u << XGC_K_INUM_PGC : 0u);
+}
+// an agent's (demo, gc, hiv) words went from (d0, g0, h0) to (d1, g1, h1): move its counts (shared-memory atomics, a handful per event)
+__device__ __noinline__ void tally_move(unsigned* row, unsigned d0, unsigned g0, unsigned h0, unsigned d1, unsigned g1, unsigned h1) {
+  const unsigned b0 = tally_bits(d0, g0, h0), b1 = tally_bits(d1, g1, h1), c0 = DM_CELL(d0), c1 = DM_CELL(d1);
+  unsigned sub = c0 == c1 ? b0 & ~b1 : b0, add = c0 == c1 ? b1 & ~b0 : b1;
+  while (sub) { const int b = __ffs(sub) - 1; sub &= sub - 1; atomicSub(&row[b * XGC_NCELL + c0], 1u); }
+  while (add) { const int b = __ffs(add) - 1; add &= add - 1; atomicAdd(&row[b * XGC_NCELL + c1], 1u); }
+}
 __device__ __forceinline__ unsigned pairkey(const int4& ed) { return (unsigned)ed.x | ((unsigned)ed.y << 16); }      // slots < 32768
 __device__ __forceinline__ int birth8(unsigned h) { return (int)((h >> XF_BIRTH_SHIFT) & XF_BIRTH_MASK); }
 // exclusive prefix of the 32 per-warp counts in cnt[] for this warp, and their total (every warp computes it redundantly)
@@ -239,6 +256,25 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
       if (lane == 0) F.sc[SC_PMAX] = __float_as_int(v);
     }
     __syncthreads();
+    // multi-week launches keep prevalence_msm's state tallies incrementally (counted here once, then moved by every change of an
+    // agent's tallied state); a single-week call counts them once at the end of its POST group instead
+    const bool incr = A.at1 > A.at0;
+    if (incr) {
+      for (int k = tid; k < XGC_K_NGROUP * XGC_NCELL; k += FT) F.row[k] = 0u;
+      __syncthreads();
+      const int n0 = F.sc[SC_NSLOTS];
+      const int AW = ((n0 + FT - 1) / FT) * 32, a0 = warp * AW, a1 = min(a0 + AW, n0);
+      for (int k = 0; k * 32 < AW; ++k) {
+        const int i = a0 + k * 32 + lane;
+        unsigned d = i < a1 ? vd[i] : 0u;
+        unsigned bits = i < a1 ? tally_bits(d, vg[i], vh[i]) & ~(1u << XGC_K_NUM) : 0u;
+        const bool live = d & DM_ACTIVE; const unsigned cell = live ? DM_CELL(d) : 31u;
+        const unsigned grp = __match_any_sync(FULL, cell);
+        if (live && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&F.row[XGC_K_NUM * XGC_NCELL + cell], (unsigned)__popc(grp));
+        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; atomicAdd(&F.row[b * XGC_NCELL + cell], 1u); }
+      }
+      __syncthreads();
+    }
     const float pmax_mort = __int_as_float(F.sc[SC_PMAX]);
     const float pmax_test = fmaxf(fmaxf(P[XGC_P_hiv_test_rate], P[XGC_P_hiv_test_rate + 1]), fmaxf(P[XGC_P_hiv_test_rate + 2], P[XGC_P_hiv_test_rate + 3]));
     // tie dissolution, Bernoulli(1 / duration) per tie-week: a 16-bit pre-test on spare bits of the tie's acts block, refined
@@ -293,7 +329,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
       const int at8 = (at + XF_BIRTH_OFF) * 8;
       // =================================================================================================== PRE
       if (A.phases & XF_PRE) {
-        for (int k = tid; k < XGC_NCOUNTER; k += FT) F.row[k] = 0u;
+        for (int k = tid; k < XGC_NCOUNTER; k += FT)            // the week's event counters start at zero; state tallies carry over
+          if (!incr || k >= XGC_K_NGROUP * XGC_NCELL || !((STATE_GROUPS >> (k / XGC_NCELL)) & 1u)) F.row[k] = 0u;
         // ---- arrival_msm: one warp
         if (warp == 0) {
           int n_slots = F.sc[SC_NSLOTS], nnew = 0;
@@ -329,6 +366,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               g.gck_a[idx] = na; g.gck_b[idx] = na; g.gck_d[idx] = na; g.hck_a[idx] = na; g.hck_b[idx] = make_short4(0, 0, -1, -1); g.tck[idx] = na;
               g.arr_t[idx] = at;
               vd[i] = demo; vg[i] = 0u; vh[i] = hiv; ind[i] = -1;
+              if (incr) tally_move(F.row, 0u, 0u, 0u, demo, 0u, hiv);
             }
           }
           if (lane == 0) {
@@ -354,6 +392,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             int ai = min(XGC_ASMR_AGES - 1, max(0, (int)((float)(at8 - birth8(vh[i])) * (float)XF_W8)));
             float pm = F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai];
             if (pm < HI_MORT && u01(x.y) * pmax_mort < pm) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+              if (incr) tally_move(F.row, d, vg[i], vh[i], 0u, 0u, 0u);
               atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); }
           });
         __syncwarp();
@@ -377,12 +416,14 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (live) {
               float age = (float)(at8 - birth8(h)) * (float)XF_W8;
               bool isnew = i >= n_pre;
-              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; if (wt) core_w[4 * (rbase + i) + 1] = d; } }
+              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { const unsigned dold = d; d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; if (wt) core_w[4 * (rbase + i) + 1] = d;
+                if (incr) tally_move(F.row, dold, vg[i], h, d, vg[i], h); } }
               if ((mask & XGC_M_DEPARTURE) && !isnew) {
                 int ai = min(XGC_ASMR_AGES - 1, max(0, (int)age));
                 if ((F.hib[DM_RACE(d) * 4 + (ai >> 5)] >> (ai & 31)) & 1u) {
                   uint4 x = frand(key, at, FS_MORTHI, (unsigned)i, 0);
                   if (bern(x.x, F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai])) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+                    if (incr) tally_move(F.row, d, vg[i], h, 0u, 0u, 0u);
                     atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); live = false; }
                 }
               }
@@ -406,6 +447,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               uint4 x = frand(key, at, FS_AG1, (unsigned)i, 0);
               if ((mask & XGC_M_DEPARTURE) && HV_STAGE(h) == 4 && bern(x.x, P[XGC_P_aids_mr])) {
                 vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * idx + 1] = d & ~DM_ACTIVE;
+                if (incr) tally_move(F.row, d, vg[i], h, 0u, 0u, 0u);
                 atomicAdd(&F.row[XGC_K_DEP_AIDS], 1u); atomicSub(&F.sc[SC_NALIVE], 1);
               } else {
                 short4 ha = g.hck_a[idx]; short4 hb = g.hck_b[idx]; float vl0 = g.aux[idx].vl;
@@ -460,7 +502,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                 }
                 if (ha_dirty) g.hck_a[idx] = ha;
                 if (hb_dirty) g.hck_b[idx] = hb;
-                if (h != h0) { vh[i] = h; if (wt) core_w[4 * idx + 3] = h; }
+                if (h != h0) { vh[i] = h; if (wt) core_w[4 * idx + 3] = h; if (incr) tally_move(F.row, d, 0u, h0, d, 0u, h); }
               }
             }
           );
@@ -468,7 +510,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         __syncthreads();
         TICK(PH_PRE);
       } else {
-        for (int k = tid; k < XGC_NCOUNTER; k += FT) F.row[k] = grow[k];      // continuing a week started by an earlier call
+        for (int k = tid; k < XGC_NCOUNTER; k += FT)            // continuing a week started by an earlier call
+          if (!incr || k >= XGC_K_NGROUP * XGC_NCELL || !((STATE_GROUPS >> (k / XGC_NCELL)) & 1u)) F.row[k] = grow[k];
         __syncthreads();
       }
       // =================================================================================================== NETWORK
@@ -679,7 +722,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                 qP = (h & HV_PREP) || (!diag && indic && (gc & FG_TESTED) && (float)at >= P[XGC_P_prep_start]);
               }
               if (gc1 != gc) vg[i] = gc1;
-              if (h1 != h) vh[i] = h1;
+              if (h1 != h) { vh[i] = h1;
+                if (incr && ((h1 ^ h) & HV_PREPELIG)) atomicAdd(&F.row[XGC_K_PREPELIG * XGC_NCELL + DM_CELL(vd[i])], (h1 & HV_PREPELIG) ? 1u : 0xFFFFFFFFu); }
               unsigned ex = (gc >> GC_EXPO_SHIFT) & 0x1Fu;
               bool cdc_active = proto == XGC_SCREEN_CDC && ((ex & 7u) || (kissx && (ex & 8u)));
               qA = (mask & (XGC_M_STIRECOV | XGC_M_STITX)) && ((gc & 7u) || ((mask & XGC_M_STITX) && ((gc & FG_AVD) || cdc_active)));
@@ -706,7 +750,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
                 h = (h & ~HV_PREPCLASS_MASK) | HV_PREP | (cl << 7);
                 short4* tq = g.tck + idx; tq->z = (short)at; tq->w = (short)at;
               }
-              if (h != h0) vh[i] = h;
+              if (h != h0) { vh[i] = h;      // (only prepStat / prepClass change here)
+                if (incr && ((h ^ h0) & HV_PREP)) atomicAdd(&F.row[XGC_K_PREPCURR * XGC_NCELL + DM_CELL(vd[i])], (h & HV_PREP) ? 1u : 0xFFFFFFFFu); }
             );
           }
           for (int k = 0; k * 32 < AW; ++k) {                   // stirecov_msm + stitx_msm on infected or visiting agents
@@ -787,7 +832,12 @@ _Pragma("unroll")
               if (gb_dirty) g.gck_b[idx] = gb;
               if (gd_dirty) g.gck_d[idx] = gd;
               // other threads OR exposure / new-infection bits into this word only in other phases: a plain store is safe here
-              if (gc != gc0) vg[i] = gc;
+              if (gc != gc0) { vg[i] = gc;
+                if (incr && ((gc ^ gc0) & 7u)) {                // recoveries: the site tallies, and the any-site tally when the last one clears
+                  const unsigned cell = DM_CELL(vd[i]); unsigned rec = (gc ^ gc0) & 7u;
+                  if (!(gc & 7u)) atomicSub(&F.row[XGC_K_INUM_GC * XGC_NCELL + cell], 1u);
+                  while (rec) { const int sb = __ffs(rec) - 1; rec &= rec - 1; atomicSub(&F.row[(XGC_K_INUM_RGC + sb) * XGC_NCELL + cell], 1u); }
+                } }
             );
           }
         }
@@ -935,16 +985,22 @@ _Pragma("unroll")
         }
         __syncthreads();
         TICK(PH_TRANS);
-        // ---------------------------------------------------------------- apply new infections, then prevalence_msm (per-warp agent ranges)
+        // ---------------------------------------------------------------- apply new infections (per-warp agent ranges)
         {
           int c0 = 0;
           for (int k = 0; k * 32 < AW; ++k) {
             const int i = a0 + k * 32 + lane;
-            bool q = i < a1 && (vd[i] & DM_ACTIVE) && ((vg[i] & GC_NEW_MASK) || (vh[i] & HV_NEW));
+            bool q = false;
+            if (i < a1 && (vd[i] & DM_ACTIVE)) {
+              const unsigned gc = vg[i];
+              if (gc & (FG_TESTED | FG_AVD)) vg[i] = gc & ~(FG_TESTED | FG_AVD);      // transient week flags
+              q = (gc & GC_NEW_MASK) || (vh[i] & HV_NEW);
+            }
             WQ_PUSH(q0, c0, q, k * 32 + lane);
             WQ_DRAIN(q0, c0, (k + 1) * 32 >= AW, item,
               const int i = a0 + (int)item; const size_t idx = rbase + i;
               unsigned gc = vg[i]; unsigned h = vh[i]; const unsigned cell = DM_CELL(vd[i]);
+              const unsigned gc_old = gc; const unsigned h_old = h;
               unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
               if (nm && (mask & XGC_M_STITRANS)) {
                 short4 ga = g.gck_a[idx]; short4 gb = g.gck_b[idx]; short4 gd = make_short4(-1, -1, -1, -1);
@@ -980,28 +1036,22 @@ _Pragma("unroll")
               }
               if (mask & XGC_M_HIVTRANS) h &= ~HV_NEW;
               vg[i] = gc; vh[i] = h;
+              if (incr) tally_move(F.row, vd[i], gc_old, h_old, vd[i], gc, h);
             );
           }
           __syncwarp();
-          // prevalence_msm: recount over the staged state; transient week flags are cleared on the way
-          for (int k = 0; k * 32 < AW; ++k) {
-            const int i = a0 + k * 32 + lane;
-            bool live = i < a1 && (vd[i] & DM_ACTIVE);
-            unsigned cell = 31u, bits = 0u;
-            if (live) {
-              unsigned gc = vg[i], h = vh[i];
-              if (gc & (FG_TESTED | FG_AVD)) vg[i] = gc & ~(FG_TESTED | FG_AVD);
-              cell = DM_CELL(vd[i]);
-              bits = ((h & HV_STATUS) ? 1u << XGC_K_INUM : 0u) | ((h & HV_DIAG) ? 1u << XGC_K_INUM_DX : 0u) | (((h & HV_DIAG) && (h & HV_VSUPP)) ? 1u << XGC_K_VSUPP : 0u) |
-                     ((h & HV_PREPELIG) ? 1u << XGC_K_PREPELIG : 0u) | ((h & HV_PREP) ? 1u << XGC_K_PREPCURR : 0u) | ((gc & 7u) ? 1u << XGC_K_INUM_GC : 0u) |
-                     ((gc & 1u) ? 1u << XGC_K_INUM_RGC : 0u) | ((gc & 2u) ? 1u << XGC_K_INUM_UGC : 0u) | ((gc & 4u) ? 1u << XGC_K_INUM_PGC : 0u);
-            }
-            if (mask & XGC_M_PREV) {
-              unsigned grp = __match_any_sync(FULL, cell);
+          // prevalence_msm.  Multi-week launches: the state tallies in F.row are current (tally_move).  A single-week call
+          // counts the staged state once, here
+          if (!incr && (mask & XGC_M_PREV))
+            for (int k = 0; k * 32 < AW; ++k) {
+              const int i = a0 + k * 32 + lane;
+              const unsigned d = i < a1 ? vd[i] : 0u;
+              unsigned bits = i < a1 ? tally_bits(d, vg[i], vh[i]) & ~(1u << XGC_K_NUM) : 0u;
+              const bool live = d & DM_ACTIVE; const unsigned cell = live ? DM_CELL(d) : 31u;
+              const unsigned grp = __match_any_sync(FULL, cell);
               if (live && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&F.row[XGC_K_NUM * XGC_NCELL + cell], (unsigned)__popc(grp));
-              while (bits) { int b = __ffs(bits) - 1; bits &= bits - 1; atomicAdd(&F.row[b * XGC_NCELL + cell], 1u); }
+              while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; atomicAdd(&F.row[b * XGC_NCELL + cell], 1u); }
             }
-          }
         }
         __syncthreads();
         TICK(PH_APPLY_TALLY);
