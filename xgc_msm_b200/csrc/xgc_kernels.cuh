@@ -23,6 +23,25 @@ __device__ __forceinline__ void warp_tally_n(unsigned* row, int idx, unsigned v)
   v = __reduce_add_sync(0xffffffffu, v);            // one REDUX instead of five shuffle + add steps
   if (v && (threadIdx.x & 31) == 0) atomicAdd(row + idx, v);
 }
+// The scalar event counters [XGC_K_PATH, XGC_K_PATH + 32) aggregated per CTA in shared memory and flushed with one global
+// atomic per touched counter: with ONE large replicate (BASELINE configs[4]) every warp of a kernel otherwise hits the same
+// few global addresses (k_agent2b: 50k same-address atomics = 0.06 ms of a 0.075 ms launch at 1M agents).
+struct CtaTally {
+  unsigned* s;
+  __device__ __forceinline__ void init(unsigned* smem) { s = smem; if (threadIdx.x < 32) s[threadIdx.x] = 0u; __syncthreads(); }
+  __device__ __forceinline__ void add(int idx, bool pred) {           // reached by every lane of the warp
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(&s[idx - XGC_K_PATH], (unsigned)__popc(m));
+  }
+  __device__ __forceinline__ void add_n(int idx, unsigned v) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (v && (threadIdx.x & 31) == 0) atomicAdd(&s[idx - XGC_K_PATH], v);
+  }
+  __device__ __forceinline__ void flush(unsigned* row) {              // reached by every thread of the CTA
+    __syncthreads();
+    if (threadIdx.x < 32) { unsigned v = s[threadIdx.x]; if (v) atomicAdd(row + XGC_K_PATH + threadIdx.x, v); }
+  }
+};
 __device__ __forceinline__ unsigned* counter_row(const Dev& g, int r, int at) {
   return g.counters + ((size_t)r * g.t_cap + (size_t)at) * XGC_NCOUNTER;
 }
@@ -177,7 +196,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
   if (t0 >= t1) return;
   extern __shared__ unsigned cq_smem[];
   CtaQueue cq; cq.init(cq_smem);
-  __syncthreads();
+  __shared__ unsigned s_tally[32];
+  CtaTally tl; tl.init(s_tally);
   int at = g.at_ptr[r], lane = threadIdx.x & 31;
   int n_pre = rp->n_slots_pre;
   const double dt = (double)(rp->t_age - rp->t_ref) * XGC_WEEK;
@@ -220,8 +240,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
         if (lane == 0) {
           atomicAnd(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), ~dm);
           atomicSub((int*)&rp->n_alive, __popc(dm));
-          if (mg) atomicAdd(row + XGC_K_DEP_GEN, (unsigned)__popc(mg));
-          if (ma) atomicAdd(row + XGC_K_DEP_AIDS, (unsigned)__popc(ma));
+          if (mg) atomicAdd(&s_tally[XGC_K_DEP_GEN - XGC_K_PATH], (unsigned)__popc(mg));
+          if (ma) atomicAdd(&s_tally[XGC_K_DEP_AIDS - XGC_K_PATH], (unsigned)__popc(ma));
         }
       }
     }
@@ -236,7 +256,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
       if ((hiv & HV_PREP) && tsl >= P[XGC_P_prep_tst_int]) tested = true;
       if (tested && !(hiv & HV_STATUS)) g.tck[idx].x = (short)at;
     }
-    if (mask & XGC_M_HIVTEST) warp_tally(row, XGC_K_HIVTESTS, tested);
+    if (mask & XGC_M_HIVTEST) tl.add(XGC_K_HIVTESTS, tested);
     if (i < n_slots && (demo != c.y || gc != c.z || hiv != c.w)) {
       uint2* q = (uint2*)&g.core[idx];
       if (demo != c.y) q[0].y = demo;
@@ -247,6 +267,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent1a(const __gri
     cq.push(queue, (unsigned)i | (tested ? 0x80000000u : 0u), lane);
   }
   cq.flush(g.qh_count + r, Q);
+  tl.flush(row);
 }
 
 // k_agent1b: HIV test result, hivtx_msm, hivprogress_msm, hivvl_msm over the queued (surviving) HIV-positive agents.
@@ -777,6 +798,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __gr
   unsigned* row = counter_row(g, r, at);
   uint4* core = g.core + (size_t)r * g.n_cap;
   const Aux* aux = g.aux + (size_t)r * g.n_cap;
+  __shared__ unsigned s_tally[32];
+  CtaTally tl; tl.init(s_tally);
   for (int fbase = blockIdx.x * TPB; fbase < ne_all; fbase += gridDim.x * TPB) {
   const int f = fbase + threadIdx.x;
   const bool live = f < ne_all;
@@ -855,9 +878,10 @@ template <bool INJ> __global__ void __launch_bounds__(TPB, 4) k_edge1(const __gr
     }
   }
   if (mask & XGC_M_ACTS) {
-    warp_tally_n(row, XGC_K_NACTS, nai); warp_tally_n(row, XGC_K_NACTS + 1, noi);
+    tl.add_n(XGC_K_NACTS, nai); tl.add_n(XGC_K_NACTS + 1, noi);
   }
   }
+  tl.flush(row);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -937,6 +961,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __gri
   const double* P = g.params + (size_t)r * XGC_NPARAM;
   const int* C = g.control + (size_t)r * XGC_NCONTROL;
   unsigned* row = counter_row(g, r, at);
+  __shared__ unsigned s_tally[32];
+  CtaTally tl; tl.init(s_tally);
   for (unsigned qbase = blockIdx.x * TPB; qbase < n; qbase += gridDim.x * TPB) {
   unsigned qi = qbase + threadIdx.x;
   unsigned visit = 0, svisit = 0, tst[3] = { 0, 0, 0 }, pos[3] = { 0, 0, 0 }, txs[3] = { 0, 0, 0 };
@@ -1025,12 +1051,13 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_agent2b(const __gri
   if (mask & XGC_M_STITX) {
     unsigned any = __ballot_sync(0xffffffffu, visit != 0);
     if (any) {
-      warp_tally(row, XGC_K_VISITS, visit); warp_tally(row, XGC_K_VISITS_SYMPT, svisit);
+      tl.add(XGC_K_VISITS, visit); tl.add(XGC_K_VISITS_SYMPT, svisit);
 #pragma unroll
-      for (int s = 0; s < 3; ++s) { warp_tally(row, XGC_K_TESTED + s, tst[s]); warp_tally(row, XGC_K_POS + s, pos[s]); warp_tally(row, XGC_K_TXSTART + s, txs[s]); }
+      for (int s = 0; s < 3; ++s) { tl.add(XGC_K_TESTED + s, tst[s]); tl.add(XGC_K_POS + s, pos[s]); tl.add(XGC_K_TXSTART + s, txs[s]); }
     }
   }
   }
+  tl.flush(row);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
