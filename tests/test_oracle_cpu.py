@@ -103,7 +103,7 @@ def test_prior_box_matches_reference():
     env = P.prior_midpoint_env()
     p = P.params_from_env(env)
     assert P.get(p, "rgc_tx_recov_pr").tolist() == pytest.approx([1 - 0.06, 0.5, 1.0])     # c(1 - INFPR_WK1, 0.5, 1)
-    assert P.get(p, "a_rate")[0] == pytest.approx(0.00042 + 1.285 / 20000)      # synthetic marginal exit rate + the reference tweak (sim1_02_lhs.r:66, sim1_batch1.sh:9)
+    assert P.get(p, "a_rate")[0] == pytest.approx(P.A_RATE_BASE + 1.285 / 20000)      # synthetic marginal exit rate + the reference tweak (sim1_02_lhs.r:66, sim1_batch1.sh:9)
     lhs = P.lhs_envs(50, 1971)
     u = np.array([[(e[k] - lo) / (hi - lo) if hi > lo else 0.5 for k, lo, hi in P.PRIORS] for e in lhs])
     free = [j for j, (_, lo, hi) in enumerate(P.PRIORS) if hi > lo]

@@ -68,54 +68,63 @@ __global__ void k_derive(const __grid_constant__ Dev g, double* pois, double* in
 // k_begin: one warp per replicate.  Sets the week, zeroes its tally row, draws the pathway order, appends arrivals.
 // arrival_msm: /root/reference/burnin/cal/sim1_02_lhs.r:204, 63-66
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
+// WIDE (replicates of > 32k slots: BASELINE configs[3] / [4]): one CTA of 512 threads per replicate; warp 0 does the bookkeeping,
+// all 16 warps append the ~500 weekly arrivals of a 1M-agent replicate (one warp alone: 0.027 ms of a 0.28 ms week).
+template <bool INJ, bool WIDE> __global__ void __launch_bounds__(WIDE ? 512 : 128) k_begin(const __grid_constant__ Dev g, const __grid_constant__ Inj inj, int at_host, unsigned mask, int zero_row) {
   pdl_prologue();
-  int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  int r = WIDE ? (int)blockIdx.x : (int)(blockIdx.x * 4 + (threadIdx.x >> 5)), lane = threadIdx.x & 31;
   if (r >= g.R) return;
   r += g.r0;
   Rep* rp = g.rep + r;
-  int at = at_host >= 0 ? at_host : g.at_ptr[r] + 1;
+  const int at = at_host >= 0 ? at_host : g.at_ptr[r] + 1;
   unsigned* row = counter_row(g, r, at);
-  if (zero_row) for (int k = lane; k < XGC_NCOUNTER; k += 32) row[k] = 0u;
   const double* P = g.params + (size_t)r * XGC_NPARAM;
-  int n_slots = rp->n_slots, t_ref = rp->t_ref;
-  int t_age = (mask & XGC_M_AGING) ? at : rp->t_age;
-  __syncwarp();
-  if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
-  if (lane == 4) g.qa_count[r] = 0u;
-  if (lane == 5) g.qh_count[r] = 0u;
-  if (lane == 6) g.q3_count[r] = 0u;
-  if (lane >= 8 && lane < 11) g.lb_ticket[r * 3 + lane - 8] = 0u;
-  if (lane == 0) {
-    ((int*)g.at_ptr)[r] = at;
-    rp->n_slots_pre = n_slots;
-    rp->t_age = t_age;
-    if (mask & XGC_M_STITRANS) {          // weekly random pathway order (stitrans_msm_rand, ambiguity A2)
-      DrawT<INJ> d(inj, g, r, at, XGC_S_PATHORDER, 0u, 0u, 0);
-      int perm[XGC_NPATH];
-      for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
-      for (int i = XGC_NPATH - 1; i >= 1; --i) {
-        int j = (int)(d(XGC_NPATH - 1 - i) * (double)(i + 1)); if (j > i) j = i;
-        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+  const int n_slots = rp->n_slots, t_ref = rp->t_ref, uid0 = rp->next_uid;
+  const int t_age = (mask & XGC_M_AGING) ? at : rp->t_age;
+  __shared__ int s_nnew;
+  if (WIDE) __syncthreads();                                // every warp has read the week and the replicate's scalars
+  const bool lead = !WIDE || threadIdx.x < 32;              // the warp that does the replicate's bookkeeping
+  int nnew = 0;
+  if (lead) {
+    if (zero_row) for (int k = lane; k < XGC_NCOUNTER; k += 32) row[k] = 0u;
+    __syncwarp();
+    if (lane < 4) g.q_count[(size_t)r * 4 + lane] = 0u;
+    if (lane == 4) g.qa_count[r] = 0u;
+    if (lane == 5) g.qh_count[r] = 0u;
+    if (lane == 6) g.q3_count[r] = 0u;
+    if (lane >= 8 && lane < 11) g.lb_ticket[r * 3 + lane - 8] = 0u;
+    if (lane == 0) {
+      ((int*)g.at_ptr)[r] = at;
+      rp->n_slots_pre = n_slots;
+      rp->t_age = t_age;
+      if (mask & XGC_M_STITRANS) {          // weekly random pathway order (stitrans_msm_rand, ambiguity A2)
+        DrawT<INJ> d(inj, g, r, at, XGC_S_PATHORDER, 0u, 0u, 0);
+        int perm[XGC_NPATH];
+        for (int k = 0; k < XGC_NPATH; ++k) perm[k] = k;
+        for (int i = XGC_NPATH - 1; i >= 1; --i) {
+          int j = (int)(d(XGC_NPATH - 1 - i) * (double)(i + 1)); if (j > i) j = i;
+          int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+        }
+        for (int k = 0; k < XGC_NPATH; ++k) rp->path_rank[perm[k]] = k;
       }
-      for (int k = 0; k < XGC_NPATH; ++k) rp->path_rank[perm[k]] = k;
     }
+    if (mask & XGC_M_ARRIVAL) {
+      // nNew ~ Poisson(a.rate * num[1]), mean split into chunks of <= 32 so the CDF walk never underflows
+      double mu = P[XGC_P_a_rate] * P[XGC_P_n_init];
+      int m = (int)ceil(mu / 32.0); if (m < 1) m = 1; if (m > 64) m = 64;
+      double muc = mu / (double)m;
+      DrawT<INJ> d(inj, g, r, at, XGC_S_ARRIVE_N, 0u, 0u, 0);
+      for (int ch = lane; ch < m; ch += 32) nnew += xgc_pois(d(ch), muc, 255);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
+      if (n_slots + nnew > g.n_cap) { nnew = g.n_cap - n_slots; if (lane == 0) atomicOr(&rp->status, XGC_ST_AGENT_OVERFLOW); }
+    }
+    if (WIDE && lane == 0) s_nnew = nnew;
   }
   if (!(mask & XGC_M_ARRIVAL)) return;
-  // nNew ~ Poisson(a.rate * num[1]), mean split into chunks of <= 32 so the CDF walk never underflows
-  double mu = P[XGC_P_a_rate] * P[XGC_P_n_init];
-  int m = (int)ceil(mu / 32.0); if (m < 1) m = 1; if (m > 64) m = 64;
-  double muc = mu / (double)m;
-  int nnew = 0;
-  {
-    DrawT<INJ> d(inj, g, r, at, XGC_S_ARRIVE_N, 0u, 0u, 0);
-    for (int ch = lane; ch < m; ch += 32) nnew += xgc_pois(d(ch), muc, 255);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
-  }
-  if (n_slots + nnew > g.n_cap) { nnew = g.n_cap - n_slots; if (lane == 0) atomicOr(&rp->status, XGC_ST_AGENT_OVERFLOW); }
-  int uid0 = rp->next_uid;
-  for (int j = lane; j < nnew; j += 32) {
+  if (WIDE) { __syncthreads(); nnew = s_nnew; }
+  const int jstep = WIDE ? 512 : 32;
+  for (int j = WIDE ? (int)threadIdx.x : lane; j < nnew; j += jstep) {
     int i = n_slots + j; size_t idx = (size_t)r * g.n_cap + i;
     unsigned uid = (unsigned)(uid0 + j);
     DrawT<INJ> d(inj, g, r, at, XGC_S_ARRIVE_ATTR, uid, 0u, uid);
@@ -139,8 +148,8 @@ template <bool INJ> __global__ void __launch_bounds__(128) k_begin(const __grid_
     g.arr_t[idx] = at;
     atomicOr(g.alive + (size_t)r * (g.n_cap / 32) + (i >> 5), 1u << (i & 31));
   }
-  __syncwarp();
-  if (lane == 0) {
+  if (WIDE) __syncthreads(); else __syncwarp();
+  if (lead && lane == 0) {
     rp->n_slots = n_slots + nnew; rp->next_uid = uid0 + nnew; atomicAdd(&rp->n_alive, nnew);
     atomicAdd(row + XGC_K_NNEW, (unsigned)nnew);
   }
@@ -494,32 +503,49 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(cons
   }
 }
 
-// k_rank: pos2slot[r][rank] = slot, from the alive bitmap.  grid (slot tiles, R): each CTA sums the bitmap words before its
-// tile (<= n_cap/32 words, a block reduction) and ranks its own 256 slots with popcounts.
+// k_rank: pos2slot[r][rank] = slot, from the alive bitmap.  grid (tiles of RANK_TILE = 8192 slots, R): each CTA sums the bitmap
+// words before its tile (a block reduction over 128-bit loads), scans the popcounts of its own 256 words and every thread
+// writes the slots of its word.  (With 256-slot tiles every one of the 3907 CTAs of a 1M-agent replicate re-summed the
+// bitmap before it: 0.025 ms per replicate-week; 8192-slot tiles re-read 32 x less.)
+#define RANK_TILE (32 * TPB)
 __global__ void __launch_bounds__(TPB) k_rank(const __grid_constant__ Dev g) {
   pdl_prologue();
   int r = blockIdx.y + g.r0, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int n_slots = g.rep[r].n_slots;
-  int i0 = blockIdx.x * TPB;
+  int i0 = blockIdx.x * RANK_TILE;
   if (i0 >= n_slots) return;
-  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  const int nwords = g.n_cap / 32;
+  const unsigned* A = g.alive + (size_t)r * nwords;
   int* P2S = g.pos2slot + (size_t)r * g.n_cap;
-  __shared__ int wsum[TPB / 32];
-  __shared__ unsigned tilebits[TPB / 32];
-  int w0 = i0 >> 5, acc = 0;                       // w0 is a multiple of 8: sum the earlier words with 128-bit loads
+  __shared__ int wsum[TPB / 32], wpre[TPB / 32];
+  const int w0 = i0 >> 5;                          // a multiple of TPB: the earlier words are summed with 128-bit loads
+  int acc = 0;
   const uint4* A4 = (const uint4*)A;
   for (int k = tid; k < (w0 >> 2); k += TPB) { uint4 v = A4[k]; acc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+  unsigned bits = w0 + tid < nwords ? A[w0 + tid] : 0u;
+  const int c = __popc(bits);
+  int inc = c;                                     // inclusive scan of the tile's popcounts inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 31) wpre[w] = inc;
   if (lane == 0) wsum[w] = acc;
-  if (tid < TPB / 32) tilebits[tid] = A[w0 + tid];
   __syncthreads();
   int base = 0;
 #pragma unroll
   for (int k = 0; k < TPB / 32; ++k) base += wsum[k];
-  for (int k = 0; k < w; ++k) base += __popc(tilebits[k]);
-  unsigned bits = tilebits[w];
-  if ((bits >> lane) & 1u) P2S[base + __popc(bits & ((1u << lane) - 1u))] = i0 + tid;
+  // the tile's slots in rank order go through shared memory so that the plane is written with coalesced stores
+  __shared__ int out[RANK_TILE];
+  int o = inc - c;
+  for (int k = 0; k < w; ++k) o += wpre[k];
+  const int slot0 = (w0 + tid) << 5;
+  while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; out[o++] = slot0 + b; }
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int k = 0; k < TPB / 32; ++k) total += wpre[k];
+  for (int k = tid; k < total; k += TPB) P2S[base + k] = out[k];
 }
 
 // k_rank for calibration-size replicates (n_cap <= 32k slots): ONE CTA per replicate builds the popcount prefix of the

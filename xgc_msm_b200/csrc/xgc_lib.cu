@@ -125,7 +125,7 @@ static void preload_kernels() {
   done = true;
   cudaFuncAttributes a;
 #define PRELOAD(k) cudaFuncGetAttributes(&a, k)
-  PRELOAD(k_derive); PRELOAD(k_begin<false>); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
+  PRELOAD(k_derive); PRELOAD((k_begin<false, false>)); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
   PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank); PRELOAD(k_rank_cta);
   PRELOAD((k_form<false, true, TPB>)); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
   PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
@@ -621,13 +621,22 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   int tiles = (g.n_cap + TPB - 1) / TPB;
   static const int TA = getenv("XGC_TUNE_A") ? atoi(getenv("XGC_TUNE_A")) : 16, TQ = getenv("XGC_TUNE_Q") ? atoi(getenv("XGC_TUNE_Q")) : 16,
                    TE = getenv("XGC_TUNE_E") ? atoi(getenv("XGC_TUNE_E")) : 32;      // CTAs per SM each kernel family is sized for
-  int tpc = std::max(1, std::min(std::min(tiles, 40), (int)(((long long)tiles * g.R) / (148 * TA))));     // <= 40 tiles: the CTA's queue staging stays under 48 KB
+  // (large replicates: fewer, longer CTAs -- every CTA of an agent pass ends with a flush of its tallies into the SAME counter row,
+  //  3907 one-tile CTAs of a 1M-agent replicate spend most of k_agent3a on ~200 same-address global atomics each)
+  const int ta = g.n_cap > 32768 ? std::min(TA, 4) : TA;
+  int tpc = std::max(1, std::min(std::min(tiles, 40), (int)(((long long)tiles * g.R) / (148 * ta))));     // <= 40 tiles: the CTA's queue staging stays under 48 KB
   dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   dim3 ge((emax + TPB - 1) / TPB, 3, g.R);
   // queue kernels: a few CTAs per replicate striding over its queue, ~2 waves of the GPU in total
   auto qgrid = [&](int max_tiles) { return (unsigned)std::max(1, std::min(max_tiles, (148 * TQ + g.R - 1) / g.R)); };
-  LAUNCHD(h, inj, k_begin, (g.R + 3) / 4, 128, g, inj, at_host, mask, zero_row);
+  prof_begin(h, "k_begin");
+  if (g.n_cap > 32768) {                  // one CTA per large replicate: 16 warps share the arrivals
+    if (inj.u) kl(h, k_begin<true, true>, g.R, 512, 0, g, inj, at_host, mask, zero_row); else kl(h, k_begin<false, true>, g.R, 512, 0, g, inj, at_host, mask, zero_row);
+  } else {
+    if (inj.u) kl(h, k_begin<true, false>, (g.R + 3) / 4, 128, 0, g, inj, at_host, mask, zero_row); else kl(h, k_begin<false, false>, (g.R + 3) / 4, 128, 0, g, inj, at_host, mask, zero_row);
+  }
+  prof_end(h); h->launches++;
   // zero_row marks the first call of a week: that is when k_agent1 takes the start-of-week snapshot bits
   const unsigned a1mods = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
   const size_t cq_smem = ((size_t)tpc * TPB + 2) * sizeof(unsigned);        // per-CTA queue staging of the agent passes
@@ -653,7 +662,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
       if (inj.u) kl(h, k_form<true, true, TPB>, g.R, TPB, form_smem, g, inj); else kl(h, k_form<false, true, TPB>, g.R, TPB, form_smem, g, inj);
       prof_end(h); h->launches++;
     } else {
-      LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+      LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
       prof_begin(h, "k_form");
       if (inj.u) kl(h, k_form_lb<true>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj); else kl(h, k_form_lb<false>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj);
       prof_end(h); h->launches++;
@@ -758,7 +767,7 @@ static int compact_impl(xgc_handle* h) {
     LAUNCH(h, k_compact_agents, g.R, TPB, g, h->d_remap);       // one CTA walks the replicate's ~40 tiles
   } else {                                                      // 100k .. 1M-agent replicates: parallel gathers through pos2slot
     dim3 gp((g.n_cap + TPB - 1) / TPB, g.R);
-    LAUNCH(h, k_rank, gp, TPB, g);
+    LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
     LAUNCH(h, k_compact_remap, gp, TPB, g, h->d_remap);
     auto move = [&](auto* plane) {
       using T = std::remove_pointer_t<decltype(plane)>;
@@ -1192,7 +1201,7 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (!h->rank_fresh) {
     if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
-    else LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+    else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
     h->rank_fresh = true;
   }
   LAUNCH(h, k_edges_upload, dim3((unsigned)((st + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr, stride);
@@ -1263,7 +1272,7 @@ extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t*
   CU(h, cudaMemcpyAsync(h->d_upd_stage[layer], delta, need * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (!h->rank_fresh) {
     if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
-    else LAUNCH(h, k_rank, dim3((g.n_cap + TPB - 1) / TPB, g.R), TPB, g);
+    else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
     h->rank_fresh = true;
   }
   prof_begin(h, "k_edges_update");

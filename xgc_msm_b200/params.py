@@ -174,7 +174,14 @@ _R4 = ("BLACK", "HISP", "OTHER", "WHITE")
 _S3 = ("RECT", "URETH", "PHAR")
 
 
-def params_from_env(env: Dict[str, float], base: Optional[np.ndarray] = None, a_rate_base: float = 0.00042,
+# Weekly arrivals per initial-population member that hold the SYNTHETIC demography (synth.make_tables: ages 18-65, the
+# age-specific mortality table, AIDS deaths) at its initial size: 1 / (52 x ~43.5 years mean residence) minus the reference's own
+# tweak.  The reference accepts a burn-in whose population stays within +-5 % of its start (inst/cal/sim0.0_setup.r:315-318);
+# tools/run_burnin.py records the 3120-week drift (profiles/burnin_3120_r02.json).
+A_RATE_BASE = 0.000378
+
+
+def params_from_env(env: Dict[str, float], base: Optional[np.ndarray] = None, a_rate_base: float = A_RATE_BASE,
                     arrive_rate_add_per20k: float = 1.285, n_init: float = 10000.0) -> np.ndarray:
     """The param_msm() call of sim1_02_lhs.r:58-178 with `env` standing for the environment variables."""
     e = lambda k: float(env[k])
