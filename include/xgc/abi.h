@@ -56,7 +56,15 @@ enum xgc_table_offset {
   XGC_T_ROLE_PROB = XGC_T_RACE_PROP + 4,                 /* [4][3] role class I,R,V by race                         */
   XGC_T_NET_DEG   = XGC_T_ROLE_PROB + 12,                /* [3] surrogate network: target mean degree by layer      */
   XGC_T_NET_DUR   = XGC_T_NET_DEG + 3,                   /* [3] surrogate network: mean duration (weeks), [2] unused*/
-  XGC_NTABLE      = XGC_T_NET_DUR + 3
+  /* surrogate formation, degree- and risk-conditioned (what the reference's formation models condition on: deg.main /
+   * deg.casl cross terms and concurrency in the main and casual models, risk.grp in the one-off model; sim1_02_lhs.r:209,226):
+   * a proposed tie (a, b) of layer l is accepted with probability w(a) * w(b),
+   *   w(i) = NET_DEGW[l][min(deg.main(i), 2)][min(deg.casl(i), 2)] * (l == 2 ? NET_RISKW[risk.grp(i) - 1] : 1),
+   * degrees counted in the network the week starts with (after the departures, before this week's dissolution: formation and
+ * dissolution both condition on the previous network, as in a separable model).  All ones = uniform formation. */
+  XGC_T_NET_DEGW  = XGC_T_NET_DUR + 3,                   /* [3][3][3] in [0, 1]                                      */
+  XGC_T_NET_RISKW = XGC_T_NET_DEGW + 27,                 /* [5] in [0, 1]                                            */
+  XGC_NTABLE      = XGC_T_NET_RISKW + 5
 };
 
 /* Control flags, one int vector per replicate (scenario arms differ per replicate: 02.00_epi.r:315-326). */
@@ -104,7 +112,7 @@ enum xgc_module_bit {
  * position in the layer's edge list), replicate (0,0; index 0), formed edge (e0 = j, e1 = 0; index = j).
  * ---------------------------------------------------------------------------------------------------------------- */
 #define XGC_MAX_ACTS 32             /* per edge, per act type, per week (Poisson draws are truncated here)          */
-#define XGC_FORM_TRIES 4
+#define XGC_FORM_TRIES 8
 enum xgc_stream {
   /* agent streams */
   XGC_S_AGENT1 = 0,    /* aging..hivvl pass: k0 natural mortality, k1 AIDS mortality, k2 HIV interval test,
@@ -153,7 +161,7 @@ static inline XGC_HD int xgc_stream_width(int s) {
       case XGC_S_AGENT1: return 4;  case XGC_S_AGENT2: return 16;
       case XGC_S_INFECT: return 6;  case XGC_S_ARRIVE_ATTR: return 8;
       case XGC_S_ARRIVE_N: return 64; case XGC_S_PATHORDER: return 6; case XGC_S_NET_N: return 3;
-      default: return 2 * XGC_FORM_TRIES;      /* XGC_S_FORM + layer */
+      default: return 3 * XGC_FORM_TRIES;      /* XGC_S_FORM + layer: two endpoint positions + the acceptance draw per try */
     }
   }
   s = (s - XGC_S_EDGE0) % XGC_EDGE_STREAMS + XGC_S_EDGE0;
@@ -257,7 +265,7 @@ enum { XGC_ST_OK = 0, XGC_ST_AGENT_OVERFLOW = 1, XGC_ST_EDGE_OVERFLOW = 2, XGC_S
   X(XGC_NPATH) X(XGC_MAX_ACTS) X(XGC_FORM_TRIES) X(XGC_ASMR_AGES) X(XGC_GLM_NCOEF) X(XGC_EDGE_STREAMS) \
   X(XGC_G_B0) X(XGC_G_DUR) X(XGC_G_DUR2) X(XGC_G_PT2) X(XGC_G_DUR_PT2) X(XGC_G_CA) X(XGC_G_CA2) X(XGC_G_HCP) X(XGC_G_PREP) X(XGC_G_RC) \
   X(XGC_T_ASMR) X(XGC_T_GLM_AI) X(XGC_T_GLM_OI) X(XGC_T_GLM_CONDMC) X(XGC_T_GLM_CONDOO) X(XGC_T_RACE_PROP) X(XGC_T_ROLE_PROB) \
-  X(XGC_T_NET_DEG) X(XGC_T_NET_DUR) \
+  X(XGC_T_NET_DEG) X(XGC_T_NET_DUR) X(XGC_T_NET_DEGW) X(XGC_T_NET_RISKW) \
   X(XGC_C_transRoute_Kissing) X(XGC_C_transRoute_Rimming) X(XGC_C_gcUntreatedRecovDist) X(XGC_C_stiScreeningProtocol) \
   X(XGC_C_cdcExposureSite_Kissing) X(XGC_C_network_mode) \
   X(XGC_RECOV_GEOM) X(XGC_RECOV_POIS) X(XGC_SCREEN_BASE) X(XGC_SCREEN_SYMPTOMATIC) X(XGC_SCREEN_CDC) X(XGC_SCREEN_UNIVERSAL) \

@@ -455,12 +455,26 @@ static int roles_compatible(const orc_dat* d, int a, int b) {
   int ra = (int)d->a[A_ROLE][a], rb = (int)d->a[A_ROLE][b];
   return !((ra == 0 && rb == 0) || (ra == 1 && rb == 1));
 }
+/* formation weight of agent i in layer l (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW): degree classes over the ties that survived
+ * this week's dissolution, the one-off layer also by risk group */
+static double form_weight(const orc_dat* d, int l, int i, const int* dm, const int* dc) {
+  int cm = dm[i] > 2 ? 2 : dm[i], cc = dc[i] > 2 ? 2 : dc[i];
+  double w = d->tb[XGC_T_NET_DEGW + l * 9 + cm * 3 + cc];
+  if (l == 2) w = w * d->tb[XGC_T_NET_RISKW + (int)d->a[A_RISK][i] - 1];
+  return w;
+}
 static void resim_nets_surrogate(orc_dat* d, int at) {
+  /* degrees (deg.main, deg.casl) in the network the week starts with: formation and dissolution both condition on it
+   * (a separable model: the ties that dissolve this week still count), fixed while this week's ties form */
+  int* dm = (int*)calloc((size_t)(d->n > 0 ? d->n : 1), sizeof(int));
+  int* dc = (int*)calloc((size_t)(d->n > 0 ? d->n : 1), sizeof(int));
+  for (int e = 0; e < d->ne[0]; ++e) { dm[d->el[0][e].p1]++; dm[d->el[0][e].p2]++; }
+  for (int e = 0; e < d->ne[1]; ++e) { dc[d->el[1][e].p1]++; dc[d->el[1][e].p2]++; }
+  /* dissolution of the persistent layers (one-off contacts last one week) */
   for (int l = 0; l < 3; ++l) {
     int w = 0, ne0 = d->ne[l];
     int es = XGC_S_EDGE0 + l * XGC_EDGE_STREAMS;
-    if (l == 2) w = 0;       /* one-off contacts last one week */
-    else {
+    if (l < 2) {
       double pd = 1.0 / d->tb[XGC_T_NET_DUR + l];
       for (int e = 0; e < ne0; ++e) {
         orc_edge g = d->el[l][e];
@@ -469,6 +483,10 @@ static void resim_nets_surrogate(orc_dat* d, int at) {
         d->el[l][w++] = g;
       }
     }
+    d->ne[l] = w;
+  }
+  for (int l = 0; l < 3; ++l) {
+    int w = d->ne[l];
     double target = d->tb[XGC_T_NET_DEG + l] * (double)d->n / 2.0;
     double mu = l == 2 ? target : target / d->tb[XGC_T_NET_DUR + l];
     double fl = floor(mu);
@@ -477,12 +495,14 @@ static void resim_nets_surrogate(orc_dat* d, int at) {
     for (int j = 0; j < nform; ++j) {
       if (d->n < 2) break;
       for (int t = 0; t < XGC_FORM_TRIES; ++t) {
-        double ua = U(d, at, XGC_S_FORM + l, (uint32_t)j, 0u, (size_t)j, 2 * t);
-        double ub = U(d, at, XGC_S_FORM + l, (uint32_t)j, 0u, (size_t)j, 2 * t + 1);
+        double ua = U(d, at, XGC_S_FORM + l, (uint32_t)j, 0u, (size_t)j, 3 * t);
+        double ub = U(d, at, XGC_S_FORM + l, (uint32_t)j, 0u, (size_t)j, 3 * t + 1);
         int a = (int)(ua * (double)d->n); if (a > d->n - 1) a = d->n - 1;
         int b = (int)(ub * (double)(d->n - 1)); if (b > d->n - 2) b = d->n - 2;
         if (b >= a) b++;
         if (!roles_compatible(d, a, b)) continue;
+        double pw = form_weight(d, l, a, dm, dc) * form_weight(d, l, b, dm, dc);
+        if (pw < 1.0 && !(U(d, at, XGC_S_FORM + l, (uint32_t)j, 0u, (size_t)j, 3 * t + 2) < pw)) continue;
         if (w >= d->ecap[l]) { d->status |= XGC_ST_EDGE_OVERFLOW; break; }
         orc_edge g; memset(&g, 0, sizeof(g));
         g.p1 = a < b ? a : b; g.p2 = a < b ? b : a; g.start = at;
@@ -493,6 +513,7 @@ static void resim_nets_surrogate(orc_dat* d, int at) {
     d->ne[l] = w;
     CNT(d, at)[XGC_K_NEDGES + l] = (uint32_t)w;
   }
+  free(dm); free(dc);
 }
 
 /* linear predictor of the act-rate / condom GLMs (Appendix E "acts"/"condoms"; ambiguity A11) */

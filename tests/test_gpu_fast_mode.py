@@ -89,6 +89,12 @@ def test_fast_mode_step_groups_equal_run():
     back to HBM and re-staged in between) gives bit for bit the trajectory of the multi-week resident run."""
     n, T, R = 2500, 24, 3
     cases = [make_case(n, 40 + r, midcourse=True, network_mode="surrogate", stiScreeningProtocol="cdc") for r in range(R)]
+    # uniform formation weights: with degree-conditioned weights the two call patterns differ in the week in which the ties of a
+    # departed agent stop counting towards its partners' degrees (pruned by the first call of the week / lazily by the acts pass)
+    from xgc_msm_b200 import synth
+    for c in cases:
+        c["tables"] = c["tables"].copy()
+        c["tables"][synth.T_NET_DEGW:synth.T_NET_RISKW + 5] = 1.0
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     ha = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); ha.set_mode("fast")
     hb = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hb.set_mode("fast")
@@ -113,6 +119,41 @@ def test_fast_mode_step_groups_equal_run():
     assert not np.array_equal(hs.counters(0, 2, T), ha.counters(0, 2, T))
     for x in (ha, hb, hc, hs):
         x.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_degree_conditioned_formation(mode):
+    """Surrogate simnet_msm: proposed ties are thinned by the endpoints' current (main, casual) degree classes and, for one-off
+    contacts, by risk group (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW; the terms the reference's formation models condition on,
+    sim1_02_lhs.r:209,226).  Structural check with hard weights: nobody with a main partner forms another main tie, casual
+    degree stops at 2, risk group 1 has no one-off contacts; and the default weights leave far fewer concurrent main ties than
+    uniform formation."""
+    from xgc_msm_b200 import synth
+    n, T = 4000, 60
+    def run(tables):
+        case = make_case(n, 21, network_mode="surrogate")
+        case["els"] = [np.zeros((0, 2), np.int32)] * 3; case["starts"] = [np.zeros(0, np.int32)] * 3       # start from an empty network
+        case["tables"] = tables
+        h = load_handle([case], SEED, t_cap=T + 4, compact_every=16)
+        h.set_mode(mode)
+        h.run(2, T)
+        out = {k: h.download_attr(0, k) for k in ("deg.main", "deg.casl", "deg.inst", "risk.grp")}
+        assert h.status(0) == 0
+        h.close()
+        return out
+    hard = synth.make_tables()
+    W = hard[synth.T_NET_DEGW:synth.T_NET_DEGW + 27].reshape(3, 3, 3)
+    W[0, 1:, :] = 0.0                   # main: only men without a main partner
+    W[1, :, 2] = 0.0                    # casual: never a third concurrent casual partner
+    hard[synth.T_NET_RISKW] = 0.0       # one-off: nobody of risk group 1
+    a = run(hard)
+    assert a["deg.main"].max() == 1 and a["deg.main"].sum() > 200
+    assert a["deg.casl"].max() == 2 and a["deg.casl"].sum() > 400
+    assert a["deg.inst"].sum() > 20 and a["deg.inst"][a["risk.grp"] == 1].sum() == 0
+    uni = synth.make_tables(); uni[synth.T_NET_DEGW:synth.T_NET_RISKW + 5] = 1.0
+    d, u = run(synth.make_tables()), run(uni)
+    assert (d["deg.main"] >= 2).mean() < 0.25 * (u["deg.main"] >= 2).mean()
+    assert d["deg.inst"][d["risk.grp"] == 5].mean() > 5 * d["deg.inst"][d["risk.grp"] == 1].mean()
 
 
 def _ks_report(g, c, names, keys, R):

@@ -352,3 +352,24 @@ def test_product_path_fails_loudly_without_a_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout) and '"value"' not in r.stdout
+
+
+def test_oracle_degree_conditioned_formation():
+    """Surrogate simnet_msm of the oracle (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW): hard weights are respected exactly -- nobody
+    with a main partner forms another main tie, casual degree stops at 2, risk group 1 has no one-off contacts."""
+    from common import load_oracle, make_case
+    from xgc_msm_b200 import synth
+    case = make_case(3000, 21, network_mode="surrogate")
+    case["els"] = [np.zeros((0, 2), np.int32)] * 3; case["starts"] = [np.zeros(0, np.int32)] * 3
+    t = synth.make_tables()
+    W = t[synth.T_NET_DEGW:synth.T_NET_DEGW + 27].reshape(3, 3, 3)
+    W[0, 1:, :] = 0.0; W[1, :, 2] = 0.0; t[synth.T_NET_RISKW] = 0.0
+    case["tables"] = t
+    o = load_oracle(case, 1971, 0, t_cap=48)
+    for at in range(2, 42):
+        o.step(at, K.M_ALL)
+    n = o.get_attr("race").size
+    deg = [np.bincount(o.get_edgelist(l)[0].ravel() - 1, minlength=n) for l in range(3)]
+    assert deg[0].max() == 1 and deg[0].sum() > 100
+    assert deg[1].max() == 2 and deg[1].sum() > 200
+    assert deg[2].sum() > 10 and deg[2][o.get_attr("risk.grp") == 1].sum() == 0

@@ -86,6 +86,8 @@ struct Dev {                 // everything a kernel needs; passed by value
   uint4* core; Aux* aux; short4 *gck_a, *gck_b, *gck_d, *hck_a, *hck_b, *tck; int* arr_t;
   unsigned* alive;           // [R][n_cap/32] bitmap of living slots
   int* pos2slot;             // [R][n_cap] rank -> slot (built by k_rank)
+  unsigned* deg;             // [R][n_cap] current degree per slot, byte l = layer l (main, casual), in the network the week starts with: counted by the dissolution pass
+                             // of the surrogate network, read by its formation step (degree-conditioned acceptance)
   int4* edge;                // [R][e_stride]: layer l at e_off[l]
   Rep* rep; const double* params; const int* control; const double* tables;
   const double* inv_ntx;     // [R][4] 1 / gc.ntx.int[site] (weekly untreated-recovery probability, "geom"): one division per replicate, not per site-week

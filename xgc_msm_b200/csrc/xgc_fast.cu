@@ -56,16 +56,18 @@ struct Fixed {                     // fixed part of the CTA's shared memory (com
   float G[4 * XGC_GLM_NCOEF];
   float asmr[4 * XGC_ASMR_AGES];
   float pk[4 * (XGC_MAX_ACTS + 1)];
+  float degw[32];                   // XGC_T_NET_DEGW [3][3][3] + XGC_T_NET_RISKW [5] as fp32
   unsigned hib[16];
   int sc[SC_N];
   int wsum[NW], wsum2[NW], wsum3[NW];
   unsigned short mq[NW][2][MQ_CAP];
 };
 static __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-struct VarOff { size_t ea, V, total; };
+struct VarOff { size_t ea, deg, V, total; };
 static __host__ __device__ VarOff fast_layout(int n_cap, size_t e_stride) {
   VarOff o; size_t p = al16(sizeof(Fixed));
   o.ea = p; p += al16(e_stride * 2);
+  o.deg = p; p += al16((size_t)n_cap);                  // one byte per slot: main degree (low nibble), casual degree (high nibble)
   o.V = p; p += al16((size_t)n_cap * 14);
   o.total = p;
   return o;
@@ -184,6 +186,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   Fixed& F = *reinterpret_cast<Fixed*>(smem_raw);
   const VarOff vo = fast_layout(g.n_cap, g.e_stride);
   unsigned short* const ea = (unsigned short*)(smem_raw + vo.ea);
+  unsigned char* const deg8 = smem_raw + vo.deg;              // current degrees, kept while the surrogate network runs on the device
+  unsigned* const deg32 = (unsigned*)deg8;
   unsigned* const vd = (unsigned*)(smem_raw + vo.V);
   unsigned* const vg = vd + g.n_cap;
   unsigned* const vh = vd + 2 * g.n_cap;
@@ -231,6 +235,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     for (int k = tid; k < 4 * XGC_GLM_NCOEF; k += FT) F.G[k] = (float)g.tables[XGC_T_GLM_AI + k];
     for (int k = tid; k < 4 * XGC_ASMR_AGES; k += FT) F.asmr[k] = (float)g.tables[XGC_T_ASMR + k];
     for (int k = tid; k < 4 * (XGC_MAX_ACTS + 1); k += FT) F.pk[k] = (float)g.pois[(size_t)r * 4 * (XGC_MAX_ACTS + 1) + k];
+    if (tid < 32) F.degw[tid] = (float)g.tables[XGC_T_NET_DEGW + tid];
+    if (surrogate) for (int k = tid; k < g.n_cap / 4; k += FT) deg32[k] = 0u;
     if (tid < 16) F.hib[tid] = 0u;
     for (int k = tid; k < (int)g.e_stride; k += FT) ea[k] = 0;   // HBM holds compact lists: no tombstones
     __syncthreads();
@@ -246,6 +252,26 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         for (int k = 0; k < 4; ++k) { const int i = min(i0 + k * FT, n0 - 1); c[k] = g.core[rbase + i]; t[k] = wt ? (short)-1 : g.tck[rbase + i].y; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) { const int i = i0 + k * FT; if (i < n0) { vd[i] = c[k].y; vg[i] = c[k].z; vh[i] = c[k].w; if (!wt) ind[i] = t[k]; } }
+      }
+    }
+    // degree-conditioned formation (abi.h XGC_T_NET_DEGW): the degrees of the staged lists, then kept current by the formation
+    // step (+) and by the tombstones of the tie sweep (-).  As in the oracle, a tie that dissolves THIS week still counts while
+    // this week's ties form (formation and dissolution both condition on the network the week starts with); the one difference:
+    // the ties of an agent who departed this week are dropped by the acts pass, i.e. after the formation step (~5 ties a week)
+    auto deg_add = [&](int s, int l) { if (((deg8[s] >> (4 * l)) & 15u) < 15u) atomicAdd(&deg32[s >> 2], (l ? 16u : 1u) << (8 * (s & 3))); };
+    auto deg_sub = [&](int s, int l) { if ((deg8[s] >> (4 * l)) & 15u) atomicSub(&deg32[s >> 2], (l ? 16u : 1u) << (8 * (s & 3))); };
+    auto form_w = [&](int l, unsigned dg, unsigned demo) -> float {
+      const int cm = min((int)(dg & 15u), 2), cc = min((int)(dg >> 4), 2);
+      float w = F.degw[l * 9 + cm * 3 + cc];
+      if (l == 2) w *= F.degw[27 + DM_RISK(demo)];
+      return w;
+    };
+    if (surrogate) {
+      const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1];
+      for (int f = tid; f < ne01; f += FT) {
+        const int l = f >= ne0, sidx = g.e_off[l] + f - (l ? ne0 : 0);
+        const int4 ed = g.edge[(size_t)r * g.e_stride + sidx];
+        deg_add(ed.x, l); deg_add(ed.y, l);
       }
     }
     if (warp == 0) {                                            // largest gap-sampled weekly death probability
@@ -549,14 +575,27 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             const int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
             const int l = j >= nf01 ? 2 : j >= nf0 ? 1 : 0, jj = j - (l == 2 ? nf01 : l == 1 ? nf0 : 0);
             if (j < nf_all) {
-              for (int t = 0; t < 2 * XGC_FORM_TRIES && !ok; t += 2) {      // endpoints by rejection over the slots: uniform over the living
-                uint4 x = frand(key, at, FS_FORM + l, (unsigned)jj, (unsigned)(t >> 1));
+              // XGC_FORM_TRIES proposals, as in the oracle.  Endpoints by rejection over the slots (= uniform over the living): a pair
+              // with a dead slot is not a proposal and does not use up a try (two pairs per Philox block, a few spare blocks)
+              int tries = 0;
+              for (int blk = 0; blk < XGC_FORM_TRIES / 2 + 3 && !ok && tries < XGC_FORM_TRIES; ++blk) {
+                uint4 x = frand(key, at, FS_FORM + l, (unsigned)jj, (unsigned)blk);
 #pragma unroll
-                for (int q = 0; q < 2 && !ok; ++q) {
+                for (int q = 0; q < 2 && !ok && tries < XGC_FORM_TRIES; ++q) {
                   int sa = (int)__umulhi(q ? x.z : x.x, (unsigned)n_slots), sb = (int)__umulhi(q ? x.w : x.y, (unsigned)(n_slots - 1));
                   if (sb >= sa) sb++;
                   const unsigned da = vd[sa], db = vd[sb];
-                  if ((da & db & DM_ACTIVE) && roles_compatible(da, db)) { ok = true; ed.x = min(sa, sb); ed.y = max(sa, sb); }
+                  if (!(da & db & DM_ACTIVE)) continue;
+                  ++tries;
+                  if (roles_compatible(da, db)) {
+                    // degree / risk-conditioned acceptance; the acceptance uniform is built from the low halves of the two position
+                    // words (the positions use their high bits)
+                    const unsigned ga8 = deg8[sa], gb8 = deg8[sb];
+                    const float pw = form_w(l, ga8, da) * form_w(l, gb8, db);
+                    const unsigned xu = ((q ? x.z : x.x) << 16) | ((q ? x.w : x.y) & 0xFFFFu);
+                    const bool full = l < 2 && ((((ga8 >> (4 * l)) & 15u) == 15u) || (((gb8 >> (4 * l)) & 15u) == 15u));      // 4-bit degree counters
+                    if (!full && (pw >= 1.f || bern(xu, pw))) { ok = true; ed.x = min(sa, sb); ed.y = max(sa, sb); }
+                  }
                 }
               }
             }
@@ -568,7 +607,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (ok) {
               const unsigned m = l == 0 ? m0 : l == 1 ? m1 : m2;
               const int dst = (l == 0 ? tail0 + base0 : l == 1 ? tail1 + base1 : tail2 + base2) + __popc(m & ((1u << lane) - 1u));
-              if (dst < g.e_cap[l]) { g.edge[(size_t)r * g.e_stride + g.e_off[l] + dst] = ed; ea[g.e_off[l] + dst] = 0; }
+              if (dst < g.e_cap[l]) { g.edge[(size_t)r * g.e_stride + g.e_off[l] + dst] = ed; ea[g.e_off[l] + dst] = 0;
+                if (l < 2) { deg_add(ed.x, l); deg_add(ed.y, l); } }        // (every read of this chunk's decisions is behind the barrier above)
               else atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_EDGE_OVERFLOW);
             }
             tail0 = min(tail0 + tot0, g.e_cap[0]); tail1 = min(tail1 + tot1, g.e_cap[1]); tail2 = min(tail2 + tot2, g.e_cap[2]);
@@ -593,7 +633,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
               if (f < ne_all && !(ea[sidx] & EA_DEAD)) {
                 bool dead = !(vd[ed.x] & vd[ed.y] & DM_ACTIVE);
                 if (!dead && form && l < 2 && ed.z < at) dead = dissolves(frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l), ed, l, at);
-                if (dead) { ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); }
+                if (dead) { ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); if (surrogate && l < 2) { deg_sub(ed.x, l); deg_sub(ed.y, l); } }
               }
             }
           }
@@ -632,7 +672,9 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             const uint4 x = frand(key, at, FS_ACTS, pairkey(ed), (unsigned)l);
             // the tie sweep: ties of departed agents (tergmLite::delete_vertices) and this week's dissolutions become tombstones
             if (!(da & db & DM_ACTIVE) || (diss_on && l < 2 && ed.z < at && dissolves(x, ed, l, at))) {
-              ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1); continue;
+              ea[sidx] = EA_DEAD; atomicAdd(&F.sc[SC_DEAD0 + l], 1);
+              if (surrogate && l < 2) { deg_sub(ed.x, l); deg_sub(ed.y, l); }
+              continue;
             }
             const float ca = (float)(2 * at8 - birth8(ha) - birth8(hb)) * (float)XF_W8;
             int ai = 0, oi = 0, ki = 0, ri = 0;

@@ -400,6 +400,8 @@ template <bool INJ, int NT, int IPT> __global__ void __launch_bounds__(NT) k_edg
         ed[q] = E[e];
         keep[q] = ((A[ed[q].x >> 5] >> (ed[q].x & 31)) & 1u) && ((A[ed[q].y >> 5] >> (ed[q].y & 31)) & 1u);
         if (keep[q] && surrogate) {
+          // degrees of the network the week starts with (formation conditions on them): counted before the dissolution draw
+          if (l < 2) { unsigned* dg = g.deg + (size_t)r * g.n_cap; atomicAdd(dg + ed[q].x, 1u << (8 * l)); atomicAdd(dg + ed[q].y, 1u << (8 * l)); }
           if (!INJ && (((unsigned)ed[q].w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep[q] = !((unsigned)ed[q].w >> 31);   // drawn ahead by k_edge1
           else { DrawT<INJ> d(inj, g, r, at, es, core[ed[q].x].x, core[ed[q].y].x, (size_t)e); keep[q] = !xgc_bern(d(0), pd); }
         }
@@ -462,6 +464,7 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_edges_resim_lb(cons
       ed[q] = E[e];
       keep[q] = ((A[ed[q].x >> 5] >> (ed[q].x & 31)) & 1u) && ((A[ed[q].y >> 5] >> (ed[q].y & 31)) & 1u);
       if (keep[q] && surrogate) {
+        if (l < 2) { unsigned* dg = g.deg + (size_t)r * g.n_cap; atomicAdd(dg + ed[q].x, 1u << (8 * l)); atomicAdd(dg + ed[q].y, 1u << (8 * l)); }
         if (!INJ && (((unsigned)ed[q].w >> 16) & 0x7FFFu) == ((unsigned)at & 0x7FFFu)) keep[q] = !((unsigned)ed[q].w >> 31);
         else { DrawT<INJ> d(inj, g, r, at, es, core[ed[q].x].x, core[ed[q].y].x, (size_t)e); keep[q] = !xgc_bern(d(0), pd); }
       }
@@ -582,6 +585,13 @@ __global__ void __launch_bounds__(TPB) k_rank_cta(const __grid_constant__ Dev g)
   }
 }
 
+// formation weight of an agent in layer l (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW): degree classes from the byte counts of g.deg
+__device__ __forceinline__ double form_weight(const double* tb, int l, unsigned dg, unsigned demo) {
+  int cm = min((int)(dg & 0xFFu), 2), cc = min((int)((dg >> 8) & 0xFFu), 2);
+  double w = tb[XGC_T_NET_DEGW + l * 9 + cm * 3 + cc];
+  if (l == 2) w = w * tb[XGC_T_NET_RISKW + DM_RISK(demo)];
+  return w;
+}
 // k_form: surrogate formation, one CTA per (replicate, layer): uniform random compatible pairs, appended in draw order.
 // R position -> slot: SMEM = true keeps the replicate's alive bitmap and its popcount prefix in shared memory and selects
 // directly (no pos2slot plane, no k_rank launch); SMEM = false (very large n_cap) reads pos2slot built by k_rank.
@@ -640,12 +650,19 @@ template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_f
       int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
       if (j < nform) {
         DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+        const unsigned* dg = g.deg + (size_t)r * g.n_cap;
         for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
-          int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
-          int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+          int a = (int)(d(3 * t) * (double)n); if (a > n - 1) a = n - 1;
+          int b = (int)(d(3 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
           if (b >= a) b++;
-          int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);
-          if (roles_compatible(core[sa].y, core[sb].y)) { ok = true; ed.x = sa; ed.y = sb; }
+          int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);       // (a < b as positions; slots keep the order)
+          unsigned da = core[sa].y, db = core[sb].y;
+          if (!roles_compatible(da, db)) continue;
+          // the weights multiply in the order of the DRAWN endpoints (a, then b), as in the oracle
+          double wa = form_weight(g.tables, l, dg[a < b ? sa : sb], a < b ? da : db), wb = form_weight(g.tables, l, dg[a < b ? sb : sa], a < b ? db : da);
+          double pw = wa * wb;
+          if (pw < 1.0 && !(d(3 * t + 2) < pw)) continue;
+          ok = true; ed.x = sa; ed.y = sb;
         }
       }
       unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -703,12 +720,18 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __gri
     int j = tile * LB_TILE + q * TPB + tid; ok[q] = false; ed[q] = make_int4(0, 0, at, 0);
     if (j < nform) {
       DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+      const unsigned* dg = g.deg + (size_t)r * g.n_cap;
       for (int t = 0; t < XGC_FORM_TRIES && !ok[q]; ++t) {
-        int a = (int)(d(2 * t) * (double)n); if (a > n - 1) a = n - 1;
-        int b = (int)(d(2 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+        int a = (int)(d(3 * t) * (double)n); if (a > n - 1) a = n - 1;
+        int b = (int)(d(3 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
         if (b >= a) b++;
         int sa = P2S[a < b ? a : b], sb = P2S[a < b ? b : a];
-        if (roles_compatible(core[sa].y, core[sb].y)) { ok[q] = true; ed[q].x = sa; ed[q].y = sb; }
+        unsigned da = core[sa].y, db = core[sb].y;
+        if (!roles_compatible(da, db)) continue;
+        double wa = form_weight(g.tables, l, dg[a < b ? sa : sb], a < b ? da : db), wb = form_weight(g.tables, l, dg[a < b ? sb : sa], a < b ? db : da);
+        double pw = wa * wb;
+        if (pw < 1.0 && !(d(3 * t + 2) < pw)) continue;
+        ok[q] = true; ed[q].x = sa; ed[q].y = sb;
       }
     }
     m[q] = __ballot_sync(0xffffffffu, ok[q]);

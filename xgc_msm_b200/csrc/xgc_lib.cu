@@ -189,7 +189,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.core, NAP); rc |= dalloc(h, &g.aux, NAP);
   rc |= dalloc(h, &g.gck_a, NAP); rc |= dalloc(h, &g.gck_b, NAP); rc |= dalloc(h, &g.gck_d, NAP);
   rc |= dalloc(h, &g.hck_a, NAP); rc |= dalloc(h, &g.hck_b, NAP); rc |= dalloc(h, &g.tck, NAP); rc |= dalloc(h, &g.arr_t, NAP);
-  rc |= dalloc(h, &g.alive, NA / 32); rc |= dalloc(h, &g.pos2slot, NA);
+  rc |= dalloc(h, &g.alive, NA / 32); rc |= dalloc(h, &g.pos2slot, NA); rc |= dalloc(h, &g.deg, NA);
   if (g.n_cap > 32768) { uint4* cs = nullptr; rc |= dalloc(h, &cs, NA); h->d_cscratch = cs; }     // parallel slot compaction, 16 B per slot
   rc |= dalloc(h, &g.edge, (size_t)g.R * g.e_stride);
   rc |= dalloc(h, &g.rep, (size_t)g.R);
@@ -655,6 +655,8 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   bool native = inj.u == nullptr;
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0, 0);
   if (mask & XGC_M_RESIM_NETS) {
+    // degrees of the ties that survive this week's dissolution: zeroed here, counted by the dissolution pass, read by k_form
+    cudaMemsetAsync(g.deg + (size_t)g.r0 * g.n_cap, 0, (size_t)g.R * g.n_cap * sizeof(unsigned), h->cur);
     launch_resim(h, inj, 1, 1);
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 8 * 1024) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory

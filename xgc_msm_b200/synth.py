@@ -23,7 +23,9 @@ T_RACE_PROP = T_GLM_CONDOO + GLM_NCOEF
 T_ROLE_PROB = T_RACE_PROP + 4
 T_NET_DEG = T_ROLE_PROB + 12
 T_NET_DUR = T_NET_DEG + 3
-NTABLE = T_NET_DUR + 3
+T_NET_DEGW = T_NET_DUR + 3
+T_NET_RISKW = T_NET_DEGW + 27
+NTABLE = T_NET_RISKW + 5
 G_B0, G_DUR, G_DUR2, G_PT2, G_DUR_PT2, G_CA, G_CA2, G_HCP, G_PREP, G_PAD, G_RC = range(11)
 
 RACE_PROP = np.array([0.13, 0.19, 0.08, 0.60])                  # B, H, O, W
@@ -31,6 +33,21 @@ ROLE_PROB = np.tile(np.array([0.24, 0.27, 0.49]), (4, 1))       # I, R, V
 NET_DEG = np.array([0.40, 0.55, 0.07])                          # main, casual, one-off (per week)
 NET_DUR = np.array([250.0, 90.0, 1.0])                          # weeks
 HIV_PREV0 = np.array([0.22, 0.13, 0.10, 0.08])
+
+
+# Degree- and risk-conditioned formation of the surrogate network (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW): acceptance weight of
+# an agent by its current (main, casual) degree class 0 / 1 / 2+ for each layer, and by risk group for one-off contacts.
+# Placeholders with the signs of the ARTnet formation models the reference fits (main partnerships close to monogamous and
+# rarer among men with casual partners; casual concurrency damped; one-off contacts concentrated in the upper risk groups).
+NET_DEGW = np.array([
+    [[1.00, 0.60, 0.35], [0.04, 0.03, 0.02], [0.00, 0.00, 0.00]],      # main:   rows = own main degree, columns = casual degree
+    [[1.00, 0.55, 0.30], [0.70, 0.40, 0.20], [0.50, 0.30, 0.15]],      # casual
+    [[1.00, 1.00, 1.00], [0.60, 0.75, 0.90], [0.60, 0.75, 0.90]],      # one-off
+])
+NET_RISKW = np.array([0.05, 0.15, 0.35, 0.65, 1.00])
+# XGC_T_NET_DEG is the PROPOSAL intensity (ties proposed per week = deg * n / 2 / duration); the weights above thin it.  These
+# factors bring the realised mean degrees of the bench workload back to NET_DEG (oracle, 700 weeks: 0.40 / 0.555 / 0.073).
+NET_DEG_PROPOSAL = np.array([1.5, 1.12, 1.55])
 
 
 def make_tables() -> np.ndarray:
@@ -54,8 +71,10 @@ def make_tables() -> np.ndarray:
     glm(T_GLM_CONDOO, 0.1, 0.0, 0.0, 0.0, 0.0, 0.003, -1.0e-5, -0.6, -0.40)                     # logit P(condom), one-off
     t[T_RACE_PROP:T_RACE_PROP + 4] = RACE_PROP
     t[T_ROLE_PROB:T_ROLE_PROB + 12] = ROLE_PROB.ravel()
-    t[T_NET_DEG:T_NET_DEG + 3] = NET_DEG
+    t[T_NET_DEG:T_NET_DEG + 3] = NET_DEG * NET_DEG_PROPOSAL
     t[T_NET_DUR:T_NET_DUR + 3] = NET_DUR
+    t[T_NET_DEGW:T_NET_DEGW + 27] = NET_DEGW.ravel()
+    t[T_NET_RISKW:T_NET_RISKW + 5] = NET_RISKW
     return t
 
 
