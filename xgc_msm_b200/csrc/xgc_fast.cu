@@ -166,13 +166,17 @@ __device__ __forceinline__ void gap_warp(uint2 key, unsigned at, unsigned stream
   }
 }
 
+// Agent ownership: warp w owns the 32-agent groups w, w + 32, w + 64, ... (slot order is arrival order, i.e. roughly age order:
+// contiguous ranges would give the warps of the early slots the older cohorts with more HIV-positive agents -- systematic
+// imbalance in front of every phase barrier).  VSLOT(p): the slot of the warp's p-th agent.
+#define VSLOT(p) ((((p) >> 5) * NW + warp) * 32 + ((p) & 31))
 // phase clocks (SM cycles summed over CTAs; thread 0 of each CTA): tools/time_modes.py
 enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE, PH_NET, PH_ACTS, PH_B, PH_TRANS, PH_APPLY_TALLY, PH_ROW, PH_WRITEBACK, PH_SQUEEZE_WB, PH_STAGE_TABLES, PH_N = 16 };
 __device__ unsigned long long g_fast_prof[PH_N];
 #define TICK(k) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fast_prof[k], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 
 // the test of one HIV-test candidate: time since the last negative test / arrival decides (item bit 15: rule-based)
-#define TEST_BODY { const int i = a0 + (int)(item & 0x7FFFu); const bool rule = item & 0x8000u; const unsigned d = vd[i], h = vh[i]; \
+#define TEST_BODY { const int i = (int)(item & 0x7FFFu); const bool rule = item & 0x8000u; const unsigned d = vd[i], h = vh[i]; \
   if (d & DM_ACTIVE) { short lnt = g.tck[rbase + i].x; int last = lnt == XGC_NA16 ? g.arr_t[rbase + i] : (int)lnt; float tsl = (float)(at - last); \
     bool tested = rule ? ((HV_STAGE(h) == 4 && tsl >= P[XGC_P_aids_test_int]) || ((h & HV_PREP) && tsl >= P[XGC_P_prep_tst_int])) : tsl >= 2.f; \
     if (tested) { const unsigned g0_ = atomicOr(&vg[i], FG_TESTED); \
@@ -406,13 +410,14 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         TICK(PH_ARRIVE);
         // ---- every warp runs its own range of agents through aging, departure, hivtest, hivtx, hivprogress, hivvl
         const int n_slots = F.sc[SC_NSLOTS], n_pre = F.sc[SC_NPRE];
-        const int AW = ((n_slots + FT - 1) / FT) * 32, a0 = warp * AW, a1 = min(a0 + AW, n_slots);
+        const int AW = ((n_slots + FT - 1) / FT) * 32;           // agents per warp (32-agent groups, interleaved: VSLOT)
         const bool hivmods = mask & (XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL);
         int c0 = 0, c1 = 0;                                     // mini-queue fills: q0 = HIV-test candidates, q1 = HIV-positive agents
         // departure_msm, natural mortality: geometric gaps at the largest table rate, thinned to (race, age)
         if (mask & XGC_M_DEPARTURE)
-          gap_warp(key, at, FS_MORT, (unsigned)warp, a0, min(a1, n_pre), pmax_mort, lane, [&](bool ok, int i, const uint4& x) {
-            if (!ok) return;
+          gap_warp(key, at, FS_MORT, (unsigned)warp, 0, AW, pmax_mort, lane, [&](bool ok, int p, const uint4& x) {
+            const int i = VSLOT(p);
+            if (!ok || i >= n_pre) return;                      // (this week's arrivals are not exposed to mortality)
             unsigned d = vd[i];
             if (!(d & DM_ACTIVE)) return;
             int ai = min(XGC_ASMR_AGES - 1, max(0, (int)((float)(at8 - birth8(vh[i])) * (float)XF_W8)));
@@ -424,19 +429,19 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         __syncwarp();
         // hivtest_msm, interval testing: gaps at the largest race rate, thinned by race
         if (mask & XGC_M_HIVTEST)
-          gap_warp(key, at, FS_TEST, (unsigned)warp, a0, a1, pmax_test, lane, [&](bool ok, int i, const uint4& x) {
-            bool cand = false;
-            if (ok) { unsigned d = vd[i], h = vh[i];
+          gap_warp(key, at, FS_TEST, (unsigned)warp, 0, AW, pmax_test, lane, [&](bool ok, int p, const uint4& x) {
+            bool cand = false; const int i = VSLOT(p);
+            if (ok && i < n_slots) { unsigned d = vd[i], h = vh[i];
               cand = (d & DM_ACTIVE) && !(d & DM_LATE) && !(h & (HV_DIAG | HV_PREP)) && u01(x.y) * pmax_test < P[XGC_P_hiv_test_rate + DM_RACE(d)]; }
-            WQ_PUSH(q0, c0, cand, i - a0);
+            WQ_PUSH(q0, c0, cand, i);
             WQ_DRAIN(q0, c0, false, item, TEST_BODY);
           });
         // scan: aging, high-rate mortality (ageing out), rule-based tests; the HIV-positive agents are remembered as a bitmap
         unsigned hword = 0u;                                    // lane k: HIV-positive bits of word k of this warp's range
         for (int k = 0; k * 32 < AW; ++k) {
-          const int i = a0 + k * 32 + lane;
+          const int i = (k * NW + warp) * 32 + lane;
           bool live = false, qpos = false, qrule = false;
-          if (i < a1) {
+          if (i < n_slots) {
             unsigned d = vd[i], h = vh[i];
             live = d & DM_ACTIVE;
             if (live) {
@@ -459,15 +464,15 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
           unsigned mp = __ballot_sync(FULL, qpos);
           if (lane == k) hword = mp;
-          WQ_PUSH(q0, c0, qrule, (i - a0) | 0x8000);
+          WQ_PUSH(q0, c0, qrule, i | 0x8000);
           WQ_DRAIN(q0, c0, (k + 1) * 32 >= AW, item, TEST_BODY);
         }
         // HIV-positive agents of this warp's range: AIDS mortality, test result, hivtx_msm, hivprogress_msm, hivvl_msm
         for (int k = 0; k * 32 < AW; ++k) {
           const unsigned mp = __shfl_sync(FULL, hword, k);
-          WQ_PUSH(q1, c1, (mp >> lane) & 1u, k * 32 + lane);
+          WQ_PUSH(q1, c1, (mp >> lane) & 1u, (k * NW + warp) * 32 + lane);
           WQ_DRAIN(q1, c1, (k + 1) * 32 >= AW, item,
-            const int i = a0 + (int)item; const size_t idx = rbase + i;
+            const int i = (int)item; const size_t idx = rbase + i;
             unsigned d = vd[i], h = vh[i];
             if (d & DM_ACTIVE) {                                // (not) died of natural causes this week
               uint4 x = frand(key, at, FS_AG1, (unsigned)i, 0);
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
       // =================================================================================================== POST
       if (A.phases & XF_POST) {
         const int n_slots = F.sc[SC_NSLOTS];
-        const int AW = ((n_slots + FT - 1) / FT) * 32, a0 = warp * AW, a1 = min(a0 + AW, n_slots);
+        const int AW = ((n_slots + FT - 1) / FT) * 32;
         const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
         const bool last_week = at == A.at1;
         if (tid == 0 && (mask & XGC_M_STITRANS)) {              // weekly random pathway order (stitrans_msm_rand)
@@ -745,13 +750,14 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         // ---------------------------------------------------------------- prep_msm, stirecov_msm, stitx_msm (per-warp agent ranges)
         if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS)) {
           const bool avd_on = (mask & XGC_M_STITX) && (proto == XGC_SCREEN_BASE || proto == XGC_SCREEN_UNIVERSAL);
-          if (avd_on) gap_warp(key, at, FS_AVD, (unsigned)warp, a0, a1, P[XGC_P_gc_asympt_visit_prob], lane, [&](bool ok, int i, const uint4&) { if (ok) vg[i] |= FG_AVD; });
+          if (avd_on) gap_warp(key, at, FS_AVD, (unsigned)warp, 0, AW, P[XGC_P_gc_asympt_visit_prob], lane, [&](bool ok, int p, const uint4&) {
+            const int i = VSLOT(p); if (ok && i < n_slots) vg[i] |= FG_AVD; });
           __syncwarp();
           int c0 = 0, c1 = 0;                                   // q0 = PrEP users / starters (processed first), q1 = agents with GC work
           unsigned aword = 0u;                                  // lane k: GC-work bits of word k of this warp's range
           for (int k = 0; k * 32 < AW; ++k) {
-            const int i = a0 + k * 32 + lane; bool qA = false, qP = false;
-            if (i < a1 && (vd[i] & DM_ACTIVE)) {
+            const int i = (k * NW + warp) * 32 + lane; bool qA = false, qP = false;
+            if (i < n_slots && (vd[i] & DM_ACTIVE)) {
               unsigned gc = vg[i], h = vh[i];
               // start-of-pass snapshot: what acts / condoms / hivtrans see (they precede prep / stirecov / stitx in the module order)
               unsigned gc1 = (gc & ~(GC_CUR_MASK << GC_PRE_SHIFT)) | ((gc & GC_CUR_MASK) << GC_PRE_SHIFT);
@@ -772,9 +778,9 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             }
             unsigned ma = __ballot_sync(FULL, qA);
             if (lane == k) aword = ma;
-            WQ_PUSH(q0, c0, qP, k * 32 + lane);
+            WQ_PUSH(q0, c0, qP, i);
             WQ_DRAIN(q0, c0, (k + 1) * 32 >= AW, item,
-              const int i = a0 + (int)item; const size_t idx = rbase + i;
+              const int i = (int)item; const size_t idx = rbase + i;
               unsigned h = vh[i]; const unsigned h0 = h; int race = (int)DM_RACE(vd[i]);
               bool diag = h & HV_DIAG; bool indic = h & HV_PREPELIG; bool tested_neg = (vg[i] & FG_TESTED) && !diag;
               uint4 x = frand(key, at, FS_PREP, (unsigned)i, 0);
@@ -798,9 +804,9 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
           for (int k = 0; k * 32 < AW; ++k) {                   // stirecov_msm + stitx_msm on infected or visiting agents
             const unsigned ma = __shfl_sync(FULL, aword, k);
-            WQ_PUSH(q1, c1, (ma >> lane) & 1u, k * 32 + lane);
+            WQ_PUSH(q1, c1, (ma >> lane) & 1u, (k * NW + warp) * 32 + lane);
             WQ_DRAIN(q1, c1, (k + 1) * 32 >= AW, item,
-              const int i = a0 + (int)item; const size_t idx = rbase + i;
+              const int i = (int)item; const size_t idx = rbase + i;
               unsigned gc = vg[i]; const unsigned gc0 = gc; const unsigned h = vh[i];
               const bool avd = gc & FG_AVD;
               short4 ga = g.gck_a[idx]; short4 gb = g.gck_b[idx]; short4 gd = make_short4(-1, -1, -1, -1);
@@ -1031,16 +1037,16 @@ _Pragma("unroll")
         {
           int c0 = 0;
           for (int k = 0; k * 32 < AW; ++k) {
-            const int i = a0 + k * 32 + lane;
+            const int i = (k * NW + warp) * 32 + lane;
             bool q = false;
-            if (i < a1 && (vd[i] & DM_ACTIVE)) {
+            if (i < n_slots && (vd[i] & DM_ACTIVE)) {
               const unsigned gc = vg[i];
               if (gc & (FG_TESTED | FG_AVD)) vg[i] = gc & ~(FG_TESTED | FG_AVD);      // transient week flags
               q = (gc & GC_NEW_MASK) || (vh[i] & HV_NEW);
             }
-            WQ_PUSH(q0, c0, q, k * 32 + lane);
+            WQ_PUSH(q0, c0, q, i);
             WQ_DRAIN(q0, c0, (k + 1) * 32 >= AW, item,
-              const int i = a0 + (int)item; const size_t idx = rbase + i;
+              const int i = (int)item; const size_t idx = rbase + i;
               unsigned gc = vg[i]; unsigned h = vh[i]; const unsigned cell = DM_CELL(vd[i]);
               const unsigned gc_old = gc; const unsigned h_old = h;
               unsigned nm = (gc >> GC_NEW_SHIFT) & 0x7Fu;
@@ -1086,9 +1092,9 @@ _Pragma("unroll")
           // counts the staged state once, here
           if (!incr && (mask & XGC_M_PREV))
             for (int k = 0; k * 32 < AW; ++k) {
-              const int i = a0 + k * 32 + lane;
-              const unsigned d = i < a1 ? vd[i] : 0u;
-              unsigned bits = i < a1 ? tally_bits(d, vg[i], vh[i]) & ~(1u << XGC_K_NUM) : 0u;
+              const int i = (k * NW + warp) * 32 + lane;
+              const unsigned d = i < n_slots ? vd[i] : 0u;
+              unsigned bits = i < n_slots ? tally_bits(d, vg[i], vh[i]) & ~(1u << XGC_K_NUM) : 0u;
               const bool live = d & DM_ACTIVE; const unsigned cell = live ? DM_CELL(d) : 31u;
               const unsigned grp = __match_any_sync(FULL, cell);
               if (live && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&F.row[XGC_K_NUM * XGC_NCELL + cell], (unsigned)__popc(grp));
