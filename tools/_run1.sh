@@ -1,5 +1,6 @@
-for G in 7 10 14; do
-python bench.py --no-cpu-baseline --steps 64 --e2e-groups $G --e2e-steps 24 > gpurun_out/e2e_g$G.json 2> gpurun_out/e2e_g$G.err
-python -c "
-import json; d=json.loads(open('gpurun_out/e2e_g$G.json').read()); print($G, d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])"
+for i in 1 2; do
+python tools/time_modes.py --modes fast --weeks 128 2>/dev/null | cut -c1-400
+cp xgc_msm_b200/libxgc.so /tmp/new.so; cp xgc_msm_b200/libxgc_alt.so xgc_msm_b200/libxgc.so
+python tools/time_modes.py --modes fast --weeks 128 2>/dev/null | head -1 | cut -c1-120
+cp /tmp/new.so xgc_msm_b200/libxgc.so
 done

@@ -57,6 +57,8 @@ struct Fixed {                     // fixed part of the CTA's shared memory (com
   float asmr[4 * XGC_ASMR_AGES];
   float pk[4 * (XGC_MAX_ACTS + 1)];
   float degw[32];                   // XGC_T_NET_DEGW [3][3][3] + XGC_T_NET_RISKW [5] as fp32
+  float netp[8];                    // XGC_T_NET_DEG [3], XGC_T_NET_DUR [3]
+  float arrp[16];                   // XGC_T_RACE_PROP [4], XGC_T_ROLE_PROB [4][3]
   unsigned hib[16];
   int sc[SC_N];
   int wsum[NW], wsum2[NW], wsum3[NW];
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     for (int k = tid; k < 4 * XGC_ASMR_AGES; k += FT) F.asmr[k] = (float)g.tables[XGC_T_ASMR + k];
     for (int k = tid; k < 4 * (XGC_MAX_ACTS + 1); k += FT) F.pk[k] = (float)g.pois[(size_t)r * 4 * (XGC_MAX_ACTS + 1) + k];
     if (tid < 32) F.degw[tid] = (float)g.tables[XGC_T_NET_DEGW + tid];
+    if (tid < 6) F.netp[tid] = (float)g.tables[XGC_T_NET_DEG + tid];
+    if (tid < 16) F.arrp[tid] = (float)g.tables[XGC_T_RACE_PROP + tid];
     if (surrogate) for (int k = tid; k < g.n_cap / 4; k += FT) deg32[k] = 0u;
     if (tid < 16) F.hib[tid] = 0u;
     for (int k = tid; k < (int)g.e_stride; k += FT) ea[k] = 0;   // HBM holds compact lists: no tombstones
@@ -376,10 +380,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             for (int j = lane; j < nnew; j += 32) {
               int i = n_slots + j; size_t idx = rbase + i;
               uint4 x = frand(key, at, FS_ARRA, (unsigned)i, 0), y = frand(key, at, FS_ARRA, (unsigned)i, 1);
-              float rp4[4] = { (float)g.tables[XGC_T_RACE_PROP], (float)g.tables[XGC_T_RACE_PROP + 1], (float)g.tables[XGC_T_RACE_PROP + 2], (float)g.tables[XGC_T_RACE_PROP + 3] };
-              int race = categorical_f(u01(x.x), rp4, 4);
-              float ro[3] = { (float)g.tables[XGC_T_ROLE_PROB + race * 3], (float)g.tables[XGC_T_ROLE_PROB + race * 3 + 1], (float)g.tables[XGC_T_ROLE_PROB + race * 3 + 2] };
-              int role = categorical_f(u01(x.y), ro, 3);
+              int race = categorical_f(u01(x.x), F.arrp, 4);
+              int role = categorical_f(u01(x.y), F.arrp + 4 + race * 3, 3);
               float insq = role == 0 ? 1.f : role == 1 ? 0.f : u01(x.z);
               unsigned circ = bern(x.w, P[XGC_P_circ_prob + race]), late = bern(y.x, P[XGC_P_hiv_test_late_prob + race]);
               float tt[3] = { P[XGC_P_tt_part_supp + race], P[XGC_P_tt_full_supp + race], P[XGC_P_tt_dur_supp + race] };
@@ -557,8 +559,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           for (int l = 0; l < 3; ++l) {
             int nf = 0;
             if (form) {
-              float target = (float)g.tables[XGC_T_NET_DEG + l] * (float)n_alive * 0.5f;
-              float mu = l == 2 ? target : target / (float)g.tables[XGC_T_NET_DUR + l];
+              float target = F.netp[l] * (float)n_alive * 0.5f;           // (staged: thread 0 holds the whole CTA at the next barrier)
+              float mu = l == 2 ? target : target / F.netp[3 + l];
               float fl = floorf(mu);
               nf = n_alive < 2 ? 0 : (int)fl + (u01(frand(key, at, FS_NETN, l, 0).x) < mu - fl);
               if (l == 2) { F.sc[SC_NE2] = 0; F.sc[SC_DEAD2] = 0; }      // one-off contacts last one week: the layer starts empty
