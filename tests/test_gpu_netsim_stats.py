@@ -152,7 +152,11 @@ def test_full_size_sweep_properties():
                 h.compact()
     for k, h in enumerate(halves):
         for t in range(2, 2 + weeks):
-            assert np.array_equal(h.counters_all(t), C[t - 1, k * (R // 2):(k + 1) * (R // 2)].astype(np.uint32)), (k, t)
+            got, want = h.counters_all(t), C[t - 1, k * (R // 2):(k + 1) * (R // 2)].astype(np.uint32)
+            if not np.array_equal(got, want):
+                rr, cc = np.nonzero(got != want)
+                raise AssertionError(f"shard {k}, week {t}: {np.unique(rr).size} replicates differ (first {np.unique(rr)[:8]}), counters {np.unique(cc)[:16]}, "
+                                     f"first: shard {got[rr[0], cc[0]]} vs full handle {want[rr[0], cc[0]]}")
         h.close()
     tg = full.targets(1 + weeks, 5)
     assert tg.shape == (R, K.NTARGET) and np.isfinite(tg[:, :3]).all()

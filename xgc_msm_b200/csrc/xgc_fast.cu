@@ -624,7 +624,10 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           if (tid == 0) { F.sc[SC_NE0] = tail0; F.sc[SC_NE1] = tail1; F.sc[SC_NE2] = tail2; }
           __syncthreads();
         }
-        if (!(A.phases & XF_POST)) {                             // no acts pass in this call: the tie sweep on its own
+        // no acts pass in this call.  With a network step to run now (dissolution + formation) the tie sweep runs on its own; without
+        // one, the ties of this week's departed agents are left to whoever touches the lists next -- the weekly-toggle kernel
+        // (k_edges_update), this kernel's acts pass, or an explicit prune before anything else reads them (h->prune_pending)
+        if (!(A.phases & XF_POST) && form) {
           const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
           for (int f0 = tid; f0 < ne_all; f0 += 4 * FT) {        // four ties per thread in flight
             int4 ed4[4];

@@ -585,6 +585,16 @@ __global__ void __launch_bounds__(TPB) k_rank_cta(const __grid_constant__ Dev g)
   }
 }
 
+// k_zero_deg: the degree plane of this launch's replicates back to zero before the dissolution pass counts into it.  A kernel,
+// not a cudaMemsetAsync: on the step-by-step path every kernel is launched with programmatic stream serialization, and only a
+// kernel's griddepcontrol.wait orders it against BOTH neighbours (a memset between two such launches is not a grid the next
+// kernel's wait covers -- the counts of its first CTAs could be zeroed under it).
+__global__ void __launch_bounds__(TPB) k_zero_deg(const __grid_constant__ Dev g) {
+  pdl_prologue();
+  uint4* p = reinterpret_cast<uint4*>(g.deg + (size_t)g.r0 * g.n_cap);
+  const size_t n = (size_t)g.R * g.n_cap / 4;
+  for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (size_t)gridDim.x * TPB) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
 // formation weight of an agent in layer l (abi.h XGC_T_NET_DEGW / XGC_T_NET_RISKW): degree classes from the byte counts of g.deg
 __device__ __forceinline__ double form_weight(const double* tb, int l, unsigned dg, unsigned demo) {
   int cm = min((int)(dg & 0xFFu), 2), cc = min((int)((dg >> 8) & 0xFFu), 2);

@@ -59,6 +59,8 @@ struct xgc_handle {
   cudaGraphExec_t l1_graph = nullptr; uint64_t l1_graph_launches = 0;
   int lanes_captured = 0;
   bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
+  bool prune_pending = false;          // a fast-path aging..hivvl call left ties of departed agents in the lists (dropped lazily:
+                                       // k_edges_update, the fast acts pass, or prune_now() before any other reader)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
   Inj last_inj;                        // draw source of the most recent xgc_step (lazy act counts must use the same)
   bool profiling = false;
@@ -327,6 +329,7 @@ static void rebuild_maps(HostRep& c) {
   c.pos2slot.clear(); c.slot2pos.assign(c.core.size(), -1);
   for (size_t i = 0; i < c.core.size(); ++i) if (c.core[i].y & DM_ACTIVE) { c.slot2pos[i] = (int)c.pos2slot.size(); c.pos2slot.push_back((int)i); }
 }
+static int prune_now(xgc_handle* h);
 static int cache_flush(xgc_handle* h) {
   HostRep& c = h->cache;
   if (c.r < 0 || !c.dirty) { return 0; }
@@ -352,6 +355,7 @@ static int cache_load(xgc_handle* h, int r) {
   HostRep& c = h->cache;
   if (c.r == r) return 0;
   int rc = cache_flush(h); if (rc) return rc;
+  rc = prune_now(h); if (rc) return rc;
   const Dev& g = h->g; size_t o = (size_t)r * g.n_cap;
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -656,7 +660,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   if ((mask & XGC_M_DEPARTURE) && !((mask & XGC_M_RESIM_NETS) && native)) launch_resim(h, inj, 0, 0);
   if (mask & XGC_M_RESIM_NETS) {
     // degrees of the ties that survive this week's dissolution: zeroed here, counted by the dissolution pass, read by k_form
-    cudaMemsetAsync(g.deg + (size_t)g.r0 * g.n_cap, 0, (size_t)g.R * g.n_cap * sizeof(unsigned), h->cur);
+    LAUNCH(h, k_zero_deg, (unsigned)std::min<size_t>(148 * 8, ((size_t)g.R * g.n_cap / 4 + TPB - 1) / TPB), TPB, g);
     launch_resim(h, inj, 1, 1);
     size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
     if (form_smem <= 8 * 1024) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
@@ -709,6 +713,16 @@ extern "C" int xgc_set_mode(xgc_handle* h, int mode) {
 extern "C" int xgc_get_mode(xgc_handle* h, int* mode) { *mode = h->mode; return 0; }
 
 static int compact_impl(xgc_handle* h);
+// the ties of departed agents are physically out of the lists after this (tergmLite::delete_vertices); no-op unless a fast-path
+// call deferred it
+static int prune_now(xgc_handle* h) {
+  if (!h->prune_pending) return 0;
+  CU(h, cudaSetDevice(h->cfg.device));
+  launch_resim(h, make_inj(h, nullptr, nullptr), 0, 0);
+  h->prune_pending = false;
+  CU(h, cudaGetLastError());
+  return 0;
+}
 // module mask -> phase groups of the replicate-resident kernel (0: not a group the fast path runs)
 static unsigned fast_phases(uint32_t mask) {
   const uint32_t PREG = XGC_M_AGING | XGC_M_DEPARTURE | XGC_M_ARRIVAL | XGC_M_HIVTEST | XGC_M_HIVTX | XGC_M_HIVPROGRESS | XGC_M_HIVVL;
@@ -751,8 +765,12 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   if (fph) {
     if (!(fph & XF_PRE) && zero_row) FAIL(h, 11, "fast mode: week %d must start with the aging..hivvl module group", at);
     h->acts_valid = false;                                        // kissing / rimming counts are not materialised in fast mode
-    return fast_enqueue(h, at, at, fph, mask, 1);
+    rc = fast_enqueue(h, at, at, fph, mask, 1);
+    // a call without the acts pass and without an on-device network step leaves the departed agents' ties to the next toucher
+    if (fph & XF_POST) h->prune_pending = false; else if (!(fph & XF_FORM)) h->prune_pending = true;
+    return rc;
   }
+  rc = prune_now(h); if (rc) return rc;
   rc = enqueue_week(h, at, mask, j, zero_row); if (rc) return rc;
   CU(h, cudaGetLastError());
   if (inj && inj->u) CU(h, cudaStreamSynchronize(h->stream));     // caller may free the table after return
@@ -790,7 +808,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   rc = compact_impl(h);
-  if (!rc) h->compacted_at = h->last_at;
+  if (!rc) { h->compacted_at = h->last_at; h->prune_pending = false; }
   return rc;
 }
 
@@ -799,6 +817,7 @@ extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   if (at1 > 32766) FAIL(h, 2, "at exceeds the 16-bit week clocks");
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
+  rc = prune_now(h); if (rc) return rc;
   if (h->mode == XGC_MODE_FAST) {       // replicate-resident kernel: one launch per stretch of weeks between slot compactions
     const int ce = h->cfg.compact_every;
     for (int at = at0; at <= at1;) {
@@ -1124,6 +1143,7 @@ extern "C" int xgc_snapshot(xgc_handle* h, void* buf, size_t bytes) {
   size_t need; xgc_snapshot_size(h, &need);
   if (bytes < need) FAIL(h, 6, "snapshot buffer too small: %zu < %zu", bytes, need);
   int rc = cache_drop(h); if (rc) return rc;
+  rc = prune_now(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   char* p = (char*)buf; memcpy(p, &h->cfg, sizeof(xgc_config)); p += sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, cudaMemcpy(p, sg.p, sg.bytes, cudaMemcpyDeviceToHost)); p += sg.bytes; }
@@ -1150,6 +1170,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   if (src->cfg.n_cap != dst->cfg.n_cap || src->g.e_stride != dst->g.e_stride || src->cfg.t_cap != dst->cfg.t_cap) FAIL(dst, 9, "fork: geometry differs");
   int rc = cache_drop(src); if (rc) return rc;
   rc = cache_drop(dst); if (rc) return rc;
+  rc = prune_now(src); if (rc) return rc;
   CU(src, cudaSetDevice(src->cfg.device)); CU(src, cudaStreamSynchronize(src->stream));
   CU(dst, cudaSetDevice(dst->cfg.device)); CU(dst, cudaStreamSynchronize(dst->stream));
   const Dev &a = src->g, &b = dst->g; size_t n = a.n_cap, so = (size_t)sr * n, doff = (size_t)dr * n;
@@ -1213,7 +1234,11 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
 }
 
 // weekly delta of a persistent layer: one CTA per replicate marks the removed ties in a shared-memory bitmap, compacts the layer
-// in place (stable) and appends the added ties (R positions -> slots through pos2slot)
+// in place (stable) and appends the added ties (R positions -> slots through pos2slot).  The ties of agents who departed this
+// week are dropped in the same pass (tergmLite::delete_vertices): the host's removal indices refer to the list WITHOUT them --
+// the list an R session holds after departure_msm -- so a tie's index is its rank among the ties whose endpoints both live.
+// (The fast path's aging..hivvl call leaves that pruning to this kernel / to its own acts pass: h->prune_pending.)
+#define UPD_IPT 4
 __global__ void __launch_bounds__(TPB) k_edges_update(const __grid_constant__ Dev g, int l, const int* delta /*[R][stride]*/, int stride, int has_start) {
   pdl_prologue();
   extern __shared__ unsigned upd_kill[];
@@ -1222,29 +1247,52 @@ __global__ void __launch_bounds__(TPB) k_edges_update(const __grid_constant__ De
   const int* row = delta + (size_t)r * stride;
   const int ne = rp->ne[l], nrem = max(0, min(row[0], stride - 2)), nadd = max(0, min(row[1], (stride - 2 - nrem) / (has_start ? 3 : 2)));
   int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
-  __shared__ int wsum[TPB / 32];
-  __shared__ int base;
+  const unsigned* A = g.alive + (size_t)r * (g.n_cap / 32);
+  __shared__ int wsum[UPD_IPT][TPB / 32], wlive[UPD_IPT][TPB / 32];
+  __shared__ int base, base_live;
   for (int k = tid; k < (ne + 31) / 32; k += TPB) upd_kill[k] = 0u;
-  if (tid == 0) base = 0;
+  if (tid == 0) { base = 0; base_live = 0; }
   __syncthreads();
   bool bad = row[0] != nrem || row[1] != nadd;
   for (int k = tid; k < nrem; k += TPB) { int e = row[2 + k]; if (e >= 0 && e < ne) atomicOr(&upd_kill[e >> 5], 1u << (e & 31)); else bad = true; }
   __syncthreads();
-  for (int e0 = 0; e0 < ne; e0 += TPB) {
-    int e = e0 + tid; bool keep = false; int4 ed = make_int4(0, 0, 0, 0);
-    if (e < ne) { ed = E[e]; keep = !((upd_kill[e >> 5] >> (e & 31)) & 1u); }
-    unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) wsum[w] = __popc(m);
+  for (int e0 = 0; e0 < ne; e0 += TPB * UPD_IPT) {          // 1024 ties per round, item q = ties e0 + q * TPB .. (stable order)
+    int4 ed[UPD_IPT]; bool live[UPD_IPT]; unsigned ml[UPD_IPT];
+#pragma unroll
+    for (int q = 0; q < UPD_IPT; ++q) {
+      const int e = e0 + q * TPB + tid; live[q] = false; ed[q] = make_int4(0, 0, 0, 0);
+      if (e < ne) { ed[q] = E[e]; live[q] = ((A[ed[q].x >> 5] >> (ed[q].x & 31)) & 1u) && ((A[ed[q].y >> 5] >> (ed[q].y & 31)) & 1u); }
+      ml[q] = __ballot_sync(0xffffffffu, live[q]);
+      if (lane == 0) wlive[q][w] = __popc(ml[q]);
+    }
     __syncthreads();
-    int off = base;
-    for (int k = 0; k < w; ++k) off += wsum[k];
-    off += __popc(m & ((1u << lane) - 1u));
-    if (keep && off != e) E[off] = ed;
+    bool keep[UPD_IPT]; unsigned mk[UPD_IPT]; int runl = base_live;
+#pragma unroll
+    for (int q = 0; q < UPD_IPT; ++q) {
+      int pl = runl, tot = 0;                                // rank of this tie among the living ties = its index for the host
+      for (int k = 0; k < TPB / 32; ++k) { int c = wlive[q][k]; tot += c; if (k < w) pl += c; }
+      pl += __popc(ml[q] & ((1u << lane) - 1u));
+      keep[q] = live[q] && !((upd_kill[pl >> 5] >> (pl & 31)) & 1u);
+      mk[q] = __ballot_sync(0xffffffffu, keep[q]);
+      if (lane == 0) wsum[q][w] = __popc(mk[q]);
+      runl += tot;
+    }
     __syncthreads();
-    if (tid == 0) { int t = 0; for (int k = 0; k < TPB / 32; ++k) t += wsum[k]; base += t; }
+    int run = base;
+#pragma unroll
+    for (int q = 0; q < UPD_IPT; ++q) {
+      int off = run, tot = 0;
+      for (int k = 0; k < TPB / 32; ++k) { int c = wsum[q][k]; tot += c; if (k < w) off += c; }
+      off += __popc(mk[q] & ((1u << lane) - 1u));
+      if (keep[q] && off != e0 + q * TPB + tid) E[off] = ed[q];
+      run += tot;
+    }
+    __syncthreads();
+    if (tid == 0) { base = run; base_live = runl; }
     __syncthreads();
   }
-  const int nk = base, na = rp->n_alive, at = g.at_ptr[r];
+  const int nk = base, nlive = base_live, na = rp->n_alive, at = g.at_ptr[r];
+  for (int k = tid; k < nrem; k += TPB) if (row[2 + k] >= nlive) bad = true;      // an index beyond the pruned list
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
   const int* tail = row + 2 + nrem; const int* head = tail + nadd; const int* st = head + nadd;
   for (int k = tid; k < nadd; k += TPB) {
