@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_calibration.py "tests/test_gpu_netsim_stats.py::test_full_size_sweep_properties" -m gpu -x -q 2>&1 | grep -n "AssertionError\|passed\|failed" | head -3
-python -m pytest tests/test_gpu_fast_mode.py "tests/test_gpu_netsim_stats.py::test_full_size_sweep_properties" -m gpu -x -q 2>&1 | grep -n "AssertionError\|passed\|failed" | head -3
-python -m pytest "tests/test_gpu_fast_mode.py::test_fast_mode_statistically_equivalent_to_oracle" "tests/test_gpu_netsim_stats.py::test_full_size_sweep_properties" -m gpu -x -q 2>&1 | grep -n "AssertionError\|passed\|failed" | head -3
-python -m pytest "tests/test_gpu_fast_mode.py::test_fast_mode_structure_and_recount" "tests/test_gpu_fast_mode.py::test_fast_mode_step_groups_equal_run" "tests/test_gpu_fast_mode.py::test_degree_conditioned_formation" "tests/test_gpu_netsim_stats.py::test_full_size_sweep_properties" -m gpu -x -q 2>&1 | grep -n "AssertionError\|passed\|failed" | head -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --no-cpu-baseline --steps 64 --e2e-steps 24 > gpurun_out/e2e_i.json 2> gpurun_out/e2e_i.err
+python -c "
+import json; d=json.loads(open('gpurun_out/e2e_i.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])"

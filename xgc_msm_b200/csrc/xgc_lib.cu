@@ -59,6 +59,8 @@ struct xgc_handle {
   cudaGraphExec_t l1_graph = nullptr; uint64_t l1_graph_launches = 0;
   int lanes_captured = 0;
   bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
+  bool plain_next = false;             // the next kernel launch follows an async copy / memset on the stream: no programmatic
+                                       // serialization for it (its griddepcontrol.wait only covers preceding GRIDS)
   bool prune_pending = false;          // a fast-path aging..hivvl call left ties of departed agents in the lists (dropped lazily:
                                        // k_edges_update, the fast acts pass, or prune_now() before any other reader)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
@@ -555,6 +557,7 @@ static int upload_inject(xgc_handle* h, const xgc_inject* inj, Inj* out) {
     h->d_inj_cap = need;
   }
   CU(h, cudaMemcpyAsync(h->d_inj, inj->u, need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->plain_next = true;
   *out = make_inj(h, inj, h->d_inj);
   return 0;
 }
@@ -576,7 +579,8 @@ static void kl(xgc_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->cur ? h->cur : h->lane_main;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling && !h->capturing) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->profiling && !h->capturing && !h->plain_next) ? 1 : 0;
+  h->plain_next = false;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
   if (e != cudaSuccess && !h->launch_err) {          // remembered for xgc_last_error; the caller's cudaGetLastError() reports it
     h->launch_err = true;
@@ -930,6 +934,7 @@ static int materialise_actcounts(xgc_handle* h, int r, const Inj& j) {      // k
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
   int* d_out; CU(h, cudaMalloc((void**)&d_out, sizeof(int) * 3 * (size_t)emax));
   cudaMemsetAsync(d_out, 0, sizeof(int) * 3 * (size_t)emax, h->stream);
+  h->plain_next = true;
   LAUNCHD(h, j, k_actcounts, dim3((emax + TPB - 1) / TPB, 3), TPB, g, j, r, d_out, emax);
   std::vector<int> all(3 * (size_t)emax);
   cudaError_t e = cudaMemcpyAsync(all.data(), d_out, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, h->stream);
@@ -964,6 +969,7 @@ extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int ca
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
   int* d_al; CU(h, cudaMalloc((void**)&d_al, sizeof(int) * 6 * (size_t)std::max(cap, 1)));
   CU(h, cudaMemcpyAsync((int*)h->g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  h->plain_next = true;
   LAUNCHD(h, j, k_actlist, 1, 32, h->g, j, r, d_al, cap, h->d_scratch);
   int n = 0;
   cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -1222,6 +1228,7 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   CU(h, cudaMemcpyAsync(d_el, el, R * st * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (start) CU(h, cudaMemcpyAsync(d_start, start, R * st * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  h->plain_next = true;
   if (!h->rank_fresh) {
     if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
     else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
@@ -1320,6 +1327,7 @@ extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t*
     h->upd_stage_cap[layer] = need;
   }
   CU(h, cudaMemcpyAsync(h->d_upd_stage[layer], delta, need * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  h->plain_next = true;
   if (!h->rank_fresh) {
     if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
     else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
