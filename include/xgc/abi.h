@@ -168,8 +168,12 @@ static inline XGC_HD int xgc_stream_width(int s) {
   if (s == XGC_S_DISSOLVE) return 1;
   if (s == XGC_S_ACTS) return 4;
   if (s == XGC_S_ANAL) return 4 * XGC_MAX_ACTS;
-  if (s == XGC_S_KISS) return 1;
-  return 3;                                        /* XGC_S_ORAL, XGC_S_RIM */
+  /* Oral, rimming and kissing acts.  NATIVE draws: one direction word (draw 0) and one any-of-m transmission trial per direction
+   * (draws 1, 2; kissing: draw 0) -- DESIGN.md A13.  INJECTED draws: PER ACT, so that a caller that replays R's runif stream can
+   * give every rbinom of every act its own uniform: oral / rimming act j takes draw 1 + 2j (direction: p1 active iff u < 0.5) and
+   * draw 2 + 2j (transmission); kissing act j takes draw j. */
+  if (s == XGC_S_KISS) return XGC_MAX_ACTS;
+  return 1 + 2 * XGC_MAX_ACTS;                     /* XGC_S_ORAL, XGC_S_RIM */
 }
 
 /* Injected-draw table for ONE replicate and ONE week.  Layout: for each stream s in increasing order, a block of

@@ -637,10 +637,16 @@ static void position_msm(orc_dat* d, int at) {
         r->p1act = orc_bern(U(d, at, base + (XGC_S_ANAL - XGC_S_EDGE0), ua, ub, (size_t)r->e, 4 * r->k + 1), pi);
       }
     } else if (r->type == 1 || r->type == 3) {
-      /* direction of oral / rimming act j: bit (31 - j) of the 32-bit direction word floor(u * 2^32) (draw k0) */
-      double u = U(d, at, base + ((r->type == 1 ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0), ua, ub, (size_t)r->e, 0);
-      uint32_t w = (uint32_t)(u * 4294967296.0);
-      r->p1act = (int)((w >> (31 - r->k)) & 1u);
+      int st = base + ((r->type == 1 ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0);
+      if (d->inj && d->inj->u) {
+        /* injected draws: one uniform per act (abi.h xgc_stream_width): p1 is the active partner iff u < 0.5 */
+        r->p1act = U(d, at, st, ua, ub, (size_t)r->e, 1 + 2 * r->k) < 0.5;
+      } else {
+        /* native draws: direction of act j = bit (31 - j) of the 32-bit direction word floor(u * 2^32) (draw 0) */
+        double u = U(d, at, st, ua, ub, (size_t)r->e, 0);
+        uint32_t w = (uint32_t)(u * 4294967296.0);
+        r->p1act = (int)((w >> (31 - r->k)) & 1u);
+      }
     }
   }
   d->al_has_pos = 1;
@@ -814,8 +820,32 @@ static void stitrans_msm_rand(orc_dat* d, int at) {
      Bernoulli(1 - (1-t)^m) trial; the act list supplies m. */
   int* cnt[3];                       /* per layer: [e][type 1..3][direction p1 active / p2 active] */
   for (int l = 0; l < 3; ++l) cnt[l] = (int*)calloc((size_t)(d->ne[l] + 1) * 6, sizeof(int));
+  const int per_act = d->inj && d->inj->u;          /* injected draws: every oral / rimming / kissing act is its own Bernoulli trial */
   for (int j = 0; j < d->nal; ++j) {
     const orc_act* r = &d->al[j];
+    if (r->type != 0 && per_act) {
+      const orc_edge* g = &d->el[r->layer][r->e];
+      int base = XGC_S_EDGE0 + r->layer * XGC_EDGE_STREAMS;
+      uint32_t ua = (uint32_t)d->a[A_UID][g->p1], ub = (uint32_t)d->a[A_UID][g->p2];
+      if (r->type == 2) {                                      /* kissing act k: pharynx <-> pharynx */
+        if (!d->c[XGC_C_transRoute_Kissing]) continue;
+        int ga = (int)d->a[A_GC + 2][g->p1] == 1, gb = (int)d->a[A_GC + 2][g->p2] == 1;
+        if (ga == gb) continue;
+        if (orc_bern(U(d, at, base + (XGC_S_KISS - XGC_S_EDGE0), ua, ub, (size_t)r->e, r->k), p[XGC_P_p2pgc_tprob]))
+          d->newmask[ga ? g->p2 : g->p1] |= 1u << XGC_PATH_P2P;
+        continue;
+      }
+      if (r->type == 3 && !d->c[XGC_C_transRoute_Rimming]) continue;
+      int sx = r->type == 1 ? 1 : 2, sy = r->type == 1 ? 2 : 0, st = r->type == 1 ? XGC_S_ORAL : XGC_S_RIM;
+      int pathA = r->type == 1 ? XGC_PATH_U2P : XGC_PATH_P2R, pathB = r->type == 1 ? XGC_PATH_P2U : XGC_PATH_R2P;
+      double tA = r->type == 1 ? p[XGC_P_u2pgc_tprob] : p[XGC_P_p2rgc_tprob], tB = r->type == 1 ? p[XGC_P_p2ugc_tprob] : p[XGC_P_r2pgc_tprob];
+      int x = r->p1act ? g->p1 : g->p2, y = r->p1act ? g->p2 : g->p1;
+      int gx = (int)d->a[A_GC + sx][x] == 1, gy = (int)d->a[A_GC + sy][y] == 1;
+      if (gx == gy) continue;
+      if (orc_bern(U(d, at, base + (st - XGC_S_EDGE0), ua, ub, (size_t)r->e, 2 + 2 * r->k), gx ? tA : tB))
+        d->newmask[gx ? y : x] |= 1u << (gx ? pathA : pathB);
+      continue;
+    }
     if (r->type != 0) { cnt[r->layer][(size_t)r->e * 6 + (r->type - 1) * 2 + (r->type == 2 ? 0 : (r->p1act ? 0 : 1))]++; continue; }
     const orc_edge* g = &d->el[r->layer][r->e];
     int base = XGC_S_EDGE0 + r->layer * XGC_EDGE_STREAMS;

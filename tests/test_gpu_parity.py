@@ -97,12 +97,15 @@ def test_injected_draws_bit_exact():
     orcs = [load_oracle(c, SEED, r) for r, c in enumerate(cases)]
     rng = np.random.default_rng(99)
     uid_cap, e_cap, form_cap = cases[0]["cap"] + 256, cases[0]["e_cap"], 256
-    for at in range(2, 6):
+    for at in range(2, 8):
         u, stride = random_inject(rng, 2, uid_cap, e_cap, form_cap)
         h.step(at, K.M_ALL, abi.make_inject(u, uid_cap, e_cap, form_cap))
         for r, o in enumerate(orcs):
             o.step(at, K.M_ALL, omake(u[r], stride, uid_cap, e_cap, form_cap))
             compare_state(h, r, o, at, f"injected week {at} r={r}")
+    # with injected draws every oral / rimming / kissing act is its own trial (abi.h xgc_stream_width): those pathways must have fired
+    paths = sum(h.counters(r, 2, 7).astype(np.int64)[:, K.K_PATH:K.K_PATH + K.NPATH].sum(0) for r in range(2))
+    assert paths[[1, 3, 4, 5, 6]].min() > 0, paths                  # p2r, p2u, u2p, r2p, p2p (u2r, r2u are the anal pathways)
 
 
 def test_actlist_condoms_position():

@@ -1208,9 +1208,21 @@ template <bool INJ> __device__ __forceinline__ void e2_directed(const Dev& g, co
   double tA = oral ? P[XGC_P_u2pgc_tprob] : P[XGC_P_p2rgc_tprob], tB = oral ? P[XGC_P_p2ugc_tprob] : P[XGC_P_r2pgc_tprob];
   unsigned pA = oral ? XGC_PATH_U2P : XGC_PATH_P2R, pB = oral ? XGC_PATH_P2U : XGC_PATH_R2P;
   DrawT<INJ> dd(inj, g, r, at, base + ((oral ? XGC_S_ORAL : XGC_S_RIM) - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
+  unsigned new_a = 0, new_b = 0;
+  if (INJ) {                                                // injected draws: every act is its own trial (abi.h xgc_stream_width)
+    for (int j = 0; j < n; ++j) {
+      bool p1 = dd(1 + 2 * j) < 0.5;                        // p1 is the active partner of act j
+      bool ix = ((p1 ? ga : gb) >> sx) & 1u, iy = ((p1 ? gb : ga) >> sy) & 1u;
+      if (ix == iy) continue;
+      if (xgc_bern(dd(2 + 2 * j), ix ? tA : tB)) {          // ix: the active partner's site infects the other partner's; else the reverse
+        if (ix) { if (p1) new_b |= 1u << pA; else new_a |= 1u << pA; } else { if (p1) new_a |= 1u << pB; else new_b |= 1u << pB; }
+      }
+    }
+    e2_flag(core, ed, new_a, new_b, false, false);
+    return;
+  }
   unsigned dirword = dd.bits32(0);                          // act j: p1 is the active partner iff bit (31 - j) is set
   int m1 = __popc(dirword >> (32 - n)), m0 = n - m1;        // acts with p1 / p2 active (n in 1..32)
-  unsigned new_a = 0, new_b = 0;
   {                                                         // p1 active: x = p1, y = p2
     bool ix = (ga >> sx) & 1u, iy = (gb >> sy) & 1u;
     if (m1 > 0 && ix != iy) {
@@ -1234,8 +1246,10 @@ template <bool INJ> __device__ __forceinline__ void e2_kiss(const Dev& g, const 
   bool pa = (ca.z >> 2) & 1u, pb = (cb.z >> 2) & 1u;
   if (pa == pb) return;
   DrawT<INJ> d(inj, g, r, at, base + (XGC_S_KISS - XGC_S_EDGE0), ca.x, cb.x, (size_t)e);
-  if (xgc_bern(d(0), xgc_any_of_n(P[XGC_P_p2pgc_tprob], n)))
-    e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
+  bool hit = false;
+  if (INJ) { for (int j = 0; j < n; ++j) hit |= (bool)xgc_bern(d(j), P[XGC_P_p2pgc_tprob]); }      // injected draws: one trial per kiss
+  else hit = xgc_bern(d(0), xgc_any_of_n(P[XGC_P_p2pgc_tprob], n));
+  if (hit) e2_flag(core, ed, pa ? 0u : 1u << XGC_PATH_P2P, pa ? 1u << XGC_PATH_P2P : 0u, false, false);
 }
 
 // k_edge2a: classify every edge and append the (edge, act type) pairs that can transmit to the replicate's per-type
@@ -1669,8 +1683,8 @@ template <bool INJ> __global__ void k_actlist(const __grid_constant__ Dev g, con
         for (int k = 0; k < cnt[type]; ++k) {
           int uai = 0, p1 = 0;
           if (type == 0) { uai = xgc_bern(dc(4 * k), 1.0 - pc); p1 = edge_ai_p1ins(x, dc, k); }
-          else if (type == 1) p1 = (doi.bits32(0) >> (31 - k)) & 1u;
-          else if (type == 3) p1 = (dri.bits32(0) >> (31 - k)) & 1u;
+          else if (type == 1) p1 = INJ ? (int)(doi(1 + 2 * k) < 0.5) : (int)((doi.bits32(0) >> (31 - k)) & 1u);
+          else if (type == 3) p1 = INJ ? (int)(dri(1 + 2 * k) < 0.5) : (int)((dri.bits32(0) >> (31 - k)) & 1u);
           if (n < cap) { al[n] = l; al[cap + n] = e; al[2 * cap + n] = type; al[3 * cap + n] = k; al[4 * cap + n] = uai; al[5 * cap + n] = p1; }
           n++;
         }

@@ -37,8 +37,10 @@ def kernel_bytes(stats: dict) -> dict:
         # dense queue: per pair 4 B item + edge record + 2 x core (+ aux for anal pairs, ~1/4 of the pairs)
         "k_edge2b_anal": e * f_disc * 0.25 * (4 + 16 + 2 * 16 + 2 * 16),
         "k_edge2b_oral_kiss_rim": e * f_disc * 0.75 * (4 + 16 + 2 * 16),
-        # in-place stable compaction: record R, survivors W, endpoint core gathers
-        "k_edges_resim": e * (16 + 16 + 2 * 16),
+        # in-place stable compaction on the alive bitmap (1 bit per endpoint, cache-resident) with the dissolution flag pre-drawn in the
+        # record: record R, and W only of the records that move (everything behind the first removed tie of a layer: about half);
+        # ncu: 93 MB per launch at 5.0 M ties = 18.6 B per tie (round 1 charged 64 B per tie here, overstating the step)
+        "k_edges_resim": e * (16 + 4),
     }
 
 
