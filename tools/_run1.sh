@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python bench.py --no-cpu-baseline --steps 64 --e2e-steps 24 > gpurun_out/e2e_i.json 2> gpurun_out/e2e_i.err
-python -c "
-import json; d=json.loads(open('gpurun_out/e2e_i.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])"
+python tools/run_calibration_round.py 1000 520 fast r02 2>&1 | tail -2
+python tools/run_screening_grid.py 500 520 260 fast r02 2>&1 | tail -7
+python -m pytest tests/test_gpu_calibration.py tests/test_gpu_netsim_stats.py -x -q -m gpu 2>&1 | tail -2

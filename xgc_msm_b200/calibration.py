@@ -129,10 +129,11 @@ class RoundResult:
 
 
 def run_round(priors: Sequence[Prior], n_sims: int, weeks: int, tailn: int = 52, n_agents: int = 10000, seed: int = 1971,
-              device: int = 0, pop_tol: float = 0.05, replicate_offset: int = 0, n_distinct: int = 4) -> RoundResult:
+              device: int = 0, pop_tol: float = 0.05, replicate_offset: int = 0, n_distinct: int = 4, mode: str = "fast") -> RoundResult:
     """One calibration round on one GPU: n_sims replicates, each with its own LHS parameter vector, `weeks` weeks on the
     device, tail-`tailn` targets, then the reference's filters.  The start populations are the synthetic ones of
-    workload.py (the fitted netest is an LFS pointer)."""
+    workload.py (the fitted netest is an LFS pointer).  mode "fast": the replicate-resident native-draw kernels (strict
+    kernels when a replicate does not fit one SM's shared memory); "strict": the bit-exact kernels."""
     from . import workload as W
     from .abi import Handle
     spec = W.SweepSpec(n_agents=n_agents, seed=seed, n_distinct=n_distinct)
@@ -143,6 +144,11 @@ def run_round(priors: Sequence[Prior], n_sims: int, weeks: int, tailn: int = 52,
     try:
         W.load_sweep(h, spec, rid0=replicate_offset)
         h.set_params(np.stack([P.params_from_env(e, n_init=n_agents) for e in envs]))
+        if mode == "fast":
+            try:
+                h.set_mode("fast")
+            except Exception:
+                pass
         h.run(2, 1 + weeks)
         tm = h.targets(1 + weeks, min(tailn, weeks))
         status = 0

@@ -38,6 +38,7 @@ def fork_arms(burnin: Handle, seed: int = 1971, device: int = 0) -> Dict[str, Ha
         for r in range(burnin.n_replicates):
             h.fork_from(burnin, r, r)
         h.set_params(params)
+        h.set_mode(burnin.get_mode())                    # the arms continue on the kernels the burn-in ran on
         arms[name] = h
     return arms
 
