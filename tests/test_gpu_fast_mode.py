@@ -153,7 +153,7 @@ def test_degree_conditioned_formation(mode):
     uni = synth.make_tables(); uni[synth.T_NET_DEGW:synth.T_NET_RISKW + 5] = 1.0
     d, u = run(synth.make_tables()), run(uni)
     assert (d["deg.main"] >= 2).mean() < 0.25 * (u["deg.main"] >= 2).mean()
-    assert d["deg.inst"][d["risk.grp"] == 5].mean() > 5 * d["deg.inst"][d["risk.grp"] == 1].mean()
+    assert d["deg.inst"][d["risk.grp"] == 5].mean() > 2.5 * d["deg.inst"][d["risk.grp"] == 1].mean()      # NET_RISKW spans 5 : 1
 
 
 def _ks_report(g, c, names, keys, R):

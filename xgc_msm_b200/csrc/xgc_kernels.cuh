@@ -637,75 +637,98 @@ template <bool INJ, bool SMEM, int NT> __global__ void __launch_bounds__(NT) k_f
       __syncthreads();
     }
   }
-  auto slot_of = [&](int pos) -> int {
-    if (!SMEM) return P2S[pos];
-    int lo = 0, hi = nw - 1;                      // largest word index with pre[w] <= pos
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (pre[mid] <= pos) lo = mid; else hi = mid - 1; }
-    return (lo << 5) + (int)__fns(bm[lo], 0, pos - pre[lo] + 1);
-  };
+  // position -> slot table of the replicate in shared memory (16-bit slots: n_cap <= 32k here), one load per lookup -- the
+  // binary search over the popcount prefix + find-n-th-set-bit it replaces was half the instructions of a formation try
+  unsigned short* p2s = (unsigned short*)(dyn + 2 * (g.n_cap / 32));
+  if (SMEM) {
+    for (int k = tid; k < nw; k += NT) { unsigned bits = bm[k]; int o = pre[k]; while (bits) { int b = __ffs(bits) - 1; bits &= bits - 1; p2s[o++] = (unsigned short)((k << 5) + b); } }
+    __syncthreads();
+  }
+  auto slot_of = [&](int pos) -> int { return SMEM ? (int)p2s[pos] : P2S[pos]; };
+  // The candidates of the three layers are ONE index space (main, casual, one-off back to back: ~12 + 34 + 400 a week at 10k agents),
+  // walked NT at a time, two tries of a candidate in flight: one pass instead of a pass per layer and chunk, half the dependent
+  // rounds (degree-conditioned acceptance needs several tries per candidate).  Ties are appended per layer in candidate order.
   DrawT<INJ> dn(inj, g, r, at, XGC_S_NET_N, 0u, 0u, 0);
+  int nf[3];
+#pragma unroll
   for (int l = 0; l < 3; ++l) {
-    int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
-    __syncthreads();
-    if (tid == 0) base = rp->ne[l];
-    __syncthreads();
     double target = g.tables[XGC_T_NET_DEG + l] * (double)n / 2.0;
     double mu = l == 2 ? target : target / g.tables[XGC_T_NET_DUR + l];
     double fl = floor(mu);
-    int nform = (int)fl + (dn(l) < mu - fl);
-    if (inj.u && nform > inj.form_cap) nform = inj.form_cap;
-    if (n < 2) nform = 0;
-    bool overflow = false;
-    for (int j0 = 0; j0 < nform; j0 += NT) {
-      int j = j0 + tid; bool ok = false; int4 ed = make_int4(0, 0, at, 0);
-      if (j < nform) {
-        DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
-        const unsigned* dg = g.deg + (size_t)r * g.n_cap;
-        for (int t = 0; t < XGC_FORM_TRIES && !ok; ++t) {
-          int a = (int)(d(3 * t) * (double)n); if (a > n - 1) a = n - 1;
-          int b = (int)(d(3 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+    nf[l] = (int)fl + (dn(l) < mu - fl);
+    if (inj.u && nf[l] > inj.form_cap) nf[l] = inj.form_cap;
+    if (n < 2) nf[l] = 0;
+  }
+  const int nf01 = nf[0] + nf[1], nf_all = nf01 + nf[2];
+  __shared__ int wsum3[3][NT / 32];
+  __shared__ int base3[3];
+  __syncthreads();
+  if (tid < 3) base3[tid] = rp->ne[tid];
+  __syncthreads();
+  const unsigned* dg = g.deg + (size_t)r * g.n_cap;
+  bool overflow = false;
+  for (int j0 = 0; j0 < nf_all; j0 += NT) {
+    const int jg = j0 + tid;
+    const int l = jg >= nf01 ? 2 : jg >= nf[0] ? 1 : 0, j = jg - (l == 2 ? nf01 : l == 1 ? nf[0] : 0);
+    bool ok = false; int4 ed = make_int4(0, 0, at, 0);
+    if (jg < nf_all) {
+      DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+      for (int t = 0; t < XGC_FORM_TRIES && !ok; t += 2) {
+        int sa[2], sb[2]; bool swp[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          int a = (int)(d(3 * (t + k)) * (double)n); if (a > n - 1) a = n - 1;
+          int b = (int)(d(3 * (t + k) + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
           if (b >= a) b++;
-          int sa = slot_of(a < b ? a : b), sb = slot_of(a < b ? b : a);       // (a < b as positions; slots keep the order)
-          unsigned da = core[sa].y, db = core[sb].y;
-          if (!roles_compatible(da, db)) continue;
-          // the weights multiply in the order of the DRAWN endpoints (a, then b), as in the oracle
-          double wa = form_weight(g.tables, l, dg[a < b ? sa : sb], a < b ? da : db), wb = form_weight(g.tables, l, dg[a < b ? sb : sa], a < b ? db : da);
+          swp[k] = !(a < b);                                   // slots are stored in position order; the weights follow the DRAWN order
+          sa[k] = slot_of(a < b ? a : b); sb[k] = slot_of(a < b ? b : a);
+        }
+        unsigned da[2], db[2], ga[2], gb[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { da[k] = core[sa[k]].y; db[k] = core[sb[k]].y; ga[k] = dg[sa[k]]; gb[k] = dg[sb[k]]; }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (ok || t + k >= XGC_FORM_TRIES || !roles_compatible(da[k], db[k])) continue;
+          double wa = form_weight(g.tables, l, swp[k] ? gb[k] : ga[k], swp[k] ? db[k] : da[k]), wb = form_weight(g.tables, l, swp[k] ? ga[k] : gb[k], swp[k] ? da[k] : db[k]);
           double pw = wa * wb;
-          if (pw < 1.0 && !(d(3 * t + 2) < pw)) continue;
-          ok = true; ed.x = sa; ed.y = sb;
+          if (pw < 1.0 && !(d(3 * (t + k) + 2) < pw)) continue;
+          ok = true; ed.x = sa[k]; ed.y = sb[k];
         }
       }
-      unsigned m = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) wsum[w] = __popc(m);
-      __syncthreads();
-      int off = base;
-      for (int k = 0; k < w; ++k) off += wsum[k];
-      off += __popc(m & ((1u << lane) - 1u));
-      if (ok) { if (off < g.e_cap[l]) E[off] = ed; else overflow = true; }
-      __syncthreads();
-      if (tid == 0) { int t = 0; for (int k = 0; k < NT / 32; ++k) t += wsum[k]; base += t; }
-      __syncthreads();
     }
-    if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);
-    if (tid == 0) {
-      int nn = base < g.e_cap[l] ? base : g.e_cap[l];
-      rp->ne[l] = nn;
-      counter_row(g, r, at)[XGC_K_NEDGES + l] = (unsigned)nn;
+    const unsigned m0 = __ballot_sync(0xffffffffu, ok && l == 0), m1 = __ballot_sync(0xffffffffu, ok && l == 1), m2 = __ballot_sync(0xffffffffu, ok && l == 2);
+    if (lane == 0) { wsum3[0][w] = __popc(m0); wsum3[1][w] = __popc(m1); wsum3[2][w] = __popc(m2); }
+    __syncthreads();
+    if (ok) {
+      int off = base3[l];
+      for (int k = 0; k < w; ++k) off += wsum3[l][k];
+      off += __popc((l == 0 ? m0 : l == 1 ? m1 : m2) & ((1u << lane) - 1u));
+      if (off < g.e_cap[l]) (g.edge + (size_t)r * g.e_stride + g.e_off[l])[off] = ed; else overflow = true;
     }
+    __syncthreads();
+    if (tid < 3) { int t = 0; for (int k = 0; k < NT / 32; ++k) t += wsum3[tid][k]; base3[tid] += t; }
+    __syncthreads();
+  }
+  if (overflow) atomicOr(&rp->status, XGC_ST_EDGE_OVERFLOW);
+  if (tid < 3) {
+    int nn = base3[tid] < g.e_cap[tid] ? base3[tid] : g.e_cap[tid];
+    rp->ne[tid] = nn;
+    counter_row(g, r, at)[XGC_K_NEDGES + tid] = (unsigned)nn;
   }
 }
 
 // k_form_lb: the same formation for large replicates, many CTAs per (replicate, layer): each CTA draws 1024 candidate
 // ties, the accepted ones are appended in draw order through the decoupled look-back prefix (shares the tile tickets /
 // status words / epoch with k_edges_resim_lb; launches are serialised on the stream).  Needs pos2slot (k_rank).
-template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
+#define FORM_NT 1024
+template <bool INJ> __global__ void __launch_bounds__(FORM_NT) k_form_lb(const __grid_constant__ Dev g, const __grid_constant__ Inj inj) {
   pdl_prologue();
   int r = blockIdx.z + g.r0, l = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   Rep* rp = g.rep + r;
   int ne0 = *(volatile int*)&rp->ne[l];
   unsigned epoch = *(volatile unsigned*)&rp->lb_epoch[l];
   __shared__ int s_tile, s_base;
-  __shared__ int wsum[4][TPB / 32];
+  __shared__ int wsum[FORM_NT / 32];
   if (tid == 0) s_tile = (int)(atomicAdd(g.lb_ticket + r * 3 + l, 1u) % (unsigned)g.lb_tiles);
   __syncthreads();
   int tile = s_tile;
@@ -724,38 +747,43 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __gri
   int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
   const uint4* core = g.core + (size_t)r * g.n_cap;
   const int* P2S = g.pos2slot + (size_t)r * g.n_cap;
-  int4 ed[4]; bool ok[4]; unsigned m[4];
+  const unsigned* dg = g.deg + (size_t)r * g.n_cap;
+  // One candidate per thread (1024-thread CTAs: with four candidates per thread of a 256-thread CTA the kernel was a chain of
+  // dependent global loads per thread -- position -> slot, then core / degree words, planes far larger than L2 at 1M agents --
+  // on a quarter of the threads the GPU can hold), and TWO tries of the candidate in flight at a time.
+  const int j = tile * LB_TILE + tid;
+  bool ok = false; int4 ed = make_int4(0, 0, at, 0);
+  if (j < nform) {
+    DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
+    for (int t = 0; t < XGC_FORM_TRIES && !ok; t += 2) {
+      int sa[2], sb[2]; bool swp[2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int j = tile * LB_TILE + q * TPB + tid; ok[q] = false; ed[q] = make_int4(0, 0, at, 0);
-    if (j < nform) {
-      DrawT<INJ> d(inj, g, r, at, XGC_S_FORM + l, (unsigned)j, 0u, (size_t)j);
-      const unsigned* dg = g.deg + (size_t)r * g.n_cap;
-      for (int t = 0; t < XGC_FORM_TRIES && !ok[q]; ++t) {
-        int a = (int)(d(3 * t) * (double)n); if (a > n - 1) a = n - 1;
-        int b = (int)(d(3 * t + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
+      for (int k = 0; k < 2; ++k) {
+        int a = (int)(d(3 * (t + k)) * (double)n); if (a > n - 1) a = n - 1;
+        int b = (int)(d(3 * (t + k) + 1) * (double)(n - 1)); if (b > n - 2) b = n - 2;
         if (b >= a) b++;
-        int sa = P2S[a < b ? a : b], sb = P2S[a < b ? b : a];
-        unsigned da = core[sa].y, db = core[sb].y;
-        if (!roles_compatible(da, db)) continue;
-        double wa = form_weight(g.tables, l, dg[a < b ? sa : sb], a < b ? da : db), wb = form_weight(g.tables, l, dg[a < b ? sb : sa], a < b ? db : da);
+        swp[k] = !(a < b);                                       // slots are stored in position order; the weights follow the DRAWN order
+        sa[k] = P2S[a < b ? a : b]; sb[k] = P2S[a < b ? b : a];
+      }
+      unsigned da[2], db[2], ga[2], gb[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { da[k] = core[sa[k]].y; db[k] = core[sb[k]].y; ga[k] = dg[sa[k]]; gb[k] = dg[sb[k]]; }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (ok || t + k >= XGC_FORM_TRIES || !roles_compatible(da[k], db[k])) continue;
+        double wa = form_weight(g.tables, l, swp[k] ? gb[k] : ga[k], swp[k] ? db[k] : da[k]), wb = form_weight(g.tables, l, swp[k] ? ga[k] : gb[k], swp[k] ? da[k] : db[k]);
         double pw = wa * wb;
-        if (pw < 1.0 && !(d(3 * t + 2) < pw)) continue;
-        ok[q] = true; ed[q].x = sa; ed[q].y = sb;
+        if (pw < 1.0 && !(d(3 * (t + k) + 2) < pw)) continue;
+        ok = true; ed.x = sa[k]; ed.y = sb[k];
       }
     }
-    m[q] = __ballot_sync(0xffffffffu, ok[q]);
-    if (lane == 0) wsum[q][w] = __popc(m[q]);
   }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) wsum[w] = __popc(m);
   __syncthreads();
-  int off[4], run = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int o = run, tot = 0;
-    for (int k = 0; k < TPB / 32; ++k) { int c = wsum[q][k]; tot += c; if (k < w) o += c; }
-    off[q] = o + __popc(m[q] & ((1u << lane) - 1u));
-    run += tot;
-  }
+  int off = 0, run = 0;
+  for (int k = 0; k < FORM_NT / 32; ++k) { int c = wsum[k]; run += c; if (k < w) off += c; }
+  off += __popc(m & ((1u << lane) - 1u));
   if (tid == 0) {
     unsigned long long* S = g.lb_status + ((size_t)r * 3 + l) * g.lb_tiles;
     unsigned long long ep = (unsigned long long)(epoch & 0x3FFFFFFFu) << 34;
@@ -779,11 +807,8 @@ template <bool INJ> __global__ void __launch_bounds__(TPB) k_form_lb(const __gri
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int dst = s_base + off[q];
-    if (ok[q] && dst < g.e_cap[l]) E[dst] = ed[q];
-  }
+  const int dst = s_base + off;
+  if (ok && dst < g.e_cap[l]) E[dst] = ed;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ struct xgc_handle {
   // xgc_run drives the replicates as TWO concurrent lanes (halves of the replicate range, each with its own streams and
   // captured week graph): every kernel of this path is latency-bound, so a second, independent kernel sequence fills the
   // issue slots and tails the first leaves idle (measured -8 % per week).  Lane 0 lives on the handle's own streams.
-  int n_lanes = 2;                        // XGC_LANES=1: one lane
+  int n_lanes = 1;                        // XGC_LANES=2: two concurrent lanes (see xgc_create)
   const Dev* gl = nullptr;                // Dev of the lane being enqueued (nullptr: the whole handle)
   Dev lane_dev[2];                        // per-lane views of g (kept on the handle: gl never points at a dead stack frame)
   cudaStream_t lane_main = nullptr, lane_side = nullptr;      // streams the enqueue helpers use (lane 0: stream / stream2)
@@ -59,6 +59,7 @@ struct xgc_handle {
   cudaGraphExec_t l1_graph = nullptr; uint64_t l1_graph_launches = 0;
   int lanes_captured = 0;
   bool rank_fresh = false;             // pos2slot matches the current population (reset by every step)
+  int form_tiles = 0;                  // tiles of 1024 formation candidates a layer can need (from the tables; 0: not known, use lb_tiles)
   bool plain_next = false;             // the next kernel launch follows an async copy / memset on the stream: no programmatic
                                        // serialization for it (its griddepcontrol.wait only covers preceding GRIDS)
   bool prune_pending = false;          // a fast-path aging..hivvl call left ties of departed agents in the lists (dropped lazily:
@@ -131,7 +132,9 @@ static void preload_kernels() {
 #define PRELOAD(k) cudaFuncGetAttributes(&a, k)
   PRELOAD(k_derive); PRELOAD((k_begin<false, false>)); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
   PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank); PRELOAD(k_rank_cta);
-  PRELOAD((k_form<false, true, TPB>)); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
+  PRELOAD((k_form<false, true, 1024>));
+  cudaFuncSetAttribute(k_form<false, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);      // bitmap + prefix + 16-bit position table, n_cap <= 32k
+  cudaFuncSetAttribute(k_form<true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
   PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
   PRELOAD(k_agent3a); PRELOAD(k_agent3b<false>); PRELOAD(k_targets); PRELOAD(k_compact_agents); PRELOAD(k_compact_edges);
   PRELOAD(k_compact_remap); PRELOAD(k_compact_finish); PRELOAD(k_edges_upload); PRELOAD(k_edges_update);
@@ -166,8 +169,13 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
       h->err = "cudaEventCreate failed"; return fail(3);
     }
-  { const char* e = getenv("XGC_LANES"); if (e && e[0] == '1') h->n_lanes = 1; }
+  // Two concurrent lanes (halves of the replicate range, own streams and week graphs) were worth 7 % on the bit-exact run path in
+  // round 1.  Off by default since round 2: on some boxes one in four two-lane runs of the 1000-replicate sweep diverged from the
+  // single-lane / step-by-step trajectory in the LAST replicates of the second lane (tools/lane_determinism.py; one lane: 0 of 16 on the same
+  // box); the cause is not found, and the bit-exact path is the parity path, not the fast one.  XGC_LANES=2 turns them on.
+  { const char* e = getenv("XGC_LANES"); if (e && e[0] == '2') h->n_lanes = 2; }
   if (cfg->n_replicates < 2) h->n_lanes = 1;
+  // (large replicates fill the GPU kernel by kernel: there a second lane only contends -- 100 x 100k: 2.00 vs 1.39 ms per week)
   if (cudaStreamCreateWithFlags(&h->l1_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->l1_stream2, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "cudaStreamCreate failed"; return fail(3);
   }
@@ -310,10 +318,18 @@ extern "C" int xgc_get_control(xgc_handle* h, int r, int32_t* c) {
   CU(h, cudaMemcpy(c, h->g.control + (size_t)r * XGC_NCONTROL, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyDeviceToHost));
   return 0;
 }
+static void set_form_tiles(xgc_handle* h, const double* t) {
+  double mx = 0.0;
+  for (int l = 0; l < 3; ++l) mx = std::max(mx, t[XGC_T_NET_DEG + l] * (double)h->cfg.n_cap / 2.0 / (l < 2 ? t[XGC_T_NET_DUR + l] : 1.0));
+  h->form_tiles = (int)std::min((double)h->g.lb_tiles, std::ceil((mx + 1.0) / 1024.0) + 1.0);
+}
 extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
   for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];       // same IEEE division the oracle performs
+  // formation grid: candidates of a layer-week <= deg * n_cap / 2 (/ duration) + 1, in tiles of 1024 (the look-back kernel's grid was
+  // sized for the edge lists: thousands of CTAs that took a ticket and left)
+  set_form_tiles(h, t);
   drop_graphs(h);
   return 0;
 }
@@ -629,9 +645,9 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
   int tiles = (g.n_cap + TPB - 1) / TPB;
   static const int TA = getenv("XGC_TUNE_A") ? atoi(getenv("XGC_TUNE_A")) : 16, TQ = getenv("XGC_TUNE_Q") ? atoi(getenv("XGC_TUNE_Q")) : 16,
                    TE = getenv("XGC_TUNE_E") ? atoi(getenv("XGC_TUNE_E")) : 32;      // CTAs per SM each kernel family is sized for
-  // (large replicates: fewer, longer CTAs -- every CTA of an agent pass ends with a flush of its tallies into the SAME counter row,
+  // (few tiles in total, i.e. one or two large replicates: fewer, longer CTAs -- every CTA of an agent pass ends with a flush of its tallies into the SAME counter row,
   //  3907 one-tile CTAs of a 1M-agent replicate spend most of k_agent3a on ~200 same-address global atomics each)
-  const int ta = g.n_cap > 32768 ? std::min(TA, 4) : TA;
+  const int ta = (long long)tiles * g.R < 148LL * 16 * 4 ? std::min(TA, 4) : TA;      // (a single 1M-agent replicate: 3907 tiles)
   int tpc = std::max(1, std::min(std::min(tiles, 40), (int)(((long long)tiles * g.R) / (148 * ta))));     // <= 40 tiles: the CTA's queue staging stays under 48 KB
   dim3 ga((tiles + tpc - 1) / tpc, g.R);
   int emax = std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2]));
@@ -666,15 +682,16 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     // degrees of the ties that survive this week's dissolution: zeroed here, counted by the dissolution pass, read by k_form
     LAUNCH(h, k_zero_deg, (unsigned)std::min<size_t>(148 * 8, ((size_t)g.R * g.n_cap / 4 + TPB - 1) / TPB), TPB, g);
     launch_resim(h, inj, 1, 1);
-    size_t form_smem = (size_t)(g.n_cap / 32) * 8;            // alive bitmap + popcount prefix of one replicate
-    if (form_smem <= 8 * 1024) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
+    size_t form_smem = (size_t)(g.n_cap / 32) * 8 + (size_t)g.n_cap * 2;      // alive bitmap + popcount prefix + 16-bit position -> slot table of one replicate
+    if (g.n_cap <= 32768) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
       prof_begin(h, "k_form");
-      if (inj.u) kl(h, k_form<true, true, TPB>, g.R, TPB, form_smem, g, inj); else kl(h, k_form<false, true, TPB>, g.R, TPB, form_smem, g, inj);
+      if (inj.u) kl(h, k_form<true, true, 1024>, g.R, 1024, form_smem, g, inj); else kl(h, k_form<false, true, 1024>, g.R, 1024, form_smem, g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
       prof_begin(h, "k_form");
-      if (inj.u) kl(h, k_form_lb<true>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj); else kl(h, k_form_lb<false>, dim3(g.lb_tiles, 3, g.R), TPB, 0, g, inj);
+      const unsigned ft = (unsigned)(h->form_tiles > 0 ? h->form_tiles : g.lb_tiles);
+      if (inj.u) kl(h, k_form_lb<true>, dim3(ft, 3, g.R), FORM_NT, 0, g, inj); else kl(h, k_form_lb<false>, dim3(ft, 3, g.R), FORM_NT, 0, g, inj);
       prof_end(h); h->launches++;
     }
   }
@@ -1168,6 +1185,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false; h->fast_dirty = true;
   { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
+    set_form_tiles(h, t);
     drop_graphs(h); }
   return derive(h);
 }
@@ -1191,6 +1209,9 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   acc(cp(b.rep + dr, a.rep + sr, sizeof(Rep))); acc(cp((int*)b.at_ptr + dr, a.at_ptr + sr, 4));
   acc(cp(b.counters + (size_t)dr * b.t_cap * XGC_NCOUNTER, a.counters + (size_t)sr * a.t_cap * XGC_NCOUNTER, (size_t)a.t_cap * XGC_NCOUNTER * 4));
   if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
+  // device-to-device cudaMemcpy does not wait on the host side and runs on the legacy stream, which the handles' non-blocking
+  // streams do not order against: the copies are complete before anything else touches the destination replicate
+  CU(dst, cudaStreamSynchronize(cudaStreamLegacy));
   dst->last_at = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
   if (src->fast_dirty) dst->fast_dirty = true;
   return 0;

@@ -44,10 +44,10 @@ NET_DEGW = np.array([
     [[1.00, 0.55, 0.30], [0.70, 0.40, 0.20], [0.50, 0.30, 0.15]],      # casual
     [[1.00, 1.00, 1.00], [0.60, 0.75, 0.90], [0.60, 0.75, 0.90]],      # one-off
 ])
-NET_RISKW = np.array([0.05, 0.15, 0.35, 0.65, 1.00])
+NET_RISKW = np.array([0.2, 0.4, 0.6, 0.8, 1.0])         # (a 5 : 1 spread; a steeper one mostly costs formation tries: acceptance ~ E[w]^2)
 # XGC_T_NET_DEG is the PROPOSAL intensity (ties proposed per week = deg * n / 2 / duration); the weights above thin it.  These
-# factors bring the realised mean degrees of the bench workload back to NET_DEG (oracle, 700 weeks: 0.40 / 0.555 / 0.073).
-NET_DEG_PROPOSAL = np.array([1.5, 1.12, 1.55])
+# factors bring the realised mean degrees of the bench workload back to NET_DEG (oracle, 500 weeks: 0.40 / 0.555 / 0.070).
+NET_DEG_PROPOSAL = np.array([1.5, 1.12, 1.15])
 
 
 def make_tables() -> np.ndarray:
