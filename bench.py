@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"],
                     help="native-draw contract of the CUDA arm: fast = replicate-resident kernel (statistical equivalence), strict = bit-exact kernels")
     ap.add_argument("--agents", type=int, default=10000)
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
