@@ -132,9 +132,9 @@ static void preload_kernels() {
 #define PRELOAD(k) cudaFuncGetAttributes(&a, k)
   PRELOAD(k_derive); PRELOAD((k_begin<false, false>)); PRELOAD(k_agent1a<false>); PRELOAD(k_agent1b<false>);
   PRELOAD((k_edges_resim<false, TPB, 1>)); PRELOAD(k_edges_resim_lb<false>); PRELOAD(k_rank); PRELOAD(k_rank_cta);
-  PRELOAD((k_form<false, true, 1024>));
-  cudaFuncSetAttribute(k_form<false, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);      // bitmap + prefix + 16-bit position table, n_cap <= 32k
-  cudaFuncSetAttribute(k_form<true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
+  PRELOAD((k_form<false, true, 512>));
+  cudaFuncSetAttribute(k_form<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);      // bitmap + prefix + 16-bit position table, n_cap <= 32k
+  cudaFuncSetAttribute(k_form<true, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); PRELOAD(k_form_lb<false>); PRELOAD(k_edge1<false>);
   PRELOAD(k_agent2a<false>); PRELOAD(k_agent2b<false>); PRELOAD(k_edge2a); PRELOAD((k_edge2b<false, true>)); PRELOAD((k_edge2b<false, false>));
   PRELOAD(k_agent3a); PRELOAD(k_agent3b<false>); PRELOAD(k_targets); PRELOAD(k_compact_agents); PRELOAD(k_compact_edges);
   PRELOAD(k_compact_remap); PRELOAD(k_compact_finish); PRELOAD(k_edges_upload); PRELOAD(k_edges_update);
@@ -685,7 +685,7 @@ static int enqueue_week(xgc_handle* h, int at_host, unsigned mask, const Inj& in
     size_t form_smem = (size_t)(g.n_cap / 32) * 8 + (size_t)g.n_cap * 2;      // alive bitmap + popcount prefix + 16-bit position -> slot table of one replicate
     if (g.n_cap <= 32768) {            // n_cap <= 32k slots: one CTA per replicate with the bitmap in shared memory
       prof_begin(h, "k_form");
-      if (inj.u) kl(h, k_form<true, true, 1024>, g.R, 1024, form_smem, g, inj); else kl(h, k_form<false, true, 1024>, g.R, 1024, form_smem, g, inj);
+      if (inj.u) kl(h, k_form<true, true, 512>, g.R, 512, form_smem, g, inj); else kl(h, k_form<false, true, 512>, g.R, 512, form_smem, g, inj);
       prof_end(h); h->launches++;
     } else {
       LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
