@@ -8,13 +8,14 @@
 //   * ONE CTA PER REPLICATE, persistent over the weeks of a launch.  The per-agent state every module reads -- the demo /
 //     gc / hiv words of the core plane (12 B per agent) and the PrEP-indication clock -- is staged ONCE in the SM's shared
 //     memory (10k agents: 188 KB of the 227 KB) and stays there for up to compact_every weeks; the endpoint gathers of the
-//     edge modules, the exposure / new-infection scatter, the work queues, the weekly tallies and the alive bitmap of
+//     edge modules, the exposure / new-infection scatter, the work queues, the weekly tallies and the degree counts of
 //     the network step are all shared-memory traffic.  HBM sees the edge records (streamed, L2-resident between weeks),
 //     the clock planes of the minority of agents whose clocks change, and the write-back at the end of the launch.
-//   * modules are PHASES of that kernel.  Inside a phase every WARP owns a contiguous range of agents (or edges) and runs
-//     it to completion on its own: it classifies 32 items at a time, collects the minority that needs work in a 64-entry
-//     shared-memory mini-queue and processes the queue 32 at a time with all lanes busy.  CTA-wide barriers separate only
-//     the phases whose data dependences cross agents (PRE | network | acts | prep/stirecov/stitx | transmission | prev).
+//   * modules are PHASES of that kernel.  Inside a phase every WARP owns its agents (32-agent groups, interleaved over the
+//     warps: VSLOT) or ties and runs them to completion on its own: it classifies 32 items at a time, collects the minority
+//     that needs work in a 64-entry shared-memory mini-queue and processes the queue 32 at a time with all lanes busy.
+//     CTA-wide barriers separate only the phases whose data dependences cross agents (PRE | formation | acts + tie sweep |
+//     prep/stirecov/stitx | transmission | apply).  prevalence_msm's state tallies are kept incrementally (tally_move).
 //   * rare per-agent events (natural mortality, HIV interval tests, background clinic visits) are drawn as geometric
 //     waiting gaps over the slot index (exact for an iid Bernoulli sequence; heterogeneous probabilities by thinning),
 //     so agents nothing happens to cost an integer scan, not a Philox block;
