@@ -156,6 +156,21 @@ def test_degree_conditioned_formation(mode):
     assert d["deg.inst"][d["risk.grp"] == 5].mean() > 2.5 * d["deg.inst"][d["risk.grp"] == 1].mean()      # NET_RISKW spans 5 : 1
 
 
+def test_netsim_mirror_in_fast_mode():
+    """The host-side mirror of EpiModel::netsim (modules.py) on the fast path: same interface, epi series consistent."""
+    from xgc_msm_b200 import modules as M
+    control = P.control_msm(nsims=3, nsteps=30, network_mode="surrogate")
+    param = P.params_from_env(P.prior_midpoint_env(), n_init=2000)
+    sim = M.netsim({"n": 2000, "seed": 3}, param, P.init_msm(0.05, 0.05, 0.05), control, mode="fast")
+    assert sim.dat.h.get_mode() == "fast" and sim.dat.at == 30
+    epi = sim.epi
+    assert epi["num"].shape == (30, 3) and np.all(epi["num"][1:] > 1900) and np.all(epi["prev.gc"][1:] >= 0)
+    assert np.allclose(epi["prev.gc"][-1], epi["i.num.gc"][-1] / epi["num"][-1]) if "i.num.gc" in epi else True
+    tg = sim.targets(10)
+    assert tg.shape == (3, K.NTARGET) and np.isfinite(tg[:, :3]).all()
+    sim.dat.h.close()
+
+
 def _ks_report(g, c, names, keys, R):
     from scipy.stats import ks_2samp
     report = {}

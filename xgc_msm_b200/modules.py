@@ -166,7 +166,7 @@ class Sim:
 
 
 def netsim(x, param, init: dict, control: P.Control, device: int = 0, seed: int = 1971, checkpoint: bool = False,
-           network_hook=None) -> Sim:
+           network_hook=None, mode: Optional[str] = None) -> Sim:
     """EpiModel::netsim: dat <- initialize.FUN(...); for at in max(2, start):nsteps, for each module: dat <- FUN(dat, at)
     (sim1_02_lhs.r:232; SURVEY Appendix E "Loop/order").  When every module is the library's own, consecutive modules
     are issued as ONE fused xgc_step per week (identical results: test_module_by_module_contract)."""
@@ -178,6 +178,8 @@ def netsim(x, param, init: dict, control: P.Control, device: int = 0, seed: int 
         dat = (init_fun or (lambda *a: initialize_msm(*a, device=device, seed=seed)))(x, param, init, control, 0)
     if network_hook is not None:
         dat.network_hook = network_hook
+    if mode is not None:                 # "fast": replicate-resident native-draw kernels (statistical contract); "strict": bit-exact
+        dat.h.set_mode(mode)
     first = max(2, control.start)
     all_native = all(getattr(f, "xgc_bit", None) is not None for f in mods)
     host_net = control.flags[P.CONTROL_INDEX["network_mode"]] == 0 and dat.network_hook is not None
