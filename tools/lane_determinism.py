@@ -20,12 +20,19 @@ def make(r0, n):
     return h
 ref = None; bad_run = bad_step = 0; info = []
 for trial in range(trials):
-    full = make(0, R); full.run(2, 1 + weeks)
+    full = make(0, R)
+    if os.environ.get("DBG_SETTLE"):
+        import torch, time
+        full.sync(); torch.cuda.synchronize(); time.sleep(0.05)
+    if os.environ.get("DBG_STEPFIRST"):
+        full.step(2); full.run(3, 1 + weeks)
+    else:
+        full.run(2, 1 + weeks)
     C = np.stack([full.counters_all(t) for t in range(2, 2 + weeks)]).astype(np.int64)
     full.close()
     if ref is None: ref = C
     elif not np.array_equal(ref, C):
-        bad_run += 1; w, rr, cc = np.nonzero(ref != C); info.append(("run", trial, "weeks", np.unique(w + 2).tolist(), "reps", int(rr.min()), int(rr.max()), np.unique(rr).size, "counters", np.unique(cc).tolist()[:40], "delta", (C - ref)[w[0], rr[0], cc[0]]))
+        bad_run += 1; w, rr, cc = np.nonzero(ref != C); info.append(("run", trial, "weeks", np.unique(w + 2).tolist(), "reps", int(rr.min()), int(rr.max()), np.unique(rr).size, "counter groups", sorted(set((np.unique(cc) // 20).tolist())), "scalars", [int(c) for c in np.unique(cc) if c >= 280]))
     half = make(R // 2, R // 2)
     for at in range(2, 2 + weeks): half.step(at)
     D = np.stack([half.counters_all(t) for t in range(2, 2 + weeks)]).astype(np.int64)

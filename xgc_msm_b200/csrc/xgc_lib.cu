@@ -49,7 +49,7 @@ struct xgc_handle {
   // xgc_run drives the replicates as TWO concurrent lanes (halves of the replicate range, each with its own streams and
   // captured week graph): every kernel of this path is latency-bound, so a second, independent kernel sequence fills the
   // issue slots and tails the first leaves idle (measured -8 % per week).  Lane 0 lives on the handle's own streams.
-  int n_lanes = 1;                        // XGC_LANES=2: two concurrent lanes (see xgc_create)
+  int n_lanes = 2;                        // XGC_LANES=1: one lane
   const Dev* gl = nullptr;                // Dev of the lane being enqueued (nullptr: the whole handle)
   Dev lane_dev[2];                        // per-lane views of g (kept on the handle: gl never points at a dead stack frame)
   cudaStream_t lane_main = nullptr, lane_side = nullptr;      // streams the enqueue helpers use (lane 0: stream / stream2)
@@ -88,7 +88,7 @@ struct xgc_handle {
 
 template <typename T> static int dalloc(xgc_handle* h, T** p, size_t n) {
   CU(h, cudaMalloc((void**)p, n * sizeof(T)));
-  CU(h, cudaMemset(*p, 0, n * sizeof(T)));
+  CU(h, cudaMemset(*p, 0, n * sizeof(T)));      // (legacy stream, asynchronous: xgc_create ends with a device synchronisation)
   h->allocs.push_back(*p);
   return 0;
 }
@@ -169,13 +169,9 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
       h->err = "cudaEventCreate failed"; return fail(3);
     }
-  // Two concurrent lanes (halves of the replicate range, own streams and week graphs) were worth 7 % on the bit-exact run path in
-  // round 1.  Off by default since round 2: on some boxes one in four two-lane runs of the 1000-replicate sweep diverged from the
-  // single-lane / step-by-step trajectory in the LAST replicates of the second lane (tools/lane_determinism.py; one lane: 0 of 16 on the same
-  // box); the cause is not found, and the bit-exact path is the parity path, not the fast one.  XGC_LANES=2 turns them on.
-  { const char* e = getenv("XGC_LANES"); if (e && e[0] == '2') h->n_lanes = 2; }
+  { const char* e = getenv("XGC_LANES"); if (e && e[0] == '1') h->n_lanes = 1; else if (e && e[0] == '2') h->n_lanes = 2; }
   if (cfg->n_replicates < 2) h->n_lanes = 1;
-  // (large replicates fill the GPU kernel by kernel: there a second lane only contends -- 100 x 100k: 2.00 vs 1.39 ms per week)
+  if (cfg->n_cap > 32768 && !getenv("XGC_LANES")) h->n_lanes = 1;      // large replicates fill the GPU kernel by kernel: a second lane only contends (100 x 100k: 2.00 vs 1.39 ms per week)
   if (cudaStreamCreateWithFlags(&h->l1_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->l1_stream2, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "cudaStreamCreate failed"; return fail(3);
   }
@@ -225,6 +221,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
 #undef XGC_PARAM
   std::vector<int32_t> C(XGC_NCONTROL, 0); C[XGC_C_transRoute_Kissing] = 1; C[XGC_C_transRoute_Rimming] = 1;
   if (xgc_set_params(h, -1, P.data()) || xgc_set_control(h, -1, C.data())) return fail(4);
+  if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device synchronisation after allocation failed"; return fail(3); }      // the zero-fills above ran on the legacy stream
   *out = h;
   return 0;
 }
@@ -258,6 +255,18 @@ extern "C" int xgc_stream_ptr(xgc_handle* h, void** s) { *s = (void*)h->stream; 
 // --------------------------------------------------------------------------------------------------------------------
 // configuration
 // --------------------------------------------------------------------------------------------------------------------
+// Host <-> device copies of a handle go through ITS stream and wait for it.  A blocking cudaMemcpy runs on the legacy stream,
+// which the handles' non-blocking streams are not ordered against, and from pageable host memory it returns once the data is
+// STAGED, not once the DMA has landed: the first kernels after xgc_set_params_all read the last replicates' parameters before
+// they arrived (about one run in four of a 1000-replicate handle diverged in its last ~150 replicates: tools/lane_determinism.py).
+static cudaError_t h2d(xgc_handle* h, void* d, const void* s, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
+static cudaError_t d2h(xgc_handle* h, void* d, const void* s, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
 static void drop_graphs(xgc_handle* h) {            // kernel arguments baked into the captured week graphs changed
   if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }
   if (h->l1_graph) { cudaGraphExecDestroy(h->l1_graph); h->l1_graph = nullptr; }
@@ -277,19 +286,19 @@ extern "C" int xgc_set_params(xgc_handle* h, int r, const double* p) {
   if (r < 0) {                           // every replicate: one host-side replication, one copy
     std::vector<double> all((size_t)h->cfg.n_replicates * XGC_NPARAM);
     for (int k = 0; k < h->cfg.n_replicates; ++k) memcpy(all.data() + (size_t)k * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM);
-    CU(h, cudaMemcpy((double*)h->g.params, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
-  } else CU(h, cudaMemcpy((double*)h->g.params + (size_t)r * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM, cudaMemcpyHostToDevice));
+    CU(h, h2d(h, (double*)h->g.params, all.data(), all.size() * sizeof(double)));
+  } else CU(h, h2d(h, (double*)h->g.params + (size_t)r * XGC_NPARAM, p, sizeof(double) * XGC_NPARAM));
   return derive(h);
 }
 extern "C" int xgc_set_params_all(xgc_handle* h, const double* p /*[R][XGC_NPARAM]*/) {
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy((double*)h->g.params, p, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates, cudaMemcpyHostToDevice));
+  CU(h, h2d(h, (double*)h->g.params, p, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates));
   return derive(h);
 }
 extern "C" int xgc_get_params(xgc_handle* h, int r, double* p) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(p, h->g.params + (size_t)r * XGC_NPARAM, sizeof(double) * XGC_NPARAM, cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, p, h->g.params + (size_t)r * XGC_NPARAM, sizeof(double) * XGC_NPARAM));
   return 0;
 }
 extern "C" int xgc_set_control(xgc_handle* h, int r, const int32_t* c) {
@@ -299,23 +308,23 @@ extern "C" int xgc_set_control(xgc_handle* h, int r, const int32_t* c) {
   if (r < 0) {
     std::vector<int32_t> all((size_t)h->cfg.n_replicates * XGC_NCONTROL);
     for (int k = 0; k < h->cfg.n_replicates; ++k) memcpy(all.data() + (size_t)k * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL);
-    CU(h, cudaMemcpy((int*)h->g.control, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  } else CU(h, cudaMemcpy((int*)h->g.control + (size_t)r * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyHostToDevice));
+    CU(h, h2d(h, (int*)h->g.control, all.data(), all.size() * sizeof(int32_t)));
+  } else CU(h, h2d(h, (int*)h->g.control + (size_t)r * XGC_NCONTROL, c, sizeof(int32_t) * XGC_NCONTROL));
   return 0;
 }
 extern "C" int xgc_get_tables(xgc_handle* h, double* t) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(t, h->g.tables, sizeof(double) * XGC_NTABLE, cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, t, h->g.tables, sizeof(double) * XGC_NTABLE));
   return 0;
 }
 extern "C" int xgc_get_params_all(xgc_handle* h, double* p) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(p, h->g.params, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates, cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, p, h->g.params, sizeof(double) * XGC_NPARAM * h->cfg.n_replicates));
   return 0;
 }
 extern "C" int xgc_get_control(xgc_handle* h, int r, int32_t* c) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(c, h->g.control + (size_t)r * XGC_NCONTROL, sizeof(int32_t) * XGC_NCONTROL, cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, c, h->g.control + (size_t)r * XGC_NCONTROL, sizeof(int32_t) * XGC_NCONTROL));
   return 0;
 }
 static void set_form_tiles(xgc_handle* h, const double* t) {
@@ -325,7 +334,7 @@ static void set_form_tiles(xgc_handle* h, const double* t) {
 }
 extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy((double*)h->g.tables, t, sizeof(double) * XGC_NTABLE, cudaMemcpyHostToDevice));
+  CU(h, h2d(h, (double*)h->g.tables, t, sizeof(double) * XGC_NTABLE));
   for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];       // same IEEE division the oracle performs
   // formation grid: candidates of a layer-week <= deg * n_cap / 2 (/ duration) + 1, in tiles of 1024 (the look-back kernel's grid was
   // sized for the edge lists: thousands of CTAs that took a ticket and left)
@@ -338,10 +347,10 @@ extern "C" int xgc_set_tables(xgc_handle* h, const double* t) {
 // host cache of one replicate
 // --------------------------------------------------------------------------------------------------------------------
 template <typename T> static int pull(xgc_handle* h, std::vector<T>& v, const T* d, size_t n) {
-  v.resize(n); if (n) CU(h, cudaMemcpy(v.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return 0;
+  v.resize(n); if (n) CU(h, d2h(h, v.data(), d, n * sizeof(T))); return 0;
 }
 template <typename T> static int push(xgc_handle* h, const std::vector<T>& v, T* d) {
-  if (!v.empty()) CU(h, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); return 0;
+  if (!v.empty()) CU(h, h2d(h, d, v.data(), v.size() * sizeof(T))); return 0;
 }
 static void rebuild_maps(HostRep& c) {
   c.pos2slot.clear(); c.slot2pos.assign(c.core.size(), -1);
@@ -360,12 +369,12 @@ static int cache_flush(xgc_handle* h) {
   if (rc) return rc;
   std::vector<unsigned> alive(g.n_cap / 32, 0u);
   for (size_t i = 0; i < c.core.size(); ++i) if (c.core[i].y & DM_ACTIVE) alive[i >> 5] |= 1u << (i & 31);
-  CU(h, cudaMemcpy(g.alive + (size_t)c.r * (g.n_cap / 32), alive.data(), alive.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  CU(h, h2d(h, g.alive + (size_t)c.r * (g.n_cap / 32), alive.data(), alive.size() * sizeof(unsigned)));
   for (int l = 0; l < 3; ++l) {
     c.rep.ne[l] = (int)c.edge[l].size();
-    if (!c.edge[l].empty()) CU(h, cudaMemcpy(g.edge + (size_t)c.r * g.e_stride + g.e_off[l], c.edge[l].data(), c.edge[l].size() * sizeof(int4), cudaMemcpyHostToDevice));
+    if (!c.edge[l].empty()) CU(h, h2d(h, g.edge + (size_t)c.r * g.e_stride + g.e_off[l], c.edge[l].data(), c.edge[l].size() * sizeof(int4)));
   }
-  CU(h, cudaMemcpy(g.rep + c.r, &c.rep, sizeof(Rep), cudaMemcpyHostToDevice));
+  CU(h, h2d(h, g.rep + c.r, &c.rep, sizeof(Rep)));
   c.dirty = false; h->rank_fresh = false;
   return 0;
 }
@@ -377,7 +386,7 @@ static int cache_load(xgc_handle* h, int r) {
   const Dev& g = h->g; size_t o = (size_t)r * g.n_cap;
   CU(h, cudaSetDevice(h->cfg.device));
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(&c.rep, g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, &c.rep, g.rep + r, sizeof(Rep)));
   size_t n = (size_t)c.rep.n_slots;
   rc |= pull(h, c.core, g.core + o, n); rc |= pull(h, c.aux, g.aux + o, n);
   rc |= pull(h, c.gck_a, g.gck_a + o, n); rc |= pull(h, c.gck_b, g.gck_b + o, n); rc |= pull(h, c.gck_d, g.gck_d + o, n);
@@ -480,8 +489,8 @@ extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
   // wipe the tail beyond n on the device (stale slots of a previous population)
   const Dev& g = h->g;
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemset(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap));
-  CU(h, cudaMemcpy((int*)g.at_ptr + r, &at, sizeof(int), cudaMemcpyHostToDevice));
+  CU(h, cudaMemsetAsync(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap, h->stream));      // in the handle's stream, like every copy
+  CU(h, h2d(h, (int*)g.at_ptr + r, &at, sizeof(int)));
   h->last_at = -1; h->acts_valid = false; h->fast_dirty = true;
   return cache_flush(h);
 }
@@ -939,8 +948,8 @@ extern "C" int xgc_num_agents_all(xgc_handle* h, int32_t* out /*[R]*/) {
 }
 extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
   CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  Rep rp; CU(h, cudaMemcpy(&rp, h->g.rep + r, sizeof(Rep), cudaMemcpyDeviceToHost));
-  unsigned ps[4]; CU(h, cudaMemcpy(ps, h->d_pstat + (size_t)r * 4, sizeof ps, cudaMemcpyDeviceToHost));
+  Rep rp; CU(h, d2h(h, &rp, h->g.rep + r, sizeof(Rep)));
+  unsigned ps[4]; CU(h, d2h(h, ps, h->d_pstat + (size_t)r * 4, sizeof ps));
   *status = rp.status | ps[0] | ps[1] | ps[2] | ps[3]; return 0;
 }
 
@@ -991,7 +1000,7 @@ extern "C" int xgc_get_actlist(xgc_handle* h, int r, int at, int32_t* al, int ca
   int n = 0;
   cudaError_t e1 = cudaMemcpyAsync(&n, h->d_scratch, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaError_t e2 = cudaStreamSynchronize(h->stream);
-  if (e1 == cudaSuccess && e2 == cudaSuccess && n <= cap) e1 = cudaMemcpy(al, d_al, sizeof(int) * 6 * (size_t)cap, cudaMemcpyDeviceToHost);
+  if (e1 == cudaSuccess && e2 == cudaSuccess && n <= cap) e1 = d2h(h, al, d_al, sizeof(int) * 6 * (size_t)cap);
   cudaFree(d_al);
   if (e1 != cudaSuccess || e2 != cudaSuccess) FAIL(h, 100, "xgc_get_actlist: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   if (n_acts) *n_acts = n;
@@ -1006,7 +1015,7 @@ extern "C" int xgc_get_counters(xgc_handle* h, int r, int at0, int at1, uint32_t
   CHECK_R(h, r);
   if (at0 < 0 || at1 >= h->cfg.t_cap || at1 < at0) FAIL(h, 2, "bad week range");
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(out, h->g.counters + ((size_t)r * h->g.t_cap + at0) * XGC_NCOUNTER, sizeof(uint32_t) * XGC_NCOUNTER * (size_t)(at1 - at0 + 1), cudaMemcpyDeviceToHost));
+  CU(h, d2h(h, out, h->g.counters + ((size_t)r * h->g.t_cap + at0) * XGC_NCOUNTER, sizeof(uint32_t) * XGC_NCOUNTER * (size_t)(at1 - at0 + 1)));
   return 0;
 }
 extern "C" int xgc_get_counters_all(xgc_handle* h, int at, uint32_t* out) {
@@ -1169,7 +1178,7 @@ extern "C" int xgc_snapshot(xgc_handle* h, void* buf, size_t bytes) {
   rc = prune_now(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   char* p = (char*)buf; memcpy(p, &h->cfg, sizeof(xgc_config)); p += sizeof(xgc_config);
-  for (auto& sg : segments(h)) { CU(h, cudaMemcpy(p, sg.p, sg.bytes, cudaMemcpyDeviceToHost)); p += sg.bytes; }
+  for (auto& sg : segments(h)) { CU(h, d2h(h, p, sg.p, sg.bytes)); p += sg.bytes; }
   return 0;
 }
 extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
@@ -1181,9 +1190,9 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
-  for (auto& sg : segments(h)) { CU(h, cudaMemcpy(sg.p, p, sg.bytes, cudaMemcpyHostToDevice)); p += sg.bytes; }
+  for (auto& sg : segments(h)) { CU(h, h2d(h, sg.p, p, sg.bytes)); p += sg.bytes; }
   h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false; h->fast_dirty = true;
-  { double t[XGC_NTABLE]; CU(h, cudaMemcpy(t, h->g.tables, sizeof t, cudaMemcpyDeviceToHost));
+  { double t[XGC_NTABLE]; CU(h, d2h(h, t, h->g.tables, sizeof t));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
     set_form_tiles(h, t);
     drop_graphs(h); }
@@ -1198,7 +1207,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   CU(src, cudaSetDevice(src->cfg.device)); CU(src, cudaStreamSynchronize(src->stream));
   CU(dst, cudaSetDevice(dst->cfg.device)); CU(dst, cudaStreamSynchronize(dst->stream));
   const Dev &a = src->g, &b = dst->g; size_t n = a.n_cap, so = (size_t)sr * n, doff = (size_t)dr * n;
-  auto cp = [&](void* d, const void* s, size_t bytes) { return cudaMemcpy(d, s, bytes, cudaMemcpyDefault); };
+  auto cp = [&](void* d, const void* s, size_t bytes) { return cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, dst->stream); };
   cudaError_t e = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   acc(cp(b.core + doff, a.core + so, n * sizeof(uint4))); acc(cp(b.aux + doff, a.aux + so, n * sizeof(Aux)));
@@ -1209,9 +1218,8 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   acc(cp(b.rep + dr, a.rep + sr, sizeof(Rep))); acc(cp((int*)b.at_ptr + dr, a.at_ptr + sr, 4));
   acc(cp(b.counters + (size_t)dr * b.t_cap * XGC_NCOUNTER, a.counters + (size_t)sr * a.t_cap * XGC_NCOUNTER, (size_t)a.t_cap * XGC_NCOUNTER * 4));
   if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
-  // device-to-device cudaMemcpy does not wait on the host side and runs on the legacy stream, which the handles' non-blocking
-  // streams do not order against: the copies are complete before anything else touches the destination replicate
-  CU(dst, cudaStreamSynchronize(cudaStreamLegacy));
+  // (the copies run on the destination handle's stream; the source handle's stream was drained above)
+  CU(dst, cudaStreamSynchronize(dst->stream));
   dst->last_at = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
   if (src->fast_dirty) dst->fast_dirty = true;
   return 0;
