@@ -42,6 +42,7 @@ def parse():
                     help="native-draw contract of the CUDA arm: fast = replicate-resident kernel (statistical equivalence), strict = bit-exact kernels")
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-no-span", action="store_true", help="fast mode: two xgc_step calls per week instead of xgc_step_span")
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
@@ -431,17 +432,27 @@ def run_xgc(args, rank, world, local_rank):
     d2h = n_host.numel() * 4 + c_host.numel() * 4
     n_np, c_np = n_host.numpy(), c_host.numpy().view(np.uint32)
 
+    # fast mode: the acts..prevalence call of week t also runs the aging..hivvl group of week t + 1 (xgc_step_span: what the last
+    # module wrapper of a week issues; netsim has nothing on the host between prevalence_msm(t) and aging_msm(t + 1)) -- one
+    # resident launch per week; every week still makes the full round trip living counts -> host -> edge lists -> device
+    span = mode == "fast" and not args.e2e_no_span
+    pre_done = [-1] * Ge
+
     def e2e_week(gi, t):
         """One week of the contract for group gi (what one host-side simnet_msm loop does); returns living agents."""
         hg, r0, Rg = groups[gi], g_off[gi], g_size[gi]
-        hg.step(t, pre)
+        if pre_done[gi] != t:
+            hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
         for l in range(2):
             d = deltas[l][t % len(deltas[l])]
             hg.update_edgelists_all(l, d[r0:r0 + Rg].data_ptr(), d.shape[1], has_start=False)
         t_el, t_ne, _t_st, _ne = oneoff[t % len(oneoff)]
         hg.set_edgelists_all(2, t_el[r0:r0 + Rg].data_ptr(), t_ne[r0:r0 + Rg].data_ptr(), 0, stride=t_el.shape[2])
-        hg.step(t, post)
+        if span:
+            hg.step_span(t, post, pre); pre_done[gi] = t + 1
+        else:
+            hg.step(t, post)
         hg.counters_all(t, c_np[r0:r0 + Rg])
         return float(c_np[r0:r0 + Rg, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
 
@@ -482,8 +493,9 @@ def run_xgc(args, rank, world, local_rank):
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
            "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
-           "path": f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: xgc_step(pre) -> xgc_num_agents_all -> 2x xgc_update_edgelists_all "
-                   "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> xgc_step(post) -> xgc_get_counters_all"}
+           "path": f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: " + ("" if span else "xgc_step(pre) -> ") + "xgc_num_agents_all -> 2x xgc_update_edgelists_all "
+                   "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> " +
+                   ("xgc_step_span(post of this week, pre of the next: one resident launch)" if span else "xgc_step(post)") + " -> xgc_get_counters_all"}
     e2e_status = 0
     for hg in groups:
         e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, hg.n_replicates, max(hg.n_replicates // 8, 1))]))

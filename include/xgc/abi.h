@@ -360,6 +360,12 @@ int  xgc_get_mode(xgc_handle* h, int* mode);
 /* the step: runs the modules selected by module_mask for week `at` on every replicate, in reference order.
  * inj = NULL -> native Philox; otherwise draws come from the injected table. */
 int  xgc_step(xgc_handle* h, int at, uint32_t module_mask, const xgc_inject* inj);
+/* the modules of mask_tail for week `at`, then the modules of mask_head for week at + 1, native draws: the call the LAST module
+ * wrapper of a week makes in a host-network loop (netsim runs prevalence_msm(at) and aging_msm(at + 1) back to back, nothing on
+ * the host in between -- EpiModel::netsim's `for (at in 2:nsteps)` loop, sim1_02_lhs.r:201-218 module order).  Same result as
+ * xgc_step(at, mask_tail) + xgc_step(at + 1, mask_head); in XGC_MODE_FAST, with mask_tail = the acts..prevalence group (with or
+ * without resim_nets) and mask_head = the aging..hivvl group, the two run in ONE launch of the resident kernel. */
+int  xgc_step_span(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head);
 /* batched loop at0..at1 inclusive, all modules, native draws, no host synchronisation inside (CUDA-graph replay). */
 int  xgc_run (xgc_handle* h, int at0, int at1);
 int  xgc_sync(xgc_handle* h);

@@ -99,26 +99,108 @@ def test_fast_mode_step_groups_equal_run():
     ha = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); ha.set_mode("fast")
     hb = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hb.set_mode("fast")
     hc = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hc.set_mode("fast")
+    hd = load_handle(cases, SEED, t_cap=T + 4, compact_every=8); hd.set_mode("fast")
     ha.run(2, T)
     for at in range(2, T + 1):
         hb.step(at, pre)
         hb.step(at, K.M_ALL & ~pre)
         hc.step(at)
+    # xgc_step_span: the rest of week t and the start of week t + 1 in one call (one resident launch: staged once, both groups)
+    hd.step(2, pre)
+    for at in range(2, T):
+        hd.step_span(at, K.M_ALL & ~pre, pre)
+    hd.step(T, K.M_ALL & ~pre)
     for r in range(R):
         ca = ha.counters(r, 2, T)
-        for what, hx in (("weekly full steps", hc), ("step groups", hb)):
+        for what, hx in (("weekly full steps", hc), ("step groups", hb), ("step spans", hd)):
             cx = hx.counters(r, 2, T)
             if not np.array_equal(ca, cx):
                 wk, col = np.argwhere(ca != cx)[0]
                 raise AssertionError(f"{what} != resident run: replicate {r}, first at week {wk + 2}, counter {col}: {cx[wk, col]} vs {ca[wk, col]}")
         for name in ("age", "rGC", "uGC.infTime", "status", "vl", "prepStat", "last.screen", "prep.ind.last", "sti.expo"):
             assert np.array_equal(ha.download_attr(r, name), hb.download_attr(r, name)), name
+            assert np.array_equal(ha.download_attr(r, name), hd.download_attr(r, name)), f"step spans: {name}"
     # and the fast path is a different sampler than the strict one, not a copy of it
     hs = load_handle(cases, SEED, t_cap=T + 4, compact_every=8)
     hs.run(2, T)
     assert not np.array_equal(hs.counters(0, 2, T), ha.counters(0, 2, T))
-    for x in (ha, hb, hc, hs):
+    for x in (ha, hb, hc, hd, hs):
         x.close()
+
+
+def test_fast_mode_hostnet_in_kernel_edge_ops():
+    """The weekly host-network contract on the fast path: the toggles of the persistent layers (xgc_update_edgelists_all) and the
+    new one-off list (xgc_set_edgelists_all) are applied by the standalone k_rank / k_edges_update / k_edges_upload kernels or, with
+    XGC_FUSE_HOSTNET=1, queued and applied by the resident kernel itself.  Same lists, same trajectory, bit for bit -- also
+    when the acts..prevalence call of week t carries the aging..hivvl group of week t + 1 (xgc_step_span)."""
+    import os
+    n, T0, T, R = 2500, 8, 30, 3
+    cases = [make_case(n, 140 + r, midcourse=True, network_mode="surrogate") for r in range(R)]
+    pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
+    post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
+    hs = {}
+    for name in ("fused+span", "standalone", "fused"):
+        os.environ["XGC_FUSE_HOSTNET"] = "0" if name == "standalone" else "1"
+        try:
+            h = load_handle(cases, SEED, t_cap=T + 4, compact_every=8)
+        finally:
+            os.environ.pop("XGC_FUSE_HOSTNET", None)
+        h.set_mode("fast")
+        h.run(2, T0)                                            # a network for the host side to edit
+        h.set_control(P.control_msm(network_mode="host").flags)
+        hs[name] = h
+    ne0 = np.array([[hs["fused"].get_edgelist(r, l)[0].shape[0] for r in range(R)] for l in range(3)])
+    assert ne0[:2].min() > 200
+    rng = np.random.default_rng(5)
+    kept = ne0.copy()                                            # lower bound of the lists' lengths as the host knows them
+    for at in range(T0 + 1, T + 1):
+        for name, h in hs.items():
+            if name != "fused+span" or at == T0 + 1:
+                h.step(at, pre)
+        nal = [h.num_agents_all() for h in hs.values()]
+        assert np.array_equal(nal[0], nal[1]) and np.array_equal(nal[0], nal[2])
+        nmin = int(nal[0].min())
+        deltas = []
+        for l in range(2):
+            nrem = rng.integers(0, 12, size=R); nadd = rng.integers(0, 14, size=R)
+            stride = int(2 + nrem.max() + 3 * nadd.max()) + 1
+            d = np.zeros((R, stride), np.int32)
+            for r in range(R):
+                k, m = int(nrem[r]), int(nadd[r])
+                d[r, 0], d[r, 1] = k, m
+                d[r, 2:2 + k] = np.sort(rng.choice(int(kept[l, r] * 0.8), size=k, replace=False))
+                a = rng.integers(1, nmin + 1, size=m); b = rng.integers(1, nmin, size=m); b = np.where(b >= a, b + 1, b)
+                d[r, 2 + k:2 + k + m] = a; d[r, 2 + k + m:2 + k + 2 * m] = b
+                d[r, 2 + k + 2 * m:2 + k + 3 * m] = at - rng.integers(0, 5, size=m)
+                kept[l, r] = int(kept[l, r] * 0.97) - k + m      # (a few ties a week also go with departed agents)
+            deltas.append(d)
+        ne2 = rng.integers(20, 150, size=R).astype(np.int32)
+        el2 = rng.integers(1, nmin + 1, size=(R, 2, 160)).astype(np.int32); el2[:, 1] = np.where(el2[:, 1] == el2[:, 0], el2[:, 0] % nmin + 1, el2[:, 1])
+        for name, h in hs.items():
+            for l in range(2):
+                h.update_edgelists_all(l, deltas[l].ctypes.data, deltas[l].shape[1], has_start=True)
+            h.set_edgelists_all(2, el2.ctypes.data, ne2.ctypes.data, 0, stride=160)
+            if name == "fused+span" and at < T:
+                h.step_span(at, post, pre)
+            else:
+                h.step(at, post)
+    ref = hs["standalone"]
+    for name in ("fused", "fused+span"):
+        h = hs[name]
+        for r in range(R):
+            assert h.status(r) == 0 and ref.status(r) == 0
+            ca, cb = ref.counters(r, T0 + 1, T), h.counters(r, T0 + 1, T)
+            if not np.array_equal(ca, cb):
+                wk, col = np.argwhere(ca != cb)[0]
+                raise AssertionError(f"{name}: replicate {r}, first at week {wk + T0 + 1}, counter {col}: {cb[wk, col]} vs {ca[wk, col]}")
+            for l in range(3):
+                ea, sa = ref.get_edgelist(r, l); eb, sb = h.get_edgelist(r, l)
+                assert np.array_equal(ea, eb) and np.array_equal(sa, sb), f"{name}: edge list {l} of replicate {r}"
+            for attr in ("age", "rGC", "uGC.infTime", "status", "vl", "prepStat", "sti.expo"):
+                assert np.array_equal(ref.download_attr(r, attr), h.download_attr(r, attr)), f"{name}: {attr}"
+    assert hs["standalone"].kernel_launches() > hs["fused"].kernel_launches() > hs["fused+span"].kernel_launches()
+    for h in hs.values():
+        h.close()
 
 
 @pytest.mark.parametrize("mode", ["strict", "fast"])

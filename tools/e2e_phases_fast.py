@@ -28,20 +28,21 @@ post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
 n_host = torch.empty(R, dtype=torch.int32).pin_memory().numpy()
 c_host = torch.empty((R, K.NCOUNTER), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
 acc = {}
+SPAN = bool(int(os.environ.get("SPAN", "0")))
 def T(name, f):
     t0 = time.perf_counter(); f(); h.sync(); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
 at = 61
 def week(timed):
     global at
     run = T if timed else (lambda name, f: f())
-    run("step_pre", lambda: h.step(at, pre))
+    if not SPAN or at == 61: run("step_pre", lambda: h.step(at, pre))
     run("num_agents_all", lambda: h.num_agents_all(n_host))
     for l in range(2):
         d = deltas[l][at % 4]
         run(f"update_edgelists_{l}", lambda: h.update_edgelists_all(l, d.data_ptr(), d.shape[1], has_start=False))
     t_el, t_ne, _, _ = oneoff[at % 4]
     run("set_edgelists_2", lambda: h.set_edgelists_all(2, t_el.data_ptr(), t_ne.data_ptr(), 0, stride=t_el.shape[2]))
-    run("step_post", lambda: h.step(at, post))
+    run("step_post", (lambda: h.step_span(at, post, pre)) if SPAN else (lambda: h.step(at, post)))
     run("counters_all", lambda: h.counters_all(at, c_host))
     at += 1
 for it in range(3): week(False)
@@ -58,3 +59,27 @@ prof = h.profile_read()
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
     print(f"{k:26s} {v[0] / 4:8.4f} ms/week  ({v[1] // 4} launches/week)")
 print("status", h.status(0))
+h.profile(False)
+if mode == "fast":
+    import ctypes as C
+    from xgc_msm_b200 import abi
+    names = ["stage", "arrive", "pre", "net", "acts", "b", "trans", "apply_tally", "row", "writeback", "squeeze_wb", "stage_tables", "hostnet"] + ["-"] * 3
+    buf = (C.c_ulonglong * 16)()
+    abi.lib.xgc_debug_fast_profile.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
+    abi.lib.xgc_debug_fast_profile(buf, 16, 1)
+    for it in range(8): week(False)
+    h.sync()
+    n = abi.lib.xgc_debug_fast_profile(buf, 16, 1)
+    print("step-mode phase cycles per replicate-week:", {names[k]: int(buf[k] / (R * 8)) for k in range(n) if buf[k]}, "total", int(sum(buf[:n]) / (R * 8)))
+    if SPAN: sys.exit(0)
+    h.set_control(control_msm(network_mode="surrogate").flags)
+    h.run(at, at + 15); h.sync(); at += 16
+    n = abi.lib.xgc_debug_fast_profile(buf, 16, 1)
+    print("resident 16-week launch, same handle:      ", {names[k]: int(buf[k] / (R * 16)) for k in range(n) if buf[k]}, "total", int(sum(buf[:n]) / (R * 16)))
+    st = torch.cuda.ExternalStream(h.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st); h.run(at, at + 15); e1.record(st); torch.cuda.synchronize(); at += 16
+    print("resident ms per week of", R, "replicates:", e0.elapsed_time(e1) / 16)
+    for it in range(16):
+        e0.record(st); h.run(at, at); e1.record(st); torch.cuda.synchronize(); at += 1
+        if it >= 12: print("one-week resident launch ms:", e0.elapsed_time(e1))

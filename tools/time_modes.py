@@ -29,7 +29,7 @@ for mode in a.modes.split(","):
     if mode == "fast":
         import ctypes as C
         from xgc_msm_b200 import abi
-        names = ["stage", "arrive", "pre", "net", "acts", "b", "trans", "apply_tally", "row", "writeback", "squeeze_wb", "stage_tables"] + ["-"] * 4
+        names = ["stage", "arrive", "pre", "net", "acts", "b", "trans", "apply_tally", "row", "writeback", "squeeze_wb", "stage_tables", "hostnet"] + ["-"] * 3
         buf = (C.c_ulonglong * 16)()
         abi.lib.xgc_debug_fast_profile.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
         n = abi.lib.xgc_debug_fast_profile(buf, 16, 1)

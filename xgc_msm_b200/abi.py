@@ -51,7 +51,7 @@ def _load() -> C.CDLL:
         "xgc_set_edgelist": [vp, ci, ci, pi, ci, pi], "xgc_get_edgelist": [vp, ci, ci, pi, ci, pi, pi],
         "xgc_get_actcounts": [vp, ci, ci, pi, ci, pi],
         "xgc_get_actlist": [vp, ci, ci, pi, ci, pi, C.POINTER(xgc_inject)],
-        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
+        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_step_span": [vp, ci, cu, cu], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
         "xgc_compact": [vp], "xgc_status": [vp, ci, pu],
         "xgc_get_counters": [vp, ci, ci, ci, pu], "xgc_get_epi": [vp, ci, C.c_char_p, pd, ci, ci],
         "xgc_get_epi_table": [vp, ci, C.POINTER(C.c_char_p), ci, pd, ci, ci],
@@ -269,6 +269,10 @@ class Handle:
     # stepping ------------------------------------------------------------------------------------------------------
     def step(self, at: int, mask: Optional[int] = None, inj: Optional[xgc_inject] = None):
         self._ck(lib.xgc_step(self._h, at, K.M_ALL if mask is None else mask, None if inj is None else C.byref(inj)))
+
+    def step_span(self, at: int, mask_tail: int, mask_head: int):
+        """The rest of week `at` and the start of week at + 1 in one call (xgc_step_span; one resident launch in fast mode)."""
+        self._ck(lib.xgc_step_span(self._h, at, mask_tail, mask_head))
 
     def run(self, at0: int, at1: int):
         self._ck(lib.xgc_run(self._h, at0, at1))

@@ -31,6 +31,7 @@
 // gates this path statistically against the oracle and structurally (recount of the tallies, accounting identities).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "xgc_fast.cuh"
 
 #define FT 1024                    /* threads per CTA: 32 warps, one CTA per SM                                   */
@@ -174,7 +175,7 @@ __device__ __forceinline__ void gap_warp(uint2 key, unsigned at, unsigned stream
 // imbalance in front of every phase barrier).  VSLOT(p): the slot of the warp's p-th agent.
 #define VSLOT(p) ((((p) >> 5) * NW + warp) * 32 + ((p) & 31))
 // phase clocks (SM cycles summed over CTAs; thread 0 of each CTA): tools/time_modes.py
-enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE, PH_NET, PH_ACTS, PH_B, PH_TRANS, PH_APPLY_TALLY, PH_ROW, PH_WRITEBACK, PH_SQUEEZE_WB, PH_STAGE_TABLES, PH_N = 16 };
+enum { PH_STAGE = 0, PH_ARRIVE, PH_PRE, PH_NET, PH_ACTS, PH_B, PH_TRANS, PH_APPLY_TALLY, PH_ROW, PH_WRITEBACK, PH_SQUEEZE_WB, PH_STAGE_TABLES, PH_HOSTNET, PH_N = 16 };
 __device__ unsigned long long g_fast_prof[PH_N];
 #define TICK(k) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fast_prof[k], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
   long long t_last = clock64();
   // a call that ends before the POST group (the aging..hivvl call of the weekly host-network pattern) changes few agents: it
   // writes every change of a core word through to HBM and skips the write-back of the plane
-  const bool wt = !(A.phases & XF_POST);
+  const bool wt = !((A.phases | A.ph_last) & XF_POST);
   unsigned* const core_w = (unsigned*)g.core;
   // Schedule: the launch's replicate-weeks, replicate-major, are cut into gridDim.x equal stretches (148 CTAs x 1000 replicates
   // would otherwise run 7 waves for 6.76 waves of work).  A CTA walks its stretch from the LAST replicate to the first: the
@@ -275,14 +276,16 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
       if (l == 2) w *= F.degw[27 + DM_RISK(demo)];
       return w;
     };
-    if (surrogate) {
+    auto count_degrees = [&]() {
       const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1];
       for (int f = tid; f < ne01; f += FT) {
         const int l = f >= ne0, sidx = g.e_off[l] + f - (l ? ne0 : 0);
+        if (ea[sidx] & EA_DEAD) continue;
         const int4 ed = g.edge[(size_t)r * g.e_stride + sidx];
         deg_add(ed.x, l); deg_add(ed.y, l);
       }
-    }
+    };
+    if (surrogate) count_degrees();
     if (warp == 0) {                                            // largest gap-sampled weekly death probability
       float v = 0.f;
       for (int k = lane; k < 4 * XGC_ASMR_AGES; k += 32) { float a = F.asmr[k]; if (a < HI_MORT) v = fmaxf(v, a); }
@@ -360,10 +363,12 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
 
     for (int at = w_first; at <= w_last; ++at) {
       const unsigned mask = A.mask;
+      // a span call (xgc_step_span) runs the rest of week at0 and the start of week at1: phase groups by week
+      const unsigned ph = at == A.at0 ? A.phases : at == A.at1 ? A.ph_last : (unsigned)XF_ALL;
       unsigned* const grow = g.counters + ((size_t)r * g.t_cap + (size_t)at) * XGC_NCOUNTER;
       const int at8 = (at + XF_BIRTH_OFF) * 8;
       // =================================================================================================== PRE
-      if (A.phases & XF_PRE) {
+      if (ph & XF_PRE) {
         for (int k = tid; k < XGC_NCOUNTER; k += FT)            // the week's event counters start at zero; state tallies carry over
           if (!incr || k >= XGC_K_NGROUP * XGC_NCELL || !((STATE_GROUPS >> (k / XGC_NCELL)) & 1u)) F.row[k] = 0u;
         // ---- arrival_msm: one warp
@@ -548,12 +553,175 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           if (!incr || k >= XGC_K_NGROUP * XGC_NCELL || !((STATE_GROUPS >> (k / XGC_NCELL)) & 1u)) F.row[k] = grow[k];
         __syncthreads();
       }
+      // =================================================================================================== HOST NETWORK
+      // The edge-list operations the host queued for this week (weekly toggles of the persistent layers, the new one-off list),
+      // same semantics as k_edges_update / k_edges_upload: removal indices are ranks among the ties whose endpoints both live,
+      // removed ties and the ties of departed agents become tombstones (squeezed out before the write-back, kept ties stay in
+      // order), added ties go to the tail, R positions -> slots through a rank structure over the staged `active` bits.
+      if (at == A.at0 && (A.hn_kind[0] | A.hn_kind[1] | A.hn_kind[2])) {
+        // Built for latency: the operation headers in one round trip to memory, then EVERY other global load of the phase (tie
+        // endpoints of both persistent layers, removal indices, added pairs, the one-off pairs) in a second one; the rest is
+        // shared-memory work on bitmaps (living agents, living ties) with popcount prefixes and rank -> item selection.
+        unsigned* const aw = reinterpret_cast<unsigned*>(&F.mq[0][0][0]);       // the mini-queues are idle between phases
+        const int n_slots = F.sc[SC_NSLOTS], words = (n_slots + 31) >> 5, na = F.sc[SC_NALIVE];
+        unsigned* const apre = aw + words;
+        int* const hdr = F.wsum2;                                 // [0..1] n_removed, [2..3] n_added (as sent), [4] one-off n
+        if (tid < 4) { const bool l1 = tid & 1; hdr[tid] = (l1 ? A.hn_kind[1] : A.hn_kind[0]) == 1 ? ((l1 ? A.hn_ptr[1] : A.hn_ptr[0]) + (size_t)r * (l1 ? A.hn_stride[1] : A.hn_stride[0]))[tid >> 1] : 0; }
+        if (tid == 32) hdr[4] = A.hn_kind[0] == 2 ? A.hn_ne[0][r] : 0;                                           // [4..6]: whole-list sizes
+        if (tid == 33) hdr[5] = A.hn_kind[1] == 2 ? A.hn_ne[1][r] : 0;
+        if (tid == 34) hdr[6] = A.hn_kind[2] == 2 ? A.hn_ne[2][r] : 0;
+        for (int k = warp; k < words; k += NW) {
+          const int i = k * 32 + lane;
+          const unsigned m = __ballot_sync(FULL, i < n_slots && (vd[i] & DM_ACTIVE));
+          if (lane == 0) aw[k] = m;
+        }
+        __syncthreads();
+        {                                                       // exclusive popcount prefix (words <= 1024 = FT)
+          const int c = tid < words ? __popc(aw[tid]) : 0; int inc = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+          if (lane == 31) F.wsum[warp] = inc;
+          __syncthreads();
+          int tot; const int base = warp_base(F.wsum, warp, lane, &tot);
+          if (tid < words) apre[tid] = (unsigned)(base + inc - c);
+          __syncthreads();
+        }
+        // rank -> item over a bitmap with an exclusive popcount prefix: the last word whose prefix is <= p holds item p
+        auto select = [&](const unsigned* bm, const unsigned* pre, int nw, int p) -> int {
+          int lo = 0, hi = nw - 1;
+          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)pre[mid] <= p) lo = mid; else hi = mid - 1; }
+          unsigned w = bm[lo];
+          for (int j = p - (int)pre[lo]; j > 0; --j) w &= w - 1u;            // drop the j lowest set bits
+          return lo * 32 + __ffs(w) - 1;
+        };
+        auto p2s = [&](int p) -> int { return select(aw, apre, words, p); };   // slot of the p-th (0-based) living agent
+        bool bad = false;
+        int ne_l[2], nrem_l[2], nadd_l[2], kw_l[2];
+        unsigned* lm_l[2]; unsigned* lp_l[2];
+        { unsigned* nx = apre + words;
+#pragma unroll
+  #pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int stride = A.hn_stride[l], hs = A.hn_has_start[l], on = A.hn_kind[l] == 1;
+            ne_l[l] = on ? F.sc[SC_NE0 + l] : 0; kw_l[l] = (ne_l[l] + 31) >> 5;
+            nrem_l[l] = on ? max(0, min(hdr[l], stride - 2)) : 0;
+            nadd_l[l] = on ? max(0, min(hdr[2 + l], (stride - 2 - nrem_l[l]) / (hs ? 3 : 2))) : 0;
+            if (on && (hdr[l] != nrem_l[l] || hdr[2 + l] != nadd_l[l])) bad = true;
+            lm_l[l] = nx; nx += kw_l[l]; lp_l[l] = nx; nx += kw_l[l];
+          } }
+        // ---- second round trip: everything else this phase reads from global memory
+        int rem_j[2] = { -1, -1 }; int add_a[2] = { 0, 0 }, add_b[2] = { 0, 0 }, add_s[2] = { 0, 0 };      // this thread's removal / added pair of each layer
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          if (A.hn_kind[l] != 1) continue;
+          const int* row = A.hn_ptr[l] + (size_t)r * A.hn_stride[l];
+          if (tid < nrem_l[l]) rem_j[l] = row[2 + tid];
+          const int* tl = row + 2 + nrem_l[l];
+          if (tid < nadd_l[l]) { add_a[l] = tl[tid]; add_b[l] = tl[nadd_l[l] + tid]; add_s[l] = A.hn_has_start[l] ? tl[2 * nadd_l[l] + tid] : at; }
+        }
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {                             // living-tie bitmaps; ties of departed agents become tombstones
+          if (A.hn_kind[l] != 1) continue;
+          const int ne = ne_l[l];
+          const int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+          unsigned short* const eal = ea + g.e_off[l];
+          for (int e0 = 0; e0 < ne; e0 += 4 * FT) {
+            int2 xy[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int e = e0 + k * FT + tid; xy[k] = e < ne ? *reinterpret_cast<const int2*>(E + e) : make_int2(0, 0); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = e0 + k * FT + tid;
+              const bool live = e < ne && (vd[xy[k].x] & vd[xy[k].y] & DM_ACTIVE);
+              const unsigned m = __ballot_sync(FULL, live);
+              if (lane == 0 && (e >> 5) < kw_l[l]) lm_l[l][e >> 5] = m;
+              if (e < ne && !live) eal[e] = EA_DEAD;
+            }
+          }
+        }
+        __syncthreads();
+        if (warp < 2 && (warp ? A.hn_kind[1] : A.hn_kind[0]) == 1) {      // popcount prefix of layer `warp`'s living-tie bitmap, by one warp
+          const int kw = warp ? kw_l[1] : kw_l[0], per = (kw + 31) >> 5;
+          const unsigned* const lm = warp ? lm_l[1] : lm_l[0]; unsigned* const lp = warp ? lp_l[1] : lp_l[0];
+          int sum = 0;
+          for (int j = 0; j < per; ++j) { const int idx = lane * per + j; sum += idx < kw ? __popc(lm[idx]) : 0; }
+          int inc = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+          int run = inc - sum;
+          for (int j = 0; j < per; ++j) { const int idx = lane * per + j; if (idx < kw) { lp[idx] = (unsigned)run; run += __popc(lm[idx]); } }
+          if (lane == 31) F.wsum3[warp] = inc;                    // living ties of the layer
+        }
+        __syncthreads();
+        bool need_sq = false;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          if (A.hn_kind[l] != 1) continue;
+          const int nlive = F.wsum3[l], nrem = nrem_l[l];
+          int nkill = 0;
+          for (int k = tid; k < nrem; k += FT) {                  // (k = tid: prefetched; a longer removal list reads the rest here)
+            const int j = k == tid ? rem_j[l] : (A.hn_ptr[l] + (size_t)r * A.hn_stride[l])[2 + k];
+            if (j < 0 || j >= nlive) { bad = true; continue; }
+            const int e = select(lm_l[l], lp_l[l], kw_l[l], j);
+            const int ei = g.e_off[l] + e; const unsigned bit = (unsigned)EA_DEAD << (16 * (ei & 1));      // (act words are 16-bit: OR into the aligned pair)
+            if (atomicOr(reinterpret_cast<unsigned*>(ea) + (ei >> 1), bit) & bit) continue;                   // listed twice
+            ++nkill;
+          }
+          nkill = __reduce_add_sync(FULL, nkill);
+          if (lane == 0 && nkill) atomicAdd(&F.sc[SC_DEAD0 + l], nkill);
+          if (tid == 0 && ne_l[l] > nlive) atomicAdd(&F.sc[SC_DEAD0 + l], ne_l[l] - nlive);
+          if (ne_l[l] + nadd_l[l] > g.e_cap[l] && (ne_l[l] > nlive || nrem > 0)) need_sq = true;
+        }
+        __syncthreads();
+        if (need_sq) squeeze();                                  // (uniform: every thread derived it from the same shared values)
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          if (A.hn_kind[l] != 1) continue;
+          const int nadd = nadd_l[l], tailpos = F.sc[SC_NE0 + l];
+          int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+          for (int k = tid; k < nadd; k += FT) {
+            int a, b, st;
+            if (k == tid) { a = add_a[l]; b = add_b[l]; st = add_s[l]; }
+            else { const int* tl = A.hn_ptr[l] + (size_t)r * A.hn_stride[l] + 2 + nrem_l[l]; a = tl[k]; b = tl[nadd + k]; st = A.hn_has_start[l] ? tl[2 * nadd + k] : at; }
+            if (a < 1 || a > na || b < 1 || b > na) { bad = true; a = b = 1; }
+            if (tailpos + k < g.e_cap[l]) { E[tailpos + k] = make_int4(p2s(a - 1), p2s(b - 1), st, 0); ea[g.e_off[l] + tailpos + k] = 0; }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int nn = tailpos + nadd;
+            if (nn > g.e_cap[l]) { nn = g.e_cap[l]; atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_EDGE_OVERFLOW); }
+            F.sc[SC_NE0 + l] = nn;
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          if (A.hn_kind[l] != 2) continue;
+          const int stride = A.hn_stride[l], n = hdr[4 + l], cap = g.e_cap[l] < stride ? g.e_cap[l] : stride, nn = n < cap ? n : cap;
+          const int* el = A.hn_ptr[l] + (size_t)r * 2 * stride;
+          int4* E = g.edge + (size_t)r * g.e_stride + g.e_off[l];
+          for (int e = tid; e < nn; e += FT) {
+            int a = el[e], b = el[stride + e];
+            if (a < 1 || a > na || b < 1 || b > na) { bad = true; a = b = 1; }
+            E[e] = make_int4(p2s(a - 1), p2s(b - 1), A.hn_start[l] ? A.hn_start[l][(size_t)r * stride + e] : at, 0); ea[g.e_off[l] + e] = 0;
+          }
+          if (tid == 0) { F.sc[SC_NE0 + l] = nn; F.sc[SC_DEAD0 + l] = 0; if (n > cap) atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_EDGE_OVERFLOW); }
+        }
+        if (bad) atomicOr(&F.sc[SC_STATUS], (int)XGC_ST_BAD_EDGE);
+        __syncthreads();
+        if (surrogate) {                                         // the degrees counted at staging were those of the old lists
+          for (int k = tid; k < g.n_cap / 4; k += FT) deg32[k] = 0u;
+          __syncthreads();
+          count_degrees();
+          __syncthreads();
+        }
+        TICK(PH_HOSTNET);
+      }
       // =================================================================================================== NETWORK
       // (tergmLite::delete_vertices for the departed + surrogate simnet_msm).  Nothing here walks the ties: deletions are
       // tombstones set by the tie sweep (fused into the acts pass when this call also runs the POST group), new ties are
       // appended at the tails.
-      if (A.phases & (XF_PRUNE | XF_FORM)) {
-        const bool form = (A.phases & XF_FORM) && surrogate;
+      if (ph & (XF_PRUNE | XF_FORM)) {
+        const bool form = (ph & XF_FORM) && surrogate;
         if (tid == 0) {
           const int n_alive = F.sc[SC_NALIVE];
           int need = 0, anydead = 0;
@@ -628,7 +796,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         // no acts pass in this call.  With a network step to run now (dissolution + formation) the tie sweep runs on its own; without
         // one, the ties of this week's departed agents are left to whoever touches the lists next -- the weekly-toggle kernel
         // (k_edges_update), this kernel's acts pass, or an explicit prune before anything else reads them (h->prune_pending)
-        if (!(A.phases & XF_POST) && form) {
+        if (!(ph & XF_POST) && form) {
           const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
           for (int f0 = tid; f0 < ne_all; f0 += 4 * FT) {        // four ties per thread in flight
             int4 ed4[4];
@@ -654,11 +822,11 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         TICK(PH_NET);
       }
       // =================================================================================================== POST
-      if (A.phases & XF_POST) {
+      if (ph & XF_POST) {
         const int n_slots = F.sc[SC_NSLOTS];
         const int AW = ((n_slots + FT - 1) / FT) * 32;
         const int ne0 = F.sc[SC_NE0], ne01 = ne0 + F.sc[SC_NE1], ne_all = ne01 + F.sc[SC_NE2];
-        const bool last_week = at == A.at1;
+        const bool last_week = at == ((A.ph_last & XF_POST) ? A.at1 : A.at1 - 1);      // the last week of the call that has an acts pass
         if (tid == 0 && (mask & XGC_M_STITRANS)) {              // weekly random pathway order (stitrans_msm_rand)
           uint4 x0 = frand(key, at, FS_PATH, 0, 0), x1 = frand(key, at, FS_PATH, 1, 0);
           unsigned dr[6] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y };
@@ -673,7 +841,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
         if (mask & (XGC_M_ACTS | XGC_M_PREP)) {
           const float sc_ai = P[XGC_P_ai_acts_scale_mc] * (1.f / 52.f), sc_oi = P[XGC_P_oi_acts_scale_mc] * (1.f / 52.f);
           unsigned tot_ai = 0, tot_oi = 0;
-          const bool diss_on = (A.phases & XF_FORM) && surrogate;
+          const bool diss_on = (ph & XF_FORM) && surrogate;
           for (int f = tid; f < ne_all; f += FT) {
             const int l = f >= ne01 ? 2 : f >= ne0 ? 1 : 0, sidx = g.e_off[l] + f - (l == 2 ? ne01 : l == 1 ? ne0 : 0);
             if (ea[sidx] & EA_DEAD) continue;
@@ -751,7 +919,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
           }
         }
         __syncthreads();
-        if (tid < 3 && (A.phases & XF_FORM) && surrogate) F.row[XGC_K_NEDGES + tid] = (unsigned)(F.sc[SC_NE0 + tid] - F.sc[SC_DEAD0 + tid]);
+        if (tid < 3 && (ph & XF_FORM) && surrogate) F.row[XGC_K_NEDGES + tid] = (unsigned)(F.sc[SC_NE0 + tid] - F.sc[SC_DEAD0 + tid]);
         TICK(PH_ACTS);
         // ---------------------------------------------------------------- prep_msm, stirecov_msm, stitx_msm (per-warp agent ranges)
         if (mask & (XGC_M_PREP | XGC_M_STIRECOV | XGC_M_STITX | XGC_M_HIVTRANS)) {
@@ -1110,7 +1278,10 @@ _Pragma("unroll")
         __syncthreads();
         TICK(PH_APPLY_TALLY);
       }
-      for (int k = tid; k < XGC_NCOUNTER; k += FT) grow[k] = F.row[k];
+      // (a week the call leaves before its POST group hands zeros on for the state tallies: the call that finishes the week counts them)
+      const bool partial = incr && !(ph & XF_POST);
+      for (int k = tid; k < XGC_NCOUNTER; k += FT)
+        grow[k] = (partial && k < XGC_K_NGROUP * XGC_NCELL && ((STATE_GROUPS >> (k / XGC_NCELL)) & 1u)) ? 0u : F.row[k];
       __syncthreads();
       TICK(PH_ROW);
     }
@@ -1162,6 +1333,10 @@ cudaError_t xgc_fast_prepare(const Dev& g, cudaStream_t s) {
   return cudaGetLastError();
 }
 const void* xgc_fast_kernel_ptr() { return (const void*)k_week_fast; }
+bool xgc_fast_hostnet_fits(int n_cap, const int* e_cap) {
+  const size_t words = (size_t)(n_cap + 31) / 32, kw = (size_t)(e_cap[0] + 31) / 32 + (size_t)(e_cap[1] + 31) / 32;
+  return n_cap <= 32768 && (2 * words + 2 * kw) * sizeof(unsigned) <= sizeof(Fixed::mq);
+}
 // phase clocks of k_week_fast (SM cycles summed over CTAs) since the last reset; instrumentation for tools/time_modes.py
 extern "C" int xgc_debug_fast_profile(unsigned long long* out, int cap, int reset) {
   unsigned long long h[PH_N];

@@ -12,9 +12,19 @@ enum { XF_PRE = 1,        // week bookkeeping, arrival, aging, departure, hivtes
 
 struct FastArgs {
   int at0, at1;           // weeks at0..at1 inclusive are run back to back inside ONE launch (at1 > at0 needs XF_ALL)
-  unsigned phases;        // XF_* bits
+  unsigned phases;        // XF_* bits of week at0 (of the only week; XF_ALL for a multi-week run)
+  unsigned ph_last;       // XF_* bits of week at1 (= phases unless the call is a span: rest of week at0 + start of week at1)
   unsigned mask;          // module mask the phases were derived from (modules inside a group can still be switched off)
   int write_acts;         // 1: the last week's anal / oral counts are written to the edge records (xgc_get_actcounts)
+  // Host-network edge-list operations the host queued since the last call (xgc_update_edgelists_all / xgc_set_edgelists_all in
+  // fast mode), applied by the kernel itself at the start of week at0 -- before the network / acts phases -- instead of by the
+  // standalone k_rank / k_edges_update / k_edges_upload launches.  Per layer: 0 = nothing, 1 = weekly delta, 2 = whole list.
+  int hn_kind[3];
+  const int* hn_ptr[3];   // 1: delta rows [R][stride]; 2: positions [R][2][stride]
+  const int* hn_ne[3];    // 2: n_edges [R]
+  const int* hn_start[3]; // 2: start weeks [R][stride] or null
+  int hn_stride[3];
+  int hn_has_start[3];    // 1: rows carry start weeks
 };
 
 // bytes of dynamic shared memory one CTA needs for (n_cap, e_stride); 0 = does not fit one SM (fast path unavailable)
@@ -24,6 +34,8 @@ size_t xgc_fast_smem_bytes(int n_cap, size_t e_stride);
 cudaError_t xgc_fast_prepare(const Dev& g, cudaStream_t s);
 cudaError_t xgc_fast_launch(const Dev& g, const FastArgs& a, size_t smem, cudaStream_t s);
 const void* xgc_fast_kernel_ptr();
+// does the rank structure of the in-kernel edge-list operations fit the kernel's scratch area (the mini-queues) for this shape?
+bool xgc_fast_hostnet_fits(int n_cap, const int* e_cap);
 
 // ---- spare bits of the core words used by the fast path (ignored by the strict kernels, preserved by all of them)
 // demo bits 16..31: ins.quot as unorm16

@@ -62,6 +62,15 @@ struct xgc_handle {
   int form_tiles = 0;                  // tiles of 1024 formation candidates a layer can need (from the tables; 0: not known, use lb_tiles)
   bool plain_next = false;             // the next kernel launch follows an async copy / memset on the stream: no programmatic
                                        // serialization for it (its griddepcontrol.wait only covers preceding GRIDS)
+  // Fast mode, XGC_FUSE_HOSTNET=1: xgc_update_edgelists_all / xgc_set_edgelists_all copy their host buffers to the device and QUEUE the
+  // operation; the next launch of the resident kernel that runs an acts pass applies it itself (no k_rank / k_edges_update /
+  // k_edges_upload launches).  Anything else that reads the lists flushes the queue through the standalone kernels first
+  // (flush_pending_edges).  Off by default: the in-kernel phase is cold code on every CTA's critical path (~40k cycles per replicate-
+  // week, instruction-fetch bound) -- it shortens the weekly round trip of ONE handle by 5 % (125 replicates: 0.294 -> 0.279 ms) but
+  // costs 3-5 % when several handles keep the GPU busy (1000 replicates in 7 handles: 1.02 -> 1.05 ms); DESIGN.md section 6.
+  struct PendEdge { int kind = 0; const int* ptr = nullptr; const int* ne = nullptr; const int* start = nullptr; int stride = 0; int has_start = 0; };
+  PendEdge pend[3];
+  bool defer_edges = false;
   bool prune_pending = false;          // a fast-path aging..hivvl call left ties of departed agents in the lists (dropped lazily:
                                        // k_edges_update, the fast acts pass, or prune_now() before any other reader)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
@@ -169,6 +178,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
       h->err = "cudaEventCreate failed"; return fail(3);
     }
+  { const char* e = getenv("XGC_FUSE_HOSTNET"); if (e) h->defer_edges = e[0] == '1'; }
   { const char* e = getenv("XGC_LANES"); if (e && e[0] == '1') h->n_lanes = 1; else if (e && e[0] == '2') h->n_lanes = 2; }
   if (cfg->n_replicates < 2) h->n_lanes = 1;
   if (cfg->n_cap > 32768 && !getenv("XGC_LANES")) h->n_lanes = 1;      // large replicates fill the GPU kernel by kernel: a second lane only contends (100 x 100k: 2.00 vs 1.39 ms per week)
@@ -357,6 +367,9 @@ static void rebuild_maps(HostRep& c) {
   for (size_t i = 0; i < c.core.size(); ++i) if (c.core[i].y & DM_ACTIVE) { c.slot2pos[i] = (int)c.pos2slot.size(); c.pos2slot.push_back((int)i); }
 }
 static int prune_now(xgc_handle* h);
+static int flush_pending_edges(xgc_handle* h);
+static int launch_edge_op(xgc_handle* h, int layer, const xgc_handle::PendEdge& q);
+static bool can_defer_edges(const xgc_handle* h) { return h->mode == XGC_MODE_FAST && h->defer_edges && xgc_fast_hostnet_fits(h->g.n_cap, h->g.e_cap); }
 static int cache_flush(xgc_handle* h) {
   HostRep& c = h->cache;
   if (c.r < 0 || !c.dirty) { return 0; }
@@ -746,6 +759,7 @@ static int compact_impl(xgc_handle* h);
 // the ties of departed agents are physically out of the lists after this (tergmLite::delete_vertices); no-op unless a fast-path
 // call deferred it
 static int prune_now(xgc_handle* h) {
+  int rcf = flush_pending_edges(h); if (rcf) return rcf;
   if (!h->prune_pending) return 0;
   CU(h, cudaSetDevice(h->cfg.device));
   launch_resim(h, make_inj(h, nullptr, nullptr), 0, 0);
@@ -764,9 +778,15 @@ static unsigned fast_phases(uint32_t mask) {
   if (mask == (POSTG | XGC_M_RESIM_NETS)) return XF_PRUNE | XF_FORM | XF_POST;
   return 0;
 }
-static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32_t mask, int write_acts) {
+static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32_t mask, int write_acts, unsigned ph_last = 0u) {
   if (h->fast_dirty) { CU(h, xgc_fast_prepare(h->g, h->stream)); h->fast_dirty = false; h->launches++; }
-  FastArgs a; a.at0 = at0; a.at1 = at1; a.phases = phases; a.mask = mask; a.write_acts = write_acts;
+  FastArgs a; a.at0 = at0; a.at1 = at1; a.phases = phases; a.ph_last = ph_last ? ph_last : phases; a.mask = mask; a.write_acts = write_acts;
+  for (int l = 0; l < 3; ++l) {         // queued host-network operations ride along with a launch whose first week has an acts pass
+    xgc_handle::PendEdge& q = h->pend[l];
+    const bool take = q.kind && (phases & XF_POST) && !(phases & XF_PRE);      // (the host computed them after this week's aging..hivvl group)
+    a.hn_kind[l] = take ? q.kind : 0; a.hn_ptr[l] = q.ptr; a.hn_ne[l] = q.ne; a.hn_start[l] = q.start; a.hn_stride[l] = q.stride; a.hn_has_start[l] = q.has_start;
+    if (take) q.kind = 0;
+  }
   prof_begin(h, "k_week_fast");
   cudaError_t e = xgc_fast_launch(h->g, a, h->fast_smem, h->stream);
   prof_end(h); h->launches++;
@@ -789,12 +809,14 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   // step-by-step boundary -- module(dat, at) calls, the host-network loop, the R shim -- never runs out of slots on a
   // reference-length burn-in.  Results do not depend on it: draws are keyed by uid, positions are preserved.
   if (zero_row && at >= 2 && (at - 1) % h->cfg.compact_every == 0 && h->compacted_at != at - 1) {
+    rc = flush_pending_edges(h); if (rc) return rc;
     rc = compact_impl(h); if (rc) return rc;
     h->compacted_at = at - 1;
   }
   if (fph) {
     if (!(fph & XF_PRE) && zero_row) FAIL(h, 11, "fast mode: week %d must start with the aging..hivvl module group", at);
     h->acts_valid = false;                                        // kissing / rimming counts are not materialised in fast mode
+    if (!(fph & XF_POST) || (fph & XF_PRE)) { rc = flush_pending_edges(h); if (rc) return rc; }
     rc = fast_enqueue(h, at, at, fph, mask, 1);
     // a call without the acts pass and without an on-device network step leaves the departed agents' ties to the next toucher
     if (fph & XF_POST) h->prune_pending = false; else if (!(fph & XF_FORM)) h->prune_pending = true;
@@ -805,6 +827,26 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
   CU(h, cudaGetLastError());
   if (inj && inj->u) CU(h, cudaStreamSynchronize(h->stream));     // caller may free the table after return
   return 0;
+}
+
+// The rest of week `at` (mask_tail: the acts..prevalence group, with or without resim_nets) and the start of week at + 1
+// (mask_head: the aging..hivvl group) in ONE call.  Nothing on the host sits between prevalence_msm(at) and aging_msm(at + 1)
+// in the reference's netsim loop, and every module is a function of (state, at, seed): the result is that of the two xgc_step
+// calls.  On the fast path the two groups run in one launch of the resident kernel -- the replicate is staged once, written
+// back once, and the host-network loop pays one launch and one device -> host wait per week instead of two.
+extern "C" int xgc_step_span(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head) {
+  const unsigned pt = h->mode == XGC_MODE_FAST ? fast_phases(mask_tail) : 0u, phd = h->mode == XGC_MODE_FAST ? fast_phases(mask_head) : 0u;
+  const bool compaction_due = at >= 1 && at % h->cfg.compact_every == 0 && h->compacted_at != at;      // xgc_step(at + 1) would compact first
+  if (!(pt & XF_POST) || (pt & XF_PRE) || phd != (unsigned)(XF_PRE | XF_PRUNE) || h->last_at != at || compaction_due || at + 1 >= h->cfg.t_cap || at + 1 > 32766) {
+    int rc = xgc_step(h, at, mask_tail, nullptr);
+    return rc ? rc : xgc_step(h, at + 1, mask_head, nullptr);
+  }
+  int rc = cache_drop(h); if (rc) return rc;
+  CU(h, cudaSetDevice(h->cfg.device));
+  h->last_inj = make_inj(h, nullptr, nullptr); h->rank_fresh = false; h->acts_valid = false; h->last_at = at + 1;
+  rc = fast_enqueue(h, at, at + 1, pt, mask_tail | mask_head, 1, XF_PRE | XF_PRUNE);
+  h->prune_pending = true;              // the ties of the agents who departed in week at + 1 are left to the next toucher
+  return rc;
 }
 
 // slot compaction of the replicates of the current lane (h->gl) or of the whole handle
@@ -837,6 +879,7 @@ static int compact_impl(xgc_handle* h) {
 extern "C" int xgc_compact(xgc_handle* h) {
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
+  rc = flush_pending_edges(h); if (rc) return rc;
   rc = compact_impl(h);
   if (!rc) { h->compacted_at = h->last_at; h->prune_pending = false; }
   return rc;
@@ -947,7 +990,9 @@ extern "C" int xgc_num_agents_all(xgc_handle* h, int32_t* out /*[R]*/) {
   return 0;
 }
 extern "C" int xgc_status(xgc_handle* h, int r, uint32_t* status) {
-  CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CHECK_R(h, r); CU(h, cudaSetDevice(h->cfg.device));
+  { int rcf = flush_pending_edges(h); if (rcf) return rcf; }      // queued edge-list operations report bad / overflowing lists here too
+  CU(h, cudaStreamSynchronize(h->stream));
   Rep rp; CU(h, d2h(h, &rp, h->g.rep + r, sizeof(Rep)));
   unsigned ps[4]; CU(h, d2h(h, ps, h->d_pstat + (size_t)r * 4, sizeof ps));
   *status = rp.status | ps[0] | ps[1] | ps[2] | ps[3]; return 0;
@@ -1247,6 +1292,9 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g; size_t st = (size_t)stride, R = g.R;
   size_t need = R * st * 3 + R;
+  if (h->pend[layer].kind || h->pend[0].kind == 2 || h->pend[1].kind == 2 || h->pend[2].kind == 2) {      // one staging buffer for whole lists
+    rc = flush_pending_edges(h); if (rc) return rc;
+  }
   if (need > h->el_stage_cap) {
     if (h->d_el_stage) cudaFree(h->d_el_stage);
     h->d_el_stage = nullptr; h->el_stage_cap = 0;
@@ -1258,15 +1306,10 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   if (start) CU(h, cudaMemcpyAsync(d_start, start, R * st * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(d_ne, n_edges, R * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   h->plain_next = true;
-  if (!h->rank_fresh) {
-    if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
-    else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
-    h->rank_fresh = true;
-  }
-  LAUNCH(h, k_edges_upload, dim3((unsigned)((st + TPB - 1) / TPB), g.R), TPB, g, layer, d_el, d_ne, start ? d_start : nullptr, stride);
   h->acts_valid = false;
-  CU(h, cudaGetLastError());
-  return 0;
+  xgc_handle::PendEdge q; q.kind = 2; q.ptr = d_el; q.ne = d_ne; q.start = start ? d_start : nullptr; q.stride = stride;
+  if (can_defer_edges(h)) { h->pend[layer] = q; return 0; }
+  return launch_edge_op(h, layer, q);
 }
 
 // weekly delta of a persistent layer: one CTA per replicate marks the removed ties in a shared-memory bitmap, compacts the layer
@@ -1349,6 +1392,7 @@ extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t*
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   const Dev& g = h->g; size_t need = (size_t)g.R * (size_t)stride;
+  if (h->pend[layer].kind) { rc = flush_pending_edges(h); if (rc) return rc; }      // (its staging buffer is about to be overwritten)
   if (need > h->upd_stage_cap[layer]) {
     if (h->d_upd_stage[layer]) cudaFree(h->d_upd_stage[layer]);
     h->d_upd_stage[layer] = nullptr; h->upd_stage_cap[layer] = 0;
@@ -1357,16 +1401,35 @@ extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t*
   }
   CU(h, cudaMemcpyAsync(h->d_upd_stage[layer], delta, need * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   h->plain_next = true;
+  h->acts_valid = false;
+  xgc_handle::PendEdge q; q.kind = 1; q.ptr = h->d_upd_stage[layer]; q.stride = stride; q.has_start = has_start;
+  if (can_defer_edges(h)) { h->pend[layer] = q; return 0; }
+  return launch_edge_op(h, layer, q);
+}
+// the standalone kernels of one edge-list operation (strict mode; fast mode when something other than the resident kernel's acts
+// pass is about to read the lists)
+static int launch_edge_op(xgc_handle* h, int layer, const xgc_handle::PendEdge& q) {
+  const Dev& g = h->g;
   if (!h->rank_fresh) {
     if (g.n_cap <= 32768) { prof_begin(h, "k_rank"); kl(h, k_rank_cta, dim3(g.R), TPB, (size_t)(g.n_cap / 32) * 8 + 8, g); prof_end(h); h->launches++; }
     else LAUNCH(h, k_rank, dim3((g.n_cap + RANK_TILE - 1) / RANK_TILE, g.R), TPB, g);
     h->rank_fresh = true;
   }
-  prof_begin(h, "k_edges_update");
-  kl(h, k_edges_update, dim3(g.R), TPB, (size_t)((g.e_cap[layer] + 31) / 32 + 1) * 4, g, layer, (const int*)h->d_upd_stage[layer], stride, has_start);
-  prof_end(h); h->launches++;
-  h->acts_valid = false;
+  if (q.kind == 1) {
+    prof_begin(h, "k_edges_update");
+    kl(h, k_edges_update, dim3(g.R), TPB, (size_t)((g.e_cap[layer] + 31) / 32 + 1) * 4, g, layer, q.ptr, q.stride, q.has_start);
+    prof_end(h); h->launches++;
+  } else LAUNCH(h, k_edges_upload, dim3((unsigned)((q.stride + TPB - 1) / TPB), g.R), TPB, g, layer, q.ptr, q.ne, q.start, q.stride);
   CU(h, cudaGetLastError());
+  return 0;
+}
+static int flush_pending_edges(xgc_handle* h) {
+  for (int l = 0; l < 3; ++l) {
+    if (!h->pend[l].kind) continue;
+    xgc_handle::PendEdge q = h->pend[l]; h->pend[l].kind = 0;
+    CU(h, cudaSetDevice(h->cfg.device));
+    int rc = launch_edge_op(h, l, q); if (rc) return rc;
+  }
   return 0;
 }
 
