@@ -17,6 +17,29 @@ prep_msm_gpu         <- .xgc_module(XGC_M[["prep"]]);        hivtrans_msm_gpu   
 stirecov_msm_gpu     <- .xgc_module(XGC_M[["stirecov"]]);    stitx_msm_gpu       <- .xgc_module(XGC_M[["stitx"]])
 stitrans_msm_rand_gpu <- .xgc_module(XGC_M[["stitrans"]]);   prevalence_msm_gpu  <- .xgc_module(XGC_M[["prev"]])
 
+# Fast mode (.Call("xgcR_set_mode", dat$xgc, 1L)): the replicate-resident kernel runs module GROUPS, not single modules.  The wrappers
+# below keep the FUN(dat, at) contract: the last module of the aging..hivvl group issues the group, the last module of the week
+# (prev.FUN) issues the acts..prevalence group TOGETHER with the aging..hivvl group of the next week (xgc_step_span: netsim has
+# nothing on the host between prevalence_msm(at) and aging_msm(at + 1)); every other wrapper returns dat unchanged.
+#   control <- do.call(control_msm, c(list(..., initialize.FUN = initialize_msm_gpu, resim_nets.FUN = simnet_msm_gpu), xgc_fast_modules()))
+xgc_fast_modules <- function() {
+  PRE  <- sum(XGC_M[c("aging", "departure", "arrival", "hivtest", "hivtx", "hivprogress", "hivvl")])
+  POST <- sum(XGC_M[c("acts", "condoms", "position", "prep", "hivtrans", "stirecov", "stitx", "stitrans", "prev")])
+  noop <- function(dat, at) dat
+  pre_last <- function(dat, at) {                                  # (already run by last week's prev.FUN unless this is the first week)
+    if (!identical(dat$xgc_pre_done, as.integer(at))) .Call("xgcR_step", dat$xgc, as.integer(at), as.numeric(PRE), NULL)
+    dat
+  }
+  post_last <- function(dat, at) {
+    if (at >= dat$control$nsteps) .Call("xgcR_step", dat$xgc, as.integer(at), as.numeric(POST), NULL)
+    else { .Call("xgcR_step_span", dat$xgc, as.integer(at), as.numeric(POST), as.numeric(PRE)); dat$xgc_pre_done <- as.integer(at) + 1L }
+    dat
+  }
+  list(aging.FUN = noop, departure.FUN = noop, arrival.FUN = noop, hivtest.FUN = noop, hivtx.FUN = noop, hivprogress.FUN = noop,
+       hivvl.FUN = pre_last, acts.FUN = noop, condoms.FUN = noop, position.FUN = noop, prep.FUN = noop, hivtrans.FUN = noop,
+       stirecov.FUN = noop, stitx.FUN = noop, stitrans.FUN = noop, prev.FUN = post_last)
+}
+
 # resim_nets.FUN: pull what tergmLite needs, run the reference's own simnet_msm on the host, push the edge lists back.
 simnet_msm_gpu <- function(dat, at) {
   # deg.main / deg.casl are derived on the device from the current edge lists (what tergmLite's formation terms condition on)

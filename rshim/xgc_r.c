@@ -71,6 +71,10 @@ SEXP xgcR_step(SEXP p, SEXP at, SEXP mask, SEXP u) {                  /* dat <- 
   CK(H(p), xgc_step(H(p), Rf_asInteger(at), (uint32_t)Rf_asReal(mask), &inj));
   return R_NilValue;
 }
+SEXP xgcR_step_span(SEXP p, SEXP at, SEXP mask_tail, SEXP mask_head) {  /* rest of week at + start of week at + 1: one resident launch in fast mode */
+  CK(H(p), xgc_step_span(H(p), Rf_asInteger(at), (uint32_t)Rf_asReal(mask_tail), (uint32_t)Rf_asReal(mask_head)));
+  return R_NilValue;
+}
 SEXP xgcR_run(SEXP p, SEXP at0, SEXP at1) { CK(H(p), xgc_run(H(p), Rf_asInteger(at0), Rf_asInteger(at1))); return R_NilValue; }
 SEXP xgcR_epi(SEXP p, SEXP r, SEXP var, SEXP at0, SEXP at1) {         /* dat$epi[[var]][at0:at1] */
   int a = Rf_asInteger(at0), b = Rf_asInteger(at1);
