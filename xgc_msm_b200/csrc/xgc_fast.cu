@@ -297,7 +297,10 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     // multi-week launches keep prevalence_msm's state tallies incrementally (counted here once, then moved by every change of an
     // agent's tallied state); a single-week call counts them once at the end of its POST group instead
     const bool incr = A.at1 > A.at0;
-    if (incr) {
+    if (incr && A.carry_in && w_first == A.at0) {                // a span continuing the previous span's week: its running tallies
+      for (int k = tid; k < XGC_K_NGROUP * XGC_NCELL; k += FT) F.row[k] = ((STATE_GROUPS >> (k / XGC_NCELL)) & 1u) ? A.carry[(size_t)r * XGC_NCOUNTER + k] : 0u;
+      __syncthreads();
+    } else if (incr) {
       for (int k = tid; k < XGC_K_NGROUP * XGC_NCELL; k += FT) F.row[k] = 0u;
       __syncthreads();
       const int n0 = F.sc[SC_NSLOTS];
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (!(d & DM_ACTIVE)) return;
             int ai = min(XGC_ASMR_AGES - 1, max(0, (int)((float)(at8 - birth8(vh[i])) * (float)XF_W8)));
             float pm = F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai];
-            if (pm < HI_MORT && u01(x.y) * pmax_mort < pm) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+            if (pm < HI_MORT && u01(x.y) * pmax_mort < pm) { vd[i] = d & ~DM_ACTIVE; core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
               if (incr) tally_move(F.row, d, vg[i], vh[i], 0u, 0u, 0u);
               atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); }
           });
@@ -455,13 +458,13 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (live) {
               float age = (float)(at8 - birth8(h)) * (float)XF_W8;
               bool isnew = i >= n_pre;
-              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { const unsigned dold = d; d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; if (wt) core_w[4 * (rbase + i) + 1] = d;
+              if ((mask & XGC_M_AGING) && !isnew) { unsigned ng = agegrp_f(age); if (ng != DM_AGEGRP(d)) { const unsigned dold = d; d = (d & ~(7u << 2)) | (ng << 2); vd[i] = d; core_w[4 * (rbase + i) + 1] = d;
                 if (incr) tally_move(F.row, dold, vg[i], h, d, vg[i], h); } }
               if ((mask & XGC_M_DEPARTURE) && !isnew) {
                 int ai = min(XGC_ASMR_AGES - 1, max(0, (int)age));
                 if ((F.hib[DM_RACE(d) * 4 + (ai >> 5)] >> (ai & 31)) & 1u) {
                   uint4 x = frand(key, at, FS_MORTHI, (unsigned)i, 0);
-                  if (bern(x.x, F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai])) { vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
+                  if (bern(x.x, F.asmr[DM_RACE(d) * XGC_ASMR_AGES + ai])) { vd[i] = d & ~DM_ACTIVE; core_w[4 * (rbase + i) + 1] = d & ~DM_ACTIVE;
                     if (incr) tally_move(F.row, d, vg[i], h, 0u, 0u, 0u);
                     atomicAdd(&F.row[XGC_K_DEP_GEN], 1u); atomicSub(&F.sc[SC_NALIVE], 1); live = false; }
                 }
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
             if (d & DM_ACTIVE) {                                // (not) died of natural causes this week
               uint4 x = frand(key, at, FS_AG1, (unsigned)i, 0);
               if ((mask & XGC_M_DEPARTURE) && HV_STAGE(h) == 4 && bern(x.x, P[XGC_P_aids_mr])) {
-                vd[i] = d & ~DM_ACTIVE; if (wt) core_w[4 * idx + 1] = d & ~DM_ACTIVE;
+                vd[i] = d & ~DM_ACTIVE; core_w[4 * idx + 1] = d & ~DM_ACTIVE;
                 if (incr) tally_move(F.row, d, vg[i], h, 0u, 0u, 0u);
                 atomicAdd(&F.row[XGC_K_DEP_AIDS], 1u); atomicSub(&F.sc[SC_NALIVE], 1);
               } else {
@@ -1285,6 +1288,9 @@ _Pragma("unroll")
       __syncthreads();
       TICK(PH_ROW);
     }
+    // a span leaves week at1 half done: its running state tallies go to the carry buffer for the call that continues the week
+    if (incr && A.carry && !(A.ph_last & XF_POST) && w_last == A.at1)
+      for (int k = tid; k < XGC_K_NGROUP * XGC_NCELL; k += FT) if ((STATE_GROUPS >> (k / XGC_NCELL)) & 1u) A.carry[(size_t)r * XGC_NCOUNTER + k] = F.row[k];
     // ------------------------------------------------------------------------------------------ write the replicate back
     if (F.sc[SC_DEAD0] | F.sc[SC_DEAD1] | F.sc[SC_DEAD2]) squeeze();     // HBM always holds compact tie lists
     TICK(PH_SQUEEZE_WB);
@@ -1295,10 +1301,8 @@ _Pragma("unroll")
         int i = i0 + tid;
         bool in = i < n_slots;
         unsigned d = in ? vd[i] : 0u;
-        if (in && !wt) {                                        // (the uid word never changes: 4 + 8 byte stores, no read-modify-write)
-          core_w[4 * (rbase + i) + 1] = d;
-          *reinterpret_cast<uint2*>(core_w + 4 * (rbase + i) + 2) = make_uint2(vg[i], vh[i]);
-        }
+        // (the demo word changes rarely -- age group, departure -- and is written through where it changes; the uid word never changes)
+        if (in && !wt) *reinterpret_cast<uint2*>(core_w + 4 * (rbase + i) + 2) = make_uint2(vg[i], vh[i]);
         unsigned m = __ballot_sync(FULL, in && (d & DM_ACTIVE));
         if (lane == 0 && i < g.n_cap) Abm[i >> 5] = m;
       }

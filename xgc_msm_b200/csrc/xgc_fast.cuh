@@ -16,6 +16,10 @@ struct FastArgs {
   unsigned ph_last;       // XF_* bits of week at1 (= phases unless the call is a span: rest of week at0 + start of week at1)
   unsigned mask;          // module mask the phases were derived from (modules inside a group can still be switched off)
   int write_acts;         // 1: the last week's anal / oral counts are written to the edge records (xgc_get_actcounts)
+  // state tallies carried from one span call to the next (week at0's running prevalence tallies as the previous span left them after
+  // its aging..hivvl group): carry_in = 1 -> loaded instead of recounted at staging; a span always leaves them in `carry` [R][NCOUNTER]
+  unsigned* carry;
+  int carry_in;
   // Host-network edge-list operations the host queued since the last call (xgc_update_edgelists_all / xgc_set_edgelists_all in
   // fast mode), applied by the kernel itself at the start of week at0 -- before the network / acts phases -- instead of by the
   // standalone k_rank / k_edges_update / k_edges_upload launches.  Per layer: 0 = nothing, 1 = weekly delta, 2 = whole list.

@@ -71,6 +71,8 @@ struct xgc_handle {
   struct PendEdge { int kind = 0; const int* ptr = nullptr; const int* ne = nullptr; const int* start = nullptr; int stride = 0; int has_start = 0; };
   PendEdge pend[3];
   bool defer_edges = false;
+  unsigned* d_carry = nullptr;         // [R][NCOUNTER] running state tallies a span call leaves for the next one (xgc_fast.cuh)
+  int carry_week = -1;                 // week whose running tallies d_carry holds (-1: none / agent state changed since)
   bool prune_pending = false;          // a fast-path aging..hivvl call left ties of departed agents in the lists (dropped lazily:
                                        // k_edges_update, the fast acts pass, or prune_now() before any other reader)
   bool acts_valid = false;             // act counts of the current week exist (lazy kissing / rimming counts may be materialised)
@@ -220,7 +222,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   rc |= dalloc(h, &g.qh_items, NA); rc |= dalloc(h, &g.qh_count, (size_t)g.R);
   g.lb_tiles = (std::max(g.e_cap[0], std::max(g.e_cap[1], g.e_cap[2])) + 1023) / 1024;
   rc |= dalloc(h, &g.lb_status, (size_t)g.R * 3 * g.lb_tiles); rc |= dalloc(h, &g.lb_ticket, (size_t)g.R * 3);
-  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1)); rc |= dalloc(h, &h->d_inv_ntx, (size_t)g.R * 4); rc |= dalloc(h, &h->d_pstat, (size_t)g.R * 4);
+  rc |= dalloc(h, &h->d_pois, (size_t)g.R * 4 * (XGC_MAX_ACTS + 1)); rc |= dalloc(h, &h->d_inv_ntx, (size_t)g.R * 4); rc |= dalloc(h, &h->d_pstat, (size_t)g.R * 4); rc |= dalloc(h, &h->d_carry, (size_t)g.R * XGC_NCOUNTER);
   rc |= dalloc(h, &h->d_remap, NA); rc |= dalloc(h, &h->d_targets, (size_t)g.R * XGC_NTARGET); rc |= dalloc(h, &h->d_scratch, 16);
   if (rc) return fail(rc);
   g.params = dp; g.control = dc; g.tables = dt; g.at_ptr = dat; g.pois = h->d_pois; g.inv_ntx = h->d_inv_ntx;
@@ -504,7 +506,7 @@ extern "C" int xgc_set_population(xgc_handle* h, int r, int n, int at) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemsetAsync(g.core + (size_t)r * g.n_cap, 0, sizeof(uint4) * (size_t)g.n_cap, h->stream));      // in the handle's stream, like every copy
   CU(h, h2d(h, (int*)g.at_ptr + r, &at, sizeof(int)));
-  h->last_at = -1; h->acts_valid = false; h->fast_dirty = true;
+  h->last_at = -1; h->acts_valid = false; h->fast_dirty = true; h->carry_week = -1;
   return cache_flush(h);
 }
 extern "C" int xgc_num_agents(xgc_handle* h, int r, int* n) {
@@ -526,7 +528,7 @@ extern "C" int xgc_upload_attr(xgc_handle* h, int r, const char* name, const voi
     a->set(c, c.pos2slot[p], v);
   }
   if (!strcmp(name, "age")) c.rep.t_ref = c.rep.t_age;      // re-base the closed-form age clock
-  h->fast_dirty = true;
+  h->fast_dirty = true; h->carry_week = -1;
   if (!strcmp(name, "uid")) { unsigned mx = 0; for (size_t p = 0; p < n; ++p) mx = std::max(mx, c.core[c.pos2slot[p]].x + 1u); c.rep.next_uid = (int)mx; }
   c.dirty = true;
   return 0;
@@ -778,9 +780,10 @@ static unsigned fast_phases(uint32_t mask) {
   if (mask == (POSTG | XGC_M_RESIM_NETS)) return XF_PRUNE | XF_FORM | XF_POST;
   return 0;
 }
-static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32_t mask, int write_acts, unsigned ph_last = 0u) {
+static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32_t mask, int write_acts, unsigned ph_last = 0u, int carry = -1) {
   if (h->fast_dirty) { CU(h, xgc_fast_prepare(h->g, h->stream)); h->fast_dirty = false; h->launches++; }
   FastArgs a; a.at0 = at0; a.at1 = at1; a.phases = phases; a.ph_last = ph_last ? ph_last : phases; a.mask = mask; a.write_acts = write_acts;
+  a.carry = carry >= 0 ? h->d_carry : nullptr; a.carry_in = carry > 0;      // (span calls only)
   for (int l = 0; l < 3; ++l) {         // queued host-network operations ride along with a launch whose first week has an acts pass
     xgc_handle::PendEdge& q = h->pend[l];
     const bool take = q.kind && (phases & XF_POST) && !(phases & XF_PRE);      // (the host computed them after this week's aging..hivvl group)
@@ -796,6 +799,7 @@ static int fast_enqueue(xgc_handle* h, int at0, int at1, unsigned phases, uint32
 extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* inj) {
   if (at < 1 || at >= h->cfg.t_cap) FAIL(h, 2, "at = %d outside [1, t_cap = %d)", at, h->cfg.t_cap);
   if (at > 32766) FAIL(h, 2, "at = %d exceeds the 16-bit week clocks", at);
+  h->carry_week = -1;
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   Inj j; rc = upload_inject(h, inj, &j); if (rc) return rc;
@@ -844,7 +848,9 @@ extern "C" int xgc_step_span(xgc_handle* h, int at, uint32_t mask_tail, uint32_t
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   h->last_inj = make_inj(h, nullptr, nullptr); h->rank_fresh = false; h->acts_valid = false; h->last_at = at + 1;
-  rc = fast_enqueue(h, at, at + 1, pt, mask_tail | mask_head, 1, XF_PRE | XF_PRUNE);
+  // the previous span left week `at` half done with its running state tallies in d_carry: no recount when nothing touched the agents since
+  rc = fast_enqueue(h, at, at + 1, pt, mask_tail | mask_head, 1, XF_PRE | XF_PRUNE, h->carry_week == at ? 1 : 0);
+  h->carry_week = rc ? -1 : at + 1;
   h->prune_pending = true;              // the ties of the agents who departed in week at + 1 are left to the next toucher
   return rc;
 }
@@ -888,6 +894,7 @@ extern "C" int xgc_compact(xgc_handle* h) {
 extern "C" int xgc_run(xgc_handle* h, int at0, int at1) {
   if (at0 < 1 || at1 >= h->cfg.t_cap || at1 < at0 - 1) FAIL(h, 2, "bad week range [%d,%d], t_cap = %d", at0, at1, h->cfg.t_cap);
   if (at1 > 32766) FAIL(h, 2, "at exceeds the 16-bit week clocks");
+  h->carry_week = -1;
   int rc = cache_drop(h); if (rc) return rc;
   CU(h, cudaSetDevice(h->cfg.device));
   rc = prune_now(h); if (rc) return rc;
@@ -1236,7 +1243,7 @@ extern "C" int xgc_restore(xgc_handle* h, const void* buf, size_t bytes) {
   CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
   const char* p = (const char*)buf + sizeof(xgc_config);
   for (auto& sg : segments(h)) { CU(h, h2d(h, sg.p, p, sg.bytes)); p += sg.bytes; }
-  h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false; h->fast_dirty = true;
+  h->last_at = -1; h->compacted_at = -1; h->acts_valid = false; h->rank_fresh = false; h->fast_dirty = true; h->carry_week = -1;
   { double t[XGC_NTABLE]; CU(h, d2h(h, t, h->g.tables, sizeof t));
     for (int l = 0; l < 2; ++l) h->g.inv_dur[l] = 1.0 / t[XGC_T_NET_DUR + l];
     set_form_tiles(h, t);
@@ -1265,7 +1272,7 @@ extern "C" int xgc_fork(xgc_handle* src, int sr, xgc_handle* dst, int dr) {
   if (e != cudaSuccess) FAIL(dst, 100 + (int)e, "fork copy failed: %s", cudaGetErrorString(e));
   // (the copies run on the destination handle's stream; the source handle's stream was drained above)
   CU(dst, cudaStreamSynchronize(dst->stream));
-  dst->last_at = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
+  dst->last_at = -1; dst->carry_week = -1; dst->rank_fresh = false; dst->acts_valid = false; memset(&dst->last_inj, 0, sizeof(Inj));
   if (src->fast_dirty) dst->fast_dirty = true;
   return 0;
 }
