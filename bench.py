@@ -42,6 +42,7 @@ def parse():
                     help="native-draw contract of the CUDA arm: fast = replicate-resident kernel (statistical equivalence), strict = bit-exact kernels")
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-separate-calls", action="store_true", help="fast mode: the week as separate ABI calls instead of one xgc_week_hostnet call")
     ap.add_argument("--e2e-no-span", action="store_true", help="fast mode: two xgc_step calls per week instead of xgc_step_span")
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
@@ -438,9 +439,27 @@ def run_xgc(args, rank, world, local_rank):
     span = mode == "fast" and not args.e2e_no_span
     pre_done = [-1] * Ge
 
+    # raw host pointers of every group's slice of the weekly buffers (pinned), taken once: the timed loop only passes integers
+    esz = 4
+    dptr = [[[d.data_ptr() + g_off[gi] * d.shape[1] * esz for d in deltas[l]] for l in range(2)] for gi in range(Ge)]
+    optr = [[(o[0].data_ptr() + g_off[gi] * 2 * o[0].shape[2] * esz, o[1].data_ptr() + g_off[gi] * esz, o[0].shape[2]) for o in oneoff] for gi in range(Ge)]
+    cptr = [c_host.data_ptr() + g_off[gi] * K.NCOUNTER * esz for gi in range(Ge)]
+    nptr = [n_host.data_ptr() + g_off[gi] * esz for gi in range(Ge)]
+
     def e2e_week(gi, t):
         """One week of the contract for group gi (what one host-side simnet_msm loop does); returns living agents."""
         hg, r0, Rg = groups[gi], g_off[gi], g_size[gi]
+        if span and not args.e2e_separate_calls:
+            # ONE ABI call a week (xgc_week_hostnet): toggles + one-off list in, rest of week t + start of week t + 1, tallies of week t
+            # and the living counts for the next network step out
+            if pre_done[gi] != t:
+                hg.step(t, pre); hg.num_agents_all(n_np[r0:r0 + Rg])
+            d0, d1 = deltas[0][t % len(deltas[0])], deltas[1][t % len(deltas[1])]
+            oe, on, ost = optr[gi][t % len(oneoff)]
+            hg.week_hostnet(t, post, pre, dptr[gi][0][t % len(deltas[0])], d0.shape[1], dptr[gi][1][t % len(deltas[1])], d1.shape[1], False,
+                            oe, on, ost, cptr[gi], nptr[gi])
+            pre_done[gi] = t + 1
+            return float(c_np[r0:r0 + Rg, K.K_NUM * G:(K.K_NUM + 1) * G].sum())
         if pre_done[gi] != t:
             hg.step(t, pre)
         hg.num_agents_all(n_np[r0:r0 + Rg])                  # what host-side simnet_msm needs before it can return edges
@@ -493,7 +512,10 @@ def run_xgc(args, rank, world, local_rank):
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
            "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
-           "path": f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: " + ("" if span else "xgc_step(pre) -> ") + "xgc_num_agents_all -> 2x xgc_update_edgelists_all "
+           "path": (f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week ONE call: xgc_week_hostnet = 2x xgc_update_edgelists_all (main / casual toggles) + "
+                    "xgc_set_edgelists_all (one-off layer), pinned -> xgc_step_span(post of this week, pre of the next: one resident launch) -> xgc_get_counters_all + xgc_num_agents_all")
+                   if span and not args.e2e_separate_calls else
+                   f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: " + ("" if span else "xgc_step(pre) -> ") + "xgc_num_agents_all -> 2x xgc_update_edgelists_all "
                    "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> " +
                    ("xgc_step_span(post of this week, pre of the next: one resident launch)" if span else "xgc_step(post)") + " -> xgc_get_counters_all"}
     e2e_status = 0

@@ -366,6 +366,14 @@ int  xgc_step(xgc_handle* h, int at, uint32_t module_mask, const xgc_inject* inj
  * xgc_step(at, mask_tail) + xgc_step(at + 1, mask_head); in XGC_MODE_FAST, with mask_tail = the acts..prevalence group (with or
  * without resim_nets) and mask_head = the aging..hivvl group, the two run in ONE launch of the resident kernel. */
 int  xgc_step_span(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head);
+/* One week of the host-network loop in one call: xgc_update_edgelists_all (main, casual: weekly toggles) + xgc_set_edgelists_all
+ * (one-off list; any of the three may be NULL = unchanged) -> xgc_step_span(at, mask_tail, mask_head) (mask_head = 0: xgc_step(at,
+ * mask_tail)) -> xgc_get_counters_all(at) and xgc_num_agents_all into the caller's buffers (NULL = not wanted), one wait.  What a
+ * resim_nets.FUN wrapper calls after the reference's simnet_msm (sim1_02_lhs.r:209) has produced the week's network changes. */
+int  xgc_week_hostnet(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head,
+                      const int32_t* delta_main, int stride_main, const int32_t* delta_casl, int stride_casl, int has_start,
+                      const int32_t* el_inst, const int32_t* ne_inst, int stride_inst,
+                      uint32_t* counters_out, int32_t* n_alive_out);
 /* batched loop at0..at1 inclusive, all modules, native draws, no host synchronisation inside (CUDA-graph replay). */
 int  xgc_run (xgc_handle* h, int at0, int at1);
 int  xgc_sync(xgc_handle* h);

@@ -75,6 +75,22 @@ SEXP xgcR_step_span(SEXP p, SEXP at, SEXP mask_tail, SEXP mask_head) {  /* rest 
   CK(H(p), xgc_step_span(H(p), Rf_asInteger(at), (uint32_t)Rf_asReal(mask_tail), (uint32_t)Rf_asReal(mask_head)));
   return R_NilValue;
 }
+/* One host-network week in one .Call: list(delta_main, delta_casl, el_inst) as integer vectors / matrix or NULL (one replicate per R
+ * process, the reference's layout); returns list(counters of week at, living agents after the aging..hivvl group of week at + 1). */
+SEXP xgcR_week_hostnet(SEXP p, SEXP at, SEXP mask_tail, SEXP mask_head, SEXP delta_main, SEXP delta_casl, SEXP has_start, SEXP el_inst) {
+  int ne = Rf_isNull(el_inst) ? 0 : Rf_nrows(el_inst), n_alive = 0;
+  SEXP cnt = PROTECT(Rf_allocVector(INTSXP, XGC_NCOUNTER));
+  int rc = xgc_week_hostnet(H(p), Rf_asInteger(at), (uint32_t)Rf_asReal(mask_tail), (uint32_t)Rf_asReal(mask_head),
+                            Rf_isNull(delta_main) ? NULL : INTEGER(delta_main), Rf_isNull(delta_main) ? 0 : LENGTH(delta_main),
+                            Rf_isNull(delta_casl) ? NULL : INTEGER(delta_casl), Rf_isNull(delta_casl) ? 0 : LENGTH(delta_casl), Rf_asInteger(has_start),
+                            Rf_isNull(el_inst) ? NULL : INTEGER(el_inst), Rf_isNull(el_inst) ? NULL : &ne, ne > 0 ? ne : 1,
+                            (uint32_t*)INTEGER(cnt), &n_alive);
+  if (rc) { UNPROTECT(1); Rf_error("xgc error %d: %s", rc, xgc_last_error(H(p))); }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, cnt); SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(n_alive));
+  UNPROTECT(2);
+  return out;
+}
 SEXP xgcR_run(SEXP p, SEXP at0, SEXP at1) { CK(H(p), xgc_run(H(p), Rf_asInteger(at0), Rf_asInteger(at1))); return R_NilValue; }
 SEXP xgcR_epi(SEXP p, SEXP r, SEXP var, SEXP at0, SEXP at1) {         /* dat$epi[[var]][at0:at1] */
   int a = Rf_asInteger(at0), b = Rf_asInteger(at1);

@@ -139,8 +139,8 @@ def test_fast_mode_hostnet_in_kernel_edge_ops():
     pre = K.M_AGING | K.M_DEPARTURE | K.M_ARRIVAL | K.M_HIVTEST | K.M_HIVTX | K.M_HIVPROGRESS | K.M_HIVVL
     post = K.M_ALL & ~pre & ~K.M_RESIM_NETS
     hs = {}
-    for name in ("fused+span", "standalone", "fused"):
-        os.environ["XGC_FUSE_HOSTNET"] = "0" if name == "standalone" else "1"
+    for name in ("fused+span", "standalone", "fused", "weekcall"):
+        os.environ["XGC_FUSE_HOSTNET"] = "0" if name in ("standalone", "weekcall") else "1"
         try:
             h = load_handle(cases, SEED, t_cap=T + 4, compact_every=8)
         finally:
@@ -155,10 +155,10 @@ def test_fast_mode_hostnet_in_kernel_edge_ops():
     kept = ne0.copy()                                            # lower bound of the lists' lengths as the host knows them
     for at in range(T0 + 1, T + 1):
         for name, h in hs.items():
-            if name != "fused+span" or at == T0 + 1:
+            if name not in ("fused+span", "weekcall") or at == T0 + 1:
                 h.step(at, pre)
         nal = [h.num_agents_all() for h in hs.values()]
-        assert np.array_equal(nal[0], nal[1]) and np.array_equal(nal[0], nal[2])
+        assert all(np.array_equal(nal[0], x) for x in nal[1:])
         nmin = int(nal[0].min())
         deltas = []
         for l in range(2):
@@ -177,6 +177,12 @@ def test_fast_mode_hostnet_in_kernel_edge_ops():
         ne2 = rng.integers(20, 150, size=R).astype(np.int32)
         el2 = rng.integers(1, nmin + 1, size=(R, 2, 160)).astype(np.int32); el2[:, 1] = np.where(el2[:, 1] == el2[:, 0], el2[:, 0] % nmin + 1, el2[:, 1])
         for name, h in hs.items():
+            if name == "weekcall":                                # the whole week as ONE ABI call (xgc_week_hostnet)
+                cw = np.empty((R, K.NCOUNTER), np.uint32); nw = np.empty(R, np.int32)
+                h.week_hostnet(at, post, pre if at < T else 0, deltas[0].ctypes.data, deltas[0].shape[1], deltas[1].ctypes.data, deltas[1].shape[1], True,
+                               el2.ctypes.data, ne2.ctypes.data, 160, cw.ctypes.data, nw.ctypes.data)
+                assert np.array_equal(cw, h.counters_all(at)) and np.array_equal(nw, h.num_agents_all())
+                continue
             for l in range(2):
                 h.update_edgelists_all(l, deltas[l].ctypes.data, deltas[l].shape[1], has_start=True)
             h.set_edgelists_all(2, el2.ctypes.data, ne2.ctypes.data, 0, stride=160)
@@ -185,7 +191,7 @@ def test_fast_mode_hostnet_in_kernel_edge_ops():
             else:
                 h.step(at, post)
     ref = hs["standalone"]
-    for name in ("fused", "fused+span"):
+    for name in ("fused", "fused+span", "weekcall"):
         h = hs[name]
         for r in range(R):
             assert h.status(r) == 0 and ref.status(r) == 0

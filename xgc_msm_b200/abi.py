@@ -51,7 +51,7 @@ def _load() -> C.CDLL:
         "xgc_set_edgelist": [vp, ci, ci, pi, ci, pi], "xgc_get_edgelist": [vp, ci, ci, pi, ci, pi, pi],
         "xgc_get_actcounts": [vp, ci, ci, pi, ci, pi],
         "xgc_get_actlist": [vp, ci, ci, pi, ci, pi, C.POINTER(xgc_inject)],
-        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_step_span": [vp, ci, cu, cu], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
+        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_step_span": [vp, ci, cu, cu], "xgc_week_hostnet": [vp, ci, cu, cu, vp, ci, vp, ci, ci, vp, vp, ci, vp, vp], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
         "xgc_compact": [vp], "xgc_status": [vp, ci, pu],
         "xgc_get_counters": [vp, ci, ci, ci, pu], "xgc_get_epi": [vp, ci, C.c_char_p, pd, ci, ci],
         "xgc_get_epi_table": [vp, ci, C.POINTER(C.c_char_p), ci, pd, ci, ci],
@@ -273,6 +273,12 @@ class Handle:
     def step_span(self, at: int, mask_tail: int, mask_head: int):
         """The rest of week `at` and the start of week at + 1 in one call (xgc_step_span; one resident launch in fast mode)."""
         self._ck(lib.xgc_step_span(self._h, at, mask_tail, mask_head))
+
+    def week_hostnet(self, at: int, mask_tail: int, mask_head: int, delta_main: int, stride_main: int, delta_casl: int, stride_casl: int,
+                     has_start: bool, el_inst: int, ne_inst: int, stride_inst: int, counters_out: int, n_alive_out: int):
+        """One week of the host-network loop in one ABI call (xgc_week_hostnet); every buffer is a raw host pointer (0 = NULL)."""
+        self._ck(lib.xgc_week_hostnet(self._h, at, mask_tail, mask_head, delta_main or None, stride_main, delta_casl or None, stride_casl,
+                                      int(has_start), el_inst or None, ne_inst or None, stride_inst, counters_out or None, n_alive_out or None))
 
     def run(self, at0: int, at1: int):
         self._ck(lib.xgc_run(self._h, at0, at1))

@@ -1440,6 +1440,29 @@ static int flush_pending_edges(xgc_handle* h) {
   return 0;
 }
 
+// One week of the host-network loop in ONE call (what the wrapper around the host's simnet_msm makes once it has the week's
+// network changes): the toggles of the main / casual layers, the new one-off list, the rest of week `at` (mask_tail), the start of
+// week at + 1 (mask_head; 0 = none), then week at's tallies and the living counts the host needs for the next network step -- one
+// crossing of the FFI boundary, one device -> host wait.  Any of the three edge-list arguments may be NULL (layer unchanged).
+extern "C" int xgc_week_hostnet(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head,
+                                const int32_t* delta_main, int stride_main, const int32_t* delta_casl, int stride_casl, int has_start,
+                                const int32_t* el_inst, const int32_t* ne_inst, int stride_inst,
+                                uint32_t* counters_out /*[R][XGC_NCOUNTER], week at*/, int32_t* n_alive_out /*[R]*/) {
+  int rc = 0;
+  if (delta_main) { rc = xgc_update_edgelists_all(h, 0, delta_main, stride_main, has_start); if (rc) return rc; }
+  if (delta_casl) { rc = xgc_update_edgelists_all(h, 1, delta_casl, stride_casl, has_start); if (rc) return rc; }
+  if (el_inst) { rc = xgc_set_edgelists_all(h, 2, el_inst, ne_inst, nullptr, stride_inst); if (rc) return rc; }
+  rc = mask_head ? xgc_step_span(h, at, mask_tail, mask_head) : xgc_step(h, at, mask_tail, nullptr);
+  if (rc) return rc;
+  if (counters_out)
+    CU(h, cudaMemcpy2DAsync(counters_out, sizeof(uint32_t) * XGC_NCOUNTER, h->g.counters + (size_t)at * XGC_NCOUNTER, sizeof(uint32_t) * XGC_NCOUNTER * (size_t)h->g.t_cap,
+                            sizeof(uint32_t) * XGC_NCOUNTER, (size_t)h->g.R, cudaMemcpyDeviceToHost, h->stream));
+  if (n_alive_out)
+    CU(h, cudaMemcpy2DAsync(n_alive_out, sizeof(int), &h->g.rep[0].n_alive, sizeof(Rep), sizeof(int), (size_t)h->g.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // debug entry points for the arithmetic-contract parity tests
 // --------------------------------------------------------------------------------------------------------------------
