@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--agents", type=int, default=10000)
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--e2e-separate-calls", action="store_true", help="fast mode: the week as separate ABI calls instead of one xgc_week_hostnet call")
+    ap.add_argument("--e2e-pack-by-cost", action="store_true", help="e2e handles hold replicates of similar cost instead of blocks of consecutive replicate ids")
     ap.add_argument("--e2e-no-span", action="store_true", help="fast mode: two xgc_step calls per week instead of xgc_step_span")
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
@@ -408,10 +409,22 @@ def run_xgc(args, rank, world, local_rank):
     g_size = [R // Ge + (1 if gi < R % Ge else 0) for gi in range(Ge)]
     g_off = [sum(g_size[:gi]) for gi in range(Ge)]
     groups = []
+    # --e2e-pack-by-cost: handles of replicates of SIMILAR cost (ranked by the SM cycles the device-resident arm above spent on each:
+    # xgc_replicate_cost; results do not depend on the packing: xgc_set_replicate_ids, Philox is keyed by the global id).  A call of the
+    # resident kernel is one wave and lasts as long as its slowest replicate (CTA times 90 .. 130 us around a mean of 109), but the
+    # measured week does not get shorter (0.948 vs 0.947 ms): the other handles' kernels already fill the tails.  Off by default.
+    pack = None
+    if mode == "fast" and args.e2e_pack_by_cost and Ge > 1:
+        cost = h.replicate_cost()
+        if cost.max() > 0:
+            pack = np.argsort(cost, kind="stable")
     for gi in range(Ge):
         hg = Handle(g_size[gi], spec.n_cap, spec.e_cap, t_cap, seed=args.seed, device=local_rank, replicate_offset=rid_base + g_off[gi],
                     compact_every=spec.weeks_between_compactions)
-        workload.load_sweep(hg, spec, rid0=rid_base + g_off[gi])
+        if pack is None:
+            workload.load_sweep(hg, spec, rid0=rid_base + g_off[gi])
+        else:
+            workload.load_sweep(hg, spec, ids=rid_base + pack[g_off[gi]:g_off[gi] + g_size[gi]])
         if mode == "fast":
             hg.set_mode("fast")
         hg.run(2, at - 1)                                   # same point of the epidemic as the kernel-resident arm
@@ -510,8 +523,9 @@ def run_xgc(args, rank, world, local_rank):
     if world > 1:
         tt = torch.tensor([dt_e], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt_e = float(tt.item())
         ta = torch.tensor([aw_e], device="cuda", dtype=torch.float64); dist.all_reduce(ta); aw_e = float(ta.item())
+    e2e_packing = "replicates of similar cost per handle (xgc_replicate_cost ranks, xgc_set_replicate_ids)" if pack is not None else "consecutive replicate ids per handle"
     e2e = {"value": aw_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": En,
-           "ms_per_step": dt_e / En * 1e3, "groups": Ge, "numa_node": numa,
+           "ms_per_step": dt_e / En * 1e3, "groups": Ge, "packing": e2e_packing, "numa_node": numa,
            "path": (f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week ONE call: xgc_week_hostnet = 2x xgc_update_edgelists_all (main / casual toggles) + "
                     "xgc_set_edgelists_all (one-off layer), pinned -> xgc_step_span(post of this week, pre of the next: one resident launch) -> xgc_get_counters_all + xgc_num_agents_all")
                    if span and not args.e2e_separate_calls else

@@ -357,6 +357,12 @@ enum { XGC_MODE_STRICT = 0, XGC_MODE_FAST = 1 };
 int  xgc_set_mode(xgc_handle* h, int mode);
 int  xgc_get_mode(xgc_handle* h, int* mode);
 
+/* Global ids of the handle's replicates (default replicate_offset + r).  Replicate r draws from Philox key (seed, ids[r]), so any
+ * subset of a sweep can be packed into a handle -- the reference's job array runs replicates as unrelated tasks, sim1_batch1.sh:6-9 --
+ * e.g. replicates of similar cost per week (xgc_replicate_cost: SM cycles of the resident kernel per replicate since the last reset). */
+int  xgc_set_replicate_ids(xgc_handle* h, const int32_t* ids /*[R]*/);
+int  xgc_replicate_cost(xgc_handle* h, uint64_t* cycles /*[R] or NULL*/, int reset);
+
 /* the step: runs the modules selected by module_mask for week `at` on every replicate, in reference order.
  * inj = NULL -> native Philox; otherwise draws come from the injected table. */
 int  xgc_step(xgc_handle* h, int at, uint32_t module_mask, const xgc_inject* inj);

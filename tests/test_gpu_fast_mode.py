@@ -300,3 +300,28 @@ def test_fast_mode_statistically_equivalent_to_oracle(R, N, WEEKS, TAIL):
     bad = {k: v for k, v in rep.items() if not (v[0] > 1e-3 and v[1] < 5.0)}
     assert not bad, bad
     h.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_replicate_ids_make_results_independent_of_the_packing(mode):
+    """xgc_set_replicate_ids: replicate r draws from Philox key (seed, ids[r]), so a handle that holds an arbitrary subset of a sweep
+    in an arbitrary order reproduces, replicate by replicate, what the contiguous handle computes; xgc_replicate_cost counts cycles."""
+    from xgc_msm_b200 import workload as W
+    from xgc_msm_b200.abi import Handle
+    spec = W.SweepSpec(n_agents=1500, seed=77)
+    R, T = 6, 12
+    ha = Handle(R, spec.n_cap, spec.e_cap, T + 4, seed=77, replicate_offset=40, compact_every=8)
+    W.load_sweep(ha, spec, rid0=40)
+    ids = np.array([44, 41, 45], dtype=np.int32)
+    hb = Handle(3, spec.n_cap, spec.e_cap, T + 4, seed=77, replicate_offset=0, compact_every=8)
+    W.load_sweep(hb, spec, ids=ids)
+    for h in (ha, hb):
+        h.set_mode(mode)
+        h.run(2, T)
+    for k, rid in enumerate(ids):
+        assert np.array_equal(ha.counters(int(rid) - 40, 2, T), hb.counters(k, 2, T)), f"replicate id {rid}"
+        assert np.array_equal(ha.download_attr(int(rid) - 40, "rGC"), hb.download_attr(k, "rGC"))
+    cost = hb.replicate_cost(reset=True)
+    assert (cost > 0).all() if mode == "fast" else (cost == 0).all()
+    assert (hb.replicate_cost() == 0).all()
+    ha.close(); hb.close()

@@ -71,6 +71,12 @@ if mode == "fast":
     h.sync()
     n = abi.lib.xgc_debug_fast_profile(buf, 16, 1)
     print("step-mode phase cycles per replicate-week:", {names[k]: int(buf[k] / (R * 8)) for k in range(n) if buf[k]}, "total", int(sum(buf[:n]) / (R * 8)))
+    for it in range(3):                                           # per-replicate CTA time of ONE call of the weekly contract
+        h.replicate_cost(reset=True)
+        week(False); h.sync()
+        c = h.replicate_cost().astype(np.float64) / 1.965e3      # us at 1965 MHz
+        print("CTA time per replicate in one week's calls (us): min %.1f  p10 %.1f  median %.1f  mean %.1f  p90 %.1f  p99 %.1f  max %.1f" %
+              (c.min(), np.percentile(c, 10), np.median(c), c.mean(), np.percentile(c, 90), np.percentile(c, 99), c.max()))
     if SPAN: sys.exit(0)
     h.set_control(control_msm(network_mode="surrogate").flags)
     h.run(at, at + 15); h.sync(); at += 16

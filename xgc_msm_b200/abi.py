@@ -51,7 +51,7 @@ def _load() -> C.CDLL:
         "xgc_set_edgelist": [vp, ci, ci, pi, ci, pi], "xgc_get_edgelist": [vp, ci, ci, pi, ci, pi, pi],
         "xgc_get_actcounts": [vp, ci, ci, pi, ci, pi],
         "xgc_get_actlist": [vp, ci, ci, pi, ci, pi, C.POINTER(xgc_inject)],
-        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_step_span": [vp, ci, cu, cu], "xgc_week_hostnet": [vp, ci, cu, cu, vp, ci, vp, ci, ci, vp, vp, ci, vp, vp], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
+        "xgc_step": [vp, ci, cu, C.POINTER(xgc_inject)], "xgc_step_span": [vp, ci, cu, cu], "xgc_set_replicate_ids": [vp, pi], "xgc_replicate_cost": [vp, C.POINTER(C.c_uint64), ci], "xgc_week_hostnet": [vp, ci, cu, cu, vp, ci, vp, ci, ci, vp, vp, ci, vp, vp], "xgc_run": [vp, ci, ci], "xgc_sync": [vp],
         "xgc_compact": [vp], "xgc_status": [vp, ci, pu],
         "xgc_get_counters": [vp, ci, ci, ci, pu], "xgc_get_epi": [vp, ci, C.c_char_p, pd, ci, ci],
         "xgc_get_epi_table": [vp, ci, C.POINTER(C.c_char_p), ci, pd, ci, ci],
@@ -269,6 +269,18 @@ class Handle:
     # stepping ------------------------------------------------------------------------------------------------------
     def step(self, at: int, mask: Optional[int] = None, inj: Optional[xgc_inject] = None):
         self._ck(lib.xgc_step(self._h, at, K.M_ALL if mask is None else mask, None if inj is None else C.byref(inj)))
+
+    def set_replicate_ids(self, ids):
+        """Global replicate ids (Philox keys) of this handle's replicates; default replicate_offset + r."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        assert ids.shape == (self.n_replicates,)
+        self._ck(lib.xgc_set_replicate_ids(self._h, _ptr(ids, C.c_int32)))
+
+    def replicate_cost(self, reset: bool = False) -> np.ndarray:
+        """SM cycles the resident (fast) kernel spent on each replicate since the last reset."""
+        out = np.zeros(self.n_replicates, dtype=np.uint64)
+        self._ck(lib.xgc_replicate_cost(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), int(reset)))
+        return out
 
     def step_span(self, at: int, mask_tail: int, mask_head: int):
         """The rest of week `at` and the start of week at + 1 in one call (xgc_step_span; one resident launch in fast mode)."""

@@ -80,6 +80,8 @@ struct Inj {                 // injected-draw table (device copy), u == nullptr 
 
 struct Dev {                 // everything a kernel needs; passed by value
   int R, n_cap, t_cap, rep0; int e_cap[3]; size_t e_off[3]; size_t e_stride;
+  const int* rep_id;         // [R] GLOBAL replicate id of each replicate (Philox key; default replicate_offset + r, xgc_set_replicate_ids)
+  unsigned long long* rep_cycles;      // [R] SM cycles the resident kernel spent on each replicate (xgc_replicate_cost)
   int r0;                    // first replicate of THIS launch and R = how many it covers: xgc_run drives the replicates as two concurrent lanes
   unsigned seed;
   double inv_dur[2];         // 1 / mean duration of main, casual ties (surrogate dissolution probability), set with the tables
@@ -124,7 +126,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox
 template <bool INJ> struct DrawT {
   const double* u; unsigned seed, rep, at, stream, e0, e1; int blk; uint4 v;
   __device__ __forceinline__ DrawT(const Inj& j, const Dev& g, int r, int at_, int stream_, unsigned e0_, unsigned e1_, size_t idx)
-      : u(nullptr), seed(g.seed), rep((unsigned)(g.rep0 + r)), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
+      : u(nullptr), seed(g.seed), rep((unsigned)g.rep_id[r]), at((unsigned)at_), stream((unsigned)stream_), e0(e0_), e1(e1_), blk(-1) {
     if (INJ) u = j.u + (size_t)r * j.stride + j.off[stream_] + idx * (size_t)xgc_stream_width(stream_);
   }
   // compute block b now, while the warp is still converged (later uses of its 4 draws are then free of divergent copies)

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(FT, 1) k_week_fast(const __grid_constant__ Dev
     const int w_first = A.at0 + (int)max(i0 - (long long)rr * W, 0LL), w_last = A.at0 + (int)min(i1 - (long long)rr * W, W) - 1;
     Rep* rp = g.rep + r;
     const size_t rbase = (size_t)r * g.n_cap;
-    const uint2 key = make_uint2(g.seed, (unsigned)(g.rep0 + r));
+    const uint2 key = make_uint2(g.seed, (unsigned)g.rep_id[r]);
+    const long long t_rep = clock64();
     const int* C = g.control + (size_t)r * XGC_NCONTROL;
     const int proto = C[XGC_C_stiScreeningProtocol], kissx = C[XGC_C_cdcExposureSite_Kissing], surrogate = C[XGC_C_network_mode] == 1;
     const bool pois_mode = C[XGC_C_gcUntreatedRecovDist] == XGC_RECOV_POIS;
@@ -1316,6 +1317,7 @@ _Pragma("unroll")
       __threadfence();                                          // the replicate's state before the week it reached is published
       __syncthreads();
       if (tid == 0) __stcg((int*)g.at_ptr + r, w_last);
+      if (tid == 0) atomicAdd(&g.rep_cycles[r], (unsigned long long)(clock64() - t_rep));
     }
     TICK(PH_WRITEBACK);
   }

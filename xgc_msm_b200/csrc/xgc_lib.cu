@@ -213,6 +213,7 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
   if (g.n_cap > 32768) { uint4* cs = nullptr; rc |= dalloc(h, &cs, NA); h->d_cscratch = cs; }     // parallel slot compaction, 16 B per slot
   rc |= dalloc(h, &g.edge, (size_t)g.R * g.e_stride);
   rc |= dalloc(h, &g.rep, (size_t)g.R);
+  { int* ids = nullptr; rc |= dalloc(h, &ids, (size_t)g.R); g.rep_id = ids; rc |= dalloc(h, &g.rep_cycles, (size_t)g.R); }
   double* dp; int* dc; double* dt; int* dat;
   rc |= dalloc(h, &dp, (size_t)g.R * XGC_NPARAM); rc |= dalloc(h, &dc, (size_t)g.R * XGC_NCONTROL);
   rc |= dalloc(h, &dt, (size_t)XGC_NTABLE); rc |= dalloc(h, &dat, (size_t)g.R);
@@ -232,6 +233,8 @@ extern "C" int xgc_create(const xgc_config* cfg, xgc_handle** out) {
 #include "xgc/params.def"
 #undef XGC_PARAM
   std::vector<int32_t> C(XGC_NCONTROL, 0); C[XGC_C_transRoute_Kissing] = 1; C[XGC_C_transRoute_Rimming] = 1;
+  { std::vector<int> ids((size_t)g.R); for (int r = 0; r < g.R; ++r) ids[r] = g.rep0 + r;
+    if (cudaMemcpy((int*)g.rep_id, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "replicate id upload failed"; return fail(3); } }
   if (xgc_set_params(h, -1, P.data()) || xgc_set_control(h, -1, C.data())) return fail(4);
   if (cudaDeviceSynchronize() != cudaSuccess) { h->err = "device synchronisation after allocation failed"; return fail(3); }      // the zero-fills above ran on the legacy stream
   *out = h;
@@ -278,6 +281,21 @@ static cudaError_t h2d(xgc_handle* h, void* d, const void* s, size_t bytes) {
 static cudaError_t d2h(xgc_handle* h, void* d, const void* s, size_t bytes) {
   cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->stream);
   return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
+// Global ids of this handle's replicates (the Philox key of replicate r is (seed, id[r])): lets a host pack ANY subset of a sweep into
+// a handle -- e.g. replicates of similar cost, so that the one-wave launches of the host-network loop have short tails -- with results
+// that do not depend on the packing.  Default: replicate_offset + r.
+extern "C" int xgc_set_replicate_ids(xgc_handle* h, const int32_t* ids) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, h2d(h, (int*)h->g.rep_id, ids, sizeof(int) * (size_t)h->g.R));
+  return 0;
+}
+// SM cycles the replicate-resident kernel has spent on each replicate since the last reset (a cost measure for such packing)
+extern "C" int xgc_replicate_cost(xgc_handle* h, uint64_t* cycles /*[R]*/, int reset) {
+  CU(h, cudaSetDevice(h->cfg.device)); CU(h, cudaStreamSynchronize(h->stream));
+  if (cycles) CU(h, d2h(h, cycles, h->g.rep_cycles, sizeof(uint64_t) * (size_t)h->g.R));
+  if (reset) { CU(h, cudaMemsetAsync(h->g.rep_cycles, 0, sizeof(uint64_t) * (size_t)h->g.R, h->stream)); CU(h, cudaStreamSynchronize(h->stream)); h->plain_next = true; }
+  return 0;
 }
 static void drop_graphs(xgc_handle* h) {            // kernel arguments baked into the captured week graphs changed
   if (h->week_graph) { cudaGraphExecDestroy(h->week_graph); h->week_graph = nullptr; }

@@ -64,14 +64,19 @@ def replicate_case(spec: SweepSpec, rid: int) -> dict:
                 tables=synth.make_tables(), attrs=a, els=els, starts=starts, cap=spec.n_cap, e_cap=spec.e_cap, at0=1)
 
 
-def load_sweep(h, spec: SweepSpec, rid0: int = 0):
-    """Fill handle `h` with replicates rid0 .. rid0 + R - 1.  The N_DISTINCT starting populations go through the
-    attribute/edge-list ABI once; the other replicates are device-to-device forks of them (xgc_fork)."""
+def load_sweep(h, spec: SweepSpec, rid0: int = 0, ids=None):
+    """Fill handle `h` with replicates rid0 .. rid0 + R - 1 (or with the global replicate ids `ids`, any subset of the sweep:
+    xgc_set_replicate_ids).  The N_DISTINCT starting populations go through the attribute/edge-list ABI once; the other
+    replicates are device-to-device forks of them (xgc_fork)."""
     R = h.n_replicates
+    rids = [rid0 + r for r in range(R)] if ids is None else [int(x) for x in ids]
+    assert len(rids) == R
+    if ids is not None:
+        h.set_replicate_ids(np.asarray(rids, dtype=np.int32))
     h.set_tables(synth.make_tables())
     first = {}
     for r in range(R):
-        rid = rid0 + r
+        rid = rids[r]
         idx = rid % spec.n_distinct
         if idx not in first:
             a, els, starts = _population(idx, spec.n_agents, spec.seed)
@@ -83,6 +88,6 @@ def load_sweep(h, spec: SweepSpec, rid0: int = 0):
             first[idx] = r
         else:
             h.fork_from(h, first[idx], r)
-    h.set_params(np.stack([replicate_params(spec, rid0 + r) for r in range(R)]))
+    h.set_params(np.stack([replicate_params(spec, rid) for rid in rids]))
     h.set_control(P.control_msm(network_mode=spec.network_mode).flags)
     h.sync()
