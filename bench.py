@@ -408,6 +408,11 @@ def run_xgc(args, rank, world, local_rank):
     Ge = max(1, min(Ge, R))
     g_size = [R // Ge + (1 if gi < R % Ge else 0) for gi in range(Ge)]
     g_off = [sum(g_size[:gi]) for gi in range(Ge)]
+    # one wave or less per GPU (the 8-GPU split of the 1000-replicate sweep: 125 per GPU): the week is the latency of ONE handle's round
+    # trip, and there the resident kernel applying the queued edge-list operations itself is worth 5 %; with several
+    # waves per GPU the standalone kernels are faster
+    if mode == "fast" and R <= torch.cuda.get_device_properties(local_rank).multi_processor_count:
+        os.environ.setdefault("XGC_FUSE_HOSTNET", "1")
     groups = []
     # --e2e-pack-by-cost: handles of replicates of SIMILAR cost (ranked by the SM cycles the device-resident arm above spent on each:
     # xgc_replicate_cost; results do not depend on the packing: xgc_set_replicate_ids, Philox is keyed by the global id).  A call of the
