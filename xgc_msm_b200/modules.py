@@ -188,12 +188,18 @@ def netsim(x, param, init: dict, control: P.Control, device: int = 0, seed: int 
             dat.h.run(first, control.nsteps)
             dat.at = control.nsteps
     else:
+        i = P.MODULE_ORDER.index("resim_nets")
+        pre_mask, post_mask = sum(P.MODULE_BIT[m] for m in P.MODULE_ORDER[:i]), sum(P.MODULE_BIT[m] for m in P.MODULE_ORDER[i + 1:])
+        pre_done = -1
         for at in range(first, control.nsteps + 1):
             if all_native:          # fuse the native modules either side of the host network step
-                i = P.MODULE_ORDER.index("resim_nets")
-                dat.h.step(at, sum(P.MODULE_BIT[m] for m in P.MODULE_ORDER[:i]))
+                if pre_done != at:
+                    dat.h.step(at, pre_mask)
                 dat = simnet_msm(dat, at)
-                dat.h.step(at, sum(P.MODULE_BIT[m] for m in P.MODULE_ORDER[i + 1:]))
+                if at < control.nsteps:     # nothing on the host between prevalence_msm(at) and aging_msm(at + 1): one call (xgc_step_span)
+                    dat.h.step_span(at, post_mask, pre_mask); pre_done = at + 1
+                else:
+                    dat.h.step(at, post_mask)
                 dat.at = at
             else:
                 for f in mods:
