@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--e2e-separate-calls", action="store_true", help="fast mode: the week as separate ABI calls instead of one xgc_week_hostnet call")
     ap.add_argument("--e2e-pack-by-cost", action="store_true", help="e2e handles hold replicates of similar cost instead of blocks of consecutive replicate ids")
+    ap.add_argument("--e2e-group-size", type=int, default=0, help="replicates per e2e handle (default: R split evenly over --e2e-groups handles)")
     ap.add_argument("--e2e-no-span", action="store_true", help="fast mode: two xgc_step calls per week instead of xgc_step_span")
     ap.add_argument("--e2e-groups", type=int, default=0, help="handles (streams) the e2e arm splits this GPU's replicates into")
     ap.add_argument("--profile-steps", type=int, default=6)
@@ -407,6 +408,9 @@ def run_xgc(args, rank, world, local_rank):
         Ge = min(Ge, max(2, -(-R // sms)))
     Ge = max(1, min(Ge, R))
     g_size = [R // Ge + (1 if gi < R % Ge else 0) for gi in range(Ge)]
+    if args.e2e_group_size > 0:                                   # explicit handle size (the last handle takes the remainder)
+        Ge = -(-R // args.e2e_group_size)
+        g_size = [min(args.e2e_group_size, R - gi * args.e2e_group_size) for gi in range(Ge)]
     g_off = [sum(g_size[:gi]) for gi in range(Ge)]
     # one wave or less per GPU (the 8-GPU split of the 1000-replicate sweep: 125 per GPU): the week is the latency of ONE handle's round
     # trip, and there the resident kernel applying the queued edge-list operations itself is worth 5 %; with several
