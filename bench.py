@@ -67,8 +67,9 @@ def workload_config(args, parallelism, mode=None):
                      "per-replicate LHS parameters over the reference prior box, all 17 weekly modules, one step = one week",
          "replicates_per_gpu": args.replicates, "agents_per_replicate": args.agents, "network": "on-device surrogate for simnet_msm",
          "parallelism": parallelism,
-         "l2": "no flush needed: the timed region sweeps ~1 GB of agent planes (1000 x 10k), >> 126 MB L2; the resident (fast) kernel "
-               "stages each replicate in shared memory for up to 64 weeks by design, so its HBM traffic is far below the per-week model"}
+         "l2": f"no flush: every week sweeps the agent planes of all replicates ({args.replicates} x {args.agents} agents x ~100 B = "
+               f"{args.replicates * args.agents * 100 / 1e9:.2f} GB per GPU against 126 MB of L2; smaller than L2 only for shapes other than the default); the resident (fast) "
+               "kernel stages each replicate in shared memory for up to 64 weeks by design, so its HBM traffic is far below the per-week model"}
     if args.total_replicates:
         c["total_replicates"] = args.total_replicates
     if mode:
