@@ -110,6 +110,9 @@ def test_fast_mode_step_groups_equal_run():
     for at in range(2, T):
         hd.step_span(at, K.M_ALL & ~pre, pre)
     hd.step(T, K.M_ALL & ~pre)
+    from xgc_msm_b200.abi import XgcError
+    with pytest.raises(XgcError):                                 # week T + 4 = t_cap does not exist: refused before anything runs
+        hd.step_span(T + 3, K.M_ALL & ~pre, pre)
     for r in range(R):
         ca = ha.counters(r, 2, T)
         for what, hx in (("weekly full steps", hc), ("step groups", hb), ("step spans", hd)):

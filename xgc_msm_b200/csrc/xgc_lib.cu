@@ -857,9 +857,10 @@ extern "C" int xgc_step(xgc_handle* h, int at, uint32_t mask, const xgc_inject* 
 // calls.  On the fast path the two groups run in one launch of the resident kernel -- the replicate is staged once, written
 // back once, and the host-network loop pays one launch and one device -> host wait per week instead of two.
 extern "C" int xgc_step_span(xgc_handle* h, int at, uint32_t mask_tail, uint32_t mask_head) {
+  if (at < 1 || at + 1 >= h->cfg.t_cap || at + 1 > 32766) FAIL(h, 2, "xgc_step_span: weeks %d and %d must lie in [1, t_cap = %d)", at, at + 1, h->cfg.t_cap);
   const unsigned pt = h->mode == XGC_MODE_FAST ? fast_phases(mask_tail) : 0u, phd = h->mode == XGC_MODE_FAST ? fast_phases(mask_head) : 0u;
   const bool compaction_due = at >= 1 && at % h->cfg.compact_every == 0 && h->compacted_at != at;      // xgc_step(at + 1) would compact first
-  if (!(pt & XF_POST) || (pt & XF_PRE) || phd != (unsigned)(XF_PRE | XF_PRUNE) || h->last_at != at || compaction_due || at + 1 >= h->cfg.t_cap || at + 1 > 32766) {
+  if (!(pt & XF_POST) || (pt & XF_PRE) || phd != (unsigned)(XF_PRE | XF_PRUNE) || h->last_at != at || compaction_due) {
     int rc = xgc_step(h, at, mask_tail, nullptr);
     return rc ? rc : xgc_step(h, at + 1, mask_head, nullptr);
   }
