@@ -525,6 +525,9 @@ def run_xgc(args, rank, world, local_rank):
         return sum(aw_g)
 
     run_weeks(at, 3); at += 3
+    if os.environ.get("XGC_DEBUG_COST") and mode == "fast":
+        for hg in groups:
+            hg.replicate_cost(reset=True)
     barrier()
     t0 = time.perf_counter()
     aw_e = run_weeks(at, En); at += En
@@ -542,6 +545,15 @@ def run_xgc(args, rank, world, local_rank):
                    f"{Ge} handles x {g_size[0]} replicates (one host thread each), each week: " + ("" if span else "xgc_step(pre) -> ") + "xgc_num_agents_all -> 2x xgc_update_edgelists_all "
                    "(main / casual toggles) + xgc_set_edgelists_all (one-off layer), pinned -> " +
                    ("xgc_step_span(post of this week, pre of the next: one resident launch)" if span else "xgc_step(post)") + " -> xgc_get_counters_all"}
+    if os.environ.get("XGC_DEBUG_COST") and mode == "fast":      # how well does the resident arm's per-replicate cost predict the one-week calls'?
+        c_res = h.replicate_cost().astype(np.float64)
+        c_e2e = np.zeros(R)
+        for gi, hg in enumerate(groups):
+            idx = pack[g_off[gi]:g_off[gi] + g_size[gi]] if pack is not None else np.arange(g_off[gi], g_off[gi] + g_size[gi])
+            c_e2e[idx] = hg.replicate_cost().astype(np.float64)
+        gmax = [float(groups[gi].replicate_cost().max()) for gi in range(Ge)]
+        print("cost: corr(resident, e2e) = %.3f; e2e CTA cycles per replicate-week: min %.3g mean %.3g max %.3g; sum of per-handle maxima / (mean x handles) = %.3f" %
+              (np.corrcoef(c_res, c_e2e)[0, 1], c_e2e.min() / En, c_e2e.mean() / En, c_e2e.max() / En, sum(gmax) / (c_e2e.mean() * Ge)), file=sys.stderr)
     e2e_status = 0
     for hg in groups:
         e2e_status |= int(np.bitwise_or.reduce([hg.status(r) for r in range(0, hg.n_replicates, max(hg.n_replicates // 8, 1))]))
