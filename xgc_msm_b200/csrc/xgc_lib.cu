@@ -1324,8 +1324,8 @@ extern "C" int xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el
   if (need > h->el_stage_cap) {
     if (h->d_el_stage) cudaFree(h->d_el_stage);
     h->d_el_stage = nullptr; h->el_stage_cap = 0;
-    CU(h, cudaMalloc((void**)&h->d_el_stage, need * sizeof(int)));
-    h->el_stage_cap = need;
+    CU(h, cudaMalloc((void**)&h->d_el_stage, (need + need / 4) * sizeof(int)));
+    h->el_stage_cap = need + need / 4;
   }
   int* d_el = h->d_el_stage; int* d_start = d_el + R * st * 2; int* d_ne = d_start + R * st;
   CU(h, cudaMemcpyAsync(d_el, el, R * st * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1422,8 +1422,10 @@ extern "C" int xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t*
   if (need > h->upd_stage_cap[layer]) {
     if (h->d_upd_stage[layer]) cudaFree(h->d_upd_stage[layer]);
     h->d_upd_stage[layer] = nullptr; h->upd_stage_cap[layer] = 0;
-    CU(h, cudaMalloc((void**)&h->d_upd_stage[layer], need * sizeof(int)));
-    h->upd_stage_cap[layer] = need;
+    // twice the first request: the weekly rows vary in length, and a reallocation (cudaFree: a device-wide wait) inside a running loop
+    // would stall every other handle of the GPU
+    CU(h, cudaMalloc((void**)&h->d_upd_stage[layer], 2 * need * sizeof(int)));
+    h->upd_stage_cap[layer] = 2 * need;
   }
   CU(h, cudaMemcpyAsync(h->d_upd_stage[layer], delta, need * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   h->plain_next = true;
