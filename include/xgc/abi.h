@@ -418,7 +418,11 @@ int  xgc_set_edgelists_all(xgc_handle* h, int layer, const int32_t* el /*[R][2][
  * i.e. after this week's departures were pruned, in the stable order both sides keep; tail/head are 1-based positions among
  * the living.  The surviving ties keep their order, the added ones are appended in the order given (start = has_start ? the
  * given week : the current week).  Same asynchrony and error flags as xgc_set_edgelists_all (a removed index outside the
- * list sets XGC_ST_BAD_EDGE). */
+ * list sets XGC_ST_BAD_EDGE).
+ * Environment, read by xgc_create: XGC_FUSE_HOSTNET=1 -- in XGC_MODE_FAST both calls only copy and QUEUE their operation, and the next
+ * acts..prevalence launch of the resident kernel applies it itself (same lists, bit for bit; the flags then appear with that step or
+ * with the next xgc_status); worth it when the handle has the GPU to itself (one wave or less), not when several handles share it.
+ * XGC_LANES=1 -- the strict xgc_run path drives the replicates as one lane instead of two concurrent ones. */
 int  xgc_update_edgelists_all(xgc_handle* h, int layer, const int32_t* delta /*[R][stride]*/, int stride, int has_start);
 int  xgc_get_counters_all (xgc_handle* h, int at, uint32_t* out /*[R][XGC_NCOUNTER]*/);
 int  xgc_num_agents_all   (xgc_handle* h, int32_t* out /*[R]*/);   /* living agents per replicate (what simnet_msm needs) */
